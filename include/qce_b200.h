@@ -1,0 +1,169 @@
+/*
+ * qce_b200.h -- C-ABI of the B200 execution engine (libqce_b200.so).
+ *
+ * This is the drop-in boundary: plain C, opaque handles, raw pointers and
+ * sizes, `int` status (0 ok / -1 error, text via qce_last_error()).  The
+ * host-side operator layer (query-compiler-executor_b200/src/filter.c, join.c,
+ * utilities.c -- same entry points as the reference's filter.h / join.h /
+ * utilities.h) calls nothing else.  Every entry point cites the reference code
+ * it replaces as path:line relative to /root/reference.
+ *
+ * Data model on the device (all resident in HBM, SoA):
+ *   base column   uint64_t[n]            one per (relation, column), uploaded once
+ *   row-id column uint32_t[m]            a mid_result's `payloads` (the reference
+ *                                        keeps a DArray of calloc'ed uint64_t*)
+ *   tuple run     packed uint64_t[m]     (key << 32 | rowid) when every key of the
+ *                                        source column is < 2^32, otherwise
+ *                 uint64_t keys[m] + uint32_t ids[m]
+ * Row ids are 32-bit on the device because the reference itself caps a relation
+ * below 2^31 tuples (`int start,size`, src/utilities.c:20; int32 histogram,
+ * src/histogram.h:5).  At the ABI they are widened to uint64_t.
+ *
+ * There is no CPU fallback: every compute entry point fails with -1 when no
+ * CUDA device is usable.
+ */
+#ifndef QCE_B200_H
+#define QCE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qce_rowids qce_rowids; /* device row-id column                   */
+typedef struct qce_tuples qce_tuples; /* device (key,rowid) run, maybe sorted   */
+
+/* ---- engine lifetime ---------------------------------------------------- */
+
+/* Bind the calling process to CUDA device `device` (one process per GPU) and
+ * create the stream / memory pool.  Idempotent.  No reference counterpart. */
+int qce_init(int device);
+void qce_shutdown(void);
+/* Last error text of the calling thread ("" when none). */
+const char *qce_last_error(void);
+/* ABI version, bumped on any signature change. */
+int qce_abi_version(void);
+/* Device-side time (ms) spent in engine kernels since the last reset, measured
+ * with CUDA events on the engine stream; used by the bench, not by the host. */
+int qce_timer_reset(void);
+int qce_timer_read(double *ms, uint64_t *kernel_launches);
+/* Block until all queued engine work is done. */
+int qce_sync(void);
+/* Per-kernel device times: CUDA events around every launch while enabled.
+ * qce_profile_json() returns {"tag": {"launches": n, "ms": total}, ...} for
+ * everything recorded since qce_profile_enable(1). */
+int qce_profile_enable(int on);
+const char *qce_profile_json(void);
+
+/* ---- base relations ------------------------------------------------------
+ * Replaces fill_data()/read_relations(), src/utilities.c:105-162: the column
+ * is uploaded as-is (SoA uint64), the row id stays implicit (= index); the
+ * reference's AoS tuple{key,payload=i} copy is never materialised.
+ * Also records max(column) so the sort knows its significant bits. */
+int qce_upload_column(uint32_t rel, uint32_t col, const uint64_t *host, uint64_t n);
+/* Same, source already in device memory (device-to-device copy). */
+int qce_upload_column_device(uint32_t rel, uint32_t col, const void *dev, uint64_t n);
+/* Adopt a device buffer without copying (caller keeps ownership, must outlive use). */
+int qce_adopt_column_device(uint32_t rel, uint32_t col, const void *dev, uint64_t n);
+int qce_column_info(uint32_t rel, uint32_t col, uint64_t *n, uint64_t *max_value);
+int qce_drop_relations(void);
+
+/* ---- filter operator -----------------------------------------------------
+ * `op` is the reference's operator character: '=', '>' or '<' (unsigned
+ * compare); any other character is an error ("Wrong operator",
+ * src/filter.c:28,58). */
+
+/* exec_filter_rel_no_exists, src/filter.c:37-64: all i with col[i] OP c, in
+ * ascending i. */
+int qce_filter_scan(uint32_t rel, uint32_t col, char op, uint64_t c, qce_rowids **out);
+/* exec_filter_rel_exists, src/filter.c:3-35: order-preserving subset of an
+ * existing row-id column, in place; *survivors = the count the reference
+ * prints at src/filter.c:32. */
+int qce_filter_refine(qce_rowids *ids, uint32_t rel, uint32_t col, char op, uint64_t c,
+                      uint64_t *survivors);
+
+/* ---- join operator primitives ------------------------------------------ */
+
+/* allocate_relation, src/join.c:122-142: (key = col[i], rowid = i), all i. */
+int qce_build_tuples_base(uint32_t rel, uint32_t col, qce_tuples **out);
+/* allocate_relation_mid_results, src/join.c:96-120: (key = col[id], rowid = id)
+ * for each id of the row-id column, in column order. */
+int qce_build_tuples_rowids(uint32_t rel, uint32_t col, const qce_rowids *ids, qce_tuples **out);
+/* iterative_sort, src/join.c:5-94 (+ build_histogram/build_psum/
+ * build_reordered_array, src/utilities.c:20-70; random_quicksort,
+ * src/quicksort.c:54-64): ascending by key.  Stable (equal keys keep their
+ * input order) -- the reference's tie order is unspecified. */
+int qce_sort_tuples(qce_tuples *t);
+/* 1 if keys are non-decreasing (the reference never checks; the host layer
+ * uses it to refuse JOIN_SORT_* merges over unsorted input). */
+int qce_tuples_is_sorted(const qce_tuples *t, int *sorted);
+
+/* join_relations, src/join.c:325-392: sort-merge equi-join of two key-sorted
+ * runs.  outR/outS = aligned row-id columns of all matching pairs, R-major
+ * (for each R tuple in order, each equal-key S tuple in order).
+ * distinctR/distinctS (may be NULL) = the R / S side of the distinct
+ * (rowid_R,rowid_S) pairs (`non_duplicates`, src/join.c:358-367); their order
+ * is (rowid_R,rowid_S)-ascending, the reference's is first-seen -- consumers
+ * (join_payloads) sort them first, so only the multiset matters. */
+int qce_merge_join(const qce_tuples *R, const qce_tuples *S, qce_rowids **outR, qce_rowids **outS,
+                   qce_rowids **distinctR, qce_rowids **distinctS);
+/* scan_join, src/join.c:395-423: positional filter keyR[i]==keyS[i] for
+ * i < min(nR,nS), keys gathered through the two row-id columns. */
+int qce_scan_join(uint32_t relR, uint32_t colR, const qce_rowids *idsR, uint32_t relS,
+                  uint32_t colS, const qce_rowids *idsS, qce_rowids **outR, qce_rowids **outS);
+/* Same with both sides read from base columns (ids = 0..n-1), the
+ * `lhs_index == -1 && rhs_index == -1` SCAN_JOIN of src/join.c:270-284. */
+int qce_scan_join_base(uint32_t relR, uint32_t colR, uint32_t relS, uint32_t colS,
+                       qce_rowids **outR, qce_rowids **outS);
+/* join_payloads, src/join.c:426-484: bystander re-join.  R' = (key=last[i],
+ * payload=edit[i]) for i < len(last); S' = driver; both sorted by key; emit
+ * edit[i] once per equal driver entry, in R'-sorted order. Fails (-1) when
+ * len(edit) < len(last) (the reference reads past the array there). */
+int qce_rejoin(const qce_rowids *driver, const qce_rowids *last, const qce_rowids *edit,
+               qce_rowids **out);
+
+/* ---- projection ----------------------------------------------------------
+ * print_sums, src/utilities.c:215-219: sums[k] = sum over ids of
+ * column (rel, cols[k])[id], modulo 2^64.  Up to 8 columns per call share one
+ * read of the row-id column. */
+int qce_checksum(const qce_rowids *ids, uint32_t rel, const uint32_t *cols, uint32_t ncols,
+                 uint64_t *sums);
+
+/* ---- handles -------------------------------------------------------------*/
+uint64_t qce_rowids_count(const qce_rowids *ids);
+int qce_rowids_from_host(const uint64_t *host, uint64_t n, qce_rowids **out);
+int qce_rowids_to_host(const qce_rowids *ids, uint64_t *host);
+int qce_rowids_clone(const qce_rowids *ids, qce_rowids **out);
+void qce_rowids_free(qce_rowids *ids);
+
+uint64_t qce_tuples_count(const qce_tuples *t);
+/* Build a run from host (key,payload) arrays -- test entry point. */
+int qce_tuples_from_host(const uint64_t *keys, const uint64_t *rowids, uint64_t n,
+                         qce_tuples **out);
+int qce_tuples_to_host(const qce_tuples *t, uint64_t *keys, uint64_t *rowids);
+void qce_tuples_free(qce_tuples *t);
+
+/* ---- multi-GPU exchange step --------------------------------
+ * Splits a tuple run by key range into `nparts` destination runs:
+ * part(key) = number of splitters <= key (splitters ascending, nparts-1 of
+ * them).  counts[p] = tuples for rank p.  The packed 8-byte words of part p
+ * are contiguous in *sendbuf (device pointer owned by the engine until
+ * qce_exchange_release) at element offset sum(counts[0..p)).  The collective
+ * itself (all-to-all over NVLink) is done by the caller's communicator
+ * (torch.distributed / NCCL) on those device pointers. */
+int qce_partition_tuples(const qce_tuples *t, const uint64_t *splitters, uint32_t nparts,
+                         uint64_t *counts, void **sendbuf);
+/* Wrap `n` received packed words (device pointer, copied) as a tuple run. */
+int qce_tuples_from_device_packed(const void *dev_words, uint64_t n, uint32_t key_bits,
+                                  qce_tuples **out);
+int qce_exchange_release(void *sendbuf);
+/* 256-bin histogram of the top 8 significant key bits of a run (for splitter
+ * selection from an all-reduced global histogram).  hist = 256 uint64 on host. */
+int qce_key_histogram(const qce_tuples *t, uint32_t key_bits, uint64_t *hist);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QCE_B200_H */

@@ -1,0 +1,252 @@
+// k_join.cuh -- sort-merge equi-join of two key-sorted tuple runs, and the
+// projection checksum.
+//
+// Replaces join_relations (src/join.c:325-392), the merge loop of join_payloads
+// (src/join.c:447-476) and print_sums' gather-sum (src/utilities.c:215-219).
+//
+// The reference walks both runs with one serial pointer pair and pushes one
+// calloc'ed element per match.  Here the join is two-phase (count, write):
+//   partition  one thread per tile of 2048 R tuples binary-searches the window
+//              of S that the tile's key range can touch
+//   bounds     per tile: stage the S window in shared memory, every R tuple
+//              finds lower/upper bound of its key there (or in global memory
+//              when the window is larger than the staging buffer); writes
+//              lb[i], cnt[i] and the tile's pair total
+//   scan       exclusive scan of tile totals -> output offsets; the same scan
+//              over ceil(total/4096) gives a work list of <=4096-pair chunks
+//   write      one CTA per chunk (load-balanced: a skewed key that produces
+//              millions of pairs is split over many CTAs): rebuilds the tile's
+//              offsets in shared memory, maps every output slot back to its R
+//              tuple by binary search and writes (rowid_R, rowid_S) coalesced.
+// Output order is the reference's: R-major, S in run order inside a key group.
+//
+// Algorithmic HBM bytes: 8 B (packed) per input tuple for the bounds pass,
+// 8 B per R tuple for lb/cnt (written then re-read), 8 B per output pair.
+#pragma once
+#include "qce_common.cuh"
+
+#define QCE_JTILE 2048     // R tuples per tile (256 threads x 8)
+#define QCE_JTHREADS 256
+#define QCE_JWIN 4096      // S window staged in shared memory (keys, 32 KB)
+#define QCE_JCHUNK 4096    // output pairs per write CTA
+
+template <bool WIDE>
+__device__ __forceinline__ u32 lower_bound_g(const TupleView &t, u32 lo, u32 hi, u64 key)
+{
+    while (lo < hi) {
+        u32 mid = lo + ((hi - lo) >> 1);
+        if (tv_key<WIDE>(t, mid) < key) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+template <bool WIDE>
+__device__ __forceinline__ u32 upper_bound_g(const TupleView &t, u32 lo, u32 hi, u64 key)
+{
+    while (lo < hi) {
+        u32 mid = lo + ((hi - lo) >> 1);
+        if (tv_key<WIDE>(t, mid) <= key) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// One thread per R tile: the S window [lo, hi) its key range can match.
+template <bool WR, bool WS>
+__global__ void __launch_bounds__(256)
+k_join_partition(TupleView R, u32 nR, TupleView S, u32 nS, u32 ntiles, uint2 *__restrict__ win)
+{
+    u32 t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= ntiles) return;
+    u32 first = t * QCE_JTILE;
+    u32 last = min(first + QCE_JTILE, nR) - 1;
+    u64 klo = tv_key<WR>(R, first), khi = tv_key<WR>(R, last);
+    u32 lo = lower_bound_g<WS>(S, 0, nS, klo);
+    u32 hi = upper_bound_g<WS>(S, lo, nS, khi);
+    win[t] = make_uint2(lo, hi);
+}
+
+template <bool WR, bool WS>
+__global__ void __launch_bounds__(QCE_JTHREADS)
+k_join_bounds(TupleView R, u32 nR, TupleView S, const uint2 *__restrict__ win,
+              u32 *__restrict__ lb_out, u32 *__restrict__ cnt_out, u64 *__restrict__ tile_total,
+              u32 *__restrict__ tile_chunks)
+{
+    __shared__ u64 skeys[QCE_JWIN];
+    __shared__ u64 scratch[33];
+    const int tid = threadIdx.x;
+    const u32 tbase = blockIdx.x * QCE_JTILE;
+    const uint2 w = win[blockIdx.x];
+    const u32 wn = w.y - w.x;
+    const bool staged = wn <= QCE_JWIN;
+    if (staged) {
+        for (u32 i = tid; i < wn; i += QCE_JTHREADS) skeys[i] = tv_key<WS>(S, w.x + i);
+    }
+    __syncthreads();
+    u64 sum = 0;
+#pragma unroll
+    for (int k = 0; k < QCE_JTILE / QCE_JTHREADS; k++) {
+        u32 i = tbase + k * QCE_JTHREADS + tid;
+        if (i < nR) {
+            u64 key = tv_key<WR>(R, i);
+            u32 lb, ub;
+            if (wn == 0) {
+                lb = ub = w.x;
+            } else if (staged) {
+                u32 lo = 0, hi = wn;
+                while (lo < hi) {
+                    u32 mid = (lo + hi) >> 1;
+                    if (skeys[mid] < key) lo = mid + 1; else hi = mid;
+                }
+                lb = lo;
+                hi = wn;
+                while (lo < hi) {
+                    u32 mid = (lo + hi) >> 1;
+                    if (skeys[mid] <= key) lo = mid + 1; else hi = mid;
+                }
+                ub = lo + w.x;
+                lb += w.x;
+            } else {
+                lb = lower_bound_g<WS>(S, w.x, w.y, key);
+                ub = upper_bound_g<WS>(S, lb, w.y, key);
+            }
+            lb_out[i] = lb;
+            cnt_out[i] = ub - lb;
+            sum += ub - lb;
+        }
+    }
+    u64 tot = block_sum<u64, QCE_JTHREADS>(sum, scratch);
+    if (tid == 0) {
+        tile_total[blockIdx.x] = tot;
+        tile_chunks[blockIdx.x] = (u32)((tot + QCE_JCHUNK - 1) / QCE_JCHUNK);
+    }
+}
+
+// One CTA per <=4096-pair chunk of one R tile.
+template <bool WR, bool WS, bool WRITE_R, bool WRITE_S>
+__global__ void __launch_bounds__(QCE_JTHREADS)
+k_join_write(TupleView R, u32 nR, TupleView S, const u32 *__restrict__ lb_in,
+             const u32 *__restrict__ cnt_in, const u64 *__restrict__ tile_off,
+             const u32 *__restrict__ chunk_off, u32 ntiles, u32 *__restrict__ outR,
+             u32 *__restrict__ outS)
+{
+    __shared__ u64 soff[QCE_JTILE + 1];
+    __shared__ u64 scratch[33];
+    __shared__ u32 s_tile;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        // largest tile t with chunk_off[t] <= blockIdx.x (tiles without output
+        // have zero chunks and are skipped by the search)
+        u32 lo = 0, hi = ntiles;
+        while (hi - lo > 1) {
+            u32 mid = (lo + hi) >> 1;
+            if (chunk_off[mid] <= blockIdx.x) lo = mid; else hi = mid;
+        }
+        s_tile = lo;
+    }
+    __syncthreads();
+    const u32 t = s_tile;
+    const u32 chunk = blockIdx.x - chunk_off[t];
+    const u32 tbase = t * QCE_JTILE;
+
+    // tile-local exclusive offsets of the R tuples (8 consecutive per thread)
+    u64 c[8], s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        u32 i = tbase + tid * 8 + k;
+        c[k] = (i < nR) ? (u64)cnt_in[i] : 0ull;
+        s += c[k];
+    }
+    u64 tot;
+    u64 ex = block_scan_excl<u64, QCE_JTHREADS>(s, scratch, &tot);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        soff[tid * 8 + k] = ex;
+        ex += c[k];
+    }
+    if (tid == QCE_JTHREADS - 1) soff[QCE_JTILE] = ex;
+    __syncthreads();
+
+    const u64 obeg = (u64)chunk * QCE_JCHUNK;
+    const u64 oend = min(obeg + QCE_JCHUNK, tot);
+    const u64 gbase = tile_off[t];
+    for (u64 o = obeg + tid; o < oend; o += QCE_JTHREADS) {
+        // largest i with soff[i] <= o (zero-count tuples share an offset with
+        // their successor and are skipped because we take the largest)
+        u32 lo = 0, hi = QCE_JTILE;
+        while (hi - lo > 1) {
+            u32 mid = (lo + hi) >> 1;
+            if (soff[mid] <= o) lo = mid; else hi = mid;
+        }
+        const u32 i = tbase + lo;
+        const u32 k = (u32)(o - soff[lo]);
+        if (WRITE_R) outR[gbase + o] = tv_id<WR>(R, i);
+        if (WRITE_S) outS[gbase + o] = tv_id<WS>(S, lb_in[i] + k);
+    }
+}
+
+// ---- projection checksum (print_sums, src/utilities.c:215-219) ------------------
+// sums[k] += sum over ids of cols[k][id] (mod 2^64).  One read of the row-id
+// column serves up to 8 projected columns of the same binding.
+struct ChecksumCols {
+    const u64 *col[8];
+};
+template <int NC>
+__global__ void __launch_bounds__(256)
+k_checksum(const u32 *__restrict__ ids, u64 n, ChecksumCols cols, u64 *__restrict__ sums)
+{
+    __shared__ u64 scratch[33];
+    u64 acc[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) acc[c] = 0;
+    const u64 stride = (u64)gridDim.x * 256 * 4;
+    const u64 n4 = n & ~3ull;
+    for (u64 i = ((u64)blockIdx.x * 256 + threadIdx.x) * 4; i < n4; i += stride) {
+        uint4 id = ld_stream_u32x4(ids + i);
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            u64 a = __ldg(cols.col[c] + id.x), b = __ldg(cols.col[c] + id.y);
+            u64 d = __ldg(cols.col[c] + id.z), e = __ldg(cols.col[c] + id.w);
+            acc[c] += (a + b) + (d + e);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n - n4)) {
+        u32 id = ids[n4 + threadIdx.x];
+#pragma unroll
+        for (int c = 0; c < NC; c++) acc[c] += __ldg(cols.col[c] + id);
+    }
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        u64 t = block_sum<u64, 256>(acc[c], scratch);
+        if (threadIdx.x == 0 && t) atomicAdd(&sums[c], t);
+    }
+}
+
+// Sum of a base column over all its rows (projection of an unfiltered binding
+// never happens in the reference -- every projected binding has a mid result --
+// but the sharded driver uses it for load-time fingerprints).
+__global__ void __launch_bounds__(256)
+k_column_stats(const u64 *__restrict__ col, u64 n, u64 *__restrict__ max_out)
+{
+    __shared__ u64 smax[8];
+    u64 m = 0;
+    const u64 stride = (u64)gridDim.x * 512;
+    for (u64 e = ((u64)blockIdx.x * 256 + threadIdx.x) * 2; e < n; e += stride) {
+        if (e + 1 < n) {
+            u64 a, b;
+            ld_stream_u64x2(col + e, a, b);
+            m = max(m, max(a, b));
+        } else {
+            m = max(m, col[e]);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(QCE_FULL_MASK, m, o));
+    if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 1; w < 8; w++) m = max(m, smax[w]);
+        atomicMax(max_out, m);
+    }
+}

@@ -1,0 +1,315 @@
+// k_radix.cuh -- tuple build, digit histograms and the one-sweep LSD radix pass.
+//
+// Replaces allocate_relation / allocate_relation_mid_results
+// (src/join.c:96-142), build_histogram / build_psum / build_reordered_array
+// (src/utilities.c:20-70), iterative_sort (src/join.c:5-94) and the
+// quicksort leaves (src/quicksort.c:54-64) of the reference.
+//
+// The reference sorts 16-byte AoS tuples MSD-first through 8 byte levels
+// (4 of them whole-array no-ops when keys < 2^32) and finishes buckets of
+// < 4096 tuples with an unstable randomized quicksort.  Here:
+//   * a run is packed to one 8-byte word (key << 32 | rowid) whenever the
+//     source column's maximum is < 2^32 (known from the load-time column
+//     statistics), halving the bytes every pass moves; wider keys use SoA
+//     uint64 keys + uint32 ids;
+//   * only the ceil(bitlen(max key)/8) significant digits are sorted;
+//   * each digit is one kernel that reads every tuple once and writes it once
+//     ("one sweep"): per-tile digit counts are published to a status array and
+//     the tile's global offsets come from a decoupled look-back over the
+//     preceding tiles, so there is no separate per-pass counting kernel;
+//   * ranks inside a tile come from warp match/popc (stable), tuples are
+//     staged in shared memory in digit order and leave in coalesced runs.
+// The sort is stable, so equal keys keep their input order (the reference's
+// tie order is unspecified).
+//
+// Algorithmic HBM bytes: 8 B/tuple once (histogram) + 16 B/tuple/pass packed
+// (32 B/tuple/pass for the reference's 16-byte tuples; 24 B wide SoA here).
+#pragma once
+#include "qce_common.cuh"
+
+#define QCE_RADIX_BITS 8
+#define QCE_RADIX_BINS 256
+#define QCE_MAX_PASSES 8
+
+struct RadixShifts {
+    int npass;
+    int shift[QCE_MAX_PASSES];
+};
+
+// ---- tuple build ---------------------------------------------------------------
+// Packed, from a base column: out[i] = col[i] << 32 | i   (src/join.c:131-134)
+__global__ void __launch_bounds__(256)
+k_build_packed_base(const u64 *__restrict__ col, u64 n, u64 *__restrict__ out)
+{
+    const u64 stride = (u64)gridDim.x * 512;
+    for (u64 e = ((u64)blockIdx.x * 256 + threadIdx.x) * 2; e < n; e += stride) {
+        if (e + 1 < n) {
+            u64 a, b;
+            ld_stream_u64x2(col + e, a, b);
+            st_stream_u64x2(out + e, (a << 32) | e, (b << 32) | (e + 1));
+        } else {
+            out[e] = (col[e] << 32) | e;
+        }
+    }
+}
+// Packed, through a row-id column: out[i] = col[ids[i]] << 32 | ids[i]
+// (src/join.c:107-112).  The gather is sector-bound unless ids are clustered
+// (filter outputs are ascending).
+__global__ void __launch_bounds__(256)
+k_build_packed_ids(const u64 *__restrict__ col, const u32 *__restrict__ ids, u64 n,
+                   u64 *__restrict__ out)
+{
+    const u64 stride = (u64)gridDim.x * 256 * 4;
+    for (u64 i0 = (u64)blockIdx.x * 256 * 4 + threadIdx.x; i0 < n; i0 += stride) {
+        u32 id[4];
+        u64 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) id[k] = (i0 + k * 256 < n) ? ids[i0 + k * 256] : 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[k] = (i0 + k * 256 < n) ? __ldg(col + id[k]) : 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (i0 + k * 256 < n) out[i0 + k * 256] = (v[k] << 32) | id[k];
+    }
+}
+// Wide (keys may exceed 32 bits): SoA keys[] / ids[].
+__global__ void __launch_bounds__(256)
+k_build_wide(const u64 *__restrict__ col, const u32 *__restrict__ ids, u64 n,
+             u64 *__restrict__ keys, u32 *__restrict__ out_ids)
+{
+    const u64 stride = (u64)gridDim.x * 256;
+    for (u64 i = (u64)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
+        u32 id = ids ? ids[i] : (u32)i;
+        keys[i] = __ldg(col + id);
+        out_ids[i] = id;
+    }
+}
+// Packed from two row-id columns: out[i] = hi[i] << 32 | (lo ? lo[i] : 0).
+// Used by the bystander re-join (R' = (key=last[i], payload=edit[i]),
+// S' = (key=driver[i], 0); src/join.c:431-442) and the distinct-pair pass.
+__global__ void __launch_bounds__(256)
+k_pack_pairs(const u32 *__restrict__ hi, const u32 *__restrict__ lo, u64 n, u64 *__restrict__ out)
+{
+    const u64 stride = (u64)gridDim.x * 256;
+    for (u64 i = (u64)blockIdx.x * 256 + threadIdx.x; i < n; i += stride)
+        out[i] = ((u64)hi[i] << 32) | (lo ? (u64)lo[i] : 0ull);
+}
+__global__ void __launch_bounds__(256)
+k_unpack_lo(const u64 *__restrict__ in, u64 n, u32 *__restrict__ out)
+{
+    const u64 stride = (u64)gridDim.x * 256;
+    for (u64 i = (u64)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) out[i] = (u32)in[i];
+}
+
+// ---- digit histograms of every pass in one read (build_histogram,
+// src/utilities.c:20-31, hoisted out of the per-bucket loop) ------------------------
+__global__ void __launch_bounds__(512)
+k_radix_hist(const u64 *__restrict__ keys, u64 n, RadixShifts rs, u32 *__restrict__ ghist)
+{
+    __shared__ u32 sh[QCE_MAX_PASSES * QCE_RADIX_BINS];
+    for (int i = threadIdx.x; i < rs.npass * QCE_RADIX_BINS; i += 512) sh[i] = 0;
+    __syncthreads();
+    const u64 stride = (u64)gridDim.x * 1024;
+    for (u64 e = ((u64)blockIdx.x * 512 + threadIdx.x) * 2; e < n; e += stride) {
+        u64 a, b = 0;
+        const bool two = e + 1 < n;
+        if (two) ld_stream_u64x2(keys + e, a, b);
+        else a = keys[e];
+#pragma unroll
+        for (int p = 0; p < QCE_MAX_PASSES; p++) {
+            if (p < rs.npass) {
+                atomicAdd(&sh[p * QCE_RADIX_BINS + ((a >> rs.shift[p]) & 255)], 1u);
+                if (two) atomicAdd(&sh[p * QCE_RADIX_BINS + ((b >> rs.shift[p]) & 255)], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < rs.npass * QCE_RADIX_BINS; i += 512)
+        if (sh[i]) atomicAdd(&ghist[i], sh[i]);
+}
+
+// build_psum (src/utilities.c:34-48): exclusive prefix over the 256 bins of
+// each pass.  One CTA of 256 threads per pass.
+__global__ void __launch_bounds__(256) k_radix_bases(const u32 *__restrict__ ghist,
+                                                     u32 *__restrict__ gbase)
+{
+    __shared__ u32 scratch[33];
+    u32 v = ghist[blockIdx.x * QCE_RADIX_BINS + threadIdx.x];
+    u32 tot;
+    u32 ex = block_scan_excl<u32, 256>(v, scratch, &tot);
+    gbase[blockIdx.x * QCE_RADIX_BINS + threadIdx.x] = ex;
+}
+
+// ---- digit functors ------------------------------------------------------------
+struct DigitShift {
+    int shift;
+    __device__ __forceinline__ u32 operator()(u64 k) const { return (u32)(k >> shift) & 255u; }
+};
+// Range partition for the multi-GPU exchange: digit = number of splitters <= key
+// (keys compared on the packed word's key field).
+struct DigitSplit {
+    u64 split[15]; // ascending, in packed-word units (key << 32)
+    int nsplit;
+    __device__ __forceinline__ u32 operator()(u64 k) const
+    {
+        u32 d = 0;
+#pragma unroll
+        for (int i = 0; i < 15; i++) d += (i < nsplit && k >= split[i]) ? 1u : 0u;
+        return d;
+    }
+};
+
+// ---- one-sweep pass ------------------------------------------------------------
+// Tile status word: top 2 bits = flag, low 30 bits = count (n < 2^30 per sort).
+#define QCE_ST_PART 0x40000000u
+#define QCE_ST_INCL 0x80000000u
+#define QCE_ST_MASK 0x3fffffffu
+
+template <int THREADS, int ITEMS> struct OnesweepSmem {
+    u32 warp_hist[(THREADS / 32) * QCE_RADIX_BINS]; // per-warp digit counts -> bases
+    u32 tile_excl[QCE_RADIX_BINS];                  // digit start inside the sorted tile
+    u32 goff[QCE_RADIX_BINS];                       // global start of digit minus tile_excl
+    u32 scratch[33];
+    u32 tile_id;
+    u64 keys[THREADS * ITEMS];
+};
+
+template <int THREADS, int ITEMS, bool HAS_VALS, typename DigitOp>
+__global__ void __launch_bounds__(THREADS)
+k_onesweep(const u64 *__restrict__ keys_in, u64 *__restrict__ keys_out,
+           const u32 *__restrict__ vals_in, u32 *__restrict__ vals_out, u32 n, DigitOp digit,
+           const u32 *__restrict__ gbase, u32 *__restrict__ status, u32 *__restrict__ tile_counter)
+{
+    constexpr int TILE = THREADS * ITEMS;
+    constexpr int WARPS = THREADS / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    OnesweepSmem<THREADS, ITEMS> &sm = *reinterpret_cast<OnesweepSmem<THREADS, ITEMS> *>(smem_raw);
+    u32 *svals = reinterpret_cast<u32 *>(smem_raw + sizeof(OnesweepSmem<THREADS, ITEMS>));
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // Tiles are claimed in launch order so that every tile a CTA may wait on in
+    // the look-back is owned by a CTA that is already resident.
+    if (tid == 0) sm.tile_id = atomicAdd(tile_counter, 1u);
+    for (int i = tid; i < WARPS * QCE_RADIX_BINS; i += THREADS) sm.warp_hist[i] = 0;
+    __syncthreads();
+    const u32 tile = sm.tile_id;
+    const u32 tbase = tile * TILE;
+    const u32 nvalid = min((u32)TILE, n - tbase);
+
+    // ---- load: warp-striped so that (warp, item, lane) order == input order
+    u64 key[ITEMS];
+    u32 val[HAS_VALS ? ITEMS : 1];
+    const u32 wbase = tbase + warp * (32 * ITEMS) + lane;
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+        u32 idx = wbase + j * 32;
+        key[j] = (idx < n) ? ld_stream_u64(keys_in + idx) : ~0ull;
+        if (HAS_VALS) val[j] = (idx < n) ? ld_stream_u32(vals_in + idx) : 0u;
+    }
+
+    // ---- rank inside the warp: match lanes with the same digit
+    u32 rank[ITEMS];
+    u32 dig[ITEMS];
+    u32 *wh = sm.warp_hist + warp * QCE_RADIX_BINS;
+    const u32 lt = lanemask_lt();
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+        // padding of the last tile must sort behind every real tuple of the tile
+        const u32 d = (key[j] == ~0ull && (wbase + j * 32) >= n) ? 255u : digit(key[j]);
+        dig[j] = d;
+        const u32 peers = __match_any_sync(QCE_FULL_MASK, d);
+        const u32 r = __popc(peers & lt);
+        const int leader = __ffs(peers) - 1;
+        u32 old = 0;
+        if (r == 0) {
+            old = wh[d];
+            wh[d] = old + __popc(peers);
+        }
+        __syncwarp();
+        old = __shfl_sync(QCE_FULL_MASK, old, leader);
+        rank[j] = old + r;
+    }
+    __syncthreads();
+
+    // ---- per digit: exclusive scan over warps, tile total
+    u32 my_count = 0;
+    if (tid < QCE_RADIX_BINS) {
+        u32 run = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; w++) {
+            u32 c = sm.warp_hist[w * QCE_RADIX_BINS + tid];
+            sm.warp_hist[w * QCE_RADIX_BINS + tid] = run;
+            run += c;
+        }
+        my_count = run;
+        // the padding of the last tile is not part of the global count
+        if (tid == 255) my_count -= (TILE - nvalid);
+        // publish the tile-local count before anything else so successors can
+        // make progress while this tile looks back
+        u32 *st = status + (size_t)tile * QCE_RADIX_BINS + tid;
+        st_relaxed_gpu_u32(st, (tile == 0 ? QCE_ST_INCL : QCE_ST_PART) | my_count);
+    }
+    // ---- digit starts inside the tile (exclusive scan over the 256 digits;
+    //      THREADS >= 256 so the first 8 warps hold one digit each)
+    {
+        u32 v = (tid < QCE_RADIX_BINS) ? my_count + ((tid == 255) ? (TILE - nvalid) : 0u) : 0u;
+        u32 tot;
+        u32 ex = block_scan_excl<u32, THREADS>(v, sm.scratch, &tot);
+        if (tid < QCE_RADIX_BINS) sm.tile_excl[tid] = ex;
+    }
+    // ---- decoupled look-back: sum the counts of the preceding tiles
+    if (tid < QCE_RADIX_BINS) {
+        u32 excl = 0;
+        if (tile > 0) {
+            int p = (int)tile - 1;
+            while (true) {
+                u32 v = ld_relaxed_gpu_u32(status + (size_t)p * QCE_RADIX_BINS + tid);
+                if ((v & ~QCE_ST_MASK) == 0) { __nanosleep(32); continue; }
+                excl += v & QCE_ST_MASK;
+                if (v & QCE_ST_INCL) break;
+                p--;
+            }
+            st_relaxed_gpu_u32(status + (size_t)tile * QCE_RADIX_BINS + tid,
+                               QCE_ST_INCL | (excl + my_count));
+        }
+        sm.goff[tid] = gbase[tid] + excl - sm.tile_excl[tid];
+    }
+    __syncthreads();
+
+    // ---- stage in shared memory in digit order
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+        const u32 d = dig[j];
+        const u32 pos = sm.tile_excl[d] + wh[d] + rank[j];
+        sm.keys[pos] = key[j];
+        if (HAS_VALS) svals[pos] = val[j];
+    }
+    __syncthreads();
+
+    // ---- coalesced write-out: consecutive threads, consecutive slots of a digit
+    //      (positions >= nvalid are exactly the padding of the last tile)
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+        const u32 p = tid + j * THREADS;
+        if (p < nvalid) {
+            const u64 k = sm.keys[p];
+            const u32 d = digit(k);
+            const u32 g = sm.goff[d] + p;
+            keys_out[g] = k;
+            if (HAS_VALS) vals_out[g] = svals[p];
+        }
+    }
+}
+
+// 1 if keys[i-1] > keys[i] anywhere (checks the "already sorted" assumption of
+// JOIN_SORT_LHS / JOIN_SORT_RHS, src/join.c:647-658).
+template <bool WIDE>
+__global__ void __launch_bounds__(256) k_is_unsorted(TupleView t, u64 n, u32 *__restrict__ flag)
+{
+    const u64 stride = (u64)gridDim.x * 256;
+    bool bad = false;
+    for (u64 i = (u64)blockIdx.x * 256 + threadIdx.x + 1; i < n; i += stride)
+        bad |= tv_key<WIDE>(t, i - 1) > tv_key<WIDE>(t, i);
+    if (__any_sync(QCE_FULL_MASK, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
+}

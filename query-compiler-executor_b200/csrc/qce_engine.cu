@@ -1,0 +1,1023 @@
+// qce_engine.cu -- libqce_b200.so: the C-ABI of include/qce_b200.h on top of
+// the sm_100a kernels in k_filter.cuh / k_radix.cuh / k_join.cuh.
+//
+// One process drives one GPU.  All work is queued on one engine stream;
+// temporaries come from the stream-ordered CUDA memory pool (no cudaMalloc /
+// cudaFree on the hot path); the only host synchronisations are the result
+// sizes the host-side operator layer needs to size the next step (filter
+// count, join pair count) and the final checksums.
+//
+// There is deliberately no CPU path: if the CUDA runtime reports no usable
+// device every entry point returns -1 and qce_last_error() says why.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/qce_b200.h"
+#include "k_filter.cuh"
+#include "k_join.cuh"
+#include "k_radix.cuh"
+
+#define QCE_ABI_VERSION 1
+
+// ------------------------------------------------------------------ handles
+struct qce_rowids {
+    u32 *d;        // device row ids
+    u64 n;
+    u32 id_bound;  // exclusive upper bound of the ids (rows of the source relation), 0 = unknown
+};
+struct qce_tuples {
+    u64 *a;        // packed words (key << 32 | rowid), or keys when wide
+    u32 *ids;      // wide only
+    u64 n;
+    bool wide;
+    int key_bits;  // significant bits of the largest possible key
+    u32 id_bound;
+    bool sorted;
+};
+
+namespace {
+
+struct Column {
+    const u64 *d = nullptr;
+    u64 n = 0;
+    u64 maxv = 0;
+    bool owned = false;
+};
+
+struct ProfRec {
+    const char *tag;
+    cudaEvent_t e0, e1;
+};
+
+struct Engine {
+    bool inited = false;
+    int device = -1;
+    int sms = 148;
+    cudaStream_t stream = nullptr;
+    std::map<u64, Column> cols;
+    u64 *d_scalars = nullptr; // 16 u64 of device scratch for totals
+    u64 *h_scalars = nullptr; // pinned mirror
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    u64 launches = 0;
+    bool profile = false;
+    std::vector<ProfRec> prof;
+    std::string prof_json;
+};
+Engine g;
+thread_local char g_err[512] = "";
+
+int fail(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return -1;
+}
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail("%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+#define NEED_INIT()                                                                 \
+    do {                                                                            \
+        if (!g.inited && qce_init(-1) != 0) return -1;                              \
+    } while (0)
+
+inline int bitlen(u64 v)
+{
+    int b = 0;
+    while (v) { b++; v >>= 1; }
+    return b;
+}
+inline u64 ceil_div(u64 a, u64 b) { return (a + b - 1) / b; }
+inline u64 col_key(u32 rel, u32 col) { return ((u64)rel << 32) | col; }
+
+// stream-ordered allocation
+template <typename T> int dalloc(T **p, u64 count)
+{
+    *p = nullptr;
+    if (count == 0) count = 1;
+    CK(cudaMallocAsync((void **)p, count * sizeof(T), g.stream));
+    return 0;
+}
+template <typename T> void dfree(T *p)
+{
+    if (p) cudaFreeAsync((void *)p, g.stream);
+}
+
+void prof_begin(const char *tag)
+{
+    if (!g.profile) return;
+    ProfRec r;
+    r.tag = tag;
+    cudaEventCreate(&r.e0);
+    cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, g.stream);
+    g.prof.push_back(r);
+}
+void prof_end()
+{
+    if (!g.profile) return;
+    cudaEventRecord(g.prof.back().e1, g.stream);
+}
+
+#define LAUNCH(tag, kern, grid, block, smem, ...)                         \
+    do {                                                                  \
+        prof_begin(tag);                                                  \
+        (kern)<<<(grid), (block), (smem), g.stream>>>(__VA_ARGS__);       \
+        prof_end();                                                       \
+        g.launches++;                                                     \
+        CK(cudaGetLastError());                                           \
+    } while (0)
+
+// read `k` device scalars (d_scalars[0..k)) back; the one sync point of an op
+int read_scalars(int k)
+{
+    CK(cudaMemcpyAsync(g.h_scalars, g.d_scalars, k * sizeof(u64), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+int get_column(u32 rel, u32 col, const Column **out)
+{
+    auto it = g.cols.find(col_key(rel, col));
+    if (it == g.cols.end()) return fail("relation %u column %u was never uploaded", rel, col);
+    *out = &it->second;
+    return 0;
+}
+
+int op_code(char op, int *code)
+{
+    switch (op) {
+    case '=': *code = QCE_OP_EQ; return 0;
+    case '>': *code = QCE_OP_GT; return 0;
+    case '<': *code = QCE_OP_LT; return 0;
+    }
+    return fail("Wrong operator '%c'", op);
+}
+
+int new_rowids(u64 n, u32 id_bound, qce_rowids **out)
+{
+    qce_rowids *r = new qce_rowids();
+    r->n = n;
+    r->id_bound = id_bound;
+    if (dalloc(&r->d, n) != 0) { delete r; return -1; }
+    *out = r;
+    return 0;
+}
+
+int grid_for(u64 items_per_block, u64 n, int waves = 8)
+{
+    u64 blocks = ceil_div(n ? n : 1, items_per_block);
+    u64 cap = (u64)g.sms * waves;
+    return (int)(blocks < cap ? blocks : cap);
+}
+
+// mask + per-tile counts -> compacted outputs (pass 2 of every filter-like op)
+int compact_from_mask(int layout, int mode, const u32 *mask, const u32 *tile_count, u64 ntiles,
+                      const void *src0, const u32 *src1, u32 id_bound0, u32 id_bound1,
+                      qce_rowids **out0, qce_rowids **out1)
+{
+    u32 *tile_off = nullptr;
+    if (dalloc(&tile_off, ntiles) != 0) return -1;
+    LAUNCH("scan_tiles", (k_scan_excl<u32, u32>), 1, 1024, 0, tile_count, tile_off, ntiles, g.d_scalars);
+    if (read_scalars(1) != 0) return -1;
+    const u64 m = g.h_scalars[0];
+    if (new_rowids(m, id_bound0, out0) != 0) return -1;
+    if (out1 && new_rowids(m, id_bound1, out1) != 0) return -1;
+    u32 *o0 = (*out0)->d, *o1 = out1 ? (*out1)->d : nullptr;
+    if (m > 0) {
+        const int grid = (int)ntiles;
+        if (layout == QCE_LAYOUT_PAIR && mode == QCE_EMIT_INDEX)
+            LAUNCH("compact_ids", (k_compact<QCE_LAYOUT_PAIR, QCE_EMIT_INDEX>), grid, QCE_FTHREADS, 0,
+                   mask, tile_off, tile_count, src0, src1, o0, o1);
+        else if (layout == QCE_LAYOUT_NATURAL && mode == QCE_EMIT_SRC)
+            LAUNCH("compact_src", (k_compact<QCE_LAYOUT_NATURAL, QCE_EMIT_SRC>), grid, QCE_FTHREADS, 0,
+                   mask, tile_off, tile_count, src0, src1, o0, o1);
+        else if (layout == QCE_LAYOUT_NATURAL && mode == QCE_EMIT_SRC2)
+            LAUNCH("compact_src2", (k_compact<QCE_LAYOUT_NATURAL, QCE_EMIT_SRC2>), grid, QCE_FTHREADS, 0,
+                   mask, tile_off, tile_count, src0, src1, o0, o1);
+        else if (layout == QCE_LAYOUT_NATURAL && mode == QCE_EMIT_PACKED)
+            LAUNCH("compact_packed", (k_compact<QCE_LAYOUT_NATURAL, QCE_EMIT_PACKED>), grid, QCE_FTHREADS, 0,
+                   mask, tile_off, tile_count, src0, src1, o0, o1);
+        else
+            return fail("internal: unsupported compaction layout/mode %d/%d", layout, mode);
+    }
+    dfree(tile_off);
+    return 0;
+}
+
+// ---- radix sort driver -------------------------------------------------------
+constexpr int RS_THREADS = 512;
+constexpr int RS_ITEMS = 8;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
+
+template <bool HAS_VALS, typename DigitOp>
+int launch_onesweep(const u64 *kin, u64 *kout, const u32 *vin, u32 *vout, u32 n, DigitOp dop,
+                    const u32 *gbase, u32 *status, u32 *counter)
+{
+    auto kern = k_onesweep<RS_THREADS, RS_ITEMS, HAS_VALS, DigitOp>;
+    const size_t smem = sizeof(OnesweepSmem<RS_THREADS, RS_ITEMS>) + (HAS_VALS ? RS_TILE * sizeof(u32) : 0);
+    static bool attr_set = false; // per instantiation
+    if (!attr_set) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const u32 ntiles = (u32)ceil_div(n, RS_TILE);
+    LAUNCH(HAS_VALS ? "onesweep_kv" : "onesweep_k", kern, ntiles, RS_THREADS, smem, kin, kout, vin, vout, n,
+           dop, gbase, status, counter);
+    return 0;
+}
+
+// Sort words (and optional 32-bit values) by the digits listed in rs, least
+// significant first.  *keys / *vals are replaced by the sorted buffers.
+int radix_sort(u64 **keys, u32 **vals, u64 n, const RadixShifts &rs)
+{
+    if (n <= 1 || rs.npass == 0) return 0;
+    if (n >= (1ull << 30)) return fail("sort of %llu tuples exceeds the 2^30 per-run limit", (unsigned long long)n);
+    const u32 ntiles = (u32)ceil_div(n, RS_TILE);
+    u64 *alt_k = nullptr;
+    u32 *alt_v = nullptr, *ghist = nullptr, *gbase = nullptr, *status = nullptr, *counters = nullptr;
+    if (dalloc(&alt_k, n) != 0) return -1;
+    if (vals && dalloc(&alt_v, n) != 0) return -1;
+    if (dalloc(&ghist, (u64)rs.npass * QCE_RADIX_BINS) != 0) return -1;
+    if (dalloc(&gbase, (u64)rs.npass * QCE_RADIX_BINS) != 0) return -1;
+    if (dalloc(&status, (u64)rs.npass * ntiles * QCE_RADIX_BINS) != 0) return -1;
+    if (dalloc(&counters, (u64)rs.npass) != 0) return -1;
+    CK(cudaMemsetAsync(ghist, 0, (u64)rs.npass * QCE_RADIX_BINS * sizeof(u32), g.stream));
+    CK(cudaMemsetAsync(status, 0, (u64)rs.npass * ntiles * QCE_RADIX_BINS * sizeof(u32), g.stream));
+    CK(cudaMemsetAsync(counters, 0, (u64)rs.npass * sizeof(u32), g.stream));
+    LAUNCH("radix_hist", k_radix_hist, grid_for(1024, n, 4), 512, 0, *keys, n, rs, ghist);
+    LAUNCH("radix_bases", k_radix_bases, rs.npass, 256, 0, ghist, gbase);
+
+    u64 *kin = *keys, *kout = alt_k;
+    u32 *vin = vals ? *vals : nullptr, *vout = alt_v;
+    for (int p = 0; p < rs.npass; p++) {
+        DigitShift dop{rs.shift[p]};
+        int rc = vals ? launch_onesweep<true>(kin, kout, vin, vout, (u32)n, dop, gbase + p * QCE_RADIX_BINS,
+                                              status + (u64)p * ntiles * QCE_RADIX_BINS, counters + p)
+                      : launch_onesweep<false>(kin, kout, vin, vout, (u32)n, dop, gbase + p * QCE_RADIX_BINS,
+                                               status + (u64)p * ntiles * QCE_RADIX_BINS, counters + p);
+        if (rc != 0) return -1;
+        std::swap(kin, kout);
+        std::swap(vin, vout);
+    }
+    // kin/vin now hold the sorted data
+    dfree(kout);
+    if (vals) dfree(vout);
+    *keys = kin;
+    if (vals) *vals = vin;
+    dfree(ghist);
+    dfree(gbase);
+    dfree(status);
+    dfree(counters);
+    return 0;
+}
+
+RadixShifts shifts_for(int base_shift, int bits)
+{
+    RadixShifts rs;
+    rs.npass = 0;
+    for (int b = 0; b < bits && rs.npass < QCE_MAX_PASSES; b += QCE_RADIX_BITS) rs.shift[rs.npass++] = base_shift + b;
+    for (int i = rs.npass; i < QCE_MAX_PASSES; i++) rs.shift[i] = 0;
+    return rs;
+}
+
+TupleView view_of(const qce_tuples *t)
+{
+    TupleView v;
+    v.a = t->a;
+    v.ids = t->ids;
+    return v;
+}
+
+// ---- merge join driver -------------------------------------------------------
+template <bool WR, bool WS>
+int merge_join_t(const qce_tuples *R, const qce_tuples *S, bool want_r, bool want_s, qce_rowids **outR,
+                 qce_rowids **outS)
+{
+    const u32 nR = (u32)R->n, nS = (u32)S->n;
+    const u32 ntiles = (u32)ceil_div(nR, QCE_JTILE);
+    uint2 *win = nullptr;
+    u32 *lb = nullptr, *cnt = nullptr, *tile_chunks = nullptr, *chunk_off = nullptr;
+    u64 *tile_total = nullptr, *tile_off = nullptr;
+    if (dalloc(&win, ntiles) || dalloc(&lb, nR) || dalloc(&cnt, nR) || dalloc(&tile_chunks, ntiles) ||
+        dalloc(&chunk_off, ntiles) || dalloc(&tile_total, ntiles) || dalloc(&tile_off, ntiles))
+        return -1;
+    TupleView vr = view_of(R), vs = view_of(S);
+    LAUNCH("join_partition", (k_join_partition<WR, WS>), (int)ceil_div(ntiles, 256), 256, 0, vr, nR, vs, nS,
+           ntiles, win);
+    LAUNCH("join_bounds", (k_join_bounds<WR, WS>), (int)ntiles, QCE_JTHREADS, 0, vr, nR, vs, win, lb, cnt,
+           tile_total, tile_chunks);
+    LAUNCH("scan_tiles", (k_scan_excl<u64, u64>), 1, 1024, 0, tile_total, tile_off, (u64)ntiles, g.d_scalars);
+    LAUNCH("scan_tiles", (k_scan_excl<u32, u32>), 1, 1024, 0, tile_chunks, chunk_off, (u64)ntiles,
+           g.d_scalars + 1);
+    if (read_scalars(2) != 0) return -1;
+    const u64 m = g.h_scalars[0], nchunks = g.h_scalars[1];
+    if (m >= (1ull << 32)) return fail("join output of %llu pairs exceeds the 2^32 row-id column limit", (unsigned long long)m);
+    qce_rowids *oR = nullptr, *oS = nullptr;
+    if (want_r && new_rowids(m, R->id_bound, &oR) != 0) return -1;
+    if (want_s && new_rowids(m, S->id_bound, &oS) != 0) return -1;
+    if (m > 0) {
+        u32 *pr = oR ? oR->d : nullptr, *ps = oS ? oS->d : nullptr;
+        if (want_r && want_s)
+            LAUNCH("join_write", (k_join_write<WR, WS, true, true>), (int)nchunks, QCE_JTHREADS, 0, vr, nR, vs, lb,
+                   cnt, tile_off, chunk_off, ntiles, pr, ps);
+        else if (want_r)
+            LAUNCH("join_write", (k_join_write<WR, WS, true, false>), (int)nchunks, QCE_JTHREADS, 0, vr, nR, vs, lb,
+                   cnt, tile_off, chunk_off, ntiles, pr, ps);
+        else
+            LAUNCH("join_write", (k_join_write<WR, WS, false, true>), (int)nchunks, QCE_JTHREADS, 0, vr, nR, vs, lb,
+                   cnt, tile_off, chunk_off, ntiles, pr, ps);
+    }
+    dfree(win); dfree(lb); dfree(cnt); dfree(tile_chunks); dfree(chunk_off); dfree(tile_total); dfree(tile_off);
+    if (outR) *outR = oR;
+    if (outS) *outS = oS;
+    return 0;
+}
+
+int merge_join_any(const qce_tuples *R, const qce_tuples *S, bool want_r, bool want_s, qce_rowids **outR,
+                   qce_rowids **outS)
+{
+    if (R->n >= (1ull << 32) || S->n >= (1ull << 32)) return fail("join input exceeds 2^32 tuples");
+    if (R->n == 0 || S->n == 0) {
+        if (outR) *outR = nullptr;
+        if (outS) *outS = nullptr;
+        if (want_r && new_rowids(0, R->id_bound, outR) != 0) return -1;
+        if (want_s && new_rowids(0, S->id_bound, outS) != 0) return -1;
+        return 0;
+    }
+    if (R->wide && S->wide) return merge_join_t<true, true>(R, S, want_r, want_s, outR, outS);
+    if (R->wide) return merge_join_t<true, false>(R, S, want_r, want_s, outR, outS);
+    if (S->wide) return merge_join_t<false, true>(R, S, want_r, want_s, outR, outS);
+    return merge_join_t<false, false>(R, S, want_r, want_s, outR, outS);
+}
+
+// distinct (rowid_R,rowid_S) pairs of a join output: pack, sort every
+// significant bit, flag heads, compact.
+int distinct_pairs(const qce_rowids *pr, const qce_rowids *ps, qce_rowids **dr, qce_rowids **ds)
+{
+    const u64 m = pr->n;
+    if (m == 0) {
+        if (new_rowids(0, pr->id_bound, dr) != 0) return -1;
+        return new_rowids(0, ps->id_bound, ds);
+    }
+    u64 *w = nullptr;
+    if (dalloc(&w, m) != 0) return -1;
+    LAUNCH("pack_pairs", k_pack_pairs, grid_for(256, m), 256, 0, pr->d, ps->d, m, w);
+    const int bits_s = ps->id_bound ? bitlen(ps->id_bound - 1) : 32;
+    const int bits_r = pr->id_bound ? bitlen(pr->id_bound - 1) : 32;
+    RadixShifts rs;
+    rs.npass = 0;
+    for (int b = 0; b < bits_s; b += 8) rs.shift[rs.npass++] = b;
+    for (int b = 0; b < bits_r; b += 8) rs.shift[rs.npass++] = 32 + b;
+    for (int i = rs.npass; i < QCE_MAX_PASSES; i++) rs.shift[i] = 0;
+    if (radix_sort(&w, nullptr, m, rs) != 0) return -1;
+    const u64 ntiles = ceil_div(m, QCE_FTILE);
+    u32 *mask = nullptr, *tile_count = nullptr;
+    if (dalloc(&mask, ntiles * QCE_FWORDS) || dalloc(&tile_count, ntiles)) return -1;
+    LAUNCH("unique_mask", k_unique_mask, (int)ntiles, QCE_FTHREADS, 0, w, m, mask, tile_count);
+    int rc = compact_from_mask(QCE_LAYOUT_NATURAL, QCE_EMIT_PACKED, mask, tile_count, ntiles, w, nullptr,
+                               pr->id_bound, ps->id_bound, dr, ds);
+    dfree(mask); dfree(tile_count); dfree(w);
+    return rc;
+}
+
+__global__ void __launch_bounds__(256)
+k_split_hist(const u64 *__restrict__ w, u64 n, DigitSplit ds, u32 *__restrict__ ghist)
+{
+    __shared__ u32 sh[16];
+    if (threadIdx.x < 16) sh[threadIdx.x] = 0;
+    __syncthreads();
+    u32 local[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) local[i] = 0;
+    const u64 stride = (u64)gridDim.x * 256;
+    for (u64 i = (u64)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
+        u32 d = ds(w[i]);
+#pragma unroll
+        for (int k = 0; k < 16; k++) local[k] += (d == (u32)k);
+    }
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        u32 s = warp_sum_u32(local[k]);
+        if ((threadIdx.x & 31) == 0 && s) atomicAdd(&sh[k], s);
+    }
+    __syncthreads();
+    if (threadIdx.x < 16 && sh[threadIdx.x]) atomicAdd(&ghist[threadIdx.x], sh[threadIdx.x]);
+}
+
+} // namespace
+
+// =============================================================== C-ABI
+extern "C" {
+
+int qce_abi_version(void) { return QCE_ABI_VERSION; }
+const char *qce_last_error(void) { return g_err; }
+
+int qce_init(int device)
+{
+    if (g.inited) return 0;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail("no CUDA device available (%s); this engine has no CPU path",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0) {
+        const char *lr = getenv("LOCAL_RANK");
+        device = lr ? atoi(lr) % count : 0;
+    }
+    if (device >= count) return fail("device %d out of range (%d visible)", device, count);
+    CK(cudaSetDevice(device));
+    g.device = device;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    g.sms = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    cudaMemPool_t pool;
+    CK(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t keep = UINT64_MAX; // never trim: temporaries are recycled across operators
+    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    CK(cudaMalloc((void **)&g.d_scalars, 16 * sizeof(u64)));
+    CK(cudaMallocHost((void **)&g.h_scalars, 16 * sizeof(u64)));
+    CK(cudaEventCreate(&g.t0));
+    CK(cudaEventCreate(&g.t1));
+    g.inited = true;
+    g_err[0] = 0;
+    return 0;
+}
+
+void qce_shutdown(void)
+{
+    if (!g.inited) return;
+    qce_drop_relations();
+    cudaStreamSynchronize(g.stream);
+    cudaFree(g.d_scalars);
+    cudaFreeHost(g.h_scalars);
+    cudaEventDestroy(g.t0);
+    cudaEventDestroy(g.t1);
+    cudaStreamDestroy(g.stream);
+    g = Engine();
+}
+
+int qce_sync(void)
+{
+    NEED_INIT();
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+int qce_timer_reset(void)
+{
+    NEED_INIT();
+    g.launches = 0;
+    CK(cudaEventRecord(g.t0, g.stream));
+    return 0;
+}
+int qce_timer_read(double *ms, uint64_t *kernel_launches)
+{
+    NEED_INIT();
+    CK(cudaEventRecord(g.t1, g.stream));
+    CK(cudaEventSynchronize(g.t1));
+    float f = 0;
+    CK(cudaEventElapsedTime(&f, g.t0, g.t1));
+    if (ms) *ms = f;
+    if (kernel_launches) *kernel_launches = g.launches;
+    return 0;
+}
+
+// Per-kernel device times (CUDA events around every launch); off by default.
+int qce_profile_enable(int on)
+{
+    NEED_INIT();
+    CK(cudaStreamSynchronize(g.stream));
+    for (auto &r : g.prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    g.prof.clear();
+    g.profile = on != 0;
+    return 0;
+}
+// JSON object {"tag": {"launches": n, "ms": total}, ...} of everything recorded
+// since qce_profile_enable(1); the pointer stays valid until the next call.
+const char *qce_profile_json(void)
+{
+    if (!g.inited) return "{}";
+    cudaStreamSynchronize(g.stream);
+    std::map<std::string, std::pair<u64, double>> agg;
+    for (auto &r : g.prof) {
+        float f = 0;
+        if (cudaEventElapsedTime(&f, r.e0, r.e1) == cudaSuccess) {
+            auto &a = agg[r.tag];
+            a.first++;
+            a.second += f;
+        }
+    }
+    g.prof_json = "{";
+    bool first = true;
+    for (auto &kv : agg) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "%s\"%s\": {\"launches\": %llu, \"ms\": %.6f}", first ? "" : ", ",
+                 kv.first.c_str(), (unsigned long long)kv.second.first, kv.second.second);
+        g.prof_json += buf;
+        first = false;
+    }
+    g.prof_json += "}";
+    return g.prof_json.c_str();
+}
+
+// ---------------------------------------------------------------- relations
+static int register_column(u32 rel, u32 col, const u64 *d, u64 n, bool owned)
+{
+    CK(cudaMemsetAsync(g.d_scalars + 8, 0, sizeof(u64), g.stream));
+    if (n > 0) LAUNCH("column_stats", k_column_stats, grid_for(512, n, 4), 256, 0, d, n, g.d_scalars + 8);
+    CK(cudaMemcpyAsync(g.h_scalars + 8, g.d_scalars + 8, sizeof(u64), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    Column c;
+    c.d = d;
+    c.n = n;
+    c.maxv = g.h_scalars[8];
+    c.owned = owned;
+    auto it = g.cols.find(col_key(rel, col));
+    if (it != g.cols.end() && it->second.owned) cudaFree((void *)it->second.d);
+    g.cols[col_key(rel, col)] = c;
+    return 0;
+}
+
+int qce_upload_column(uint32_t rel, uint32_t col, const uint64_t *host, uint64_t n)
+{
+    NEED_INIT();
+    if (n >= (1ull << 32)) return fail("relation %u has %llu rows; device row ids are 32-bit", rel, (unsigned long long)n);
+    u64 *d = nullptr;
+    CK(cudaMalloc((void **)&d, (n ? n : 1) * sizeof(u64)));
+    if (n) CK(cudaMemcpyAsync(d, host, n * sizeof(u64), cudaMemcpyHostToDevice, g.stream));
+    return register_column(rel, col, d, n, true);
+}
+int qce_upload_column_device(uint32_t rel, uint32_t col, const void *dev, uint64_t n)
+{
+    NEED_INIT();
+    if (n >= (1ull << 32)) return fail("relation %u has %llu rows; device row ids are 32-bit", rel, (unsigned long long)n);
+    u64 *d = nullptr;
+    CK(cudaMalloc((void **)&d, (n ? n : 1) * sizeof(u64)));
+    if (n) CK(cudaMemcpyAsync(d, dev, n * sizeof(u64), cudaMemcpyDeviceToDevice, g.stream));
+    return register_column(rel, col, d, n, true);
+}
+int qce_adopt_column_device(uint32_t rel, uint32_t col, const void *dev, uint64_t n)
+{
+    NEED_INIT();
+    if (n >= (1ull << 32)) return fail("relation %u has %llu rows; device row ids are 32-bit", rel, (unsigned long long)n);
+    if (((uintptr_t)dev & 15) != 0) return fail("adopted column must be 16-byte aligned");
+    return register_column(rel, col, (const u64 *)dev, n, false);
+}
+int qce_column_info(uint32_t rel, uint32_t col, uint64_t *n, uint64_t *max_value)
+{
+    NEED_INIT();
+    const Column *c;
+    if (get_column(rel, col, &c) != 0) return -1;
+    if (n) *n = c->n;
+    if (max_value) *max_value = c->maxv;
+    return 0;
+}
+int qce_drop_relations(void)
+{
+    if (!g.inited) return 0;
+    cudaStreamSynchronize(g.stream);
+    for (auto &kv : g.cols)
+        if (kv.second.owned) cudaFree((void *)kv.second.d);
+    g.cols.clear();
+    return 0;
+}
+
+// ---------------------------------------------------------------- filter
+int qce_filter_scan(uint32_t rel, uint32_t col, char op, uint64_t c, qce_rowids **out)
+{
+    NEED_INIT();
+    const Column *cl;
+    int code;
+    if (get_column(rel, col, &cl) != 0 || op_code(op, &code) != 0) return -1;
+    const u64 n = cl->n;
+    if (n == 0) return new_rowids(0, 0, out);
+    const u64 ntiles = ceil_div(n, QCE_FTILE);
+    u32 *mask = nullptr, *tile_count = nullptr;
+    if (dalloc(&mask, ntiles * QCE_FWORDS) || dalloc(&tile_count, ntiles)) return -1;
+    if (code == QCE_OP_EQ)
+        LAUNCH("filter_scan", (k_filter_mask_base<QCE_OP_EQ>), (int)ntiles, QCE_FTHREADS, 0, cl->d, n, c, mask, tile_count);
+    else if (code == QCE_OP_GT)
+        LAUNCH("filter_scan", (k_filter_mask_base<QCE_OP_GT>), (int)ntiles, QCE_FTHREADS, 0, cl->d, n, c, mask, tile_count);
+    else
+        LAUNCH("filter_scan", (k_filter_mask_base<QCE_OP_LT>), (int)ntiles, QCE_FTHREADS, 0, cl->d, n, c, mask, tile_count);
+    int rc = compact_from_mask(QCE_LAYOUT_PAIR, QCE_EMIT_INDEX, mask, tile_count, ntiles, nullptr, nullptr,
+                               (u32)n, 0, out, nullptr);
+    dfree(mask);
+    dfree(tile_count);
+    return rc;
+}
+
+int qce_filter_refine(qce_rowids *ids, uint32_t rel, uint32_t col, char op, uint64_t c, uint64_t *survivors)
+{
+    NEED_INIT();
+    const Column *cl;
+    int code;
+    if (!ids) return fail("null row-id column");
+    if (get_column(rel, col, &cl) != 0 || op_code(op, &code) != 0) return -1;
+    const u64 n = ids->n;
+    if (n == 0) { if (survivors) *survivors = 0; return 0; }
+    const u64 ntiles = ceil_div(n, QCE_FTILE);
+    u32 *mask = nullptr, *tile_count = nullptr;
+    if (dalloc(&mask, ntiles * QCE_FWORDS) || dalloc(&tile_count, ntiles)) return -1;
+    if (code == QCE_OP_EQ)
+        LAUNCH("filter_refine", (k_refine_mask<QCE_OP_EQ>), (int)ntiles, QCE_FTHREADS, 0, ids->d, n, cl->d, c, mask, tile_count);
+    else if (code == QCE_OP_GT)
+        LAUNCH("filter_refine", (k_refine_mask<QCE_OP_GT>), (int)ntiles, QCE_FTHREADS, 0, ids->d, n, cl->d, c, mask, tile_count);
+    else
+        LAUNCH("filter_refine", (k_refine_mask<QCE_OP_LT>), (int)ntiles, QCE_FTHREADS, 0, ids->d, n, cl->d, c, mask, tile_count);
+    qce_rowids *kept = nullptr;
+    int rc = compact_from_mask(QCE_LAYOUT_NATURAL, QCE_EMIT_SRC, mask, tile_count, ntiles, ids->d, nullptr,
+                               ids->id_bound, 0, &kept, nullptr);
+    dfree(mask);
+    dfree(tile_count);
+    if (rc != 0) return -1;
+    dfree(ids->d);
+    ids->d = kept->d;
+    ids->n = kept->n;
+    delete kept;
+    if (survivors) *survivors = ids->n;
+    return 0;
+}
+
+// ---------------------------------------------------------------- tuples
+static int build_tuples(const Column *cl, const qce_rowids *ids, qce_tuples **out)
+{
+    const u64 n = ids ? ids->n : cl->n;
+    qce_tuples *t = new qce_tuples();
+    t->n = n;
+    t->key_bits = bitlen(cl->maxv) ? bitlen(cl->maxv) : 1;
+    t->wide = t->key_bits > 32;
+    t->id_bound = (u32)cl->n;
+    t->sorted = false;
+    t->ids = nullptr;
+    if (dalloc(&t->a, n) != 0) { delete t; return -1; }
+    if (t->wide && dalloc(&t->ids, n) != 0) { delete t; return -1; }
+    if (n > 0) {
+        if (t->wide)
+            LAUNCH("build_tuples", k_build_wide, grid_for(256, n), 256, 0, cl->d, ids ? ids->d : nullptr, n, t->a, t->ids);
+        else if (ids)
+            LAUNCH("build_tuples", k_build_packed_ids, grid_for(1024, n), 256, 0, cl->d, ids->d, n, t->a);
+        else
+            LAUNCH("build_tuples", k_build_packed_base, grid_for(512, n), 256, 0, cl->d, n, t->a);
+    }
+    *out = t;
+    return 0;
+}
+int qce_build_tuples_base(uint32_t rel, uint32_t col, qce_tuples **out)
+{
+    NEED_INIT();
+    const Column *cl;
+    if (get_column(rel, col, &cl) != 0) return -1;
+    return build_tuples(cl, nullptr, out);
+}
+int qce_build_tuples_rowids(uint32_t rel, uint32_t col, const qce_rowids *ids, qce_tuples **out)
+{
+    NEED_INIT();
+    const Column *cl;
+    if (!ids) return fail("null row-id column");
+    if (get_column(rel, col, &cl) != 0) return -1;
+    return build_tuples(cl, ids, out);
+}
+
+int qce_sort_tuples(qce_tuples *t)
+{
+    NEED_INIT();
+    if (!t) return fail("null tuple run");
+    RadixShifts rs = shifts_for(t->wide ? 0 : 32, t->key_bits);
+    int rc = t->wide ? radix_sort(&t->a, &t->ids, t->n, rs) : radix_sort(&t->a, nullptr, t->n, rs);
+    if (rc == 0) t->sorted = true;
+    return rc;
+}
+
+int qce_tuples_is_sorted(const qce_tuples *t, int *sorted)
+{
+    NEED_INIT();
+    if (!t || !sorted) return fail("null argument");
+    if (t->n < 2) { *sorted = 1; return 0; }
+    u32 *flag = (u32 *)(g.d_scalars + 9);
+    CK(cudaMemsetAsync(flag, 0, sizeof(u64), g.stream));
+    if (t->wide)
+        LAUNCH("is_sorted", (k_is_unsorted<true>), grid_for(256, t->n), 256, 0, view_of(t), t->n, flag);
+    else
+        LAUNCH("is_sorted", (k_is_unsorted<false>), grid_for(256, t->n), 256, 0, view_of(t), t->n, flag);
+    CK(cudaMemcpyAsync(g.h_scalars + 9, g.d_scalars + 9, sizeof(u64), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    *sorted = (g.h_scalars[9] & 0xffffffffu) ? 0 : 1;
+    return 0;
+}
+
+// ---------------------------------------------------------------- joins
+int qce_merge_join(const qce_tuples *R, const qce_tuples *S, qce_rowids **outR, qce_rowids **outS,
+                   qce_rowids **distinctR, qce_rowids **distinctS)
+{
+    NEED_INIT();
+    if (!R || !S || !outR || !outS) return fail("null argument");
+    if (merge_join_any(R, S, true, true, outR, outS) != 0) return -1;
+    if (distinctR || distinctS) {
+        qce_rowids *dr = nullptr, *ds = nullptr;
+        if (distinct_pairs(*outR, *outS, &dr, &ds) != 0) return -1;
+        if (distinctR) *distinctR = dr; else qce_rowids_free(dr);
+        if (distinctS) *distinctS = ds; else qce_rowids_free(ds);
+    }
+    return 0;
+}
+
+static int scan_join_impl(const Column *cr, const qce_rowids *idsR, const Column *cs, const qce_rowids *idsS,
+                          qce_rowids **outR, qce_rowids **outS)
+{
+    const u64 nr = idsR ? idsR->n : cr->n, ns = idsS ? idsS->n : cs->n;
+    const u64 n = nr < ns ? nr : ns;
+    if (n == 0) {
+        if (new_rowids(0, (u32)cr->n, outR) != 0) return -1;
+        return new_rowids(0, (u32)cs->n, outS);
+    }
+    const u64 ntiles = ceil_div(n, QCE_FTILE);
+    u32 *mask = nullptr, *tile_count = nullptr;
+    if (dalloc(&mask, ntiles * QCE_FWORDS) || dalloc(&tile_count, ntiles)) return -1;
+    LAUNCH("scan_join", k_scanjoin_mask, (int)ntiles, QCE_FTHREADS, 0, idsR ? idsR->d : nullptr, cr->d,
+           idsS ? idsS->d : nullptr, cs->d, n, mask, tile_count);
+    int rc = compact_from_mask(QCE_LAYOUT_NATURAL, QCE_EMIT_SRC2, mask, tile_count, ntiles,
+                               idsR ? idsR->d : nullptr, idsS ? idsS->d : nullptr, (u32)cr->n, (u32)cs->n, outR, outS);
+    dfree(mask);
+    dfree(tile_count);
+    return rc;
+}
+int qce_scan_join(uint32_t relR, uint32_t colR, const qce_rowids *idsR, uint32_t relS, uint32_t colS,
+                  const qce_rowids *idsS, qce_rowids **outR, qce_rowids **outS)
+{
+    NEED_INIT();
+    const Column *cr, *cs;
+    if (!idsR || !idsS || !outR || !outS) return fail("null argument");
+    if (get_column(relR, colR, &cr) != 0 || get_column(relS, colS, &cs) != 0) return -1;
+    return scan_join_impl(cr, idsR, cs, idsS, outR, outS);
+}
+int qce_scan_join_base(uint32_t relR, uint32_t colR, uint32_t relS, uint32_t colS, qce_rowids **outR,
+                       qce_rowids **outS)
+{
+    NEED_INIT();
+    const Column *cr, *cs;
+    if (!outR || !outS) return fail("null argument");
+    if (get_column(relR, colR, &cr) != 0 || get_column(relS, colS, &cs) != 0) return -1;
+    return scan_join_impl(cr, nullptr, cs, nullptr, outR, outS);
+}
+
+int qce_rejoin(const qce_rowids *driver, const qce_rowids *last, const qce_rowids *edit, qce_rowids **out)
+{
+    NEED_INIT();
+    if (!driver || !last || !edit || !out) return fail("null argument");
+    if (edit->n < last->n)
+        return fail("bystander column has %llu row ids but its entity's joined column has %llu "
+                    "(the reference reads past the array here, src/join.c:433)",
+                    (unsigned long long)edit->n, (unsigned long long)last->n);
+    const int bits = last->id_bound ? bitlen(last->id_bound - 1) : 32;
+    qce_tuples R, S;
+    R.n = last->n; R.wide = false; R.ids = nullptr; R.key_bits = bits ? bits : 1; R.id_bound = edit->id_bound; R.sorted = false; R.a = nullptr;
+    S.n = driver->n; S.wide = false; S.ids = nullptr; S.key_bits = R.key_bits; S.id_bound = 0; S.sorted = false; S.a = nullptr;
+    if (dalloc(&R.a, R.n) || dalloc(&S.a, S.n)) return -1;
+    if (R.n) LAUNCH("pack_pairs", k_pack_pairs, grid_for(256, R.n), 256, 0, last->d, edit->d, R.n, R.a);
+    if (S.n) LAUNCH("pack_pairs", k_pack_pairs, grid_for(256, S.n), 256, 0, driver->d, (const u32 *)nullptr, S.n, S.a);
+    RadixShifts rs = shifts_for(32, R.key_bits);
+    if (radix_sort(&R.a, nullptr, R.n, rs) != 0 || radix_sort(&S.a, nullptr, S.n, rs) != 0) return -1;
+    int rc = merge_join_any(&R, &S, true, false, out, nullptr);
+    dfree(R.a);
+    dfree(S.a);
+    return rc;
+}
+
+// ---------------------------------------------------------------- projection
+int qce_checksum(const qce_rowids *ids, uint32_t rel, const uint32_t *cols, uint32_t ncols, uint64_t *sums)
+{
+    NEED_INIT();
+    if (!ids || !cols || !sums) return fail("null argument");
+    if (ncols == 0) return 0;
+    if (ncols > 8) return fail("at most 8 columns per checksum call");
+    ChecksumCols cc;
+    for (u32 k = 0; k < 8; k++) cc.col[k] = nullptr;
+    for (u32 k = 0; k < ncols; k++) {
+        const Column *cl;
+        if (get_column(rel, cols[k], &cl) != 0) return -1;
+        cc.col[k] = cl->d;
+    }
+    CK(cudaMemsetAsync(g.d_scalars, 0, 8 * sizeof(u64), g.stream));
+    if (ids->n > 0) {
+        const int grid = grid_for(1024, ids->n);
+        switch (ncols) {
+        case 1: LAUNCH("checksum", (k_checksum<1>), grid, 256, 0, ids->d, ids->n, cc, g.d_scalars); break;
+        case 2: LAUNCH("checksum", (k_checksum<2>), grid, 256, 0, ids->d, ids->n, cc, g.d_scalars); break;
+        case 3: LAUNCH("checksum", (k_checksum<3>), grid, 256, 0, ids->d, ids->n, cc, g.d_scalars); break;
+        case 4: LAUNCH("checksum", (k_checksum<4>), grid, 256, 0, ids->d, ids->n, cc, g.d_scalars); break;
+        case 5: LAUNCH("checksum", (k_checksum<5>), grid, 256, 0, ids->d, ids->n, cc, g.d_scalars); break;
+        case 6: LAUNCH("checksum", (k_checksum<6>), grid, 256, 0, ids->d, ids->n, cc, g.d_scalars); break;
+        case 7: LAUNCH("checksum", (k_checksum<7>), grid, 256, 0, ids->d, ids->n, cc, g.d_scalars); break;
+        default: LAUNCH("checksum", (k_checksum<8>), grid, 256, 0, ids->d, ids->n, cc, g.d_scalars); break;
+        }
+    }
+    if (read_scalars((int)ncols) != 0) return -1;
+    for (u32 k = 0; k < ncols; k++) sums[k] = g.h_scalars[k];
+    return 0;
+}
+
+// ---------------------------------------------------------------- handles
+uint64_t qce_rowids_count(const qce_rowids *ids) { return ids ? ids->n : 0; }
+
+int qce_rowids_from_host(const uint64_t *host, uint64_t n, qce_rowids **out)
+{
+    NEED_INIT();
+    std::vector<u32> tmp(n ? n : 1);
+    u32 mx = 0;
+    for (u64 i = 0; i < n; i++) {
+        if (host[i] >= (1ull << 32)) return fail("row id %llu does not fit 32 bits", (unsigned long long)host[i]);
+        tmp[i] = (u32)host[i];
+        if (tmp[i] > mx) mx = tmp[i];
+    }
+    if (new_rowids(n, n ? (mx == 0xffffffffu ? 0 : mx + 1) : 0, out) != 0) return -1;
+    if (n) CK(cudaMemcpyAsync((*out)->d, tmp.data(), n * sizeof(u32), cudaMemcpyHostToDevice, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+int qce_rowids_to_host(const qce_rowids *ids, uint64_t *host)
+{
+    NEED_INIT();
+    if (!ids) return fail("null row-id column");
+    std::vector<u32> tmp(ids->n ? ids->n : 1);
+    if (ids->n) CK(cudaMemcpyAsync(tmp.data(), ids->d, ids->n * sizeof(u32), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    for (u64 i = 0; i < ids->n; i++) host[i] = tmp[i];
+    return 0;
+}
+int qce_rowids_clone(const qce_rowids *ids, qce_rowids **out)
+{
+    NEED_INIT();
+    if (!ids) return fail("null row-id column");
+    if (new_rowids(ids->n, ids->id_bound, out) != 0) return -1;
+    if (ids->n) CK(cudaMemcpyAsync((*out)->d, ids->d, ids->n * sizeof(u32), cudaMemcpyDeviceToDevice, g.stream));
+    return 0;
+}
+void qce_rowids_free(qce_rowids *ids)
+{
+    if (!ids) return;
+    if (g.inited) dfree(ids->d);
+    delete ids;
+}
+
+uint64_t qce_tuples_count(const qce_tuples *t) { return t ? t->n : 0; }
+
+int qce_tuples_from_host(const uint64_t *keys, const uint64_t *rowids, uint64_t n, qce_tuples **out)
+{
+    NEED_INIT();
+    u64 mk = 0, mi = 0;
+    for (u64 i = 0; i < n; i++) {
+        if (keys[i] > mk) mk = keys[i];
+        if (rowids[i] > mi) mi = rowids[i];
+    }
+    if (mi >= (1ull << 32)) return fail("row id %llu does not fit 32 bits", (unsigned long long)mi);
+    qce_tuples *t = new qce_tuples();
+    t->n = n;
+    t->key_bits = bitlen(mk) ? bitlen(mk) : 1;
+    t->wide = t->key_bits > 32;
+    t->id_bound = (mi + 1 >= (1ull << 32)) ? 0 : (u32)(mi + 1);
+    t->sorted = false;
+    t->ids = nullptr;
+    if (dalloc(&t->a, n) != 0) { delete t; return -1; }
+    if (t->wide) {
+        if (dalloc(&t->ids, n) != 0) { delete t; return -1; }
+        std::vector<u32> tmp(n ? n : 1);
+        for (u64 i = 0; i < n; i++) tmp[i] = (u32)rowids[i];
+        if (n) {
+            CK(cudaMemcpyAsync(t->a, keys, n * sizeof(u64), cudaMemcpyHostToDevice, g.stream));
+            CK(cudaMemcpyAsync(t->ids, tmp.data(), n * sizeof(u32), cudaMemcpyHostToDevice, g.stream));
+        }
+        CK(cudaStreamSynchronize(g.stream));
+    } else {
+        std::vector<u64> tmp(n ? n : 1);
+        for (u64 i = 0; i < n; i++) tmp[i] = (keys[i] << 32) | rowids[i];
+        if (n) CK(cudaMemcpyAsync(t->a, tmp.data(), n * sizeof(u64), cudaMemcpyHostToDevice, g.stream));
+        CK(cudaStreamSynchronize(g.stream));
+    }
+    *out = t;
+    return 0;
+}
+int qce_tuples_to_host(const qce_tuples *t, uint64_t *keys, uint64_t *rowids)
+{
+    NEED_INIT();
+    if (!t) return fail("null tuple run");
+    const u64 n = t->n;
+    if (t->wide) {
+        std::vector<u32> tmp(n ? n : 1);
+        if (n) {
+            CK(cudaMemcpyAsync(keys, t->a, n * sizeof(u64), cudaMemcpyDeviceToHost, g.stream));
+            CK(cudaMemcpyAsync(tmp.data(), t->ids, n * sizeof(u32), cudaMemcpyDeviceToHost, g.stream));
+        }
+        CK(cudaStreamSynchronize(g.stream));
+        for (u64 i = 0; i < n; i++) rowids[i] = tmp[i];
+    } else {
+        std::vector<u64> tmp(n ? n : 1);
+        if (n) CK(cudaMemcpyAsync(tmp.data(), t->a, n * sizeof(u64), cudaMemcpyDeviceToHost, g.stream));
+        CK(cudaStreamSynchronize(g.stream));
+        for (u64 i = 0; i < n; i++) { keys[i] = tmp[i] >> 32; rowids[i] = tmp[i] & 0xffffffffu; }
+    }
+    return 0;
+}
+void qce_tuples_free(qce_tuples *t)
+{
+    if (!t) return;
+    if (g.inited) { dfree(t->a); dfree(t->ids); }
+    delete t;
+}
+
+// ---------------------------------------------------------------- exchange
+int qce_key_histogram(const qce_tuples *t, uint32_t key_bits, uint64_t *hist)
+{
+    NEED_INIT();
+    if (!t || !hist) return fail("null argument");
+    if (t->wide) return fail("the sharded exchange supports packed (key < 2^32) runs only");
+    u32 *gh = nullptr;
+    if (dalloc(&gh, QCE_RADIX_BINS) != 0) return -1;
+    CK(cudaMemsetAsync(gh, 0, QCE_RADIX_BINS * sizeof(u32), g.stream));
+    RadixShifts rs;
+    rs.npass = 1;
+    for (int i = 0; i < QCE_MAX_PASSES; i++) rs.shift[i] = 0;
+    rs.shift[0] = 32 + (key_bits > 8 ? (int)key_bits - 8 : 0);
+    if (t->n) LAUNCH("radix_hist", k_radix_hist, grid_for(1024, t->n, 4), 512, 0, t->a, t->n, rs, gh);
+    std::vector<u32> tmp(QCE_RADIX_BINS);
+    CK(cudaMemcpyAsync(tmp.data(), gh, QCE_RADIX_BINS * sizeof(u32), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    for (int i = 0; i < QCE_RADIX_BINS; i++) hist[i] = tmp[i];
+    dfree(gh);
+    return 0;
+}
+
+int qce_partition_tuples(const qce_tuples *t, const uint64_t *splitters, uint32_t nparts, uint64_t *counts,
+                         void **sendbuf)
+{
+    NEED_INIT();
+    if (!t || !counts || !sendbuf) return fail("null argument");
+    if (t->wide) return fail("the sharded exchange supports packed (key < 2^32) runs only");
+    if (nparts < 1 || nparts > 16) return fail("nparts must be in 1..16");
+    if (t->n >= (1ull << 30)) return fail("partition of %llu tuples exceeds the 2^30 per-run limit", (unsigned long long)t->n);
+    DigitSplit ds;
+    ds.nsplit = (int)nparts - 1;
+    for (int i = 0; i < 15; i++) ds.split[i] = (i < ds.nsplit) ? (splitters[i] << 32) : ~0ull;
+    const u64 n = t->n;
+    u64 *out = nullptr;
+    u32 *ghist = nullptr, *gbase = nullptr, *status = nullptr, *counter = nullptr;
+    const u32 ntiles = (u32)ceil_div(n ? n : 1, RS_TILE);
+    if (dalloc(&out, n) || dalloc(&ghist, QCE_RADIX_BINS) || dalloc(&gbase, QCE_RADIX_BINS) ||
+        dalloc(&status, (u64)ntiles * QCE_RADIX_BINS) || dalloc(&counter, 1))
+        return -1;
+    CK(cudaMemsetAsync(ghist, 0, QCE_RADIX_BINS * sizeof(u32), g.stream));
+    CK(cudaMemsetAsync(status, 0, (u64)ntiles * QCE_RADIX_BINS * sizeof(u32), g.stream));
+    CK(cudaMemsetAsync(counter, 0, sizeof(u32), g.stream));
+    if (n) {
+        LAUNCH("split_hist", k_split_hist, grid_for(256 * 8, n), 256, 0, t->a, n, ds, ghist);
+        LAUNCH("radix_bases", k_radix_bases, 1, 256, 0, ghist, gbase);
+        if (launch_onesweep<false>(t->a, out, nullptr, nullptr, (u32)n, ds, gbase, status, counter) != 0) return -1;
+    }
+    std::vector<u32> tmp(QCE_RADIX_BINS);
+    CK(cudaMemcpyAsync(tmp.data(), ghist, QCE_RADIX_BINS * sizeof(u32), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    for (u32 p = 0; p < nparts; p++) counts[p] = tmp[p];
+    dfree(ghist); dfree(gbase); dfree(status); dfree(counter);
+    *sendbuf = out;
+    return 0;
+}
+int qce_exchange_release(void *sendbuf)
+{
+    NEED_INIT();
+    dfree((u64 *)sendbuf);
+    return 0;
+}
+int qce_tuples_from_device_packed(const void *dev_words, uint64_t n, uint32_t key_bits, qce_tuples **out)
+{
+    NEED_INIT();
+    if (!out) return fail("null argument");
+    if (key_bits == 0 || key_bits > 32) return fail("packed runs carry keys of 1..32 bits");
+    qce_tuples *t = new qce_tuples();
+    t->n = n;
+    t->key_bits = (int)key_bits;
+    t->wide = false;
+    t->id_bound = 0;
+    t->sorted = false;
+    t->ids = nullptr;
+    if (dalloc(&t->a, n) != 0) { delete t; return -1; }
+    // the caller's buffer may live on another stream (torch): order by a full device sync
+    CK(cudaDeviceSynchronize());
+    if (n) CK(cudaMemcpyAsync(t->a, dev_words, n * sizeof(u64), cudaMemcpyDeviceToDevice, g.stream));
+    *out = t;
+    return 0;
+}
+
+} // extern "C"
