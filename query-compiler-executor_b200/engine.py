@@ -1,0 +1,242 @@
+"""ctypes binding of libqce_b200.so (the C-ABI in include/qce_b200.h).
+
+This is harness plumbing for tests and bench.py: the product is the C library
+and the C host layer in src/.  Nothing here computes anything -- every method
+is one C-ABI call, and a missing library or a missing GPU raises immediately
+(there is no CPU path to fall back to).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libqce_b200.so")
+
+# every symbol include/qce_b200.h declares (tests check the library exports them all)
+SYMBOLS = [
+    "qce_init", "qce_shutdown", "qce_last_error", "qce_abi_version", "qce_timer_reset", "qce_timer_read",
+    "qce_sync", "qce_profile_enable", "qce_profile_json", "qce_upload_column", "qce_upload_column_device",
+    "qce_adopt_column_device", "qce_column_info", "qce_drop_relations", "qce_filter_scan", "qce_filter_refine",
+    "qce_build_tuples_base", "qce_build_tuples_rowids", "qce_sort_tuples", "qce_tuples_is_sorted",
+    "qce_merge_join", "qce_scan_join", "qce_scan_join_base", "qce_rejoin", "qce_checksum", "qce_rowids_count",
+    "qce_rowids_from_host", "qce_rowids_to_host", "qce_rowids_clone", "qce_rowids_free", "qce_tuples_count",
+    "qce_tuples_from_host", "qce_tuples_to_host", "qce_tuples_free", "qce_partition_tuples",
+    "qce_tuples_from_device_packed", "qce_exchange_release", "qce_key_histogram",
+]
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def load_library(path: str = LIB_PATH) -> C.CDLL:
+    if not os.path.exists(path):
+        raise EngineError(f"{path} is missing: build it with `make -C {HERE} engine` "
+                          "(or __graft_entry__.build()); there is no CPU fallback")
+    lib = C.CDLL(path)
+    vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
+    P = C.POINTER
+    sig = {
+        "qce_init": (i32, [i32]), "qce_shutdown": (None, []), "qce_last_error": (C.c_char_p, []),
+        "qce_abi_version": (i32, []), "qce_timer_reset": (i32, []),
+        "qce_timer_read": (i32, [P(C.c_double), P(u64)]), "qce_sync": (i32, []),
+        "qce_profile_enable": (i32, [i32]), "qce_profile_json": (C.c_char_p, []),
+        "qce_upload_column": (i32, [u32, u32, vp, u64]), "qce_upload_column_device": (i32, [u32, u32, vp, u64]),
+        "qce_adopt_column_device": (i32, [u32, u32, vp, u64]),
+        "qce_column_info": (i32, [u32, u32, P(u64), P(u64)]), "qce_drop_relations": (i32, []),
+        "qce_filter_scan": (i32, [u32, u32, C.c_char, u64, P(vp)]),
+        "qce_filter_refine": (i32, [vp, u32, u32, C.c_char, u64, P(u64)]),
+        "qce_build_tuples_base": (i32, [u32, u32, P(vp)]), "qce_build_tuples_rowids": (i32, [u32, u32, vp, P(vp)]),
+        "qce_sort_tuples": (i32, [vp]), "qce_tuples_is_sorted": (i32, [vp, P(i32)]),
+        "qce_merge_join": (i32, [vp, vp, P(vp), P(vp), P(vp), P(vp)]),
+        "qce_scan_join": (i32, [u32, u32, vp, u32, u32, vp, P(vp), P(vp)]),
+        "qce_scan_join_base": (i32, [u32, u32, u32, u32, P(vp), P(vp)]),
+        "qce_rejoin": (i32, [vp, vp, vp, P(vp)]), "qce_checksum": (i32, [vp, u32, P(u32), u32, P(u64)]),
+        "qce_rowids_count": (u64, [vp]), "qce_rowids_from_host": (i32, [vp, u64, P(vp)]),
+        "qce_rowids_to_host": (i32, [vp, vp]), "qce_rowids_clone": (i32, [vp, P(vp)]),
+        "qce_rowids_free": (None, [vp]), "qce_tuples_count": (u64, [vp]),
+        "qce_tuples_from_host": (i32, [vp, vp, u64, P(vp)]), "qce_tuples_to_host": (i32, [vp, vp, vp]),
+        "qce_tuples_free": (None, [vp]), "qce_partition_tuples": (i32, [vp, vp, u32, P(u64), P(vp)]),
+        "qce_tuples_from_device_packed": (i32, [vp, u64, u32, P(vp)]), "qce_exchange_release": (i32, [vp]),
+        "qce_key_histogram": (i32, [vp, u32, P(u64)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+def _u64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+class Engine:
+    """One engine per process / per GPU."""
+
+    def __init__(self, device: int = -1):
+        self.lib = load_library()
+        self._ck(self.lib.qce_init(device))
+
+    # ---- plumbing
+    def _ck(self, rc: int) -> None:
+        if rc != 0:
+            raise EngineError(self.lib.qce_last_error().decode())
+
+    def sync(self) -> None:
+        self._ck(self.lib.qce_sync())
+
+    def timer_reset(self) -> None:
+        self._ck(self.lib.qce_timer_reset())
+
+    def timer_read(self) -> Tuple[float, int]:
+        ms, n = C.c_double(), C.c_uint64()
+        self._ck(self.lib.qce_timer_read(C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def profile(self, on: bool) -> None:
+        self._ck(self.lib.qce_profile_enable(1 if on else 0))
+
+    def profile_read(self) -> dict:
+        return json.loads(self.lib.qce_profile_json().decode())
+
+    # ---- relations
+    def upload_column(self, rel: int, col: int, values) -> None:
+        v = _u64(values)
+        self._ck(self.lib.qce_upload_column(rel, col, v.ctypes.data, len(v)))
+
+    def upload_column_device(self, rel: int, col: int, dev_ptr: int, n: int, adopt: bool = False) -> None:
+        fn = self.lib.qce_adopt_column_device if adopt else self.lib.qce_upload_column_device
+        self._ck(fn(rel, col, dev_ptr, n))
+
+    def upload_db(self, db: Sequence[Sequence[np.ndarray]]) -> None:
+        for r, cols in enumerate(db):
+            for c, v in enumerate(cols):
+                self.upload_column(r, c, v)
+
+    def column_info(self, rel: int, col: int) -> Tuple[int, int]:
+        n, mx = C.c_uint64(), C.c_uint64()
+        self._ck(self.lib.qce_column_info(rel, col, C.byref(n), C.byref(mx)))
+        return n.value, mx.value
+
+    def drop_relations(self) -> None:
+        self._ck(self.lib.qce_drop_relations())
+
+    # ---- handles
+    def rowids_from_host(self, ids) -> int:
+        v = _u64(ids)
+        h = C.c_void_p()
+        self._ck(self.lib.qce_rowids_from_host(v.ctypes.data, len(v), C.byref(h)))
+        return h.value
+
+    def rowids_to_host(self, h: int) -> np.ndarray:
+        n = self.lib.qce_rowids_count(h)
+        out = np.empty(n, dtype=np.uint64)
+        self._ck(self.lib.qce_rowids_to_host(h, out.ctypes.data))
+        return out
+
+    def rowids_count(self, h: int) -> int:
+        return self.lib.qce_rowids_count(h)
+
+    def rowids_free(self, h: Optional[int]) -> None:
+        if h:
+            self.lib.qce_rowids_free(h)
+
+    def tuples_from_host(self, keys, rowids) -> int:
+        k, r = _u64(keys), _u64(rowids)
+        h = C.c_void_p()
+        self._ck(self.lib.qce_tuples_from_host(k.ctypes.data, r.ctypes.data, len(k), C.byref(h)))
+        return h.value
+
+    def tuples_to_host(self, h: int) -> Tuple[np.ndarray, np.ndarray]:
+        n = self.lib.qce_tuples_count(h)
+        k, r = np.empty(n, dtype=np.uint64), np.empty(n, dtype=np.uint64)
+        self._ck(self.lib.qce_tuples_to_host(h, k.ctypes.data, r.ctypes.data))
+        return k, r
+
+    def tuples_count(self, h: int) -> int:
+        return self.lib.qce_tuples_count(h)
+
+    def tuples_free(self, h: Optional[int]) -> None:
+        if h:
+            self.lib.qce_tuples_free(h)
+
+    # ---- operators
+    def filter_scan(self, rel: int, col: int, op: str, c: int) -> int:
+        h = C.c_void_p()
+        self._ck(self.lib.qce_filter_scan(rel, col, op.encode(), c, C.byref(h)))
+        return h.value
+
+    def filter_refine(self, h: int, rel: int, col: int, op: str, c: int) -> int:
+        n = C.c_uint64()
+        self._ck(self.lib.qce_filter_refine(h, rel, col, op.encode(), c, C.byref(n)))
+        return n.value
+
+    def build_tuples(self, rel: int, col: int, rowids: Optional[int] = None) -> int:
+        h = C.c_void_p()
+        if rowids is None:
+            self._ck(self.lib.qce_build_tuples_base(rel, col, C.byref(h)))
+        else:
+            self._ck(self.lib.qce_build_tuples_rowids(rel, col, rowids, C.byref(h)))
+        return h.value
+
+    def sort_tuples(self, h: int) -> None:
+        self._ck(self.lib.qce_sort_tuples(h))
+
+    def is_sorted(self, h: int) -> bool:
+        s = C.c_int()
+        self._ck(self.lib.qce_tuples_is_sorted(h, C.byref(s)))
+        return bool(s.value)
+
+    def merge_join(self, R: int, S: int, distinct: bool = False):
+        oR, oS, dR, dS = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._ck(self.lib.qce_merge_join(R, S, C.byref(oR), C.byref(oS),
+                                         C.byref(dR) if distinct else None, C.byref(dS) if distinct else None))
+        return (oR.value, oS.value, dR.value, dS.value) if distinct else (oR.value, oS.value)
+
+    def scan_join(self, relR, colR, idsR, relS, colS, idsS):
+        oR, oS = C.c_void_p(), C.c_void_p()
+        if idsR is None and idsS is None:
+            self._ck(self.lib.qce_scan_join_base(relR, colR, relS, colS, C.byref(oR), C.byref(oS)))
+        else:
+            self._ck(self.lib.qce_scan_join(relR, colR, idsR, relS, colS, idsS, C.byref(oR), C.byref(oS)))
+        return oR.value, oS.value
+
+    def rejoin(self, driver: int, last: int, edit: int) -> int:
+        h = C.c_void_p()
+        self._ck(self.lib.qce_rejoin(driver, last, edit, C.byref(h)))
+        return h.value
+
+    def checksum(self, ids: int, rel: int, cols: Sequence[int]) -> List[int]:
+        n = len(cols)
+        ca = (C.c_uint32 * n)(*cols)
+        out = (C.c_uint64 * n)()
+        self._ck(self.lib.qce_checksum(ids, rel, ca, n, out))
+        return [int(x) for x in out]
+
+    # ---- exchange
+    def key_histogram(self, t: int, key_bits: int) -> np.ndarray:
+        out = np.zeros(256, dtype=np.uint64)
+        self._ck(self.lib.qce_key_histogram(t, key_bits, out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return out
+
+    def partition_tuples(self, t: int, splitters, nparts: int):
+        sp = _u64(splitters if len(splitters) else [0])
+        counts = (C.c_uint64 * nparts)()
+        buf = C.c_void_p()
+        self._ck(self.lib.qce_partition_tuples(t, sp.ctypes.data, nparts, counts, C.byref(buf)))
+        return [int(x) for x in counts], buf.value
+
+    def tuples_from_device_packed(self, dev_ptr: int, n: int, key_bits: int) -> int:
+        h = C.c_void_p()
+        self._ck(self.lib.qce_tuples_from_device_packed(dev_ptr, n, key_bits, C.byref(h)))
+        return h.value
+
+    def exchange_release(self, buf: Optional[int]) -> None:
+        if buf:
+            self._ck(self.lib.qce_exchange_release(buf))

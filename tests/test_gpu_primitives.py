@@ -1,0 +1,260 @@
+"""GPU parity, primitive by primitive: every CUDA operator called through the
+C-ABI (libqce_b200.so) against the numpy oracle on the same seeded inputs.
+Bar: bit-exact (all arithmetic on this path is uint64 / index work)."""
+import numpy as np
+import pytest
+
+from oracle import qce_oracle as orc
+
+pytestmark = pytest.mark.gpu
+U64 = np.uint64
+
+SIZES = [0, 1, 2, 31, 32, 33, 63, 64, 65, 4095, 4096, 4097, 8191, 12289, 100003, 1 << 20]
+
+
+def _col(rng, n, domain):
+    return rng.integers(0, max(1, domain), n, dtype=np.uint64)
+
+
+# ------------------------------------------------------------------ filter scan
+@pytest.mark.parametrize("n", SIZES)
+@pytest.mark.parametrize("op", ["<", ">", "="])
+def test_filter_scan(engine, n, op):
+    rng = np.random.default_rng(n * 3 + ord(op))
+    col = _col(rng, n, 1000)
+    engine.upload_column(100, 0, col)
+    c = 500 if op != "=" else (int(col[n // 2]) if n else 7)
+    h = engine.filter_scan(100, 0, op, c)
+    got = engine.rowids_to_host(h)
+    engine.rowids_free(h)
+    np.testing.assert_array_equal(got, orc.filter_scan(col, op, c))
+
+
+@pytest.mark.parametrize("sel", [0.0, 1.0, 0.001, 0.999])
+def test_filter_scan_selectivity_extremes(engine, sel):
+    rng = np.random.default_rng(5)
+    n = 300007
+    col = _col(rng, n, 1 << 40)  # wide values: compare is 64-bit unsigned
+    c = int(sel * (1 << 40))
+    engine.upload_column(100, 1, col)
+    h = engine.filter_scan(100, 1, "<", c)
+    np.testing.assert_array_equal(engine.rowids_to_host(h), orc.filter_scan(col, "<", c))
+    engine.rowids_free(h)
+
+
+def test_filter_wrong_operator(engine):
+    import qce_b200
+    engine.upload_column(100, 2, np.arange(10, dtype=U64))
+    with pytest.raises(qce_b200.EngineError, match="Wrong operator"):
+        engine.filter_scan(100, 2, "!", 3)
+
+
+# ------------------------------------------------------------------ filter refine
+@pytest.mark.parametrize("n", [0, 1, 33, 4096, 4097, 70001])
+@pytest.mark.parametrize("op", ["<", ">", "="])
+def test_filter_refine(engine, n, op):
+    rng = np.random.default_rng(n + ord(op))
+    rows = 50000
+    col = _col(rng, rows, 100)
+    engine.upload_column(101, 0, col)
+    ids = rng.integers(0, rows, n, dtype=np.uint64)  # unsorted, with repeats
+    h = engine.rowids_from_host(ids)
+    cnt = engine.filter_refine(h, 101, 0, op, 40)
+    want = orc.filter_refine(ids, col, op, 40)
+    assert cnt == len(want)
+    np.testing.assert_array_equal(engine.rowids_to_host(h), want)
+    engine.rowids_free(h)
+
+
+# ------------------------------------------------------------------ build + sort
+@pytest.mark.parametrize("n", [0, 1, 2, 100, 4095, 4096, 4097, 8192, 100003, 1 << 20])
+@pytest.mark.parametrize("domain", [1, 7, 1 << 8, 1 << 20, (1 << 32) - 1, 1 << 33, 1 << 62])
+def test_build_and_sort_base(engine, n, domain):
+    rng = np.random.default_rng(n ^ domain & 0xFFFF)
+    col = _col(rng, n, domain)
+    engine.upload_column(102, 0, col)
+    t = engine.build_tuples(102, 0)
+    k, p = engine.tuples_to_host(t)
+    wk, wp = orc.build_tuples(col)
+    np.testing.assert_array_equal(k, wk)
+    np.testing.assert_array_equal(p, wp)
+    engine.sort_tuples(t)
+    assert engine.is_sorted(t)
+    k, p = engine.tuples_to_host(t)
+    sk, sp = orc.sort_tuples(wk, wp)
+    np.testing.assert_array_equal(k, sk)
+    np.testing.assert_array_equal(p, sp)  # stable: ties in input order
+    engine.tuples_free(t)
+
+
+def test_sort_skewed_and_presorted(engine):
+    rng = np.random.default_rng(9)
+    n = 500000
+    for keys in (np.zeros(n, dtype=U64), np.arange(n, dtype=U64), np.arange(n, dtype=U64)[::-1].copy(),
+                 (rng.zipf(1.2, n) % (1 << 30)).astype(U64)):
+        t = engine.tuples_from_host(keys, np.arange(n, dtype=U64))
+        engine.sort_tuples(t)
+        k, p = engine.tuples_to_host(t)
+        sk, sp = orc.sort_tuples(keys, np.arange(n, dtype=U64))
+        np.testing.assert_array_equal(k, sk)
+        np.testing.assert_array_equal(p, sp)
+        engine.tuples_free(t)
+
+
+def test_build_through_rowids(engine):
+    rng = np.random.default_rng(3)
+    col = _col(rng, 100000, 1 << 20)
+    engine.upload_column(103, 0, col)
+    ids = np.sort(rng.choice(100000, 30000, replace=False)).astype(U64)
+    h = engine.rowids_from_host(ids)
+    t = engine.build_tuples(103, 0, h)
+    k, p = engine.tuples_to_host(t)
+    wk, wp = orc.build_tuples(col, ids)
+    np.testing.assert_array_equal(k, wk)
+    np.testing.assert_array_equal(p, wp)
+    assert not engine.is_sorted(t)
+    engine.tuples_free(t)
+    engine.rowids_free(h)
+
+
+# ------------------------------------------------------------------ merge join
+def _join_case(engine, kR, pR, kS, pS, distinct=False):
+    kR, pR = orc.sort_tuples(kR, pR)
+    kS, pS = orc.sort_tuples(kS, pS)
+    R = engine.tuples_from_host(kR, pR)
+    S = engine.tuples_from_host(kS, pS)
+    res = engine.merge_join(R, S, distinct=distinct)
+    gR, gS = engine.rowids_to_host(res[0]), engine.rowids_to_host(res[1])
+    wR, wS = orc.merge_join(kR, pR, kS, pS)
+    np.testing.assert_array_equal(gR, wR)
+    np.testing.assert_array_equal(gS, wS)
+    if distinct:
+        dR, dS = engine.rowids_to_host(res[2]), engine.rowids_to_host(res[3])
+        wdR, wdS = orc.distinct_pairs(wR, wS)
+        np.testing.assert_array_equal(dR, wdR)
+        np.testing.assert_array_equal(dS, wdS)
+    for h in res:
+        engine.rowids_free(h)
+    engine.tuples_free(R)
+    engine.tuples_free(S)
+    return len(wR)
+
+
+@pytest.mark.parametrize("nR,nS,domain", [
+    (0, 10, 5), (10, 0, 5), (1, 1, 1), (100, 100, 10), (5000, 3000, 1000), (2048, 2049, 4096),
+    (100000, 100000, 100000), (300000, 1000, 1 << 20), (1000, 300000, 1 << 20), (50000, 50000, 1 << 34),
+    (4097, 200000, 50),  # every R tile spans a window larger than the staging buffer
+])
+def test_merge_join(engine, nR, nS, domain):
+    rng = np.random.default_rng(nR * 7 + nS)
+    kR, kS = _col(rng, nR, domain), _col(rng, nS, domain)
+    _join_case(engine, kR, np.arange(nR, dtype=U64), kS, np.arange(nS, dtype=U64))
+
+
+def test_merge_join_heavy_key(engine):
+    """One key with 3000 x 2000 matches: the pair list of a single group is split
+    over many write CTAs."""
+    rng = np.random.default_rng(1)
+    kR = np.concatenate([np.full(3000, 77, dtype=U64), _col(rng, 5000, 1000)])
+    kS = np.concatenate([np.full(2000, 77, dtype=U64), _col(rng, 5000, 1000)])
+    m = _join_case(engine, kR, np.arange(len(kR), dtype=U64), kS, np.arange(len(kS), dtype=U64))
+    assert m >= 6_000_000
+
+
+def test_merge_join_distinct_pairs(engine):
+    """Row ids repeat on both sides (as after an earlier join): the distinct
+    (rowid_R,rowid_S) pairs are what the reference's Hashmap dedup keeps."""
+    rng = np.random.default_rng(2)
+    col_r, col_s = _col(rng, 400, 50), _col(rng, 300, 50)
+    pR = rng.integers(0, 400, 3000, dtype=np.uint64)
+    pS = rng.integers(0, 300, 2000, dtype=np.uint64)
+    _join_case(engine, col_r[pR], pR, col_s[pS], pS, distinct=True)
+
+
+# ------------------------------------------------------------------ scan join / rejoin / checksum
+@pytest.mark.parametrize("nR,nS", [(0, 5), (100, 100), (5000, 4097), (70000, 90000)])
+def test_scan_join(engine, nR, nS):
+    rng = np.random.default_rng(nR + nS)
+    colR, colS = _col(rng, 1000, 4), _col(rng, 2000, 4)
+    engine.upload_column(104, 0, colR)
+    engine.upload_column(105, 0, colS)
+    iR, iS = rng.integers(0, 1000, nR, dtype=np.uint64), rng.integers(0, 2000, nS, dtype=np.uint64)
+    hR, hS = engine.rowids_from_host(iR), engine.rowids_from_host(iS)
+    oR, oS = engine.scan_join(104, 0, hR, 105, 0, hS)
+    wR, wS = orc.scan_join(colR[iR], iR, colS[iS], iS)
+    np.testing.assert_array_equal(engine.rowids_to_host(oR), wR)
+    np.testing.assert_array_equal(engine.rowids_to_host(oS), wS)
+    for h in (hR, hS, oR, oS):
+        engine.rowids_free(h)
+
+
+def test_scan_join_base(engine):
+    rng = np.random.default_rng(8)
+    a, b = _col(rng, 10000, 3), _col(rng, 10000, 3)
+    engine.upload_column(106, 0, a)
+    engine.upload_column(106, 1, b)
+    oR, oS = engine.scan_join(106, 0, None, 106, 1, None)
+    want = np.nonzero(a == b)[0].astype(U64)
+    np.testing.assert_array_equal(engine.rowids_to_host(oR), want)
+    np.testing.assert_array_equal(engine.rowids_to_host(oS), want)
+    engine.rowids_free(oR)
+    engine.rowids_free(oS)
+
+
+@pytest.mark.parametrize("n,m", [(0, 0), (10, 0), (1000, 700), (50000, 120000)])
+def test_rejoin(engine, n, m):
+    rng = np.random.default_rng(n + m)
+    last = rng.integers(0, 5000, n, dtype=np.uint64)
+    edit = rng.integers(0, 9000, n + 3, dtype=np.uint64)  # longer than `last`: the tail is ignored
+    driver = rng.integers(0, 5000, m, dtype=np.uint64)
+    hd, hl, he = engine.rowids_from_host(driver), engine.rowids_from_host(last), engine.rowids_from_host(edit)
+    out = engine.rejoin(hd, hl, he)
+    np.testing.assert_array_equal(engine.rowids_to_host(out), orc.join_payloads(driver, last, edit))
+    for h in (hd, hl, he, out):
+        engine.rowids_free(h)
+
+
+def test_rejoin_short_bystander_is_refused(engine):
+    import qce_b200
+    hd = engine.rowids_from_host(np.arange(4, dtype=U64))
+    hl = engine.rowids_from_host(np.arange(10, dtype=U64))
+    he = engine.rowids_from_host(np.arange(5, dtype=U64))
+    with pytest.raises(qce_b200.EngineError, match="reads past"):
+        engine.rejoin(hd, hl, he)
+    for h in (hd, hl, he):
+        engine.rowids_free(h)
+
+
+@pytest.mark.parametrize("m", [0, 1, 3, 4, 5, 1023, 100001])
+def test_checksum(engine, m):
+    rng = np.random.default_rng(m)
+    cols = [rng.integers(0, 1 << 63, 20000, dtype=np.uint64) * U64(2) + U64(1) for _ in range(3)]  # sums wrap
+    for c, v in enumerate(cols):
+        engine.upload_column(107, c, v)
+    ids = rng.integers(0, 20000, m, dtype=np.uint64)
+    h = engine.rowids_from_host(ids)
+    got = engine.checksum(h, 107, [0, 1, 2])
+    assert got == [orc.checksum(c, ids) for c in cols]
+    assert engine.checksum(h, 107, [2]) == [orc.checksum(cols[2], ids)]
+    engine.rowids_free(h)
+
+
+# ------------------------------------------------------------------ exchange step
+@pytest.mark.parametrize("nparts", [1, 2, 4, 8])
+def test_partition_tuples(engine, nparts):
+    rng = np.random.default_rng(nparts)
+    n = 200003
+    keys = _col(rng, n, 1 << 24)
+    t = engine.tuples_from_host(keys, np.arange(n, dtype=U64))
+    splitters = [(i + 1) * (1 << 24) // nparts for i in range(nparts - 1)]
+    counts, buf = engine.partition_tuples(t, splitters, nparts)
+    part = np.searchsorted(np.array(splitters, dtype=U64), keys, side="right") if nparts > 1 else np.zeros(n, dtype=int)
+    assert counts == [int((part == p).sum()) for p in range(nparts)]
+    back = engine.tuples_from_device_packed(buf, n, 24)
+    k, p = engine.tuples_to_host(back)
+    order = np.argsort(part, kind="stable")  # partitioning is stable
+    np.testing.assert_array_equal(k, keys[order])
+    np.testing.assert_array_equal(p, np.arange(n, dtype=U64)[order])
+    engine.exchange_release(buf)
+    engine.tuples_free(back)
+    engine.tuples_free(t)
