@@ -109,6 +109,11 @@ int qce_tuples_is_sorted(const qce_tuples *t, int *sorted);
  * (join_payloads) sort them first, so only the multiset matters. */
 int qce_merge_join(const qce_tuples *R, const qce_tuples *S, qce_rowids **outR, qce_rowids **outS,
                    qce_rowids **distinctR, qce_rowids **distinctS);
+/* The non_duplicates of join_relations computed on their own (Hashmap dedup,
+ * src/join.c:358-367), so the host layer can skip the pass when no bystander
+ * column consumes them. */
+int qce_distinct_pairs(const qce_rowids *pairsR, const qce_rowids *pairsS, qce_rowids **distinctR,
+                       qce_rowids **distinctS);
 /* scan_join, src/join.c:395-423: positional filter keyR[i]==keyS[i] for
  * i < min(nR,nS), keys gathered through the two row-id columns. */
 int qce_scan_join(uint32_t relR, uint32_t colR, const qce_rowids *idsR, uint32_t relS,

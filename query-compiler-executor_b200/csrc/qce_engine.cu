@@ -735,6 +735,15 @@ int qce_merge_join(const qce_tuples *R, const qce_tuples *S, qce_rowids **outR, 
     return 0;
 }
 
+int qce_distinct_pairs(const qce_rowids *pairsR, const qce_rowids *pairsS, qce_rowids **distinctR,
+                       qce_rowids **distinctS)
+{
+    NEED_INIT();
+    if (!pairsR || !pairsS || !distinctR || !distinctS) return fail("null argument");
+    if (pairsR->n != pairsS->n) return fail("pair columns differ in length");
+    return distinct_pairs(pairsR, pairsS, distinctR, distinctS);
+}
+
 static int scan_join_impl(const Column *cr, const qce_rowids *idsR, const Column *cs, const qce_rowids *idsS,
                           qce_rowids **outR, qce_rowids **outS)
 {

@@ -1,0 +1,312 @@
+/* join.c -- join operator on the GPU.
+ *
+ * Same contract as execute_join, /root/reference/src/join.c:630-679.  The
+ * host keeps the part that is tiny, serial and decides what runs -- the
+ * mid-result state machine -- and every loop over tuples is a kernel behind
+ * the C-ABI (include/qce_b200.h):
+ *
+ *   reference (src/join.c)                      here
+ *   build_relations :152-292                    plan_join()      host, O(#entries)
+ *   allocate_relation(_mid_results) :96-142     qce_build_tuples_base / _rowids
+ *   iterative_sort :5-94                        qce_sort_tuples
+ *   join_relations :325-392                     qce_merge_join
+ *   scan_join :395-423                          qce_scan_join / qce_scan_join_base
+ *   Hashmap dedup :358-367                      qce_distinct_pairs, only when a
+ *                                               bystander column needs it
+ *   join_payloads :426-484                      qce_rejoin
+ *   update_mid_results / fix_all :486-628       install_results()  host
+ *
+ * The state machine is mirrored decision for decision (including the
+ * asymmetric constants of :253-267 and the relation-id bystander test of
+ * :495), because it selects which kernels run and so defines the reference's
+ * output.  One difference, stated in the header: a JOIN_SORT_* merge whose
+ * "already sorted" side is in fact not sorted is refused with a diagnostic --
+ * the reference's serial pointer walk gives an order-dependent result there
+ * that no parallel merge reproduces.
+ */
+#include "join.h"
+
+#include "../../include/qce_b200.h"
+
+/* one operand of the predicate, resolved against the entity list */
+typedef struct join_side {
+    uint32_t rel;       /* relation id */
+    uint64_t binding;   /* binding index in the query */
+    uint32_t col;       /* join column */
+    mid_result *source; /* row-id column the tuples are built from; NULL = base column */
+} join_side;
+
+typedef struct join_plan {
+    int kind;
+    join_side lhs, rhs;
+} join_plan;
+
+static mid_result *entry_at(DArray *entities, exists_info where)
+{
+    DArray *entity = *(DArray **)DArray_get(entities, where.mid_result);
+    return (mid_result *)DArray_get(entity, where.index);
+}
+
+static DArray *push_entity(DArray *entities)
+{
+    DArray *fresh = DArray_create(sizeof(mid_result), 4);
+    if (fresh != NULL) DArray_push(entities, &fresh);
+    return fresh;
+}
+
+/* Decide the join kind and where each side's tuples come from.
+ * Decision table of build_relations, src/join.c:152-292:
+ *   (0) same relation id and same column (bindings ignored)        -> DO_NOTHING
+ *   (1) lhs in the current (last) entity, rhs not                  -> :181-220
+ *   (2) both in the current entity                                 -> SCAN_JOIN
+ *   (3) rhs in the current entity, lhs not (mirror of (1) with the
+ *       reference's swapped constants)                             -> :229-269
+ *   (4) neither: new entity, both sides from the base relations    -> :270-285 */
+static int plan_join(predicate *pred, uint32_t *relations, DArray *entities, join_plan *plan)
+{
+    relation_column *second = (relation_column *)pred->second;
+    join_side *L = &plan->lhs, *R = &plan->rhs;
+    L->binding = pred->first.relation;
+    L->rel = relations[L->binding];
+    L->col = (uint32_t)pred->first.column;
+    L->source = NULL;
+    R->binding = second->relation;
+    R->rel = relations[R->binding];
+    R->col = (uint32_t)second->column;
+    R->source = NULL;
+
+    if (L->rel == R->rel && L->col == R->col) {
+        plan->kind = DO_NOTHING;
+        return 0;
+    }
+
+    DArray *current = DArray_count(entities) == 0 ? push_entity(entities) : *(DArray **)DArray_last(entities);
+    if (current == NULL) return -1;
+
+    const ssize_t li = relation_exists_current(current, L->rel, L->binding);
+    const ssize_t ri = relation_exists_current(current, R->rel, R->binding);
+
+    if (li != -1 && ri != -1) {
+        L->source = (mid_result *)DArray_get(current, li);
+        R->source = (mid_result *)DArray_get(current, ri);
+        plan->kind = SCAN_JOIN;
+    } else if (li != -1 || ri != -1) {
+        /* `in` is the side found in the current entity, `out` the other one */
+        const int lhs_in = li != -1;
+        join_side *in = lhs_in ? L : R, *out = lhs_in ? R : L;
+        in->source = (mid_result *)DArray_get(current, lhs_in ? li : ri);
+        const int in_sorted = in->source->last_column_sorted == (int32_t)in->col;
+
+        exists_info elsewhere = relation_exists(entities, out->rel, out->binding);
+        if (elsewhere.index == -1) {
+            /* other side straight from its base relation */
+            if (in_sorted) {
+                plan->kind = lhs_in ? JOIN_SORT_RHS : JOIN_SORT_LHS;
+            } else {
+                in->source->last_column_sorted = (int32_t)in->col;
+                plan->kind = CLASSIC_JOIN;
+            }
+        } else {
+            out->source = entry_at(entities, elsewhere);
+            if (lhs_in) {
+                const int out_sorted = out->source->last_column_sorted == (int32_t)out->col;
+                plan->kind = (in_sorted && out_sorted) ? SCAN_JOIN
+                             : in_sorted               ? JOIN_SORT_RHS
+                             : out_sorted              ? JOIN_SORT_LHS
+                                                       : CLASSIC_JOIN;
+            } else {
+                /* src/join.c:253-267: the rhs-sorted case answers JOIN_SORT_RHS and
+                 * the third test looks at the *rhs* entry with the lhs column */
+                const int out_sorted = out->source->last_column_sorted == (int32_t)out->col;
+                const int in_has_lhs_col = in->source->last_column_sorted == (int32_t)L->col;
+                plan->kind = (in_sorted && out_sorted) ? SCAN_JOIN
+                             : in_sorted               ? JOIN_SORT_RHS
+                             : in_has_lhs_col          ? JOIN_SORT_LHS
+                                                       : CLASSIC_JOIN;
+            }
+        }
+    } else {
+        if (push_entity(entities) == NULL) return -1;
+        plan->kind = (R->rel != L->rel || L->binding != R->binding) ? CLASSIC_JOIN : SCAN_JOIN;
+    }
+    return 0;
+}
+
+static int build_side(const join_side *s, qce_tuples **out)
+{
+    return s->source ? qce_build_tuples_rowids(s->rel, s->col, s->source->payloads, out)
+                     : qce_build_tuples_base(s->rel, s->col, out);
+}
+
+static int require_sorted(const qce_tuples *t, const char *which)
+{
+    int sorted = 0;
+    if (qce_tuples_is_sorted(t, &sorted) != 0) return -1;
+    if (!sorted) {
+        log_err("%s side of a JOIN_SORT merge is not in key order; the reference's result is "
+                "order-dependent here (outside the parity-defined query class), query refused",
+                which);
+        return -1;
+    }
+    return 0;
+}
+
+/* Run the planned join on the device: res->results[] = aligned row-id columns. */
+static int run_join(const join_plan *plan, join_result *res)
+{
+    qce_tuples *tl = NULL, *tr = NULL;
+    int rc = -1;
+
+    if (plan->kind == SCAN_JOIN) {
+        const join_side *L = &plan->lhs, *R = &plan->rhs;
+        if (L->source == NULL && R->source == NULL)
+            rc = qce_scan_join_base(L->rel, L->col, R->rel, R->col, &res->results[0], &res->results[1]);
+        else if (L->source != NULL && R->source != NULL)
+            rc = qce_scan_join(L->rel, L->col, L->source->payloads, R->rel, R->col, R->source->payloads,
+                               &res->results[0], &res->results[1]);
+        if (rc != 0) log_err("scan join failed: %s", qce_last_error());
+        return rc;
+    }
+
+    check(build_side(&plan->lhs, &tl) == 0 && build_side(&plan->rhs, &tr) == 0, "Couldn't allocate relations: %s",
+          qce_last_error());
+    if (plan->kind == CLASSIC_JOIN || plan->kind == JOIN_SORT_LHS) {
+        check(qce_sort_tuples(tl) == 0, "sort failed: %s", qce_last_error());
+    } else {
+        check(require_sorted(tl, "left") == 0, "Join failed!");
+    }
+    if (plan->kind == CLASSIC_JOIN || plan->kind == JOIN_SORT_RHS) {
+        check(qce_sort_tuples(tr) == 0, "sort failed: %s", qce_last_error());
+    } else {
+        check(require_sorted(tr, "right") == 0, "Join failed!");
+    }
+    check(qce_merge_join(tl, tr, &res->results[0], &res->results[1], NULL, NULL) == 0, "merge join failed: %s",
+          qce_last_error());
+    rc = 0;
+
+error:
+    qce_tuples_free(tl);
+    qce_tuples_free(tr);
+    return rc;
+}
+
+/* The distinct (rowid_lhs,rowid_rhs) pairs are only ever consumed by a
+ * bystander re-join, so they are computed the first time one is needed. */
+static int need_distinct(join_result *res)
+{
+    if (res->non_duplicates[0] != NULL) return 0;
+    if (qce_distinct_pairs(res->results[0], res->results[1], &res->non_duplicates[0], &res->non_duplicates[1]) != 0) {
+        log_err("distinct pairs failed: %s", qce_last_error());
+        return -1;
+    }
+    return 0;
+}
+
+/* fix_all_mid_results, src/join.c:486-505: every other column of the entity
+ * (test is on the relation id, :495) is re-joined against the distinct pairs'
+ * `side`, then the joined binding's entry is replaced. */
+static int replace_and_rejoin(join_result *res, DArray *entities, exists_info where, const join_plan *plan,
+                              mid_result fresh, int side)
+{
+    DArray *entity = *(DArray **)DArray_get(entities, where.mid_result);
+    mid_result *joined = (mid_result *)DArray_get(entity, where.index);
+
+    for (size_t i = 0; i < DArray_count(entity); i++) {
+        mid_result *bystander = (mid_result *)DArray_get(entity, i);
+        if (bystander->relation == plan->lhs.rel || bystander->relation == plan->rhs.rel) continue;
+        if (need_distinct(res) != 0) return -1;
+        struct qce_rowids *rejoined = NULL;
+        if (qce_rejoin(res->non_duplicates[side], joined->payloads, bystander->payloads, &rejoined) != 0) {
+            log_err("bystander re-join failed: %s", qce_last_error());
+            return -1;
+        }
+        qce_rowids_free(bystander->payloads);
+        bystander->payloads = rejoined;
+    }
+    qce_rowids_free(joined->payloads);
+    *joined = fresh;
+    return 0;
+}
+
+static void fatal_inconsistent(void)
+{
+    log_err("Something went really wrong");
+    exit(EXIT_FAILURE); /* src/join.c:563,601,610,620 */
+}
+
+/* update_mid_results, src/join.c:507-628. */
+static int install_results(join_result *res, DArray *entities, const join_plan *plan)
+{
+    mid_result fresh[2];
+    const join_side *sides[2] = {&plan->lhs, &plan->rhs};
+    for (int s = 0; s < 2; s++) {
+        fresh[s].relation = sides[s]->rel;
+        fresh[s].predicate_id = sides[s]->binding;
+        fresh[s].last_column_sorted = (int32_t)sides[s]->col;
+        fresh[s].payloads = res->results[s];
+    }
+
+    if (plan->kind == SCAN_JOIN) {
+        /* only the row-id columns are swapped in; bystanders and the sorted
+         * column marker stay as they were (:607-627) */
+        for (int s = 0; s < 2; s++) {
+            exists_info where = relation_exists(entities, sides[s]->rel, sides[s]->binding);
+            if (where.index == -1) fatal_inconsistent();
+            mid_result *entry = entry_at(entities, where);
+            if (entry->payloads != res->results[0] && entry->payloads != res->results[1])
+                qce_rowids_free(entry->payloads); /* the reference leaks the old array */
+            entry->payloads = res->results[s];
+        }
+        return 0;
+    }
+
+    /* order and strictness per kind:
+     *   CLASSIC        lhs then rhs, each pushed if new else re-joined
+     *   JOIN_SORT_LHS  lhs pushed or plainly replaced, then rhs must exist and is re-joined
+     *   JOIN_SORT_RHS  rhs pushed or plainly replaced, then lhs must exist and is re-joined */
+    const int first = plan->kind == JOIN_SORT_RHS ? 1 : 0;
+    for (int step = 0; step < 2; step++) {
+        const int s = step == 0 ? first : 1 - first;
+        const int plain_replace = plan->kind != CLASSIC_JOIN && step == 0;
+        const int must_exist = plan->kind != CLASSIC_JOIN && step == 1;
+        exists_info where = relation_exists(entities, sides[s]->rel, sides[s]->binding);
+        if (where.index == -1) {
+            if (must_exist) fatal_inconsistent();
+            DArray *last = *(DArray **)DArray_last(entities);
+            DArray_push(last, &fresh[s]);
+        } else if (plain_replace) {
+            mid_result *entry = entry_at(entities, where);
+            qce_rowids_free(entry->payloads);
+            *entry = fresh[s];
+        } else if (replace_and_rejoin(res, entities, where, plan, fresh[s], s) != 0) {
+            return -1;
+        }
+    }
+    return 0;
+}
+
+int execute_join(predicate *pred, uint32_t *relations, DArray *metadata_arr, DArray *mid_results_array)
+{
+    (void)metadata_arr;
+    join_plan plan;
+    join_result res = {{NULL, NULL}, {NULL, NULL}};
+
+    if (plan_join(pred, relations, mid_results_array, &plan) != 0) return -1;
+    if (plan.kind == DO_NOTHING) return 0;
+    debug("join kind %d", plan.kind);
+
+    if (run_join(&plan, &res) != 0) goto error;
+    if (install_results(&res, mid_results_array, &plan) != 0) goto error_installed;
+
+    qce_rowids_free(res.non_duplicates[0]);
+    qce_rowids_free(res.non_duplicates[1]);
+    return 0;
+
+error:
+    qce_rowids_free(res.results[0]);
+    qce_rowids_free(res.results[1]);
+error_installed:
+    qce_rowids_free(res.non_duplicates[0]);
+    qce_rowids_free(res.non_duplicates[1]);
+    return -1;
+}

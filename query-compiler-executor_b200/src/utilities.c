@@ -1,0 +1,216 @@
+/* utilities.c -- loader, mid-result lookup, projection and the query loop.
+ *
+ * Same entry points as /root/reference/src/utilities.c (read_relations :124,
+ * relation_exists :164, relation_exists_current :183, execute_queries :289);
+ * what they do with the data is different:
+ *   - read_relations maps each relation file and uploads its columns to HBM
+ *     as they are on disk (column-major uint64).  The reference's fill_data
+ *     (:105-121) rewrites every column into a 16-byte AoS tuple array with
+ *     payload = row index; here the row id is implicit and `tuples` stays NULL.
+ *   - print_sums (:197-224) becomes one gather-and-reduce kernel per projected
+ *     binding (qce_checksum sums every selected column of a binding in a single
+ *     read of its row-id column); only the formatting is host code.
+ */
+#define _GNU_SOURCE
+#include "utilities.h"
+
+#include <fcntl.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include "../../include/qce_b200.h"
+#include "filter.h"
+#include "join.h"
+#include "pred_arrange.h"
+
+/* ------------------------------------------------------------------ loader */
+static int load_relation_file(const char *path, uint32_t rel_index, metadata *out)
+{
+    int rc = -1;
+    uint64_t *map = MAP_FAILED;
+    struct stat sb;
+    int fd = open(path, O_RDONLY);
+    check(fd != -1, "open failed");
+    check(fstat(fd, &sb) != -1, "fstat failed");
+    check((size_t)sb.st_size >= 2 * sizeof(uint64_t), "relation file too short");
+    map = (uint64_t *)mmap(NULL, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    check(map != MAP_FAILED, "mmap failed");
+
+    out->tuples = map[0];
+    out->columns = map[1];
+    check((uint64_t)sb.st_size >= (2 + out->tuples * out->columns) * sizeof(uint64_t), "relation file truncated");
+    out->data = MALLOC(relation *, out->columns ? out->columns : 1);
+    check_mem(out->data);
+    for (uint64_t c = 0; c < out->columns; c++) {
+        relation *col = MALLOC(relation, 1);
+        check_mem(col);
+        col->num_tuples = out->tuples;
+        col->tuples = NULL; /* resident in HBM; the driver's FREE(tuples) is NULL-safe */
+        out->data[c] = col;
+        check(qce_upload_column(rel_index, (uint32_t)c, map + 2 + c * out->tuples, out->tuples) == 0,
+              "column upload failed: %s", qce_last_error());
+    }
+    rc = 0;
+
+error:
+    if (map != MAP_FAILED) munmap(map, (size_t)sb.st_size);
+    if (fd != -1) close(fd);
+    return rc;
+}
+
+int read_relations_from(FILE *in, DArray *metadata_arr)
+{
+    char *line = NULL;
+    size_t cap = 0;
+    int rc = 0;
+    while (getline(&line, &cap, in) != -1) {
+        if (strncmp(line, "Done\n", 5) == 0 || strncmp(line, "done\n", 5) == 0) break;
+        size_t len = strlen(line);
+        if (len && line[len - 1] == '\n') line[len - 1] = '\0';
+        metadata m;
+        if (load_relation_file(line, (uint32_t)DArray_count(metadata_arr), &m) != 0) {
+            rc = -1;
+            break;
+        }
+        DArray_push(metadata_arr, &m);
+    }
+    free(line);
+    return rc;
+}
+
+int read_relations(DArray *metadata_arr) { return read_relations_from(stdin, metadata_arr); }
+
+/* ------------------------------------------------------------------ lookups */
+exists_info relation_exists(DArray *mid_results_array, uint64_t relation, uint64_t predicate_id)
+{
+    exists_info found = {0, -1};
+    for (ssize_t e = (ssize_t)DArray_count(mid_results_array) - 1; e >= 0; e--) {
+        DArray *entity = *(DArray **)DArray_get(mid_results_array, e);
+        for (ssize_t j = 0; j < (ssize_t)DArray_count(entity); j++) {
+            const mid_result *m = (const mid_result *)DArray_get(entity, j);
+            if (m->relation == relation && m->predicate_id == predicate_id) {
+                found.mid_result = e;
+                found.index = j;
+                return found;
+            }
+        }
+    }
+    return found;
+}
+
+ssize_t relation_exists_current(DArray *mid_results, uint64_t relation, uint64_t predicate_id)
+{
+    ssize_t last_hit = -1;
+    for (ssize_t j = 0; j < (ssize_t)DArray_count(mid_results); j++) {
+        const mid_result *m = (const mid_result *)DArray_get(mid_results, j);
+        if (m->relation == relation && m->predicate_id == predicate_id) last_hit = j;
+    }
+    return last_hit;
+}
+
+/* ------------------------------------------------------------------ projection */
+#define MAX_SELECTS 64
+
+/* One checksum token per select, in select order: "<sum> " or "NULL " when the
+ * binding's row-id column is empty; newline after the last one. */
+static int print_sums(DArray *entities, const query *q, FILE *out)
+{
+    uint64_t sums[MAX_SELECTS];
+    int is_null[MAX_SELECTS], done[MAX_SELECTS];
+    mid_result *entry[MAX_SELECTS];
+    const size_t ns = q->select_size;
+    if (ns > MAX_SELECTS) {
+        log_err("too many selects");
+        return -1;
+    }
+    for (size_t i = 0; i < ns; i++) {
+        const uint64_t binding = q->selects[i].relation;
+        exists_info where = relation_exists(entities, q->relations[binding], binding);
+        if (where.index == -1) {
+            log_err("Something went really wrong...");
+            exit(EXIT_FAILURE); /* src/utilities.c:204-207 */
+        }
+        DArray *entity = *(DArray **)DArray_get(entities, where.mid_result);
+        entry[i] = (mid_result *)DArray_get(entity, where.index);
+        is_null[i] = qce_rowids_count(entry[i]->payloads) == 0;
+        done[i] = is_null[i];
+    }
+    /* every selected column of one binding in a single pass over its row ids */
+    for (size_t i = 0; i < ns; i++) {
+        if (done[i]) continue;
+        uint32_t cols[8];
+        size_t slot[8];
+        uint32_t k = 0;
+        for (size_t j = i; j < ns && k < 8; j++) {
+            if (!done[j] && entry[j] == entry[i]) {
+                cols[k] = (uint32_t)q->selects[j].column;
+                slot[k++] = j;
+            }
+        }
+        uint64_t part[8];
+        if (qce_checksum(entry[i]->payloads, (uint32_t)entry[i]->relation, cols, k, part) != 0) {
+            log_err("checksum failed: %s", qce_last_error());
+            return -1;
+        }
+        for (uint32_t t = 0; t < k; t++) {
+            sums[slot[t]] = part[t];
+            done[slot[t]] = 1;
+        }
+    }
+    for (size_t i = 0; i < ns; i++) {
+        if (is_null[i]) fputs("NULL ", out);
+        else fprintf(out, "%lu ", (unsigned long)sums[i]);
+    }
+    fputc('\n', out);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ query loop */
+static void destroy_entities(DArray *entities)
+{
+    for (size_t e = 0; e < DArray_count(entities); e++) {
+        DArray *entity = *(DArray **)DArray_get(entities, e);
+        for (size_t j = 0; j < DArray_count(entity); j++) {
+            mid_result *m = (mid_result *)DArray_get(entity, j);
+            qce_rowids_free(m->payloads);
+        }
+        DArray_destroy(entity);
+    }
+    DArray_destroy(entities);
+}
+
+int execute_query_to(query *q, DArray *metadata_arr, FILE *out)
+{
+    int rc = -1;
+    DArray *entities = DArray_create(sizeof(DArray *), 2);
+    if (entities == NULL) return -1;
+    qce_set_query_stdout(out ? out : stdout);
+
+    for (size_t i = 0; i < q->predicates_size; i++) {
+        predicate *p = &q->predicates[i];
+        if (p->type == 1) {
+            check(execute_filter(p, q->relations, metadata_arr, entities) != -1, "Filter failed!");
+        } else {
+            check(execute_join(p, q->relations, metadata_arr, entities) != -1, "Join failed!");
+        }
+    }
+    check(print_sums(entities, q, out ? out : stdout) == 0, "Projection failed!");
+    rc = 0;
+
+error:
+    destroy_entities(entities);
+    qce_set_query_stdout(NULL);
+    return rc;
+}
+
+void execute_queries(DArray *q_list, DArray *metadata_arr)
+{
+    for (size_t i = 0; i < DArray_count(q_list); i++) {
+        query *q = (query *)DArray_get(q_list, i);
+        arrange_predicates(q);
+        execute_query_to(q, metadata_arr, stdout); /* a failed query prints nothing, as in the reference */
+    }
+    fflush(stdout);
+}

@@ -1,0 +1,157 @@
+"""GPU parity, end to end: the C host layer (build/queries -> libqce_b200.so)
+fed the reference's stdin protocol, stdout compared byte-for-byte with
+(a) the reference's recorded outputs (tests/golden), (b) the numpy oracle on
+fresh seeded workloads, and (c) size-independent properties at larger sizes."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from oracle import qce_oracle as orc
+from oracle import workload as wl
+from tests.helpers import QUERIES_BIN, REFMAIN_BIN, load_db, load_json, run_queries_bin
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def binaries():
+    assert os.path.exists(QUERIES_BIN), "build/queries missing: run __graft_entry__.build()"
+    return [b for b in (QUERIES_BIN, REFMAIN_BIN) if os.path.exists(b)]
+
+
+def _paths(db):
+    return wl.write_db(tempfile.mkdtemp(), db)
+
+
+@pytest.mark.parametrize("db_name,batch", [("ops_db.npz", "ops.json"), ("small_db.npz", "small_batch.json")])
+def test_golden_stdout_byte_exact(binaries, db_name, batch):
+    """Every PDQ query of the golden batches, one process per query (like the
+    fixture was recorded).  PDQ-T must match; PDQ-D must match or be refused
+    (nothing on stdout + a diagnostic) -- never a different checksum."""
+    db = load_db(db_name)
+    paths = _paths(db)
+    recs = [r for r in load_json(batch) if r["class"] in ("PDQ-T", "PDQ-D")]
+    text = "".join(r["query"] + "\n" for r in recs)
+    want = "".join(r["stdout"] for r in recs)
+    for binary in binaries:
+        out, err, rc = run_queries_bin(binary, paths, text)
+        assert rc == 0, err
+        if out != want:  # locate the first differing query for the report
+            for r in recs:
+                o, e, _ = run_queries_bin(binary, paths, r["query"] + "\n")
+                refused = o == "" and "refused" in e
+                assert o == r["stdout"] or (r["class"] == "PDQ-D" and refused), (r, o, e)
+
+
+def test_reference_abort_is_mirrored(binaries):
+    db = load_db("ops_db.npz")
+    out, err, rc = run_queries_bin(binaries[0], _paths(db), "0|0.1=0.2|0.0\n")
+    assert rc != 0 and out == "" and "Something went really wrong" in err  # src/join.c:608-611
+
+
+def test_batch_order_and_count_lines(binaries):
+    """stdout order == query order; stacked-filter count lines precede their
+    query's result line (src/filter.c:32)."""
+    db = load_db("ops_db.npz")
+    text = "0|0.1<10&0.2>500|0.0 0.2\n0 1|0.2>5000|0.0\nF\n0 1|0.1=1.0&0.2<300&0.3>100|0.2 1.2\n"
+    out, err, rc = run_queries_bin(binaries[0], _paths(db), text)
+    assert rc == 0, err
+    assert out == orc.run_batch(db, text)
+    assert out.splitlines()[0] == "3"
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_random_workload_against_oracle(binaries, seed):
+    """Mid-size C1-shaped database; queries whose oracle run is well-defined."""
+    db = wl.gen_small_db(seed=seed, scale=0.05)
+    paths = _paths(db)
+    lines, want = [], []
+    for q in wl.gen_queries(db, 60, seed=seed * 3, max_joins=2):  # <= 2 joins: inside PDQ
+        try:
+            w = orc.run_batch(db, q + "\n")
+        except orc.ReferenceAbort:
+            continue
+        lines.append(q + "\n")
+        want.append(w)
+    out, err, rc = run_queries_bin(binaries[0], paths, "".join(lines))
+    assert rc == 0, err
+    assert out == "".join(want)
+
+
+def test_c2_scaled_twin(binaries):
+    """Config 2 at 1/50 scale (same generator family): filter + 2-way join + 3 checksums."""
+    n = 2_000_000
+    db = wl.gen_pair_db(n, n)
+    q = "0 1|0.1=1.1&0.2>500000|0.0 1.0 1.2\n"
+    for binary in binaries:
+        out, err, rc = run_queries_bin(binary, _paths(db), q)
+        assert rc == 0, err
+        assert out == orc.run_batch(db, q)
+
+
+def test_c3_chain_scaled_twin(binaries):
+    """Config 3 shape: self-join predicate + 3-join PK-FK chain + filter (PDQ form)."""
+    db = wl.gen_chain_db(200_000, nrel=4, seed=3)
+    q = "0 1 2 3|0.1=0.2&0.1=1.0&1.1=2.0&2.1=3.0&0.3<900|0.3 1.3 2.3 3.3\n"
+    out, err, rc = run_queries_bin(binaries[0], _paths(db), q)
+    assert rc == 0, err
+    assert out == orc.run_batch(db, q)
+    assert out.splitlines()[-1] == wl.truth_query(orc.parse_query(q), db).strip("\n")
+
+
+def test_c4_zipf_scaled_twin(binaries):
+    """Config 4 shape: FK side Zipf(1.2) skewed against a unique PK."""
+    db = wl.gen_zipf_db(300_000, seed=4)
+    q = "0 1 2|0.1=1.0&1.1=2.0|0.0 1.2 2.1\n"
+    out, err, rc = run_queries_bin(binaries[0], _paths(db), q)
+    assert rc == 0, err
+    assert out == orc.run_batch(db, q)
+
+
+def test_wide_keys_join(binaries):
+    """Keys >= 2^32 take the wide (SoA uint64 key) path."""
+    rng = np.random.default_rng(5)
+    n = 300_000
+    dom = rng.integers(1 << 40, 1 << 62, 50_000, dtype=np.uint64)
+    db = [[np.arange(n, dtype=np.uint64), dom[rng.integers(0, len(dom), n)], rng.integers(0, 1000, n, dtype=np.uint64)]
+          for _ in range(2)]
+    q = "0 1|0.1=1.1&0.2<500|0.0 1.0 0.1\n"
+    out, err, rc = run_queries_bin(binaries[0], _paths(db), q)
+    assert rc == 0, err
+    assert out == orc.run_batch(db, q)
+
+
+def test_full_size_properties(engine):
+    """At a size the CPU reference cannot run (10M x 10M here; bench.py runs
+    100M): properties that do not need the oracle.  FK->PK join: every FK row
+    matches exactly once, so the join output has n pairs, sum(col0 of the FK
+    side) is the closed form n(n-1)/2, the gathered PK keys equal the FK column
+    and the sorted run is a sorted permutation of its input."""
+    n = 10_000_000
+    rng = np.random.default_rng(77)
+    pk = rng.permutation(n).astype(np.uint64)
+    fk = rng.integers(0, n, n, dtype=np.uint64)
+    engine.upload_column(200, 0, np.arange(n, dtype=np.uint64))
+    engine.upload_column(200, 1, fk)
+    engine.upload_column(201, 0, pk)
+    L = engine.build_tuples(200, 1)
+    R = engine.build_tuples(201, 0)
+    engine.sort_tuples(L)
+    engine.sort_tuples(R)
+    assert engine.is_sorted(L) and engine.is_sorted(R)
+    oL, oR = engine.merge_join(L, R)
+    assert engine.rowids_count(oL) == n
+    assert engine.checksum(oL, 200, [0])[0] == n * (n - 1) // 2          # each FK row exactly once
+    with np.errstate(over="ignore"):
+        fk_sum = int(np.sum(fk, dtype=np.uint64))
+    assert engine.checksum(oL, 200, [1])[0] == fk_sum                    # sum of matched FK values
+    assert engine.checksum(oR, 201, [0])[0] == fk_sum                    # == sum of the PK keys they met
+    k, p = engine.tuples_to_host(R)
+    np.testing.assert_array_equal(k, np.arange(n, dtype=np.uint64))      # sorted permutation
+    np.testing.assert_array_equal(pk[p.astype(np.int64)], k)             # payload still points at its key
+    for h in (oL, oR):
+        engine.rowids_free(h)
+    engine.tuples_free(L)
+    engine.tuples_free(R)

@@ -1,0 +1,61 @@
+"""CPU: the C host layer's parser/arranger against the reference's recorded
+orders, and the C-ABI library's exported symbols against include/qce_b200.h."""
+import os
+import re
+import subprocess
+
+import pytest
+
+from tests.helpers import HOST_PROBE, ROOT, load_json
+
+
+def _build():
+    import __graft_entry__
+    __graft_entry__.build()
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    if not os.path.exists(HOST_PROBE):
+        _build()
+
+
+def _probe(lines):
+    out = subprocess.run([HOST_PROBE], input="".join(lines).encode(), stdout=subprocess.PIPE, check=True).stdout.decode()
+    rows = out.splitlines()
+    return rows[0::2], rows[1::2]
+
+
+def test_host_arranger_matches_reference():
+    recs = load_json("arrange.json")
+    orders, _ = _probe([f"0 1 2 3|{r['written']}|0.0\n" for r in recs])
+    assert len(orders) == len(recs)
+    for got, rec in zip(orders, recs):
+        assert got == rec["executed"], rec["written"]
+
+
+def test_host_parser_sections():
+    orders, meta = _probe(["F\n", "3 0 1|0.2=1.0&0.1=2.0&0.2>3499|1.2 0.1\n", "\n", "0|0.1=4294967297|0.0\n"])
+    assert orders == ["0.2>3499 0.2=1.0 0.1=2.0", "0.1=1"]
+    assert meta[0] == "#rels=3 sels=2 r3 r0 r1 s1.2 s0.1"
+    assert meta[1] == "#rels=1 sels=1 r0 s0.0"
+
+
+def test_library_exports_every_declared_symbol():
+    import qce_b200
+    header = open(os.path.join(ROOT, "include", "qce_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(qce_[a-z0-9_]+)\s*\(", header)))
+    assert declared == sorted(qce_b200.SYMBOLS)
+    lib = qce_b200.load_library()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.qce_abi_version() >= 1
+
+
+def test_engine_refuses_to_run_without_a_gpu():
+    import torch
+    import qce_b200
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(qce_b200.EngineError, match="no CPU path"):
+        qce_b200.Engine()

@@ -1,0 +1,40 @@
+"""CPU: the numpy oracle against the reference's recorded outputs
+(tests/golden, made by tests/golden/make_golden.py from oracle/_ref)."""
+import pytest
+
+from oracle import qce_oracle as orc
+from tests.helpers import load_db, load_json
+
+
+def test_arrange_matches_reference():
+    for rec in load_json("arrange.json"):
+        q = orc.parse_query(f"0 1 2 3|{rec['written']}|0.0")
+        orc.arrange_predicates(q)
+        assert " ".join(p.text() for p in q.predicates) == rec["executed"], rec["written"]
+
+
+@pytest.mark.parametrize("db_name,batch", [("ops_db.npz", "ops.json"), ("small_db.npz", "small_batch.json")])
+def test_oracle_matches_reference_stdout(db_name, batch):
+    db = load_db(db_name)
+    checked = 0
+    for rec in load_json(batch):
+        if rec["class"] not in ("PDQ-T", "PDQ-D"):
+            continue  # tie-dependent or crashing in the reference: undefined, excluded
+        assert orc.run_batch(db, rec["query"] + "\n") == rec["stdout"], rec["query"]
+        checked += 1
+    assert checked >= 15
+
+
+def test_oracle_mirrors_reference_abort():
+    db = load_db("ops_db.npz")
+    with pytest.raises(orc.ReferenceAbort):
+        orc.run_batch(db, "0|0.1=0.2|0.0\n")  # self-join on a fresh binding: exit(1), src/join.c:608-611
+
+
+def test_parser_edge_cases():
+    assert orc.parse_query("F\n") is None
+    q = orc.parse_query("3 0 1|0.2=1.0&0.1=2.0&0.2>3499|1.2 0.1\n")
+    assert q.relations == [3, 0, 1] and len(q.predicates) == 3 and q.selects == [(1, 2), (0, 1)]
+    assert q.predicates[2].type == 1 and q.predicates[2].second == 3499
+    q = orc.parse_query("0|0.1=4294967297|0.0\n")  # constant parsed as uint32 (src/parsing.c:64-70)
+    assert q.predicates[0].second == 1
