@@ -67,6 +67,7 @@ struct Engine {
     u64 launches = 0;
     bool profile = false;
     std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> ev_pool; // recycled profiling events
     std::string prof_json;
 };
 Engine g;
@@ -119,8 +120,11 @@ void prof_begin(const char *tag)
     if (!g.profile) return;
     ProfRec r;
     r.tag = tag;
-    cudaEventCreate(&r.e0);
-    cudaEventCreate(&r.e1);
+    cudaEvent_t *ev[2] = {&r.e0, &r.e1};
+    for (auto e : ev) {
+        if (!g.ev_pool.empty()) { *e = g.ev_pool.back(); g.ev_pool.pop_back(); }
+        else cudaEventCreate(e);
+    }
     cudaEventRecord(r.e0, g.stream);
     g.prof.push_back(r);
 }
@@ -500,7 +504,7 @@ int qce_profile_enable(int on)
 {
     NEED_INIT();
     CK(cudaStreamSynchronize(g.stream));
-    for (auto &r : g.prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    for (auto &r : g.prof) { g.ev_pool.push_back(r.e0); g.ev_pool.push_back(r.e1); }
     g.prof.clear();
     g.profile = on != 0;
     return 0;
@@ -534,6 +538,15 @@ const char *qce_profile_json(void)
 }
 
 // ---------------------------------------------------------------- relations
+// A column uploaded again with the same row count (a refreshed batch of the
+// same relation) reuses its HBM buffer instead of cudaFree + cudaMalloc.
+static u64 *reusable_buffer(u32 rel, u32 col, u64 n)
+{
+    auto it = g.cols.find(col_key(rel, col));
+    if (it != g.cols.end() && it->second.owned && it->second.n == n) return (u64 *)it->second.d;
+    return nullptr;
+}
+
 static int register_column(u32 rel, u32 col, const u64 *d, u64 n, bool owned)
 {
     CK(cudaMemsetAsync(g.d_scalars + 8, 0, sizeof(u64), g.stream));
@@ -546,7 +559,7 @@ static int register_column(u32 rel, u32 col, const u64 *d, u64 n, bool owned)
     c.maxv = g.h_scalars[8];
     c.owned = owned;
     auto it = g.cols.find(col_key(rel, col));
-    if (it != g.cols.end() && it->second.owned) cudaFree((void *)it->second.d);
+    if (it != g.cols.end() && it->second.owned && it->second.d != d) cudaFree((void *)it->second.d);
     g.cols[col_key(rel, col)] = c;
     return 0;
 }
@@ -555,8 +568,8 @@ int qce_upload_column(uint32_t rel, uint32_t col, const uint64_t *host, uint64_t
 {
     NEED_INIT();
     if (n >= (1ull << 32)) return fail("relation %u has %llu rows; device row ids are 32-bit", rel, (unsigned long long)n);
-    u64 *d = nullptr;
-    CK(cudaMalloc((void **)&d, (n ? n : 1) * sizeof(u64)));
+    u64 *d = reusable_buffer(rel, col, n);
+    if (!d) CK(cudaMalloc((void **)&d, (n ? n : 1) * sizeof(u64)));
     if (n) CK(cudaMemcpyAsync(d, host, n * sizeof(u64), cudaMemcpyHostToDevice, g.stream));
     return register_column(rel, col, d, n, true);
 }
@@ -564,8 +577,8 @@ int qce_upload_column_device(uint32_t rel, uint32_t col, const void *dev, uint64
 {
     NEED_INIT();
     if (n >= (1ull << 32)) return fail("relation %u has %llu rows; device row ids are 32-bit", rel, (unsigned long long)n);
-    u64 *d = nullptr;
-    CK(cudaMalloc((void **)&d, (n ? n : 1) * sizeof(u64)));
+    u64 *d = reusable_buffer(rel, col, n);
+    if (!d) CK(cudaMalloc((void **)&d, (n ? n : 1) * sizeof(u64)));
     if (n) CK(cudaMemcpyAsync(d, dev, n * sizeof(u64), cudaMemcpyDeviceToDevice, g.stream));
     return register_column(rel, col, d, n, true);
 }
