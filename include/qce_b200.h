@@ -109,6 +109,13 @@ int qce_tuples_is_sorted(const qce_tuples *t, int *sorted);
  * (join_payloads) sort them first, so only the multiset matters. */
 int qce_merge_join(const qce_tuples *R, const qce_tuples *S, qce_rowids **outR, qce_rowids **outS,
                    qce_rowids **distinctR, qce_rowids **distinctS);
+/* join_relations run over an outer run R that is NOT sorted (S sorted): the
+ * result of the reference's serial pointer walk, src/join.c:342-377, which it
+ * executes when build_relations wrongly assumes R is in key order
+ * (JOIN_SORT_RHS via src/join.c:253-267).  An R tuple yields its full match
+ * range iff its key >= every earlier R key, nothing otherwise; output R-major. */
+int qce_merge_join_walk(const qce_tuples *R, const qce_tuples *S, qce_rowids **outR,
+                        qce_rowids **outS);
 /* The non_duplicates of join_relations computed on their own (Hashmap dedup,
  * src/join.c:358-367), so the host layer can skip the pass when no bystander
  * column consumes them. */

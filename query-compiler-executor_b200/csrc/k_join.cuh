@@ -122,6 +122,103 @@ k_join_bounds(TupleView R, u32 nR, TupleView S, const uint2 *__restrict__ win,
     }
 }
 
+// ---- "walk" variant: outer run R in arbitrary order, inner run S sorted -------------
+// The reference's merge is one serial pointer walk (src/join.c:342-377) that it
+// also runs when build_relations wrongly assumes R is already sorted
+// (JOIN_SORT_RHS after the asymmetric tests of src/join.c:253-267).  With S
+// sorted the walk has a closed form: s_start only ever advances to
+// lower_bound(S, max of the R keys seen so far), so an R tuple matches its full
+// [lb, ub) range iff its key >= every earlier R key, and nothing otherwise.
+// That is a prefix-max scan plus two binary searches per tuple -- no serial walk.
+template <bool WR>
+__global__ void __launch_bounds__(QCE_JTHREADS)
+k_tile_keymax(TupleView R, u32 nR, u64 *__restrict__ tile_max)
+{
+    __shared__ u64 smax[QCE_JTHREADS / 32];
+    const u32 tbase = blockIdx.x * QCE_JTILE;
+    u64 m = 0;
+    for (int k = 0; k < QCE_JTILE / QCE_JTHREADS; k++) {
+        u32 i = tbase + k * QCE_JTHREADS + threadIdx.x;
+        if (i < nR) m = max(m, tv_key<WR>(R, i));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(QCE_FULL_MASK, m, o));
+    if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < QCE_JTHREADS / 32; w++) m = max(m, smax[w]);
+        tile_max[blockIdx.x] = m;
+    }
+}
+// exclusive prefix max over the tiles; has_prev[t] = 0 for the first tile
+__global__ void k_scan_excl_max(const u64 *__restrict__ tile_max, u64 *__restrict__ tile_pm, u32 ntiles)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        u64 run = 0;
+        for (u32 t = 0; t < ntiles; t++) {
+            tile_pm[t] = run;
+            run = max(run, tile_max[t]);
+        }
+    }
+}
+template <bool WR, bool WS>
+__global__ void __launch_bounds__(QCE_JTHREADS)
+k_join_bounds_walk(TupleView R, u32 nR, TupleView S, u32 nS, const u64 *__restrict__ tile_pm,
+                   u32 *__restrict__ lb_out, u32 *__restrict__ cnt_out, u64 *__restrict__ tile_total,
+                   u32 *__restrict__ tile_chunks)
+{
+    __shared__ u64 wmax[QCE_JTHREADS / 32];
+    __shared__ u64 scratch[33];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 tbase = blockIdx.x * QCE_JTILE;
+    // 8 consecutive tuples per thread so that thread order == run order
+    u64 key[8], local = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        u32 i = tbase + tid * 8 + k;
+        key[k] = (i < nR) ? tv_key<WR>(R, i) : 0;
+        local = max(local, key[k]);
+    }
+    // exclusive max-scan of `local` across the block
+    u64 incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u64 nb = __shfl_up_sync(QCE_FULL_MASK, incl, o);
+        if (lane >= o) incl = max(incl, nb);
+    }
+    u64 excl = __shfl_up_sync(QCE_FULL_MASK, incl, 1);
+    if (lane == 0) excl = 0;
+    if (lane == 31) wmax[warp] = incl;
+    __syncthreads();
+    u64 before = tile_pm[blockIdx.x];
+    for (int w = 0; w < warp; w++) before = max(before, wmax[w]);
+    before = max(before, excl);
+    const bool first_thread = (blockIdx.x == 0 && tid == 0);
+
+    u64 sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        u32 i = tbase + tid * 8 + k;
+        if (i < nR) {
+            u32 lb = 0, c = 0;
+            const bool first = first_thread && k == 0; // nothing precedes the very first tuple
+            if (first || key[k] >= before) {
+                lb = lower_bound_g<WS>(S, 0, nS, key[k]);
+                c = upper_bound_g<WS>(S, lb, nS, key[k]) - lb;
+            }
+            lb_out[i] = lb;
+            cnt_out[i] = c;
+            sum += c;
+            before = max(before, key[k]);
+        }
+    }
+    u64 tot = block_sum<u64, QCE_JTHREADS>(sum, scratch);
+    if (tid == 0) {
+        tile_total[blockIdx.x] = tot;
+        tile_chunks[blockIdx.x] = (u32)((tot + QCE_JCHUNK - 1) / QCE_JCHUNK);
+    }
+}
+
 // One CTA per <=4096-pair chunk of one R tile.
 template <bool WR, bool WS, bool WRITE_R, bool WRITE_S>
 __global__ void __launch_bounds__(QCE_JTHREADS)

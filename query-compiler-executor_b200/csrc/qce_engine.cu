@@ -307,7 +307,7 @@ TupleView view_of(const qce_tuples *t)
 // ---- merge join driver -------------------------------------------------------
 template <bool WR, bool WS>
 int merge_join_t(const qce_tuples *R, const qce_tuples *S, bool want_r, bool want_s, qce_rowids **outR,
-                 qce_rowids **outS)
+                 qce_rowids **outS, bool walk)
 {
     const u32 nR = (u32)R->n, nS = (u32)S->n;
     const u32 ntiles = (u32)ceil_div(nR, QCE_JTILE);
@@ -318,10 +318,21 @@ int merge_join_t(const qce_tuples *R, const qce_tuples *S, bool want_r, bool wan
         dalloc(&chunk_off, ntiles) || dalloc(&tile_total, ntiles) || dalloc(&tile_off, ntiles))
         return -1;
     TupleView vr = view_of(R), vs = view_of(S);
-    LAUNCH("join_partition", (k_join_partition<WR, WS>), (int)ceil_div(ntiles, 256), 256, 0, vr, nR, vs, nS,
-           ntiles, win);
-    LAUNCH("join_bounds", (k_join_bounds<WR, WS>), (int)ntiles, QCE_JTHREADS, 0, vr, nR, vs, win, lb, cnt,
-           tile_total, tile_chunks);
+    if (walk) {
+        u64 *tile_max = nullptr, *tile_pm = nullptr;
+        if (dalloc(&tile_max, ntiles) || dalloc(&tile_pm, ntiles)) return -1;
+        LAUNCH("join_keymax", (k_tile_keymax<WR>), (int)ntiles, QCE_JTHREADS, 0, vr, nR, tile_max);
+        LAUNCH("join_keymax", k_scan_excl_max, 1, 32, 0, tile_max, tile_pm, ntiles);
+        LAUNCH("join_bounds_walk", (k_join_bounds_walk<WR, WS>), (int)ntiles, QCE_JTHREADS, 0, vr, nR, vs, nS,
+               tile_pm, lb, cnt, tile_total, tile_chunks);
+        dfree(tile_max);
+        dfree(tile_pm);
+    } else {
+        LAUNCH("join_partition", (k_join_partition<WR, WS>), (int)ceil_div(ntiles, 256), 256, 0, vr, nR, vs, nS,
+               ntiles, win);
+        LAUNCH("join_bounds", (k_join_bounds<WR, WS>), (int)ntiles, QCE_JTHREADS, 0, vr, nR, vs, win, lb, cnt,
+               tile_total, tile_chunks);
+    }
     LAUNCH("scan_tiles", (k_scan_excl<u64, u64>), 1, 1024, 0, tile_total, tile_off, (u64)ntiles, g.d_scalars);
     LAUNCH("scan_tiles", (k_scan_excl<u32, u32>), 1, 1024, 0, tile_chunks, chunk_off, (u64)ntiles,
            g.d_scalars + 1);
@@ -350,7 +361,7 @@ int merge_join_t(const qce_tuples *R, const qce_tuples *S, bool want_r, bool wan
 }
 
 int merge_join_any(const qce_tuples *R, const qce_tuples *S, bool want_r, bool want_s, qce_rowids **outR,
-                   qce_rowids **outS)
+                   qce_rowids **outS, bool walk = false)
 {
     if (R->n >= (1ull << 32) || S->n >= (1ull << 32)) return fail("join input exceeds 2^32 tuples");
     if (R->n == 0 || S->n == 0) {
@@ -360,10 +371,10 @@ int merge_join_any(const qce_tuples *R, const qce_tuples *S, bool want_r, bool w
         if (want_s && new_rowids(0, S->id_bound, outS) != 0) return -1;
         return 0;
     }
-    if (R->wide && S->wide) return merge_join_t<true, true>(R, S, want_r, want_s, outR, outS);
-    if (R->wide) return merge_join_t<true, false>(R, S, want_r, want_s, outR, outS);
-    if (S->wide) return merge_join_t<false, true>(R, S, want_r, want_s, outR, outS);
-    return merge_join_t<false, false>(R, S, want_r, want_s, outR, outS);
+    if (R->wide && S->wide) return merge_join_t<true, true>(R, S, want_r, want_s, outR, outS, walk);
+    if (R->wide) return merge_join_t<true, false>(R, S, want_r, want_s, outR, outS, walk);
+    if (S->wide) return merge_join_t<false, true>(R, S, want_r, want_s, outR, outS, walk);
+    return merge_join_t<false, false>(R, S, want_r, want_s, outR, outS, walk);
 }
 
 // distinct (rowid_R,rowid_S) pairs of a join output: pack, sort every
@@ -746,6 +757,13 @@ int qce_merge_join(const qce_tuples *R, const qce_tuples *S, qce_rowids **outR, 
         if (distinctS) *distinctS = ds; else qce_rowids_free(ds);
     }
     return 0;
+}
+
+int qce_merge_join_walk(const qce_tuples *R, const qce_tuples *S, qce_rowids **outR, qce_rowids **outS)
+{
+    NEED_INIT();
+    if (!R || !S || !outR || !outS) return fail("null argument");
+    return merge_join_any(R, S, true, true, outR, outS, true);
 }
 
 int qce_distinct_pairs(const qce_rowids *pairsR, const qce_rowids *pairsS, qce_rowids **distinctR,

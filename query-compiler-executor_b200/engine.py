@@ -23,7 +23,7 @@ SYMBOLS = [
     "qce_sync", "qce_profile_enable", "qce_profile_json", "qce_upload_column", "qce_upload_column_device",
     "qce_adopt_column_device", "qce_column_info", "qce_drop_relations", "qce_filter_scan", "qce_filter_refine",
     "qce_build_tuples_base", "qce_build_tuples_rowids", "qce_sort_tuples", "qce_tuples_is_sorted",
-    "qce_merge_join", "qce_distinct_pairs", "qce_scan_join", "qce_scan_join_base", "qce_rejoin", "qce_checksum", "qce_rowids_count",
+    "qce_merge_join", "qce_merge_join_walk", "qce_distinct_pairs", "qce_scan_join", "qce_scan_join_base", "qce_rejoin", "qce_checksum", "qce_rowids_count",
     "qce_rowids_from_host", "qce_rowids_to_host", "qce_rowids_clone", "qce_rowids_free", "qce_tuples_count",
     "qce_tuples_from_host", "qce_tuples_to_host", "qce_tuples_free", "qce_partition_tuples",
     "qce_tuples_from_device_packed", "qce_exchange_release", "qce_key_histogram",
@@ -54,6 +54,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "qce_build_tuples_base": (i32, [u32, u32, P(vp)]), "qce_build_tuples_rowids": (i32, [u32, u32, vp, P(vp)]),
         "qce_sort_tuples": (i32, [vp]), "qce_tuples_is_sorted": (i32, [vp, P(i32)]),
         "qce_merge_join": (i32, [vp, vp, P(vp), P(vp), P(vp), P(vp)]),
+        "qce_merge_join_walk": (i32, [vp, vp, P(vp), P(vp)]),
         "qce_distinct_pairs": (i32, [vp, vp, P(vp), P(vp)]),
         "qce_scan_join": (i32, [u32, u32, vp, u32, u32, vp, P(vp), P(vp)]),
         "qce_scan_join_base": (i32, [u32, u32, u32, u32, P(vp), P(vp)]),
@@ -199,6 +200,11 @@ class Engine:
         self._ck(self.lib.qce_merge_join(R, S, C.byref(oR), C.byref(oS),
                                          C.byref(dR) if distinct else None, C.byref(dS) if distinct else None))
         return (oR.value, oS.value, dR.value, dS.value) if distinct else (oR.value, oS.value)
+
+    def merge_join_walk(self, R: int, S: int):
+        oR, oS = C.c_void_p(), C.c_void_p()
+        self._ck(self.lib.qce_merge_join_walk(R, S, C.byref(oR), C.byref(oS)))
+        return oR.value, oS.value
 
     def distinct_pairs(self, pR: int, pS: int):
         dR, dS = C.c_void_p(), C.c_void_p()

@@ -19,10 +19,12 @@
  * The state machine is mirrored decision for decision (including the
  * asymmetric constants of :253-267 and the relation-id bystander test of
  * :495), because it selects which kernels run and so defines the reference's
- * output.  One difference, stated in the header: a JOIN_SORT_* merge whose
- * "already sorted" side is in fact not sorted is refused with a diagnostic --
- * the reference's serial pointer walk gives an order-dependent result there
- * that no parallel merge reproduces.
+ * output.  A JOIN_SORT_RHS merge whose "already sorted" lhs is in fact not
+ * sorted is computed with the closed form of the reference's pointer walk
+ * (qce_merge_join_walk).  One case is refused with a diagnostic: a JOIN_SORT_LHS
+ * merge whose *inner* (rhs) run is not sorted -- the walk's result there is a
+ * serial scan over an unsorted array, outside the
+ * parity-defined query class.
  */
 #include "join.h"
 
@@ -173,18 +175,27 @@ static int run_join(const join_plan *plan, join_result *res)
     /* with an empty side the pointer walk of src/join.c:342 never starts: the
      * result is empty whatever the order of the other side */
     const int trivially_empty = qce_tuples_count(tl) == 0 || qce_tuples_count(tr) == 0;
+    int outer_in_order = 1;
     if (plan->kind == CLASSIC_JOIN || plan->kind == JOIN_SORT_LHS) {
         check(qce_sort_tuples(tl) == 0, "sort failed: %s", qce_last_error());
     } else if (!trivially_empty) {
-        check(require_sorted(tl, "left") == 0, "Join failed!");
+        /* JOIN_SORT_RHS trusts the lhs to be in key order.  When it is not (the
+         * asymmetric tests of src/join.c:253-267), the reference's walk is still a
+         * function of the data -- qce_merge_join_walk computes it. */
+        check(qce_tuples_is_sorted(tl, &outer_in_order) == 0, "%s", qce_last_error());
     }
     if (plan->kind == CLASSIC_JOIN || plan->kind == JOIN_SORT_RHS) {
         check(qce_sort_tuples(tr) == 0, "sort failed: %s", qce_last_error());
     } else if (!trivially_empty) {
         check(require_sorted(tr, "right") == 0, "Join failed!");
     }
-    check(qce_merge_join(tl, tr, &res->results[0], &res->results[1], NULL, NULL) == 0, "merge join failed: %s",
-          qce_last_error());
+    if (outer_in_order) {
+        check(qce_merge_join(tl, tr, &res->results[0], &res->results[1], NULL, NULL) == 0, "merge join failed: %s",
+              qce_last_error());
+    } else {
+        check(qce_merge_join_walk(tl, tr, &res->results[0], &res->results[1]) == 0, "merge join failed: %s",
+              qce_last_error());
+    }
     rc = 0;
 
 error:

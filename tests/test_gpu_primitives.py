@@ -258,3 +258,21 @@ def test_partition_tuples(engine, nparts):
     engine.exchange_release(buf)
     engine.tuples_free(back)
     engine.tuples_free(t)
+
+
+@pytest.mark.parametrize("nR,nS,domain", [(1, 1, 1), (500, 400, 50), (5000, 9000, 300), (30000, 20000, 1 << 33)])
+def test_merge_join_walk_unsorted_outer(engine, nR, nS, domain):
+    """Outer run in arbitrary order, inner sorted: must equal the reference's
+    literal pointer walk (oracle._merge_serial restates src/join.c:342-377)."""
+    rng = np.random.default_rng(nR + nS)
+    kR, pR = _col(rng, nR, domain), np.arange(nR, dtype=U64)
+    kS, pS = orc.sort_tuples(_col(rng, nS, domain), np.arange(nS, dtype=U64))
+    R, S = engine.tuples_from_host(kR, pR), engine.tuples_from_host(kS, pS)
+    oR, oS = engine.merge_join_walk(R, S)
+    wR, wS = orc._merge_serial(kR, pR, kS, pS)
+    np.testing.assert_array_equal(engine.rowids_to_host(oR), wR)
+    np.testing.assert_array_equal(engine.rowids_to_host(oS), wS)
+    for h in (oR, oS):
+        engine.rowids_free(h)
+    engine.tuples_free(R)
+    engine.tuples_free(S)
