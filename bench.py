@@ -48,43 +48,66 @@ def peaks():
 
 # ------------------------------------------------------------------ clocks
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region.  In-process
+    NVML (a `nvidia-smi -lms 100` child perturbed the CUDA driver enough to cost
+    ~25 % of a 10 ms step); nvidia-smi at 200 ms is the fallback."""
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, period=0.02):
+        self.index, self.period, self.sm, self.reasons, self.max_mhz = index, period, [], set(), None
+        self._stop, self._thr, self._smi = threading.Event(), None, None
 
     def start(self):
+        if self.period <= 0:
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        for name, bit in self.BAD.items():
+                            if r & bit:
+                                self.reasons.add(name)
+                    except Exception:
+                        pass
+                    self._stop.wait(self.period)
+            self._thr = threading.Thread(target=loop, daemon=True)
+            self._thr.start()
+        except Exception:
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            try:
+                self._smi = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                              "--format=csv,noheader,nounits", "-lms", "200"],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            except Exception:
+                self._smi = None
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except Exception:
-                continue
-            for n, v in zip(names, f[2:6]):
-                if v == "Active":
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop.set()
+        if self._thr:
+            self._thr.join(timeout=1.0)
+        if self._smi:
+            time.sleep(0.25)
+            self._smi.terminate()
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for line in self._smi.stdout.read().splitlines():
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    self.sm.append(float(f[0])); self.max_mhz = float(f[1])
+                except Exception:
+                    continue
+                for nme, v in zip(names, f[2:6]):
+                    if v == "Active":
+                        self.reasons.add(nme)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 # ------------------------------------------------------------------ workload
@@ -219,24 +242,35 @@ def main():
     upload_all()
     want = run_query(lib, q)  # first (cold) run doubles as the result every later step must reproduce
 
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, period=float(os.environ.get('QCE_BENCH_CLOCK_PERIOD', '0.05')))
     # ---- value: columns resident in HBM
     for _ in range(args.warmup):
         assert run_query(lib, q) == want
     eng.sync(); torch.cuda.synchronize()
     sampler.start()
-    eng.profile(True)
     eng.timer_reset()
     wall = time.time()
+    step_wall = []
     for _ in range(args.steps):
-        out = run_query(lib, q)
+        t_step = time.perf_counter()
+        out = run_query(lib, q)  # ends with the checksum read-back, i.e. synchronised
+        step_wall.append(round(1e3 * (time.perf_counter() - t_step), 3))
     ms, launches = eng.timer_read()
     wall = time.time() - wall
-    prof = eng.profile_read()
-    eng.profile(False)
     assert out == want
     ms_per_step = ms / args.steps
     value = 2 * rows / (ms_per_step / 1e3)
+    # the same K steps again with CUDA events around every kernel launch (adds
+    # ~1.5 % to a step, so it is kept out of `value`): per-kernel times for the roofline
+    eng.profile(True)
+    eng.timer_reset()
+    for _ in range(args.steps):
+        out = run_query(lib, q)
+    ms_prof, _ = eng.timer_read()
+    prof_all = eng.profile_read()
+    prof = {k: v for k, v in prof_all.items() if not k.startswith("gap_before")}
+    eng.profile(False)
+    assert out == want
 
     # ---- e2e: host buffers in, checksums out, every step
     for _ in range(min(args.warmup, 2)):
@@ -312,7 +346,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": 6 * col_bytes, "d2h_bytes_per_step": 3 * 8 + 5 * 16,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-        "wall_ms_per_step": 1e3 * wall / args.steps,
+        "wall_ms_per_step": 1e3 * wall / args.steps, "step_wall_ms": step_wall, "ms_per_step_with_kernel_events": ms_prof / args.steps,
     }
     print(json.dumps(line))
     return 0

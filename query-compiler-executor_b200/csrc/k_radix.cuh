@@ -159,6 +159,23 @@ struct DigitSplit {
     }
 };
 
+// Lanes of the warp holding the same 8-bit digit.  `match.any` gives this in one
+// instruction, but on sm_100a it runs on the address-divergence unit at about
+// one warp instruction per 60 cycles per SM (ncu: pipe_adu 73 % busy, the pass
+// capped at ~2 TB/s).  Eight ballots -- one per digit bit, intersected -- go
+// through the vote path at two warps per clock instead.
+__device__ __forceinline__ u32 warp_peers_8bit(u32 d)
+{
+    u32 peers = QCE_FULL_MASK;
+#pragma unroll
+    for (int b = 0; b < QCE_RADIX_BITS; b++) {
+        const bool bit = (d >> b) & 1u;
+        const u32 m = __ballot_sync(QCE_FULL_MASK, bit);
+        peers &= bit ? m : ~m;
+    }
+    return peers;
+}
+
 // ---- one-sweep pass ------------------------------------------------------------
 // Tile status word: top 2 bits = flag, low 30 bits = count (n < 2^30 per sort).
 #define QCE_ST_PART 0x40000000u
@@ -169,33 +186,25 @@ template <int THREADS, int ITEMS> struct OnesweepSmem {
     u32 warp_hist[(THREADS / 32) * QCE_RADIX_BINS]; // per-warp digit counts -> bases
     u32 tile_excl[QCE_RADIX_BINS];                  // digit start inside the sorted tile
     u32 goff[QCE_RADIX_BINS];                       // global start of digit minus tile_excl
+    u32 tile_cnt[QCE_RADIX_BINS];                   // early digit counts of the tile
     u32 scratch[33];
     u32 tile_id;
     u64 keys[THREADS * ITEMS];
 };
 
-template <int THREADS, int ITEMS, bool HAS_VALS, typename DigitOp>
-__global__ void __launch_bounds__(THREADS)
-k_onesweep(const u64 *__restrict__ keys_in, u64 *__restrict__ keys_out,
-           const u32 *__restrict__ vals_in, u32 *__restrict__ vals_out, u32 n, DigitOp digit,
-           const u32 *__restrict__ gbase, u32 *__restrict__ status, u32 *__restrict__ tile_counter)
+// One tile of the pass.  FULL = every slot of the tile holds a real tuple (no
+// bounds checks, no padding logic): all tiles but the last.
+template <int THREADS, int ITEMS, bool HAS_VALS, bool FULL, typename DigitOp>
+__device__ __forceinline__ void
+onesweep_tile(OnesweepSmem<THREADS, ITEMS> &sm, u32 *svals, const u64 *__restrict__ keys_in,
+              u64 *__restrict__ keys_out, const u32 *__restrict__ vals_in, u32 *__restrict__ vals_out, u32 n,
+              const DigitOp &digit, const u32 *__restrict__ gbase, u32 *__restrict__ status, u32 tile)
 {
     constexpr int TILE = THREADS * ITEMS;
     constexpr int WARPS = THREADS / 32;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    OnesweepSmem<THREADS, ITEMS> &sm = *reinterpret_cast<OnesweepSmem<THREADS, ITEMS> *>(smem_raw);
-    u32 *svals = reinterpret_cast<u32 *>(smem_raw + sizeof(OnesweepSmem<THREADS, ITEMS>));
-
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    // Tiles are claimed in launch order so that every tile a CTA may wait on in
-    // the look-back is owned by a CTA that is already resident.
-    if (tid == 0) sm.tile_id = atomicAdd(tile_counter, 1u);
-    for (int i = tid; i < WARPS * QCE_RADIX_BINS; i += THREADS) sm.warp_hist[i] = 0;
-    __syncthreads();
-    const u32 tile = sm.tile_id;
     const u32 tbase = tile * TILE;
-    const u32 nvalid = min((u32)TILE, n - tbase);
+    const u32 nvalid = FULL ? (u32)TILE : (n - tbase);
 
     // ---- load: warp-striped so that (warp, item, lane) order == input order
     u64 key[ITEMS];
@@ -203,75 +212,92 @@ k_onesweep(const u64 *__restrict__ keys_in, u64 *__restrict__ keys_out,
     const u32 wbase = tbase + warp * (32 * ITEMS) + lane;
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
-        u32 idx = wbase + j * 32;
-        key[j] = (idx < n) ? ld_stream_u64(keys_in + idx) : ~0ull;
-        if (HAS_VALS) val[j] = (idx < n) ? ld_stream_u32(vals_in + idx) : 0u;
+        const u32 idx = wbase + j * 32;
+        if (FULL || idx < n) {
+            key[j] = ld_stream_u64(keys_in + idx);
+            if (HAS_VALS) val[j] = ld_stream_u32(vals_in + idx);
+        } else {
+            key[j] = ~0ull;
+            if (HAS_VALS) val[j] = 0u;
+        }
     }
 
-    // ---- rank inside the warp: match lanes with the same digit
-    u32 rank[ITEMS];
-    u32 dig[ITEMS];
-    u32 *wh = sm.warp_hist + warp * QCE_RADIX_BINS;
-    const u32 lt = lanemask_lt();
+    // ---- early counts: tile digit histogram with no-return shared atomics, so
+    // the tile's PARTIAL status is published before the (long) ranking phase and
+    // successors' look-back finds it without spinning.
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
-        // padding of the last tile must sort behind every real tuple of the tile
-        const u32 d = (key[j] == ~0ull && (wbase + j * 32) >= n) ? 255u : digit(key[j]);
-        dig[j] = d;
-        const u32 peers = __match_any_sync(QCE_FULL_MASK, d);
-        const u32 r = __popc(peers & lt);
-        const int leader = __ffs(peers) - 1;
-        u32 old = 0;
-        if (r == 0) {
-            old = wh[d];
-            wh[d] = old + __popc(peers);
-        }
-        __syncwarp();
-        old = __shfl_sync(QCE_FULL_MASK, old, leader);
-        rank[j] = old + r;
+        const u32 d = (!FULL && (wbase + j * 32) >= n) ? 255u : digit(key[j]);
+        atomicAdd(&sm.tile_cnt[d], 1u);
     }
     __syncthreads();
-
-    // ---- per digit: exclusive scan over warps, tile total
     u32 my_count = 0;
+    if (tid < QCE_RADIX_BINS) {
+        my_count = sm.tile_cnt[tid];
+        // the padding of the last tile is not part of the global count
+        const u32 pub = my_count - ((!FULL && tid == 255) ? (TILE - nvalid) : 0u);
+        st_relaxed_gpu_u32(status + (size_t)tile * QCE_RADIX_BINS + tid,
+                           (tile == 0 ? QCE_ST_INCL : QCE_ST_PART) | pub);
+    }
+
+    // ---- rank inside the warp.  Lanes with the same digit are found with
+    // per-bit ballots (warp_peers_8bit); the lowest of them reserves the group's slots with one shared
+    // atomicAdd (program order within the warp keeps items in input order) and
+    // hands the base to its peers.  Done in chunks of CH items with the three
+    // long-latency steps (ballots, ATOMS, SHFL) each issued back to back, so their
+    // latencies overlap instead of adding up.
+    u32 rd[ITEMS]; // digit << 16 | rank inside (warp, digit)
+    u32 *wh = sm.warp_hist + warp * QCE_RADIX_BINS;
+    const u32 lt = lanemask_lt();
+    constexpr int CH = (ITEMS % 4 == 0) ? 4 : ((ITEMS % 3 == 0) ? 3 : 1);
+#pragma unroll
+    for (int j0 = 0; j0 < ITEMS; j0 += CH) {
+        u32 d[CH], peers[CH], old[CH];
+#pragma unroll
+        for (int c = 0; c < CH; c++) {
+            d[c] = (!FULL && (wbase + (j0 + c) * 32) >= n) ? 255u : digit(key[j0 + c]);
+            peers[c] = warp_peers_8bit(d[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < CH; c++) {
+            old[c] = 0;
+            if ((peers[c] & lt) == 0) old[c] = atomicAdd(&wh[d[c]], (u32)__popc(peers[c]));
+        }
+#pragma unroll
+        for (int c = 0; c < CH; c++) {
+            old[c] = __shfl_sync(QCE_FULL_MASK, old[c], __ffs(peers[c]) - 1);
+            rd[j0 + c] = (d[c] << 16) | (old[c] + __popc(peers[c] & lt));
+        }
+    }
+    // ---- digit starts inside the tile (exclusive scan over the 256 digits)
+    {
+        u32 tot;
+        u32 ex = block_scan_excl<u32, THREADS>((tid < QCE_RADIX_BINS) ? my_count : 0u, sm.scratch, &tot);
+        if (tid < QCE_RADIX_BINS) sm.tile_excl[tid] = ex;
+    }
+    // ---- per digit: exclusive scan of the warp counts (all warps have ranked:
+    //      the block scan above contains the barrier)
     if (tid < QCE_RADIX_BINS) {
         u32 run = 0;
 #pragma unroll
         for (int w = 0; w < WARPS; w++) {
-            u32 c = sm.warp_hist[w * QCE_RADIX_BINS + tid];
+            const u32 c = sm.warp_hist[w * QCE_RADIX_BINS + tid];
             sm.warp_hist[w * QCE_RADIX_BINS + tid] = run;
             run += c;
         }
-        my_count = run;
-        // the padding of the last tile is not part of the global count
-        if (tid == 255) my_count -= (TILE - nvalid);
-        // publish the tile-local count before anything else so successors can
-        // make progress while this tile looks back
-        u32 *st = status + (size_t)tile * QCE_RADIX_BINS + tid;
-        st_relaxed_gpu_u32(st, (tile == 0 ? QCE_ST_INCL : QCE_ST_PART) | my_count);
-    }
-    // ---- digit starts inside the tile (exclusive scan over the 256 digits;
-    //      THREADS >= 256 so the first 8 warps hold one digit each)
-    {
-        u32 v = (tid < QCE_RADIX_BINS) ? my_count + ((tid == 255) ? (TILE - nvalid) : 0u) : 0u;
-        u32 tot;
-        u32 ex = block_scan_excl<u32, THREADS>(v, sm.scratch, &tot);
-        if (tid < QCE_RADIX_BINS) sm.tile_excl[tid] = ex;
-    }
-    // ---- decoupled look-back: sum the counts of the preceding tiles
-    if (tid < QCE_RADIX_BINS) {
+        // ---- decoupled look-back: sum the counts of the preceding tiles
         u32 excl = 0;
         if (tile > 0) {
+            const u32 pub = my_count - ((!FULL && tid == 255) ? (TILE - nvalid) : 0u);
             int p = (int)tile - 1;
             while (true) {
-                u32 v = ld_relaxed_gpu_u32(status + (size_t)p * QCE_RADIX_BINS + tid);
-                if ((v & ~QCE_ST_MASK) == 0) { __nanosleep(32); continue; }
+                const u32 v = ld_relaxed_gpu_u32(status + (size_t)p * QCE_RADIX_BINS + tid);
+                if ((v & ~QCE_ST_MASK) == 0) { __nanosleep(20); continue; }
                 excl += v & QCE_ST_MASK;
                 if (v & QCE_ST_INCL) break;
                 p--;
             }
-            st_relaxed_gpu_u32(status + (size_t)tile * QCE_RADIX_BINS + tid,
-                               QCE_ST_INCL | (excl + my_count));
+            st_relaxed_gpu_u32(status + (size_t)tile * QCE_RADIX_BINS + tid, QCE_ST_INCL | (excl + pub));
         }
         sm.goff[tid] = gbase[tid] + excl - sm.tile_excl[tid];
     }
@@ -280,8 +306,8 @@ k_onesweep(const u64 *__restrict__ keys_in, u64 *__restrict__ keys_out,
     // ---- stage in shared memory in digit order
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
-        const u32 d = dig[j];
-        const u32 pos = sm.tile_excl[d] + wh[d] + rank[j];
+        const u32 d = rd[j] >> 16;
+        const u32 pos = sm.tile_excl[d] + wh[d] + (rd[j] & 0xffffu);
         sm.keys[pos] = key[j];
         if (HAS_VALS) svals[pos] = val[j];
     }
@@ -292,14 +318,41 @@ k_onesweep(const u64 *__restrict__ keys_in, u64 *__restrict__ keys_out,
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
         const u32 p = tid + j * THREADS;
-        if (p < nvalid) {
+        if (FULL || p < nvalid) {
             const u64 k = sm.keys[p];
-            const u32 d = digit(k);
-            const u32 g = sm.goff[d] + p;
+            const u32 g = sm.goff[digit(k)] + p;
             keys_out[g] = k;
             if (HAS_VALS) vals_out[g] = svals[p];
         }
     }
+}
+
+template <int THREADS, int ITEMS, int MIN_CTAS, bool HAS_VALS, typename DigitOp>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS)
+k_onesweep(const u64 *__restrict__ keys_in, u64 *__restrict__ keys_out,
+           const u32 *__restrict__ vals_in, u32 *__restrict__ vals_out, u32 n, DigitOp digit,
+           const u32 *__restrict__ gbase, u32 *__restrict__ status, u32 *__restrict__ tile_counter)
+{
+    static_assert(THREADS >= QCE_RADIX_BINS && THREADS * ITEMS <= 65536, "tile shape");
+    constexpr int TILE = THREADS * ITEMS;
+    constexpr int WARPS = THREADS / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    OnesweepSmem<THREADS, ITEMS> &sm = *reinterpret_cast<OnesweepSmem<THREADS, ITEMS> *>(smem_raw);
+    u32 *svals = reinterpret_cast<u32 *>(smem_raw + sizeof(OnesweepSmem<THREADS, ITEMS>));
+
+    // Tiles are claimed in launch order so that every tile a CTA may wait on in
+    // the look-back is owned by a CTA that is already resident.
+    if (threadIdx.x == 0) sm.tile_id = atomicAdd(tile_counter, 1u);
+    for (int i = threadIdx.x; i < WARPS * QCE_RADIX_BINS; i += THREADS) sm.warp_hist[i] = 0;
+    if (threadIdx.x < QCE_RADIX_BINS) sm.tile_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const u32 tile = sm.tile_id;
+    if ((tile + 1) * (u32)TILE <= n)
+        onesweep_tile<THREADS, ITEMS, HAS_VALS, true>(sm, svals, keys_in, keys_out, vals_in, vals_out, n, digit,
+                                                      gbase, status, tile);
+    else
+        onesweep_tile<THREADS, ITEMS, HAS_VALS, false>(sm, svals, keys_in, keys_out, vals_in, vals_out, n, digit,
+                                                       gbase, status, tile);
 }
 
 // 1 if keys[i-1] > keys[i] anywhere (checks the "already sorted" assumption of

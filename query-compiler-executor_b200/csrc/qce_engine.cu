@@ -221,25 +221,62 @@ int compact_from_mask(int layout, int mode, const u32 *mask, const u32 *tile_cou
 }
 
 // ---- radix sort driver -------------------------------------------------------
-constexpr int RS_THREADS = 512;
-constexpr int RS_ITEMS = 8;
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
-
-template <bool HAS_VALS, typename DigitOp>
-int launch_onesweep(const u64 *kin, u64 *kout, const u32 *vin, u32 *vout, u32 n, DigitOp dop,
-                    const u32 *gbase, u32 *status, u32 *counter)
+// Tile shapes of the one-sweep pass.  The default was picked by sweeping them on
+// B200 (tools/sort_bench.py, profiles/); QCE_ONESWEEP_CFG=<index> overrides it.
+struct OnesweepCfg { int threads, items, min_ctas; };
+static const OnesweepCfg kOnesweepCfgs[] = {{512, 8, 2}, {512, 8, 3}, {256, 16, 3}, {256, 16, 4}, {384, 12, 2},
+                                            {384, 12, 3}, {512, 12, 2}, {256, 24, 2}, {1024, 4, 2}, {256, 8, 6}};
+constexpr int kNumOnesweepCfgs = (int)(sizeof(kOnesweepCfgs) / sizeof(kOnesweepCfgs[0]));
+static int g_onesweep_cfg = -1;
+static int onesweep_cfg()
 {
-    auto kern = k_onesweep<RS_THREADS, RS_ITEMS, HAS_VALS, DigitOp>;
-    const size_t smem = sizeof(OnesweepSmem<RS_THREADS, RS_ITEMS>) + (HAS_VALS ? RS_TILE * sizeof(u32) : 0);
+    if (g_onesweep_cfg < 0) {
+        const char *e = getenv("QCE_ONESWEEP_CFG");
+        int c = e ? atoi(e) : 3;
+        g_onesweep_cfg = (c >= 0 && c < kNumOnesweepCfgs) ? c : 0;
+    }
+    return g_onesweep_cfg;
+}
+static int onesweep_tile_size() { const OnesweepCfg &c = kOnesweepCfgs[onesweep_cfg()]; return c.threads * c.items; }
+
+template <int THREADS, int ITEMS, int MIN_CTAS, bool HAS_VALS, typename DigitOp>
+int launch_onesweep_cfg(const u64 *kin, u64 *kout, const u32 *vin, u32 *vout, u32 n, DigitOp dop,
+                        const u32 *gbase, u32 *status, u32 *counter)
+{
+    auto kern = k_onesweep<THREADS, ITEMS, MIN_CTAS, HAS_VALS, DigitOp>;
+    constexpr int TILE = THREADS * ITEMS;
+    const size_t smem = sizeof(OnesweepSmem<THREADS, ITEMS>) + (HAS_VALS ? TILE * sizeof(u32) : 0);
     static bool attr_set = false; // per instantiation
     if (!attr_set) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    const u32 ntiles = (u32)ceil_div(n, RS_TILE);
-    LAUNCH(HAS_VALS ? "onesweep_kv" : "onesweep_k", kern, ntiles, RS_THREADS, smem, kin, kout, vin, vout, n,
-           dop, gbase, status, counter);
+    const u32 ntiles = (u32)ceil_div(n, TILE);
+    LAUNCH(HAS_VALS ? "onesweep_kv" : "onesweep_k", kern, ntiles, THREADS, smem, kin, kout, vin, vout, n, dop, gbase,
+           status, counter);
     return 0;
+}
+
+template <bool HAS_VALS, typename DigitOp>
+int launch_onesweep(const u64 *kin, u64 *kout, const u32 *vin, u32 *vout, u32 n, DigitOp dop,
+                    const u32 *gbase, u32 *status, u32 *counter)
+{
+#define QCE_OS_CASE(I, T, IT, MC) \
+    case I: return launch_onesweep_cfg<T, IT, MC, HAS_VALS>(kin, kout, vin, vout, n, dop, gbase, status, counter);
+    switch (onesweep_cfg()) {
+        QCE_OS_CASE(0, 512, 8, 2)
+        QCE_OS_CASE(1, 512, 8, 3)
+        QCE_OS_CASE(2, 256, 16, 3)
+        QCE_OS_CASE(3, 256, 16, 4)
+        QCE_OS_CASE(4, 384, 12, 2)
+        QCE_OS_CASE(5, 384, 12, 3)
+        QCE_OS_CASE(6, 512, 12, 2)
+        QCE_OS_CASE(7, 256, 24, 2)
+        QCE_OS_CASE(8, 1024, 4, 2)
+        QCE_OS_CASE(9, 256, 8, 6)
+    }
+#undef QCE_OS_CASE
+    return fail("bad one-sweep configuration");
 }
 
 // Sort words (and optional 32-bit values) by the digits listed in rs, least
@@ -248,7 +285,7 @@ int radix_sort(u64 **keys, u32 **vals, u64 n, const RadixShifts &rs)
 {
     if (n <= 1 || rs.npass == 0) return 0;
     if (n >= (1ull << 30)) return fail("sort of %llu tuples exceeds the 2^30 per-run limit", (unsigned long long)n);
-    const u32 ntiles = (u32)ceil_div(n, RS_TILE);
+    const u32 ntiles = (u32)ceil_div(n, onesweep_tile_size());
     u64 *alt_k = nullptr;
     u32 *alt_v = nullptr, *ghist = nullptr, *gbase = nullptr, *status = nullptr, *counters = nullptr;
     if (dalloc(&alt_k, n) != 0) return -1;
@@ -527,10 +564,18 @@ const char *qce_profile_json(void)
     if (!g.inited) return "{}";
     cudaStreamSynchronize(g.stream);
     std::map<std::string, std::pair<u64, double>> agg;
-    for (auto &r : g.prof) {
+    for (size_t k = 0; k < g.prof.size(); k++) {
+        auto &r = g.prof[k];
         float f = 0;
         if (cudaEventElapsedTime(&f, r.e0, r.e1) == cudaSuccess) {
             auto &a = agg[r.tag];
+            a.first++;
+            a.second += f;
+        }
+        // stream time between the end of the previous kernel and the start of
+        // this one: memsets, copies and host round trips
+        if (k > 0 && cudaEventElapsedTime(&f, g.prof[k - 1].e1, r.e0) == cudaSuccess) {
+            auto &a = agg[std::string("gap_before:") + r.tag];
             a.first++;
             a.second += f;
         }
@@ -1014,7 +1059,7 @@ int qce_partition_tuples(const qce_tuples *t, const uint64_t *splitters, uint32_
     const u64 n = t->n;
     u64 *out = nullptr;
     u32 *ghist = nullptr, *gbase = nullptr, *status = nullptr, *counter = nullptr;
-    const u32 ntiles = (u32)ceil_div(n ? n : 1, RS_TILE);
+    const u32 ntiles = (u32)ceil_div(n ? n : 1, onesweep_tile_size());
     if (dalloc(&out, n) || dalloc(&ghist, QCE_RADIX_BINS) || dalloc(&gbase, QCE_RADIX_BINS) ||
         dalloc(&status, (u64)ntiles * QCE_RADIX_BINS) || dalloc(&counter, 1))
         return -1;

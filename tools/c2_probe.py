@@ -37,7 +37,7 @@ for i in range(reps):
     print(f"rep {i}: pairs {m} sums {sums} device {ms:.3f} ms wall {1e3*(time.time()-w):.3f} ms launches {launches}", flush=True)
 e.profile(True)
 run()
-prof = e.profile_read()
+prof = {k: v for k, v in e.profile_read().items() if not k.startswith("gap_before")}
 e.profile(False)
 tot = sum(v["ms"] for v in prof.values())
 for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
