@@ -27,7 +27,7 @@
 
 #define QCE_JTILE 2048     // R tuples per tile (256 threads x 8)
 #define QCE_JTHREADS 256
-#define QCE_JWIN 4096      // S window staged in shared memory (keys, 32 KB)
+#define QCE_JWIN 8192      // S window staged in shared memory (keys, 64 KB + skew, dynamic)
 #define QCE_JCHUNK 4096    // output pairs per write CTA
 
 template <bool WIDE>
@@ -66,13 +66,31 @@ k_join_partition(TupleView R, u32 nR, TupleView S, u32 nS, u32 ntiles, uint2 *__
     win[t] = make_uint2(lo, hi);
 }
 
+#define QCE_JSMEM_BYTES (QCE_JWIN * sizeof(u64))
+
+// Branch-light lower/upper bound over the staged window (fixed trip count for a
+// window of <= QCE_JWIN slots; the lanes of a warp stay converged).
+template <bool LT> __device__ __forceinline__ u32 bound_s(const u64 *skeys, u32 wn, u64 key)
+{
+    u32 lo = 0, len = wn;
+#pragma unroll 1
+    while (len > 0) {
+        const u32 half = len >> 1;
+        const u64 v = skeys[lo + half];
+        const bool right = LT ? (v < key) : (v <= key);
+        lo = right ? lo + half + 1 : lo;
+        len = right ? len - half - 1 : half;
+    }
+    return lo;
+}
+
 template <bool WR, bool WS>
 __global__ void __launch_bounds__(QCE_JTHREADS)
 k_join_bounds(TupleView R, u32 nR, TupleView S, const uint2 *__restrict__ win,
               u32 *__restrict__ lb_out, u32 *__restrict__ cnt_out, u64 *__restrict__ tile_total,
               u32 *__restrict__ tile_chunks)
 {
-    __shared__ u64 skeys[QCE_JWIN];
+    extern __shared__ __align__(16) u64 skeys[]; // QCE_JSMEM_BYTES
     __shared__ u64 scratch[33];
     const int tid = threadIdx.x;
     const u32 tbase = blockIdx.x * QCE_JTILE;
@@ -82,33 +100,29 @@ k_join_bounds(TupleView R, u32 nR, TupleView S, const uint2 *__restrict__ win,
     if (staged) {
         for (u32 i = tid; i < wn; i += QCE_JTHREADS) skeys[i] = tv_key<WS>(S, w.x + i);
     }
+    // consecutive lanes take consecutive R tuples: their probes into the staged
+    // window are a few slots apart (few bank conflicts) and the 8 searches of a
+    // thread are independent (they overlap)
+    u64 key[QCE_JTILE / QCE_JTHREADS];
+#pragma unroll
+    for (int k = 0; k < QCE_JTILE / QCE_JTHREADS; k++) {
+        const u32 i = tbase + k * QCE_JTHREADS + tid;
+        key[k] = (i < nR) ? tv_key<WR>(R, i) : ~0ull;
+    }
     __syncthreads();
     u64 sum = 0;
 #pragma unroll
     for (int k = 0; k < QCE_JTILE / QCE_JTHREADS; k++) {
-        u32 i = tbase + k * QCE_JTHREADS + tid;
+        const u32 i = tbase + k * QCE_JTHREADS + tid;
         if (i < nR) {
-            u64 key = tv_key<WR>(R, i);
             u32 lb, ub;
-            if (wn == 0) {
-                lb = ub = w.x;
-            } else if (staged) {
-                u32 lo = 0, hi = wn;
-                while (lo < hi) {
-                    u32 mid = (lo + hi) >> 1;
-                    if (skeys[mid] < key) lo = mid + 1; else hi = mid;
-                }
-                lb = lo;
-                hi = wn;
-                while (lo < hi) {
-                    u32 mid = (lo + hi) >> 1;
-                    if (skeys[mid] <= key) lo = mid + 1; else hi = mid;
-                }
-                ub = lo + w.x;
-                lb += w.x;
+            if (staged) {
+                lb = bound_s<true>(skeys, wn, key[k]) + w.x;
+                ub = bound_s<false>(skeys, wn, key[k]) + w.x;
             } else {
-                lb = lower_bound_g<WS>(S, w.x, w.y, key);
-                ub = upper_bound_g<WS>(S, lb, w.y, key);
+                // S is much denser than R here (or one key is very heavy)
+                lb = lower_bound_g<WS>(S, w.x, w.y, key[k]);
+                ub = upper_bound_g<WS>(S, lb, w.y, key[k]);
             }
             lb_out[i] = lb;
             cnt_out[i] = ub - lb;

@@ -128,6 +128,27 @@ k_radix_hist(const u64 *__restrict__ keys, u64 n, RadixShifts rs, u32 *__restric
         if (sh[i]) atomicAdd(&ghist[i], sh[i]);
 }
 
+// One-digit histogram of 32-bit keys (row ids), for the bucketed checksum.
+__global__ void __launch_bounds__(512)
+k_hist_u32(const u32 *__restrict__ keys, u64 n, int shift, u32 *__restrict__ ghist)
+{
+    __shared__ u32 sh[QCE_RADIX_BINS];
+    if (threadIdx.x < QCE_RADIX_BINS) sh[threadIdx.x] = 0;
+    __syncthreads();
+    const u64 stride = (u64)gridDim.x * 2048;
+    const u64 n4 = n & ~3ull;
+    for (u64 e = ((u64)blockIdx.x * 512 + threadIdx.x) * 4; e < n4; e += stride) {
+        uint4 k = ld_stream_u32x4(keys + e);
+        atomicAdd(&sh[(k.x >> shift) & 255], 1u);
+        atomicAdd(&sh[(k.y >> shift) & 255], 1u);
+        atomicAdd(&sh[(k.z >> shift) & 255], 1u);
+        atomicAdd(&sh[(k.w >> shift) & 255], 1u);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n - n4)) atomicAdd(&sh[(keys[n4 + threadIdx.x] >> shift) & 255], 1u);
+    __syncthreads();
+    if (threadIdx.x < QCE_RADIX_BINS && sh[threadIdx.x]) atomicAdd(&ghist[threadIdx.x], sh[threadIdx.x]);
+}
+
 // build_psum (src/utilities.c:34-48): exclusive prefix over the 256 bins of
 // each pass.  One CTA of 256 threads per pass.
 __global__ void __launch_bounds__(256) k_radix_bases(const u32 *__restrict__ ghist,
@@ -144,6 +165,7 @@ __global__ void __launch_bounds__(256) k_radix_bases(const u32 *__restrict__ ghi
 struct DigitShift {
     int shift;
     __device__ __forceinline__ u32 operator()(u64 k) const { return (u32)(k >> shift) & 255u; }
+    __device__ __forceinline__ u32 operator()(u32 k) const { return (k >> shift) & 255u; }
 };
 // Range partition for the multi-GPU exchange: digit = number of splitters <= key
 // (keys compared on the packed word's key field).
@@ -182,22 +204,26 @@ __device__ __forceinline__ u32 warp_peers_8bit(u32 d)
 #define QCE_ST_INCL 0x80000000u
 #define QCE_ST_MASK 0x3fffffffu
 
-template <int THREADS, int ITEMS> struct OnesweepSmem {
+template <typename KeyT> __device__ __forceinline__ KeyT ld_stream_key(const KeyT *p);
+template <> __device__ __forceinline__ u64 ld_stream_key<u64>(const u64 *p) { return ld_stream_u64(p); }
+template <> __device__ __forceinline__ u32 ld_stream_key<u32>(const u32 *p) { return ld_stream_u32(p); }
+
+template <int THREADS, int ITEMS, typename KeyT = u64> struct OnesweepSmem {
     u32 warp_hist[(THREADS / 32) * QCE_RADIX_BINS]; // per-warp digit counts -> bases
     u32 tile_excl[QCE_RADIX_BINS];                  // digit start inside the sorted tile
     u32 goff[QCE_RADIX_BINS];                       // global start of digit minus tile_excl
     u32 tile_cnt[QCE_RADIX_BINS];                   // early digit counts of the tile
     u32 scratch[33];
     u32 tile_id;
-    u64 keys[THREADS * ITEMS];
+    KeyT keys[THREADS * ITEMS];
 };
 
 // One tile of the pass.  FULL = every slot of the tile holds a real tuple (no
 // bounds checks, no padding logic): all tiles but the last.
-template <int THREADS, int ITEMS, bool HAS_VALS, bool FULL, typename DigitOp>
+template <int THREADS, int ITEMS, bool HAS_VALS, bool FULL, bool EARLY, int MATCH_EVERY, typename KeyT, typename DigitOp>
 __device__ __forceinline__ void
-onesweep_tile(OnesweepSmem<THREADS, ITEMS> &sm, u32 *svals, const u64 *__restrict__ keys_in,
-              u64 *__restrict__ keys_out, const u32 *__restrict__ vals_in, u32 *__restrict__ vals_out, u32 n,
+onesweep_tile(OnesweepSmem<THREADS, ITEMS, KeyT> &sm, u32 *svals, const KeyT *__restrict__ keys_in,
+              KeyT *__restrict__ keys_out, const u32 *__restrict__ vals_in, u32 *__restrict__ vals_out, u32 n,
               const DigitOp &digit, const u32 *__restrict__ gbase, u32 *__restrict__ status, u32 tile)
 {
     constexpr int TILE = THREADS * ITEMS;
@@ -207,37 +233,39 @@ onesweep_tile(OnesweepSmem<THREADS, ITEMS> &sm, u32 *svals, const u64 *__restric
     const u32 nvalid = FULL ? (u32)TILE : (n - tbase);
 
     // ---- load: warp-striped so that (warp, item, lane) order == input order
-    u64 key[ITEMS];
+    KeyT key[ITEMS];
     u32 val[HAS_VALS ? ITEMS : 1];
     const u32 wbase = tbase + warp * (32 * ITEMS) + lane;
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
         const u32 idx = wbase + j * 32;
         if (FULL || idx < n) {
-            key[j] = ld_stream_u64(keys_in + idx);
+            key[j] = ld_stream_key<KeyT>(keys_in + idx);
             if (HAS_VALS) val[j] = ld_stream_u32(vals_in + idx);
         } else {
-            key[j] = ~0ull;
+            key[j] = (KeyT)~(KeyT)0;
             if (HAS_VALS) val[j] = 0u;
         }
     }
 
-    // ---- early counts: tile digit histogram with no-return shared atomics, so
-    // the tile's PARTIAL status is published before the (long) ranking phase and
-    // successors' look-back finds it without spinning.
-#pragma unroll
-    for (int j = 0; j < ITEMS; j++) {
-        const u32 d = (!FULL && (wbase + j * 32) >= n) ? 255u : digit(key[j]);
-        atomicAdd(&sm.tile_cnt[d], 1u);
-    }
-    __syncthreads();
+    // ---- early counts (EARLY): tile digit histogram with no-return shared
+    // atomics, so the tile's PARTIAL status is published before the (long)
+    // ranking phase and successors' look-back finds it without spinning.
     u32 my_count = 0;
-    if (tid < QCE_RADIX_BINS) {
-        my_count = sm.tile_cnt[tid];
-        // the padding of the last tile is not part of the global count
-        const u32 pub = my_count - ((!FULL && tid == 255) ? (TILE - nvalid) : 0u);
-        st_relaxed_gpu_u32(status + (size_t)tile * QCE_RADIX_BINS + tid,
-                           (tile == 0 ? QCE_ST_INCL : QCE_ST_PART) | pub);
+    if (EARLY) {
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) {
+            const u32 d = (!FULL && (wbase + j * 32) >= n) ? 255u : digit(key[j]);
+            atomicAdd(&sm.tile_cnt[d], 1u);
+        }
+        __syncthreads();
+        if (tid < QCE_RADIX_BINS) {
+            my_count = sm.tile_cnt[tid];
+            // the padding of the last tile is not part of the global count
+            const u32 pub = my_count - ((!FULL && tid == 255) ? (TILE - nvalid) : 0u);
+            st_relaxed_gpu_u32(status + (size_t)tile * QCE_RADIX_BINS + tid,
+                               (tile == 0 ? QCE_ST_INCL : QCE_ST_PART) | pub);
+        }
     }
 
     // ---- rank inside the warp.  Lanes with the same digit are found with
@@ -256,7 +284,11 @@ onesweep_tile(OnesweepSmem<THREADS, ITEMS> &sm, u32 *svals, const u64 *__restric
 #pragma unroll
         for (int c = 0; c < CH; c++) {
             d[c] = (!FULL && (wbase + (j0 + c) * 32) >= n) ? 255u : digit(key[j0 + c]);
-            peers[c] = warp_peers_8bit(d[c]);
+            // every MATCH_EVERY-th item goes to match.any: the ADU pipe is idle
+            // otherwise, so it takes a share of the ranking off the ALU ballots
+            peers[c] = (MATCH_EVERY > 0 && ((j0 + c) % (MATCH_EVERY > 0 ? MATCH_EVERY : 1)) == MATCH_EVERY - 1)
+                           ? __match_any_sync(QCE_FULL_MASK, d[c])
+                           : warp_peers_8bit(d[c]);
         }
 #pragma unroll
         for (int c = 0; c < CH; c++) {
@@ -269,14 +301,8 @@ onesweep_tile(OnesweepSmem<THREADS, ITEMS> &sm, u32 *svals, const u64 *__restric
             rd[j0 + c] = (d[c] << 16) | (old[c] + __popc(peers[c] & lt));
         }
     }
-    // ---- digit starts inside the tile (exclusive scan over the 256 digits)
-    {
-        u32 tot;
-        u32 ex = block_scan_excl<u32, THREADS>((tid < QCE_RADIX_BINS) ? my_count : 0u, sm.scratch, &tot);
-        if (tid < QCE_RADIX_BINS) sm.tile_excl[tid] = ex;
-    }
-    // ---- per digit: exclusive scan of the warp counts (all warps have ranked:
-    //      the block scan above contains the barrier)
+    __syncthreads(); // all warps have ranked
+    // ---- per digit: exclusive scan of the warp counts
     if (tid < QCE_RADIX_BINS) {
         u32 run = 0;
 #pragma unroll
@@ -285,6 +311,20 @@ onesweep_tile(OnesweepSmem<THREADS, ITEMS> &sm, u32 *svals, const u64 *__restric
             sm.warp_hist[w * QCE_RADIX_BINS + tid] = run;
             run += c;
         }
+        if (!EARLY) {
+            my_count = run;
+            const u32 pub = my_count - ((!FULL && tid == 255) ? (TILE - nvalid) : 0u);
+            st_relaxed_gpu_u32(status + (size_t)tile * QCE_RADIX_BINS + tid,
+                               (tile == 0 ? QCE_ST_INCL : QCE_ST_PART) | pub);
+        }
+    }
+    // ---- digit starts inside the tile (exclusive scan over the 256 digits)
+    {
+        u32 tot;
+        u32 ex = block_scan_excl<u32, THREADS>((tid < QCE_RADIX_BINS) ? my_count : 0u, sm.scratch, &tot);
+        if (tid < QCE_RADIX_BINS) sm.tile_excl[tid] = ex;
+    }
+    if (tid < QCE_RADIX_BINS) {
         // ---- decoupled look-back: sum the counts of the preceding tiles
         u32 excl = 0;
         if (tile > 0) {
@@ -319,7 +359,7 @@ onesweep_tile(OnesweepSmem<THREADS, ITEMS> &sm, u32 *svals, const u64 *__restric
     for (int j = 0; j < ITEMS; j++) {
         const u32 p = tid + j * THREADS;
         if (FULL || p < nvalid) {
-            const u64 k = sm.keys[p];
+            const KeyT k = sm.keys[p];
             const u32 g = sm.goff[digit(k)] + p;
             keys_out[g] = k;
             if (HAS_VALS) vals_out[g] = svals[p];
@@ -327,9 +367,9 @@ onesweep_tile(OnesweepSmem<THREADS, ITEMS> &sm, u32 *svals, const u64 *__restric
     }
 }
 
-template <int THREADS, int ITEMS, int MIN_CTAS, bool HAS_VALS, typename DigitOp>
+template <int THREADS, int ITEMS, int MIN_CTAS, bool EARLY, int MATCH_EVERY, bool HAS_VALS, typename KeyT, typename DigitOp>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
-k_onesweep(const u64 *__restrict__ keys_in, u64 *__restrict__ keys_out,
+k_onesweep(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out,
            const u32 *__restrict__ vals_in, u32 *__restrict__ vals_out, u32 n, DigitOp digit,
            const u32 *__restrict__ gbase, u32 *__restrict__ status, u32 *__restrict__ tile_counter)
 {
@@ -337,8 +377,8 @@ k_onesweep(const u64 *__restrict__ keys_in, u64 *__restrict__ keys_out,
     constexpr int TILE = THREADS * ITEMS;
     constexpr int WARPS = THREADS / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    OnesweepSmem<THREADS, ITEMS> &sm = *reinterpret_cast<OnesweepSmem<THREADS, ITEMS> *>(smem_raw);
-    u32 *svals = reinterpret_cast<u32 *>(smem_raw + sizeof(OnesweepSmem<THREADS, ITEMS>));
+    OnesweepSmem<THREADS, ITEMS, KeyT> &sm = *reinterpret_cast<OnesweepSmem<THREADS, ITEMS, KeyT> *>(smem_raw);
+    u32 *svals = reinterpret_cast<u32 *>(smem_raw + sizeof(OnesweepSmem<THREADS, ITEMS, KeyT>));
 
     // Tiles are claimed in launch order so that every tile a CTA may wait on in
     // the look-back is owned by a CTA that is already resident.
@@ -348,10 +388,10 @@ k_onesweep(const u64 *__restrict__ keys_in, u64 *__restrict__ keys_out,
     __syncthreads();
     const u32 tile = sm.tile_id;
     if ((tile + 1) * (u32)TILE <= n)
-        onesweep_tile<THREADS, ITEMS, HAS_VALS, true>(sm, svals, keys_in, keys_out, vals_in, vals_out, n, digit,
+        onesweep_tile<THREADS, ITEMS, HAS_VALS, true, EARLY, MATCH_EVERY, KeyT>(sm, svals, keys_in, keys_out, vals_in, vals_out, n, digit,
                                                       gbase, status, tile);
     else
-        onesweep_tile<THREADS, ITEMS, HAS_VALS, false>(sm, svals, keys_in, keys_out, vals_in, vals_out, n, digit,
+        onesweep_tile<THREADS, ITEMS, HAS_VALS, false, EARLY, MATCH_EVERY, KeyT>(sm, svals, keys_in, keys_out, vals_in, vals_out, n, digit,
                                                        gbase, status, tile);
 }
 

@@ -223,9 +223,10 @@ int compact_from_mask(int layout, int mode, const u32 *mask, const u32 *tile_cou
 // ---- radix sort driver -------------------------------------------------------
 // Tile shapes of the one-sweep pass.  The default was picked by sweeping them on
 // B200 (tools/sort_bench.py, profiles/); QCE_ONESWEEP_CFG=<index> overrides it.
-struct OnesweepCfg { int threads, items, min_ctas; };
-static const OnesweepCfg kOnesweepCfgs[] = {{512, 8, 2}, {512, 8, 3}, {256, 16, 3}, {256, 16, 4}, {384, 12, 2},
-                                            {384, 12, 3}, {512, 12, 2}, {256, 24, 2}, {1024, 4, 2}, {256, 8, 6}};
+struct OnesweepCfg { int threads, items, min_ctas, early, match_every; };
+static const OnesweepCfg kOnesweepCfgs[] = {{256, 16, 4, 1, 0}, {256, 16, 4, 0, 0}, {256, 16, 4, 1, 4}, {256, 16, 4, 0, 4},
+                                            {256, 16, 3, 0, 4}, {384, 12, 3, 0, 4}, {512, 8, 3, 0, 4},  {256, 24, 2, 0, 4},
+                                            {256, 16, 4, 0, 2}, {256, 16, 3, 0, 0}};
 constexpr int kNumOnesweepCfgs = (int)(sizeof(kOnesweepCfgs) / sizeof(kOnesweepCfgs[0]));
 static int g_onesweep_cfg = -1;
 static int onesweep_cfg()
@@ -239,41 +240,41 @@ static int onesweep_cfg()
 }
 static int onesweep_tile_size() { const OnesweepCfg &c = kOnesweepCfgs[onesweep_cfg()]; return c.threads * c.items; }
 
-template <int THREADS, int ITEMS, int MIN_CTAS, bool HAS_VALS, typename DigitOp>
-int launch_onesweep_cfg(const u64 *kin, u64 *kout, const u32 *vin, u32 *vout, u32 n, DigitOp dop,
+template <int THREADS, int ITEMS, int MIN_CTAS, bool EARLY, int MATCH_EVERY, bool HAS_VALS, typename KeyT, typename DigitOp>
+int launch_onesweep_cfg(const KeyT *kin, KeyT *kout, const u32 *vin, u32 *vout, u32 n, DigitOp dop,
                         const u32 *gbase, u32 *status, u32 *counter)
 {
-    auto kern = k_onesweep<THREADS, ITEMS, MIN_CTAS, HAS_VALS, DigitOp>;
+    auto kern = k_onesweep<THREADS, ITEMS, MIN_CTAS, EARLY, MATCH_EVERY, HAS_VALS, KeyT, DigitOp>;
     constexpr int TILE = THREADS * ITEMS;
-    const size_t smem = sizeof(OnesweepSmem<THREADS, ITEMS>) + (HAS_VALS ? TILE * sizeof(u32) : 0);
+    const size_t smem = sizeof(OnesweepSmem<THREADS, ITEMS, KeyT>) + (HAS_VALS ? TILE * sizeof(u32) : 0);
     static bool attr_set = false; // per instantiation
     if (!attr_set) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     const u32 ntiles = (u32)ceil_div(n, TILE);
-    LAUNCH(HAS_VALS ? "onesweep_kv" : "onesweep_k", kern, ntiles, THREADS, smem, kin, kout, vin, vout, n, dop, gbase,
-           status, counter);
+    LAUNCH(sizeof(KeyT) == 4 ? "onesweep_u32" : (HAS_VALS ? "onesweep_kv" : "onesweep_k"), kern, ntiles, THREADS, smem,
+           kin, kout, vin, vout, n, dop, gbase, status, counter);
     return 0;
 }
 
-template <bool HAS_VALS, typename DigitOp>
-int launch_onesweep(const u64 *kin, u64 *kout, const u32 *vin, u32 *vout, u32 n, DigitOp dop,
+template <bool HAS_VALS, typename KeyT, typename DigitOp>
+int launch_onesweep(const KeyT *kin, KeyT *kout, const u32 *vin, u32 *vout, u32 n, DigitOp dop,
                     const u32 *gbase, u32 *status, u32 *counter)
 {
-#define QCE_OS_CASE(I, T, IT, MC) \
-    case I: return launch_onesweep_cfg<T, IT, MC, HAS_VALS>(kin, kout, vin, vout, n, dop, gbase, status, counter);
+#define QCE_OS_CASE(I, T, IT, MC, EA, ME) \
+    case I: return launch_onesweep_cfg<T, IT, MC, EA, ME, HAS_VALS, KeyT>(kin, kout, vin, vout, n, dop, gbase, status, counter);
     switch (onesweep_cfg()) {
-        QCE_OS_CASE(0, 512, 8, 2)
-        QCE_OS_CASE(1, 512, 8, 3)
-        QCE_OS_CASE(2, 256, 16, 3)
-        QCE_OS_CASE(3, 256, 16, 4)
-        QCE_OS_CASE(4, 384, 12, 2)
-        QCE_OS_CASE(5, 384, 12, 3)
-        QCE_OS_CASE(6, 512, 12, 2)
-        QCE_OS_CASE(7, 256, 24, 2)
-        QCE_OS_CASE(8, 1024, 4, 2)
-        QCE_OS_CASE(9, 256, 8, 6)
+        QCE_OS_CASE(0, 256, 16, 4, true, 0)
+        QCE_OS_CASE(1, 256, 16, 4, false, 0)
+        QCE_OS_CASE(2, 256, 16, 4, true, 4)
+        QCE_OS_CASE(3, 256, 16, 4, false, 4)
+        QCE_OS_CASE(4, 256, 16, 3, false, 4)
+        QCE_OS_CASE(5, 384, 12, 3, false, 4)
+        QCE_OS_CASE(6, 512, 8, 3, false, 4)
+        QCE_OS_CASE(7, 256, 24, 2, false, 4)
+        QCE_OS_CASE(8, 256, 16, 4, false, 2)
+        QCE_OS_CASE(9, 256, 16, 3, false, 0)
     }
 #undef QCE_OS_CASE
     return fail("bad one-sweep configuration");
@@ -304,9 +305,9 @@ int radix_sort(u64 **keys, u32 **vals, u64 n, const RadixShifts &rs)
     u32 *vin = vals ? *vals : nullptr, *vout = alt_v;
     for (int p = 0; p < rs.npass; p++) {
         DigitShift dop{rs.shift[p]};
-        int rc = vals ? launch_onesweep<true>(kin, kout, vin, vout, (u32)n, dop, gbase + p * QCE_RADIX_BINS,
+        int rc = vals ? launch_onesweep<true, u64>(kin, kout, vin, vout, (u32)n, dop, gbase + p * QCE_RADIX_BINS,
                                               status + (u64)p * ntiles * QCE_RADIX_BINS, counters + p)
-                      : launch_onesweep<false>(kin, kout, vin, vout, (u32)n, dop, gbase + p * QCE_RADIX_BINS,
+                      : launch_onesweep<false, u64>(kin, kout, vin, vout, (u32)n, dop, gbase + p * QCE_RADIX_BINS,
                                                status + (u64)p * ntiles * QCE_RADIX_BINS, counters + p);
         if (rc != 0) return -1;
         std::swap(kin, kout);
@@ -367,8 +368,14 @@ int merge_join_t(const qce_tuples *R, const qce_tuples *S, bool want_r, bool wan
     } else {
         LAUNCH("join_partition", (k_join_partition<WR, WS>), (int)ceil_div(ntiles, 256), 256, 0, vr, nR, vs, nS,
                ntiles, win);
-        LAUNCH("join_bounds", (k_join_bounds<WR, WS>), (int)ntiles, QCE_JTHREADS, 0, vr, nR, vs, win, lb, cnt,
-               tile_total, tile_chunks);
+        static bool attr_set = false; // per instantiation
+        if (!attr_set) {
+            CK(cudaFuncSetAttribute(k_join_bounds<WR, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)QCE_JSMEM_BYTES));
+            attr_set = true;
+        }
+        LAUNCH("join_bounds", (k_join_bounds<WR, WS>), (int)ntiles, QCE_JTHREADS, QCE_JSMEM_BYTES, vr, nR, vs, win,
+               lb, cnt, tile_total, tile_chunks);
     }
     LAUNCH("scan_tiles", (k_scan_excl<u64, u64>), 1, 1024, 0, tile_total, tile_off, (u64)ntiles, g.d_scalars);
     LAUNCH("scan_tiles", (k_scan_excl<u32, u32>), 1, 1024, 0, tile_chunks, chunk_off, (u64)ntiles,
@@ -442,6 +449,44 @@ int distinct_pairs(const qce_rowids *pr, const qce_rowids *ps, qce_rowids **dr, 
                                pr->id_bound, ps->id_bound, dr, ds);
     dfree(mask); dfree(tile_count); dfree(w);
     return rc;
+}
+
+
+// ---- bucketed gather support (qce_checksum) ------------------------------------
+// Worth it when the column is much larger than L2 and there are enough ids for
+// the extra pass (8 B/id) to cost less than the DRAM over-fetch it removes.
+bool bucketed_checksum_pays(const qce_rowids *ids, u64 col_rows)
+{
+    static int mode = -1; // QCE_BUCKETED_CHECKSUM=0 disables, =1 forces
+    if (mode < 0) {
+        const char *e = getenv("QCE_BUCKETED_CHECKSUM");
+        mode = e ? atoi(e) + 1 : 0;
+    }
+    if (mode == 1) return false;
+    if (mode == 2) return ids->n >= 2;
+    return col_rows * sizeof(u64) > (256ull << 20) && ids->n >= (4ull << 20) && ids->n < (1ull << 30);
+}
+
+int partition_ids_by_top_bits(const qce_rowids *ids, u32 **out)
+{
+    const u64 n = ids->n;
+    const int bits = ids->id_bound ? bitlen(ids->id_bound - 1) : 32;
+    const int shift = bits > 8 ? bits - 8 : 0;
+    const u32 ntiles = (u32)ceil_div(n, onesweep_tile_size());
+    u32 *ghist = nullptr, *gbase = nullptr, *status = nullptr, *counter = nullptr, *dst = nullptr;
+    if (dalloc(&dst, n) || dalloc(&ghist, QCE_RADIX_BINS) || dalloc(&gbase, QCE_RADIX_BINS) ||
+        dalloc(&status, (u64)ntiles * QCE_RADIX_BINS) || dalloc(&counter, 1))
+        return -1;
+    CK(cudaMemsetAsync(ghist, 0, QCE_RADIX_BINS * sizeof(u32), g.stream));
+    CK(cudaMemsetAsync(status, 0, (u64)ntiles * QCE_RADIX_BINS * sizeof(u32), g.stream));
+    CK(cudaMemsetAsync(counter, 0, sizeof(u32), g.stream));
+    LAUNCH("hist_u32", k_hist_u32, grid_for(2048, n, 4), 512, 0, ids->d, n, shift, ghist);
+    LAUNCH("radix_bases", k_radix_bases, 1, 256, 0, ghist, gbase);
+    DigitShift dop{shift};
+    if (launch_onesweep<false, u32>(ids->d, dst, nullptr, nullptr, (u32)n, dop, gbase, status, counter) != 0) return -1;
+    dfree(ghist); dfree(gbase); dfree(status); dfree(counter);
+    *out = dst;
+    return 0;
 }
 
 __global__ void __launch_bounds__(256)
@@ -890,25 +935,39 @@ int qce_checksum(const qce_rowids *ids, uint32_t rel, const uint32_t *cols, uint
     if (ncols == 0) return 0;
     if (ncols > 8) return fail("at most 8 columns per checksum call");
     ChecksumCols cc;
+    u64 col_rows = 0;
     for (u32 k = 0; k < 8; k++) cc.col[k] = nullptr;
     for (u32 k = 0; k < ncols; k++) {
         const Column *cl;
         if (get_column(rel, cols[k], &cl) != 0) return -1;
         cc.col[k] = cl->d;
+        col_rows = cl->n;
     }
     CK(cudaMemsetAsync(g.d_scalars, 0, 8 * sizeof(u64), g.stream));
     if (ids->n > 0) {
+        // A large row-id column in arbitrary order makes every gather a DRAM miss
+        // that moves ~77 B for 8 useful bytes (ncu, profiles/).  The sum does not
+        // depend on the order, so the ids are first partitioned by their top 8
+        // bits (one one-sweep pass over 4-byte keys): the gathers then walk the
+        // column region by region and are served from L2.
+        const u32 *src = ids->d;
+        u32 *bucketed = nullptr;
+        if (bucketed_checksum_pays(ids, col_rows)) {
+            if (partition_ids_by_top_bits(ids, &bucketed) != 0) return -1;
+            src = bucketed;
+        }
         const int grid = grid_for(1024, ids->n);
         switch (ncols) {
-        case 1: LAUNCH("checksum", (k_checksum<1>), grid, 256, 0, ids->d, ids->n, cc, g.d_scalars); break;
-        case 2: LAUNCH("checksum", (k_checksum<2>), grid, 256, 0, ids->d, ids->n, cc, g.d_scalars); break;
-        case 3: LAUNCH("checksum", (k_checksum<3>), grid, 256, 0, ids->d, ids->n, cc, g.d_scalars); break;
-        case 4: LAUNCH("checksum", (k_checksum<4>), grid, 256, 0, ids->d, ids->n, cc, g.d_scalars); break;
-        case 5: LAUNCH("checksum", (k_checksum<5>), grid, 256, 0, ids->d, ids->n, cc, g.d_scalars); break;
-        case 6: LAUNCH("checksum", (k_checksum<6>), grid, 256, 0, ids->d, ids->n, cc, g.d_scalars); break;
-        case 7: LAUNCH("checksum", (k_checksum<7>), grid, 256, 0, ids->d, ids->n, cc, g.d_scalars); break;
-        default: LAUNCH("checksum", (k_checksum<8>), grid, 256, 0, ids->d, ids->n, cc, g.d_scalars); break;
+        case 1: LAUNCH("checksum", (k_checksum<1>), grid, 256, 0, src, ids->n, cc, g.d_scalars); break;
+        case 2: LAUNCH("checksum", (k_checksum<2>), grid, 256, 0, src, ids->n, cc, g.d_scalars); break;
+        case 3: LAUNCH("checksum", (k_checksum<3>), grid, 256, 0, src, ids->n, cc, g.d_scalars); break;
+        case 4: LAUNCH("checksum", (k_checksum<4>), grid, 256, 0, src, ids->n, cc, g.d_scalars); break;
+        case 5: LAUNCH("checksum", (k_checksum<5>), grid, 256, 0, src, ids->n, cc, g.d_scalars); break;
+        case 6: LAUNCH("checksum", (k_checksum<6>), grid, 256, 0, src, ids->n, cc, g.d_scalars); break;
+        case 7: LAUNCH("checksum", (k_checksum<7>), grid, 256, 0, src, ids->n, cc, g.d_scalars); break;
+        default: LAUNCH("checksum", (k_checksum<8>), grid, 256, 0, src, ids->n, cc, g.d_scalars); break;
         }
+        dfree(bucketed);
     }
     if (read_scalars((int)ncols) != 0) return -1;
     for (u32 k = 0; k < ncols; k++) sums[k] = g.h_scalars[k];
@@ -1069,7 +1128,7 @@ int qce_partition_tuples(const qce_tuples *t, const uint64_t *splitters, uint32_
     if (n) {
         LAUNCH("split_hist", k_split_hist, grid_for(256 * 8, n), 256, 0, t->a, n, ds, ghist);
         LAUNCH("radix_bases", k_radix_bases, 1, 256, 0, ghist, gbase);
-        if (launch_onesweep<false>(t->a, out, nullptr, nullptr, (u32)n, ds, gbase, status, counter) != 0) return -1;
+        if (launch_onesweep<false, u64>((const u64 *)t->a, out, nullptr, nullptr, (u32)n, ds, gbase, status, counter) != 0) return -1;
     }
     std::vector<u32> tmp(QCE_RADIX_BINS);
     CK(cudaMemcpyAsync(tmp.data(), ghist, QCE_RADIX_BINS * sizeof(u32), cudaMemcpyDeviceToHost, g.stream));

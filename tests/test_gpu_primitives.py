@@ -276,3 +276,31 @@ def test_merge_join_walk_unsorted_outer(engine, nR, nS, domain):
         engine.rowids_free(h)
     engine.tuples_free(R)
     engine.tuples_free(S)
+
+
+def test_checksum_bucketed_path():
+    """The L2-bucketed gather (ids partitioned by their top bits first) is chosen
+    by size; force it in a child process and compare with the oracle."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+import qce_b200
+from oracle import qce_oracle as orc
+e = qce_b200.Engine()
+rng = np.random.default_rng(3)
+for rows, m in ((1000, 1), (70000, 5), (300000, 123457), (1 << 20, 3000001)):
+    cols = [rng.integers(0, 1 << 63, rows, dtype=np.uint64) * np.uint64(2) + np.uint64(1) for _ in range(2)]
+    for c, v in enumerate(cols):
+        e.upload_column(7, c, v)
+    ids = rng.integers(0, rows, m, dtype=np.uint64)
+    h = e.filter_scan(7, 0, ">", 0) if False else e.rowids_from_host(ids)
+    assert e.checksum(h, 7, [0, 1]) == [orc.checksum(c, ids) for c in cols], (rows, m)
+    e.rowids_free(h)
+print("bucketed ok", e.profile_read())
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, QCE_BUCKETED_CHECKSUM="1")
+    p = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert p.returncode == 0 and "bucketed ok" in p.stdout, p.stderr[-2000:]
