@@ -303,9 +303,10 @@ def main():
     passes = (max(1, int(key_max).bit_length()) + 7) // 8
     alg_bytes = 16.0 * passes * (lhs + rows) * args.steps
     achieved = alg_bytes / (os_prof["ms"] / 1e3) / 1e9 if os_prof["ms"] else 0.0
-    traffic = None
+    traffic = None  # DRAM bytes per launch from the committed ncu --set full capture (per tuple x tuples/launch)
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "onesweep_traffic.json")))["dram_bytes_per_launch"]
+        per_tuple = json.load(open(os.path.join(ROOT, "profiles", "onesweep_traffic.json")))["dram_bytes_per_tuple"]
+        traffic = per_tuple * passes * (lhs + rows) / max(1, os_prof["launches"] // args.steps)
     except Exception:
         pass
     total_kernel_ms = sum(v["ms"] for v in prof.values())
@@ -314,7 +315,8 @@ def main():
         + 16 * (lhs + rows) + 16 * pairs + 3 * 16 * pairs
     roofline = {"bound": "hbm", "kernel": "k_onesweep (radix pass over packed 8-byte tuples)", "achieved": achieved,
                 "peak": pk["hbm_gbs"], "peak_source": pk_src, "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                "traffic": traffic, "launches": os_prof["launches"],
+                "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes / max(1, os_prof["launches"]),
+                "launches": os_prof["launches"],
                 "avg_launch_ms": os_prof["ms"] / max(1, os_prof["launches"]),
                 "share_of_kernel_time": os_prof["ms"] / total_kernel_ms if total_kernel_ms else None,
                 "algorithmic_bytes": "16 B per tuple per pass (8 read + 8 written; the reference's 16-byte tuples would be 32 B)",
