@@ -213,7 +213,11 @@ def main():
 
     if world > 1:
         from qce_b200 import sharded
+        rows = rows // 4096 * 4096  # equal, vector-aligned row windows on every rank
+        sampler = ClockSampler(local_rank, period=float(os.environ.get('QCE_BENCH_CLOCK_PERIOD', '0.05')))
+        sampler.start()
         res = sharded.bench(eng, lib, dist, rank, world, rows, args.steps, args.warmup)
+        res["clocks"] = sampler.stop()
         if rank == 0:
             res_line = res
             res_line.update({"metric": METRIC, "unit": "rows/s", "n_gpus": world, "steps": args.steps,

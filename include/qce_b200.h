@@ -78,6 +78,11 @@ int qce_drop_relations(void);
 /* exec_filter_rel_no_exists, src/filter.c:37-64: all i with col[i] OP c, in
  * ascending i. */
 int qce_filter_scan(uint32_t rel, uint32_t col, char op, uint64_t c, qce_rowids **out);
+/* Same over the row window [row_begin, row_begin + row_count) only (row ids stay
+ * relation-global): one rank's share of the scan when a join is sharded by row
+ * range across GPUs.  row_begin must be even. */
+int qce_filter_scan_range(uint32_t rel, uint32_t col, char op, uint64_t c, uint64_t row_begin,
+                          uint64_t row_count, qce_rowids **out);
 /* exec_filter_rel_exists, src/filter.c:3-35: order-preserving subset of an
  * existing row-id column, in place; *survivors = the count the reference
  * prints at src/filter.c:32. */
@@ -88,6 +93,9 @@ int qce_filter_refine(qce_rowids *ids, uint32_t rel, uint32_t col, char op, uint
 
 /* allocate_relation, src/join.c:122-142: (key = col[i], rowid = i), all i. */
 int qce_build_tuples_base(uint32_t rel, uint32_t col, qce_tuples **out);
+/* Same over a row window (row ids relation-global), for row-range sharding. */
+int qce_build_tuples_base_range(uint32_t rel, uint32_t col, uint64_t row_begin, uint64_t row_count,
+                                qce_tuples **out);
 /* allocate_relation_mid_results, src/join.c:96-120: (key = col[id], rowid = id)
  * for each id of the row-id column, in column order. */
 int qce_build_tuples_rowids(uint32_t rel, uint32_t col, const qce_rowids *ids, qce_tuples **out);
@@ -167,9 +175,10 @@ void qce_tuples_free(qce_tuples *t);
  * (torch.distributed / NCCL) on those device pointers. */
 int qce_partition_tuples(const qce_tuples *t, const uint64_t *splitters, uint32_t nparts,
                          uint64_t *counts, void **sendbuf);
-/* Wrap `n` received packed words (device pointer, copied) as a tuple run. */
+/* Wrap `n` received packed words (device pointer, copied) as a tuple run.
+ * id_bound = exclusive upper bound of the row ids they carry (0 = unknown). */
 int qce_tuples_from_device_packed(const void *dev_words, uint64_t n, uint32_t key_bits,
-                                  qce_tuples **out);
+                                  uint32_t id_bound, qce_tuples **out);
 int qce_exchange_release(void *sendbuf);
 /* 256-bin histogram of the top 8 significant key bits of a run (for splitter
  * selection from an all-reduced global histogram).  hist = 256 uint64 on host. */

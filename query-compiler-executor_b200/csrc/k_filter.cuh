@@ -217,7 +217,7 @@ template <int LAYOUT, int MODE>
 __global__ void __launch_bounds__(QCE_FTHREADS)
 k_compact(const u32 *__restrict__ mask, const u32 *__restrict__ tile_off,
           const u32 *__restrict__ tile_count, const void *__restrict__ src0,
-          const u32 *__restrict__ src1, u32 *__restrict__ out0, u32 *__restrict__ out1)
+          const u32 *__restrict__ src1, u32 *__restrict__ out0, u32 *__restrict__ out1, u32 id_base)
 {
     __shared__ u32 s0[QCE_FTILE];
     __shared__ u32 s1[(MODE >= QCE_EMIT_SRC2) ? QCE_FTILE : 1];
@@ -257,8 +257,8 @@ k_compact(const u32 *__restrict__ mask, const u32 *__restrict__ tile_off,
             rb = goff[g] + __popc(b0) + __popc(b1 & lt);
         }
         if (MODE == QCE_EMIT_INDEX) {
-            if (pa) s0[ra] = (u32)ea;
-            if (pb) s0[rb] = (u32)eb;
+            if (pa) s0[ra] = (u32)ea + id_base;
+            if (pb) s0[rb] = (u32)eb + id_base;
         } else if (MODE == QCE_EMIT_SRC) {
             const u32 *s = (const u32 *)src0;
             if (pa) s0[ra] = s[ea];

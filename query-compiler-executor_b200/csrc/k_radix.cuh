@@ -39,16 +39,17 @@ struct RadixShifts {
 // ---- tuple build ---------------------------------------------------------------
 // Packed, from a base column: out[i] = col[i] << 32 | i   (src/join.c:131-134)
 __global__ void __launch_bounds__(256)
-k_build_packed_base(const u64 *__restrict__ col, u64 n, u64 *__restrict__ out)
+k_build_packed_base(const u64 *__restrict__ col, u64 n, u64 *__restrict__ out, u64 id_base)
 {
+    // id_base: first row id of the window when a rank builds only its row range
     const u64 stride = (u64)gridDim.x * 512;
     for (u64 e = ((u64)blockIdx.x * 256 + threadIdx.x) * 2; e < n; e += stride) {
         if (e + 1 < n) {
             u64 a, b;
             ld_stream_u64x2(col + e, a, b);
-            st_stream_u64x2(out + e, (a << 32) | e, (b << 32) | (e + 1));
+            st_stream_u64x2(out + e, (a << 32) | (e + id_base), (b << 32) | (e + 1 + id_base));
         } else {
-            out[e] = (col[e] << 32) | e;
+            out[e] = (col[e] << 32) | (e + id_base);
         }
     }
 }
@@ -75,12 +76,12 @@ k_build_packed_ids(const u64 *__restrict__ col, const u32 *__restrict__ ids, u64
 // Wide (keys may exceed 32 bits): SoA keys[] / ids[].
 __global__ void __launch_bounds__(256)
 k_build_wide(const u64 *__restrict__ col, const u32 *__restrict__ ids, u64 n,
-             u64 *__restrict__ keys, u32 *__restrict__ out_ids)
+             u64 *__restrict__ keys, u32 *__restrict__ out_ids, u32 id_base)
 {
     const u64 stride = (u64)gridDim.x * 256;
     for (u64 i = (u64)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
-        u32 id = ids ? ids[i] : (u32)i;
-        keys[i] = __ldg(col + id);
+        u32 id = ids ? ids[i] : (u32)i + id_base;
+        keys[i] = __ldg(col + (ids ? (u64)id : i));
         out_ids[i] = id;
     }
 }

@@ -189,7 +189,7 @@ int grid_for(u64 items_per_block, u64 n, int waves = 8)
 // mask + per-tile counts -> compacted outputs (pass 2 of every filter-like op)
 int compact_from_mask(int layout, int mode, const u32 *mask, const u32 *tile_count, u64 ntiles,
                       const void *src0, const u32 *src1, u32 id_bound0, u32 id_bound1,
-                      qce_rowids **out0, qce_rowids **out1)
+                      qce_rowids **out0, qce_rowids **out1, u32 id_base = 0)
 {
     u32 *tile_off = nullptr;
     if (dalloc(&tile_off, ntiles) != 0) return -1;
@@ -203,16 +203,16 @@ int compact_from_mask(int layout, int mode, const u32 *mask, const u32 *tile_cou
         const int grid = (int)ntiles;
         if (layout == QCE_LAYOUT_PAIR && mode == QCE_EMIT_INDEX)
             LAUNCH("compact_ids", (k_compact<QCE_LAYOUT_PAIR, QCE_EMIT_INDEX>), grid, QCE_FTHREADS, 0,
-                   mask, tile_off, tile_count, src0, src1, o0, o1);
+                   mask, tile_off, tile_count, src0, src1, o0, o1, id_base);
         else if (layout == QCE_LAYOUT_NATURAL && mode == QCE_EMIT_SRC)
             LAUNCH("compact_src", (k_compact<QCE_LAYOUT_NATURAL, QCE_EMIT_SRC>), grid, QCE_FTHREADS, 0,
-                   mask, tile_off, tile_count, src0, src1, o0, o1);
+                   mask, tile_off, tile_count, src0, src1, o0, o1, id_base);
         else if (layout == QCE_LAYOUT_NATURAL && mode == QCE_EMIT_SRC2)
             LAUNCH("compact_src2", (k_compact<QCE_LAYOUT_NATURAL, QCE_EMIT_SRC2>), grid, QCE_FTHREADS, 0,
-                   mask, tile_off, tile_count, src0, src1, o0, o1);
+                   mask, tile_off, tile_count, src0, src1, o0, o1, id_base);
         else if (layout == QCE_LAYOUT_NATURAL && mode == QCE_EMIT_PACKED)
             LAUNCH("compact_packed", (k_compact<QCE_LAYOUT_NATURAL, QCE_EMIT_PACKED>), grid, QCE_FTHREADS, 0,
-                   mask, tile_off, tile_count, src0, src1, o0, o1);
+                   mask, tile_off, tile_count, src0, src1, o0, o1, id_base);
         else
             return fail("internal: unsupported compaction layout/mode %d/%d", layout, mode);
     }
@@ -710,28 +710,46 @@ int qce_drop_relations(void)
 }
 
 // ---------------------------------------------------------------- filter
-int qce_filter_scan(uint32_t rel, uint32_t col, char op, uint64_t c, qce_rowids **out)
+static int filter_scan_window(uint32_t rel, uint32_t col, char op, uint64_t c, uint64_t begin, uint64_t count,
+                              bool whole, qce_rowids **out)
 {
-    NEED_INIT();
     const Column *cl;
     int code;
     if (get_column(rel, col, &cl) != 0 || op_code(op, &code) != 0) return -1;
-    const u64 n = cl->n;
-    if (n == 0) return new_rowids(0, 0, out);
+    if (whole) { begin = 0; count = cl->n; }
+    if (begin > cl->n || count > cl->n - begin) return fail("row window [%llu, +%llu) outside relation %u (%llu rows)",
+                                                           (unsigned long long)begin, (unsigned long long)count, rel,
+                                                           (unsigned long long)cl->n);
+    if (begin & 1) return fail("row window must start on an even row (128-bit loads)");
+    const u64 n = count;
+    if (n == 0) return new_rowids(0, (u32)cl->n, out);
+    const u64 *d = cl->d + begin;
     const u64 ntiles = ceil_div(n, QCE_FTILE);
     u32 *mask = nullptr, *tile_count = nullptr;
     if (dalloc(&mask, ntiles * QCE_FWORDS) || dalloc(&tile_count, ntiles)) return -1;
     if (code == QCE_OP_EQ)
-        LAUNCH("filter_scan", (k_filter_mask_base<QCE_OP_EQ>), (int)ntiles, QCE_FTHREADS, 0, cl->d, n, c, mask, tile_count);
+        LAUNCH("filter_scan", (k_filter_mask_base<QCE_OP_EQ>), (int)ntiles, QCE_FTHREADS, 0, d, n, c, mask, tile_count);
     else if (code == QCE_OP_GT)
-        LAUNCH("filter_scan", (k_filter_mask_base<QCE_OP_GT>), (int)ntiles, QCE_FTHREADS, 0, cl->d, n, c, mask, tile_count);
+        LAUNCH("filter_scan", (k_filter_mask_base<QCE_OP_GT>), (int)ntiles, QCE_FTHREADS, 0, d, n, c, mask, tile_count);
     else
-        LAUNCH("filter_scan", (k_filter_mask_base<QCE_OP_LT>), (int)ntiles, QCE_FTHREADS, 0, cl->d, n, c, mask, tile_count);
+        LAUNCH("filter_scan", (k_filter_mask_base<QCE_OP_LT>), (int)ntiles, QCE_FTHREADS, 0, d, n, c, mask, tile_count);
     int rc = compact_from_mask(QCE_LAYOUT_PAIR, QCE_EMIT_INDEX, mask, tile_count, ntiles, nullptr, nullptr,
-                               (u32)n, 0, out, nullptr);
+                               (u32)cl->n, 0, out, nullptr, (u32)begin);
     dfree(mask);
     dfree(tile_count);
     return rc;
+}
+
+int qce_filter_scan(uint32_t rel, uint32_t col, char op, uint64_t c, qce_rowids **out)
+{
+    NEED_INIT();
+    return filter_scan_window(rel, col, op, c, 0, 0, true, out);
+}
+int qce_filter_scan_range(uint32_t rel, uint32_t col, char op, uint64_t c, uint64_t row_begin, uint64_t row_count,
+                          qce_rowids **out)
+{
+    NEED_INIT();
+    return filter_scan_window(rel, col, op, c, row_begin, row_count, false, out);
 }
 
 int qce_filter_refine(qce_rowids *ids, uint32_t rel, uint32_t col, char op, uint64_t c, uint64_t *survivors)
@@ -767,9 +785,11 @@ int qce_filter_refine(qce_rowids *ids, uint32_t rel, uint32_t col, char op, uint
 }
 
 // ---------------------------------------------------------------- tuples
-static int build_tuples(const Column *cl, const qce_rowids *ids, qce_tuples **out)
+static int build_tuples(const Column *cl, const qce_rowids *ids, qce_tuples **out, u64 begin = 0,
+                        u64 count = ~0ull)
 {
-    const u64 n = ids ? ids->n : cl->n;
+    if (count == ~0ull) count = cl->n - begin;
+    const u64 n = ids ? ids->n : count;
     qce_tuples *t = new qce_tuples();
     t->n = n;
     t->key_bits = bitlen(cl->maxv) ? bitlen(cl->maxv) : 1;
@@ -781,11 +801,12 @@ static int build_tuples(const Column *cl, const qce_rowids *ids, qce_tuples **ou
     if (t->wide && dalloc(&t->ids, n) != 0) { delete t; return -1; }
     if (n > 0) {
         if (t->wide)
-            LAUNCH("build_tuples", k_build_wide, grid_for(256, n), 256, 0, cl->d, ids ? ids->d : nullptr, n, t->a, t->ids);
+            LAUNCH("build_tuples", k_build_wide, grid_for(256, n), 256, 0, ids ? cl->d : cl->d + begin,
+                   ids ? ids->d : nullptr, n, t->a, t->ids, (u32)begin);
         else if (ids)
             LAUNCH("build_tuples", k_build_packed_ids, grid_for(1024, n), 256, 0, cl->d, ids->d, n, t->a);
         else
-            LAUNCH("build_tuples", k_build_packed_base, grid_for(512, n), 256, 0, cl->d, n, t->a);
+            LAUNCH("build_tuples", k_build_packed_base, grid_for(512, n), 256, 0, cl->d + begin, n, t->a, begin);
     }
     *out = t;
     return 0;
@@ -796,6 +817,15 @@ int qce_build_tuples_base(uint32_t rel, uint32_t col, qce_tuples **out)
     const Column *cl;
     if (get_column(rel, col, &cl) != 0) return -1;
     return build_tuples(cl, nullptr, out);
+}
+int qce_build_tuples_base_range(uint32_t rel, uint32_t col, uint64_t row_begin, uint64_t row_count, qce_tuples **out)
+{
+    NEED_INIT();
+    const Column *cl;
+    if (get_column(rel, col, &cl) != 0) return -1;
+    if (row_begin > cl->n || row_count > cl->n - row_begin) return fail("row window outside relation %u", rel);
+    if (row_begin & 1) return fail("row window must start on an even row (128-bit loads)");
+    return build_tuples(cl, nullptr, out, row_begin, row_count);
 }
 int qce_build_tuples_rowids(uint32_t rel, uint32_t col, const qce_rowids *ids, qce_tuples **out)
 {
@@ -1144,7 +1174,8 @@ int qce_exchange_release(void *sendbuf)
     dfree((u64 *)sendbuf);
     return 0;
 }
-int qce_tuples_from_device_packed(const void *dev_words, uint64_t n, uint32_t key_bits, qce_tuples **out)
+int qce_tuples_from_device_packed(const void *dev_words, uint64_t n, uint32_t key_bits, uint32_t id_bound,
+                                  qce_tuples **out)
 {
     NEED_INIT();
     if (!out) return fail("null argument");
@@ -1153,7 +1184,7 @@ int qce_tuples_from_device_packed(const void *dev_words, uint64_t n, uint32_t ke
     t->n = n;
     t->key_bits = (int)key_bits;
     t->wide = false;
-    t->id_bound = 0;
+    t->id_bound = id_bound;
     t->sorted = false;
     t->ids = nullptr;
     if (dalloc(&t->a, n) != 0) { delete t; return -1; }

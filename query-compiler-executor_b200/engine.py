@@ -21,7 +21,8 @@ LIB_PATH = os.path.join(HERE, "libqce_b200.so")
 SYMBOLS = [
     "qce_init", "qce_shutdown", "qce_last_error", "qce_abi_version", "qce_timer_reset", "qce_timer_read",
     "qce_sync", "qce_profile_enable", "qce_profile_json", "qce_upload_column", "qce_upload_column_device",
-    "qce_adopt_column_device", "qce_column_info", "qce_drop_relations", "qce_filter_scan", "qce_filter_refine",
+    "qce_adopt_column_device", "qce_column_info", "qce_drop_relations", "qce_filter_scan", "qce_filter_scan_range",
+    "qce_build_tuples_base_range", "qce_filter_refine",
     "qce_build_tuples_base", "qce_build_tuples_rowids", "qce_sort_tuples", "qce_tuples_is_sorted",
     "qce_merge_join", "qce_merge_join_walk", "qce_distinct_pairs", "qce_scan_join", "qce_scan_join_base", "qce_rejoin", "qce_checksum", "qce_rowids_count",
     "qce_rowids_from_host", "qce_rowids_to_host", "qce_rowids_clone", "qce_rowids_free", "qce_tuples_count",
@@ -50,6 +51,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "qce_adopt_column_device": (i32, [u32, u32, vp, u64]),
         "qce_column_info": (i32, [u32, u32, P(u64), P(u64)]), "qce_drop_relations": (i32, []),
         "qce_filter_scan": (i32, [u32, u32, C.c_char, u64, P(vp)]),
+        "qce_filter_scan_range": (i32, [u32, u32, C.c_char, u64, u64, u64, P(vp)]),
+        "qce_build_tuples_base_range": (i32, [u32, u32, u64, u64, P(vp)]),
         "qce_filter_refine": (i32, [vp, u32, u32, C.c_char, u64, P(u64)]),
         "qce_build_tuples_base": (i32, [u32, u32, P(vp)]), "qce_build_tuples_rowids": (i32, [u32, u32, vp, P(vp)]),
         "qce_sort_tuples": (i32, [vp]), "qce_tuples_is_sorted": (i32, [vp, P(i32)]),
@@ -64,7 +67,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "qce_rowids_free": (None, [vp]), "qce_tuples_count": (u64, [vp]),
         "qce_tuples_from_host": (i32, [vp, vp, u64, P(vp)]), "qce_tuples_to_host": (i32, [vp, vp, vp]),
         "qce_tuples_free": (None, [vp]), "qce_partition_tuples": (i32, [vp, vp, u32, P(u64), P(vp)]),
-        "qce_tuples_from_device_packed": (i32, [vp, u64, u32, P(vp)]), "qce_exchange_release": (i32, [vp]),
+        "qce_tuples_from_device_packed": (i32, [vp, u64, u32, u32, P(vp)]), "qce_exchange_release": (i32, [vp]),
         "qce_key_histogram": (i32, [vp, u32, P(u64)]),
     }
     for name, (res, args) in sig.items():
@@ -169,9 +172,12 @@ class Engine:
             self.lib.qce_tuples_free(h)
 
     # ---- operators
-    def filter_scan(self, rel: int, col: int, op: str, c: int) -> int:
+    def filter_scan(self, rel: int, col: int, op: str, c: int, rows: Optional[Tuple[int, int]] = None) -> int:
         h = C.c_void_p()
-        self._ck(self.lib.qce_filter_scan(rel, col, op.encode(), c, C.byref(h)))
+        if rows is None:
+            self._ck(self.lib.qce_filter_scan(rel, col, op.encode(), c, C.byref(h)))
+        else:
+            self._ck(self.lib.qce_filter_scan_range(rel, col, op.encode(), c, rows[0], rows[1], C.byref(h)))
         return h.value
 
     def filter_refine(self, h: int, rel: int, col: int, op: str, c: int) -> int:
@@ -179,9 +185,12 @@ class Engine:
         self._ck(self.lib.qce_filter_refine(h, rel, col, op.encode(), c, C.byref(n)))
         return n.value
 
-    def build_tuples(self, rel: int, col: int, rowids: Optional[int] = None) -> int:
+    def build_tuples(self, rel: int, col: int, rowids: Optional[int] = None,
+                     rows: Optional[Tuple[int, int]] = None) -> int:
         h = C.c_void_p()
-        if rowids is None:
+        if rows is not None:
+            self._ck(self.lib.qce_build_tuples_base_range(rel, col, rows[0], rows[1], C.byref(h)))
+        elif rowids is None:
             self._ck(self.lib.qce_build_tuples_base(rel, col, C.byref(h)))
         else:
             self._ck(self.lib.qce_build_tuples_rowids(rel, col, rowids, C.byref(h)))
@@ -244,9 +253,9 @@ class Engine:
         self._ck(self.lib.qce_partition_tuples(t, sp.ctypes.data, nparts, counts, C.byref(buf)))
         return [int(x) for x in counts], buf.value
 
-    def tuples_from_device_packed(self, dev_ptr: int, n: int, key_bits: int) -> int:
+    def tuples_from_device_packed(self, dev_ptr: int, n: int, key_bits: int, id_bound: int = 0) -> int:
         h = C.c_void_p()
-        self._ck(self.lib.qce_tuples_from_device_packed(dev_ptr, n, key_bits, C.byref(h)))
+        self._ck(self.lib.qce_tuples_from_device_packed(dev_ptr, n, key_bits, id_bound, C.byref(h)))
         return h.value
 
     def exchange_release(self, buf: Optional[int]) -> None:

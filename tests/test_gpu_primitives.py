@@ -304,3 +304,21 @@ print("bucketed ok", e.profile_read())
     env = dict(os.environ, QCE_BUCKETED_CHECKSUM="1")
     p = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
     assert p.returncode == 0 and "bucketed ok" in p.stdout, p.stderr[-2000:]
+
+
+@pytest.mark.parametrize("begin,count", [(0, 0), (0, 5000), (4096, 4097), (8192, 91808), (99998, 2)])
+def test_row_window_scan_and_build(engine, begin, count):
+    """Row-window variants (one rank's share of a sharded scan/build): row ids stay
+    relation-global."""
+    rng = np.random.default_rng(begin + count)
+    col = _col(rng, 100000, 1 << 20)
+    engine.upload_column(108, 0, col)
+    h = engine.filter_scan(108, 0, "<", 1 << 19, rows=(begin, count))
+    want = orc.filter_scan(col[begin:begin + count], "<", 1 << 19) + U64(begin)
+    np.testing.assert_array_equal(engine.rowids_to_host(h), want)
+    engine.rowids_free(h)
+    t = engine.build_tuples(108, 0, rows=(begin, count))
+    k, p = engine.tuples_to_host(t)
+    np.testing.assert_array_equal(k, col[begin:begin + count])
+    np.testing.assert_array_equal(p, np.arange(begin, begin + count, dtype=U64))
+    engine.tuples_free(t)

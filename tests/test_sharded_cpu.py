@@ -1,0 +1,125 @@
+"""CPU, world_size 2, gloo: the multi-GPU orchestration (row windows, global
+histogram -> splitters, partition bookkeeping, all-to-all, checksum reduce) with a
+numpy stand-in for the engine.  The stand-in is test infrastructure (it uses the
+oracle's primitives); the product's backend is EngineOps (GPU only)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import qce_oracle as orc  # noqa: E402
+from oracle import workload as wl  # noqa: E402
+
+
+class NumpyOps:
+    """Same interface as sharded.EngineOps, on host arrays."""
+    comm_device = torch.device("cpu")
+
+    def __init__(self, db):
+        self.db = db
+
+    def key_bits(self, rel, col):
+        return max(1, int(self.db[rel][col].max()).bit_length())
+
+    def filter_window(self, rel, col, op, c, begin, count):
+        return orc.filter_scan(self.db[rel][col][begin:begin + count], op, c) + np.uint64(begin)
+
+    def build_from_ids(self, rel, col, ids):
+        k, p = orc.build_tuples(self.db[rel][col], ids)
+        return (k << np.uint64(32)) | p
+
+    def build_window(self, rel, col, begin, count):
+        k = self.db[rel][col][begin:begin + count]
+        return (k << np.uint64(32)) | np.arange(begin, begin + count, dtype=np.uint64)
+
+    def histogram(self, t, key_bits):
+        d = ((t >> np.uint64(32)) >> np.uint64(max(key_bits - 8, 0))) & np.uint64(255)
+        return np.bincount(d.astype(np.int64), minlength=256).astype(np.uint64)
+
+    def partition(self, t, splitters, nparts):
+        part = np.searchsorted(np.array(splitters, dtype=np.uint64), t >> np.uint64(32), side="right") \
+            if nparts > 1 else np.zeros(len(t), dtype=np.int64)
+        order = np.argsort(part, kind="stable")
+        counts = [int((part == p).sum()) for p in range(nparts)]
+        return counts, torch.from_numpy(t[order].view(np.int64).copy()), None
+
+    def release_partition(self, buf):
+        pass
+
+    def from_exchange(self, recv, key_bits, id_bound=0):
+        return recv.numpy().view(np.uint64).copy()
+
+    def sort(self, t):
+        t[:] = t[np.argsort(t >> np.uint64(32), kind="stable")]
+
+    def merge_join(self, L, R):
+        m = np.uint64(0xFFFFFFFF)
+        return orc.merge_join(L >> np.uint64(32), L & m, R >> np.uint64(32), R & m)
+
+    def checksum(self, ids, rel, cols):
+        return [orc.checksum(self.db[rel][c], ids) for c in cols]
+
+    def count(self, ids):
+        return len(ids)
+
+    def tuples_count(self, t):
+        return len(t)
+
+    def free_ids(self, h):
+        pass
+
+    def free_tuples(self, h):
+        pass
+
+
+def _worker(rank, world, port, rows, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import qce_b200  # noqa: F401
+    from qce_b200 import sharded
+    db = wl.gen_pair_db(rows, rows // 3, filt_domain=1000)
+    spec = sharded.JoinSpec(lhs=(0, 1), rhs=(1, 1), lhs_filter=(2, ">", 500), lhs_selects=[0], rhs_selects=[0, 2])
+    sj = sharded.ShardedJoin(NumpyOps(db), dist, torch, rank, world)
+    res = sj.run(spec, rows, rows)
+    if rank == 0:
+        out.put((sharded.format_result(res), res["pairs"], sj.stats["splitters"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_join_matches_oracle(world):
+    rows = 20011
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29500 + os.getpid() % 2000 + world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, rows, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    line, pairs, splitters = out.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    db = wl.gen_pair_db(rows, rows // 3, filt_domain=1000)
+    assert line == orc.run_batch(db, "0 1|0.1=1.1&0.2>500|0.0 1.0 1.2\n")
+    assert pairs > 0 and len(splitters) == world - 1 and splitters == sorted(splitters)
+
+
+def test_choose_splitters_balances():
+    import qce_b200  # noqa: F401
+    from qce_b200 import sharded
+    hist = np.zeros(256, dtype=np.uint64)
+    hist[:100] = 10
+    sp = sharded.choose_splitters(hist, 27, 4)
+    assert sp == [25 << 19, 50 << 19, 75 << 19]
+    hist[:] = 0
+    hist[7] = 1000  # one heavy bin: cannot be split, the later parts are empty
+    sp = sharded.choose_splitters(hist, 16, 4)
+    assert sp == sorted(sp) and all(s >= (8 << 8) for s in sp)
+    assert sharded.row_window(10_000, 1, 4) == (4096, 4096) and sharded.row_window(10_000, 3, 4) == (10_000, 0)
