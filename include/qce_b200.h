@@ -51,6 +51,8 @@ int qce_timer_reset(void);
 int qce_timer_read(double *ms, uint64_t *kernel_launches);
 /* Block until all queued engine work is done. */
 int qce_sync(void);
+/* Bytes the engine's HBM arena currently holds (slabs) / has handed out. */
+int qce_mempool_stats(uint64_t *reserved_bytes, uint64_t *used_bytes);
 /* Per-kernel device times: CUDA events around every launch while enabled.
  * qce_profile_json() returns {"tag": {"launches": n, "ms": total}, ...} for
  * everything recorded since qce_profile_enable(1). */

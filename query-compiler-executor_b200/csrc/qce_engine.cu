@@ -2,8 +2,8 @@
 // the sm_100a kernels in k_filter.cuh / k_radix.cuh / k_join.cuh.
 //
 // One process drives one GPU.  All work is queued on one engine stream;
-// temporaries come from the stream-ordered CUDA memory pool (no cudaMalloc /
-// cudaFree on the hot path); the only host synchronisations are the result
+// temporaries come from the engine's own HBM arena (no cudaMalloc / cudaFree on
+// the hot path once the slabs exist); the only host synchronisations are the result
 // sizes the host-side operator layer needs to size the next step (filter
 // count, join pair count) and the final checksums.
 //
@@ -14,7 +14,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -102,18 +104,115 @@ inline int bitlen(u64 v)
 inline u64 ceil_div(u64 a, u64 b) { return (a + b - 1) / b; }
 inline u64 col_key(u32 rel, u32 col) { return ((u64)rel << 32) | col; }
 
-// stream-ordered allocation
+// ---- HBM arena ----------------------------------------------------------------
+// Temporaries (tuple runs, ping-pong buffers, masks, look-back words, join
+// scratch, row-id columns) are GB-sized and short-lived.  cudaMallocAsync's pool
+// handled the steady single-query loop, but as soon as the pool ran tight it
+// defragmented by remapping virtual ranges: single allocations took 40-340 ms
+// (tools/sharded_probe.py).  The engine therefore owns its memory: large slabs
+// from cudaMalloc, a best-fit free list with coalescing on the host.  All engine
+// work is ordered on one stream, so a block freed by the host may be handed out
+// again immediately -- any kernel that still reads it was enqueued earlier.
+class Arena {
+  public:
+    static constexpr u64 kAlign = 512;
+    static constexpr u64 kMinSlab = 1ull << 30;
+
+    int alloc(void **out, u64 bytes)
+    {
+        bytes = (bytes + kAlign - 1) / kAlign * kAlign;
+        if (bytes == 0) bytes = kAlign;
+        auto it = by_size_.lower_bound({bytes, 0});
+        if (it == by_size_.end()) {
+            if (grow(bytes) != 0) return -1;
+            it = by_size_.lower_bound({bytes, 0});
+        }
+        const u64 size = it->first, addr = it->second;
+        by_size_.erase(it);
+        by_addr_.erase(addr);
+        if (size > bytes) insert_free(addr + bytes, size - bytes);
+        live_[addr] = bytes;
+        used_ += bytes;
+        *out = (void *)addr;
+        return 0;
+    }
+    void free(void *p)
+    {
+        if (!p) return;
+        auto it = live_.find((u64)p);
+        if (it == live_.end()) return; // not ours (adopted buffer)
+        u64 addr = it->first, size = it->second;
+        live_.erase(it);
+        used_ -= size;
+        // coalesce with the free neighbours (never across slab boundaries)
+        auto next = by_addr_.find(addr + size);
+        if (next != by_addr_.end() && !slab_starts_.count(addr + size)) {
+            size += next->second;
+            by_size_.erase({next->second, next->first});
+            by_addr_.erase(next);
+        }
+        auto prev = by_addr_.lower_bound(addr);
+        if (prev != by_addr_.begin()) {
+            --prev;
+            if (prev->first + prev->second == addr && !slab_starts_.count(addr)) {
+                addr = prev->first;
+                size += prev->second;
+                by_size_.erase({prev->second, prev->first});
+                by_addr_.erase(prev);
+            }
+        }
+        insert_free(addr, size);
+    }
+    void release_all()
+    {
+        for (auto &s : slabs_) cudaFree((void *)s.first);
+        slabs_.clear(); slab_starts_.clear(); by_addr_.clear(); by_size_.clear(); live_.clear();
+        reserved_ = used_ = 0;
+    }
+    u64 reserved() const { return reserved_; }
+    u64 used() const { return used_; }
+
+  private:
+    int grow(u64 need)
+    {
+        // at least as much again as is already reserved, so the slab count stays small
+        u64 bytes = std::max<u64>(std::max<u64>(need, kMinSlab), reserved_);
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess && bytes > need) {
+            cudaGetLastError();
+            bytes = need;
+            e = cudaMalloc(&p, bytes);
+        }
+        if (e != cudaSuccess)
+            return fail("out of device memory: %llu bytes requested, %llu reserved (%s)", (unsigned long long)need,
+                        (unsigned long long)reserved_, cudaGetErrorString(e));
+        slabs_.push_back({(u64)p, bytes});
+        slab_starts_.insert((u64)p);
+        reserved_ += bytes;
+        insert_free((u64)p, bytes);
+        return 0;
+    }
+    void insert_free(u64 addr, u64 size)
+    {
+        by_addr_[addr] = size;
+        by_size_.insert({size, addr});
+    }
+    std::vector<std::pair<u64, u64>> slabs_;
+    std::set<u64> slab_starts_;
+    std::map<u64, u64> by_addr_;            // free blocks: addr -> size
+    std::set<std::pair<u64, u64>> by_size_; // free blocks: (size, addr)
+    std::map<u64, u64> live_;               // handed out: addr -> size
+    u64 reserved_ = 0, used_ = 0;
+};
+Arena g_arena;
+
 template <typename T> int dalloc(T **p, u64 count)
 {
     *p = nullptr;
-    if (count == 0) count = 1;
-    CK(cudaMallocAsync((void **)p, count * sizeof(T), g.stream));
-    return 0;
+    return g_arena.alloc((void **)p, (count ? count : 1) * sizeof(T));
 }
-template <typename T> void dfree(T *p)
-{
-    if (p) cudaFreeAsync((void *)p, g.stream);
-}
+template <typename T> void dfree(T *p) { g_arena.free((void *)p); }
 
 void prof_begin(const char *tag)
 {
@@ -540,10 +639,6 @@ int qce_init(int device)
     CK(cudaGetDeviceProperties(&prop, device));
     g.sms = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
-    cudaMemPool_t pool;
-    CK(cudaDeviceGetDefaultMemPool(&pool, device));
-    uint64_t keep = UINT64_MAX; // never trim: temporaries are recycled across operators
-    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     CK(cudaMalloc((void **)&g.d_scalars, 16 * sizeof(u64)));
     CK(cudaMallocHost((void **)&g.h_scalars, 16 * sizeof(u64)));
     CK(cudaEventCreate(&g.t0));
@@ -558,6 +653,7 @@ void qce_shutdown(void)
     if (!g.inited) return;
     qce_drop_relations();
     cudaStreamSynchronize(g.stream);
+    g_arena.release_all();
     cudaFree(g.d_scalars);
     cudaFreeHost(g.h_scalars);
     cudaEventDestroy(g.t0);
@@ -589,6 +685,14 @@ int qce_timer_read(double *ms, uint64_t *kernel_launches)
     CK(cudaEventElapsedTime(&f, g.t0, g.t1));
     if (ms) *ms = f;
     if (kernel_launches) *kernel_launches = g.launches;
+    return 0;
+}
+
+int qce_mempool_stats(uint64_t *reserved_bytes, uint64_t *used_bytes)
+{
+    NEED_INIT();
+    if (reserved_bytes) *reserved_bytes = g_arena.reserved();
+    if (used_bytes) *used_bytes = g_arena.used();
     return 0;
 }
 

@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(HERE, "libqce_b200.so")
 # every symbol include/qce_b200.h declares (tests check the library exports them all)
 SYMBOLS = [
     "qce_init", "qce_shutdown", "qce_last_error", "qce_abi_version", "qce_timer_reset", "qce_timer_read",
-    "qce_sync", "qce_profile_enable", "qce_profile_json", "qce_upload_column", "qce_upload_column_device",
+    "qce_sync", "qce_mempool_stats", "qce_profile_enable", "qce_profile_json", "qce_upload_column", "qce_upload_column_device",
     "qce_adopt_column_device", "qce_column_info", "qce_drop_relations", "qce_filter_scan", "qce_filter_scan_range",
     "qce_build_tuples_base_range", "qce_filter_refine",
     "qce_build_tuples_base", "qce_build_tuples_rowids", "qce_sort_tuples", "qce_tuples_is_sorted",
@@ -46,7 +46,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "qce_init": (i32, [i32]), "qce_shutdown": (None, []), "qce_last_error": (C.c_char_p, []),
         "qce_abi_version": (i32, []), "qce_timer_reset": (i32, []),
         "qce_timer_read": (i32, [P(C.c_double), P(u64)]), "qce_sync": (i32, []),
-        "qce_profile_enable": (i32, [i32]), "qce_profile_json": (C.c_char_p, []),
+        "qce_mempool_stats": (i32, [P(u64), P(u64)]), "qce_profile_enable": (i32, [i32]), "qce_profile_json": (C.c_char_p, []),
         "qce_upload_column": (i32, [u32, u32, vp, u64]), "qce_upload_column_device": (i32, [u32, u32, vp, u64]),
         "qce_adopt_column_device": (i32, [u32, u32, vp, u64]),
         "qce_column_info": (i32, [u32, u32, P(u64), P(u64)]), "qce_drop_relations": (i32, []),
@@ -103,6 +103,11 @@ class Engine:
         ms, n = C.c_double(), C.c_uint64()
         self._ck(self.lib.qce_timer_read(C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def mempool_stats(self) -> Tuple[int, int]:
+        r, u = C.c_uint64(), C.c_uint64()
+        self._ck(self.lib.qce_mempool_stats(C.byref(r), C.byref(u)))
+        return r.value, u.value
 
     def profile(self, on: bool) -> None:
         self._ck(self.lib.qce_profile_enable(1 if on else 0))
