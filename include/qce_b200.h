@@ -170,13 +170,14 @@ void qce_tuples_free(qce_tuples *t);
 /* ---- multi-GPU exchange step --------------------------------
  * Splits a tuple run by key range into `nparts` destination runs:
  * part(key) = number of splitters <= key (splitters ascending, nparts-1 of
- * them).  counts[p] = tuples for rank p.  The packed 8-byte words of part p
- * are contiguous in *sendbuf (device pointer owned by the engine until
- * qce_exchange_release) at element offset sum(counts[0..p)).  The collective
- * itself (all-to-all over NVLink) is done by the caller's communicator
- * (torch.distributed / NCCL) on those device pointers. */
-int qce_partition_tuples(const qce_tuples *t, const uint64_t *splitters, uint32_t nparts,
-                         uint64_t *counts, void **sendbuf);
+ * them, each a multiple of 2^(key_bits-8): a boundary of the 256-bin histogram
+ * qce_key_histogram returns).  counts[p] = tuples for rank p.  The packed 8-byte
+ * words of part p are contiguous in *sendbuf (device pointer owned by the
+ * engine until qce_exchange_release) at element offset sum(counts[0..p)); the
+ * grouping is stable.  The collective itself (all-to-all over NVLink) is done
+ * by the caller's communicator (torch.distributed / NCCL) on those pointers. */
+int qce_partition_tuples(const qce_tuples *t, uint32_t key_bits, const uint64_t *splitters,
+                         uint32_t nparts, uint64_t *counts, void **sendbuf);
 /* Wrap `n` received packed words (device pointer, copied) as a tuple run.
  * id_bound = exclusive upper bound of the row ids they carry (0 = unknown). */
 int qce_tuples_from_device_packed(const void *dev_words, uint64_t n, uint32_t key_bits,

@@ -168,17 +168,18 @@ struct DigitShift {
     __device__ __forceinline__ u32 operator()(u64 k) const { return (u32)(k >> shift) & 255u; }
     __device__ __forceinline__ u32 operator()(u32 k) const { return (k >> shift) & 255u; }
 };
-// Range partition for the multi-GPU exchange: digit = number of splitters <= key
-// (keys compared on the packed word's key field).
+// Range partition for the multi-GPU exchange.  Splitters sit on the boundaries of
+// the 256-bin histogram of the top 8 significant key bits, so the destination of
+// a tuple is a table lookup on those bits (4 destinations per table word).
 struct DigitSplit {
-    u64 split[15]; // ascending, in packed-word units (key << 32)
-    int nsplit;
+    const u32 *lut; // device memory, 256 x uint8: histogram bin -> destination rank.  Not a
+                    // kernel-parameter array: lanes index it divergently, which the
+                    // constant bank serialises; 256 B in global memory stay in L1.
+    int shift;      // 32 + key_bits - 8 (packed word)
     __device__ __forceinline__ u32 operator()(u64 k) const
     {
-        u32 d = 0;
-#pragma unroll
-        for (int i = 0; i < 15; i++) d += (i < nsplit && k >= split[i]) ? 1u : 0u;
-        return d;
+        const u32 bin = (u32)(k >> shift) & 255u;
+        return (__ldg(lut + (bin >> 2)) >> ((bin & 3u) * 8)) & 255u;
     }
 };
 

@@ -588,30 +588,6 @@ int partition_ids_by_top_bits(const qce_rowids *ids, u32 **out)
     return 0;
 }
 
-__global__ void __launch_bounds__(256)
-k_split_hist(const u64 *__restrict__ w, u64 n, DigitSplit ds, u32 *__restrict__ ghist)
-{
-    __shared__ u32 sh[16];
-    if (threadIdx.x < 16) sh[threadIdx.x] = 0;
-    __syncthreads();
-    u32 local[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) local[i] = 0;
-    const u64 stride = (u64)gridDim.x * 256;
-    for (u64 i = (u64)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
-        u32 d = ds(w[i]);
-#pragma unroll
-        for (int k = 0; k < 16; k++) local[k] += (d == (u32)k);
-    }
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-        u32 s = warp_sum_u32(local[k]);
-        if ((threadIdx.x & 31) == 0 && s) atomicAdd(&sh[k], s);
-    }
-    __syncthreads();
-    if (threadIdx.x < 16 && sh[threadIdx.x]) atomicAdd(&ghist[threadIdx.x], sh[threadIdx.x]);
-}
-
 } // namespace
 
 // =============================================================== C-ABI
@@ -1238,37 +1214,61 @@ int qce_key_histogram(const qce_tuples *t, uint32_t key_bits, uint64_t *hist)
     return 0;
 }
 
-int qce_partition_tuples(const qce_tuples *t, const uint64_t *splitters, uint32_t nparts, uint64_t *counts,
-                         void **sendbuf)
+int qce_partition_tuples(const qce_tuples *t, uint32_t key_bits, const uint64_t *splitters, uint32_t nparts,
+                         uint64_t *counts, void **sendbuf)
 {
     NEED_INIT();
     if (!t || !counts || !sendbuf) return fail("null argument");
     if (t->wide) return fail("the sharded exchange supports packed (key < 2^32) runs only");
-    if (nparts < 1 || nparts > 16) return fail("nparts must be in 1..16");
+    if (nparts < 1 || nparts > 256) return fail("nparts must be in 1..256");
+    if (key_bits == 0 || key_bits > 32) return fail("packed runs carry keys of 1..32 bits");
     if (t->n >= (1ull << 30)) return fail("partition of %llu tuples exceeds the 2^30 per-run limit", (unsigned long long)t->n);
+    const int bin_shift = key_bits > 8 ? (int)key_bits - 8 : 0;
     DigitSplit ds;
-    ds.nsplit = (int)nparts - 1;
-    for (int i = 0; i < 15; i++) ds.split[i] = (i < ds.nsplit) ? (splitters[i] << 32) : ~0ull;
+    ds.shift = 32 + bin_shift;
+    unsigned char lut[256];
+    for (u32 b = 0; b < 256; b++) {
+        u32 part = 0;
+        for (u32 k = 0; k + 1 < nparts; k++) {
+            if ((splitters[k] & ((1ull << bin_shift) - 1)) != 0)
+                return fail("splitter %llu is not on a boundary of the top-8-bit histogram bins", (unsigned long long)splitters[k]);
+            if (((u64)b << bin_shift) >= splitters[k]) part++;
+        }
+        lut[b] = (unsigned char)part;
+    }
     const u64 n = t->n;
     u64 *out = nullptr;
-    u32 *ghist = nullptr, *gbase = nullptr, *status = nullptr, *counter = nullptr;
+    u32 *ghist = nullptr, *gbase = nullptr, *status = nullptr, *counter = nullptr, *dlut = nullptr;
+    if (dalloc(&dlut, 64) != 0) return -1;
+    CK(cudaMemcpyAsync(dlut, lut, sizeof lut, cudaMemcpyHostToDevice, g.stream));
+    ds.lut = dlut;
     const u32 ntiles = (u32)ceil_div(n ? n : 1, onesweep_tile_size());
-    if (dalloc(&out, n) || dalloc(&ghist, QCE_RADIX_BINS) || dalloc(&gbase, QCE_RADIX_BINS) ||
+    if (dalloc(&out, n) || dalloc(&ghist, 2 * QCE_RADIX_BINS) || dalloc(&gbase, QCE_RADIX_BINS) ||
         dalloc(&status, (u64)ntiles * QCE_RADIX_BINS) || dalloc(&counter, 1))
         return -1;
-    CK(cudaMemsetAsync(ghist, 0, QCE_RADIX_BINS * sizeof(u32), g.stream));
+    CK(cudaMemsetAsync(ghist, 0, 2 * QCE_RADIX_BINS * sizeof(u32), g.stream));
     CK(cudaMemsetAsync(status, 0, (u64)ntiles * QCE_RADIX_BINS * sizeof(u32), g.stream));
     CK(cudaMemsetAsync(counter, 0, sizeof(u32), g.stream));
+    // per-destination counts = the bin histogram folded through the table (host, 256 adds)
+    RadixShifts rs;
+    rs.npass = 1;
+    for (int i = 0; i < QCE_MAX_PASSES; i++) rs.shift[i] = 0;
+    rs.shift[0] = ds.shift;
+    std::vector<u32> bins(QCE_RADIX_BINS, 0), parts(QCE_RADIX_BINS, 0);
     if (n) {
-        LAUNCH("split_hist", k_split_hist, grid_for(256 * 8, n), 256, 0, t->a, n, ds, ghist);
-        LAUNCH("radix_bases", k_radix_bases, 1, 256, 0, ghist, gbase);
-        if (launch_onesweep<false, u64>((const u64 *)t->a, out, nullptr, nullptr, (u32)n, ds, gbase, status, counter) != 0) return -1;
+        LAUNCH("radix_hist", k_radix_hist, grid_for(1024, n, 4), 512, 0, t->a, n, rs, ghist);
+        CK(cudaMemcpyAsync(bins.data(), ghist, QCE_RADIX_BINS * sizeof(u32), cudaMemcpyDeviceToHost, g.stream));
+        CK(cudaStreamSynchronize(g.stream));
+        for (u32 b = 0; b < 256; b++) parts[lut[b]] += bins[b];
+        u32 *part_hist = ghist + QCE_RADIX_BINS;
+        CK(cudaMemcpyAsync(part_hist, parts.data(), QCE_RADIX_BINS * sizeof(u32), cudaMemcpyHostToDevice, g.stream));
+        LAUNCH("radix_bases", k_radix_bases, 1, 256, 0, part_hist, gbase);
+        if (launch_onesweep<false, u64>((const u64 *)t->a, out, nullptr, nullptr, (u32)n, ds, gbase, status, counter) != 0)
+            return -1;
+        CK(cudaStreamSynchronize(g.stream)); // the caller hands *sendbuf to another stream
     }
-    std::vector<u32> tmp(QCE_RADIX_BINS);
-    CK(cudaMemcpyAsync(tmp.data(), ghist, QCE_RADIX_BINS * sizeof(u32), cudaMemcpyDeviceToHost, g.stream));
-    CK(cudaStreamSynchronize(g.stream));
-    for (u32 p = 0; p < nparts; p++) counts[p] = tmp[p];
-    dfree(ghist); dfree(gbase); dfree(status); dfree(counter);
+    for (u32 p = 0; p < nparts; p++) counts[p] = parts[p];
+    dfree(ghist); dfree(gbase); dfree(status); dfree(counter); dfree(dlut);
     *sendbuf = out;
     return 0;
 }

@@ -66,7 +66,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "qce_rowids_to_host": (i32, [vp, vp]), "qce_rowids_clone": (i32, [vp, P(vp)]),
         "qce_rowids_free": (None, [vp]), "qce_tuples_count": (u64, [vp]),
         "qce_tuples_from_host": (i32, [vp, vp, u64, P(vp)]), "qce_tuples_to_host": (i32, [vp, vp, vp]),
-        "qce_tuples_free": (None, [vp]), "qce_partition_tuples": (i32, [vp, vp, u32, P(u64), P(vp)]),
+        "qce_tuples_free": (None, [vp]), "qce_partition_tuples": (i32, [vp, u32, vp, u32, P(u64), P(vp)]),
         "qce_tuples_from_device_packed": (i32, [vp, u64, u32, u32, P(vp)]), "qce_exchange_release": (i32, [vp]),
         "qce_key_histogram": (i32, [vp, u32, P(u64)]),
     }
@@ -251,11 +251,11 @@ class Engine:
         self._ck(self.lib.qce_key_histogram(t, key_bits, out.ctypes.data_as(C.POINTER(C.c_uint64))))
         return out
 
-    def partition_tuples(self, t: int, splitters, nparts: int):
+    def partition_tuples(self, t: int, key_bits: int, splitters, nparts: int):
         sp = _u64(splitters if len(splitters) else [0])
         counts = (C.c_uint64 * nparts)()
         buf = C.c_void_p()
-        self._ck(self.lib.qce_partition_tuples(t, sp.ctypes.data, nparts, counts, C.byref(buf)))
+        self._ck(self.lib.qce_partition_tuples(t, key_bits, sp.ctypes.data, nparts, counts, C.byref(buf)))
         return [int(x) for x in counts], buf.value
 
     def tuples_from_device_packed(self, dev_ptr: int, n: int, key_bits: int, id_bound: int = 0) -> int:

@@ -95,10 +95,9 @@ class EngineOps:
     def histogram(self, t, key_bits):
         return self.e.key_histogram(t, key_bits)
 
-    def partition(self, t, splitters, nparts):
-        counts, buf = self.e.partition_tuples(t, splitters, nparts)
+    def partition(self, t, key_bits, splitters, nparts):
+        counts, buf = self.e.partition_tuples(t, key_bits, splitters, nparts)  # returns synchronised
         n = sum(counts)
-        self.e.sync()  # the exchange runs on torch's stream
         send = self.torch.as_tensor(self._DevArray(buf, n), device=self.comm_device) if n else \
             self.torch.empty(0, dtype=self.torch.int64, device=self.comm_device)
         return counts, send, buf
@@ -180,7 +179,7 @@ class ShardedJoin:
         sent = 0
         recv_runs = []
         for run, nrows in ((L, rows_lhs), (R, rows_rhs)):
-            counts, send, buf = ops.partition(run, splitters, world)
+            counts, send, buf = ops.partition(run, key_bits, splitters, world)
             sent += sum(counts) - counts[rank]
             recv, _ = self._exchange(counts, send)
             recv_runs.append(ops.from_exchange(recv, key_bits, nrows))

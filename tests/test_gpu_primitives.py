@@ -247,10 +247,10 @@ def test_partition_tuples(engine, nparts):
     keys = _col(rng, n, 1 << 24)
     t = engine.tuples_from_host(keys, np.arange(n, dtype=U64))
     splitters = [(i + 1) * (1 << 24) // nparts for i in range(nparts - 1)]
-    counts, buf = engine.partition_tuples(t, splitters, nparts)
+    counts, buf = engine.partition_tuples(t, 24, splitters, nparts)
     part = np.searchsorted(np.array(splitters, dtype=U64), keys, side="right") if nparts > 1 else np.zeros(n, dtype=int)
     assert counts == [int((part == p).sum()) for p in range(nparts)]
-    back = engine.tuples_from_device_packed(buf, n, 24)
+    back = engine.tuples_from_device_packed(buf, n, 24, n)
     k, p = engine.tuples_to_host(back)
     order = np.argsort(part, kind="stable")  # partitioning is stable
     np.testing.assert_array_equal(k, keys[order])

@@ -42,7 +42,7 @@ class NumpyOps:
         d = ((t >> np.uint64(32)) >> np.uint64(max(key_bits - 8, 0))) & np.uint64(255)
         return np.bincount(d.astype(np.int64), minlength=256).astype(np.uint64)
 
-    def partition(self, t, splitters, nparts):
+    def partition(self, t, key_bits, splitters, nparts):
         part = np.searchsorted(np.array(splitters, dtype=np.uint64), t >> np.uint64(32), side="right") \
             if nparts > 1 else np.zeros(len(t), dtype=np.int64)
         order = np.argsort(part, kind="stable")
