@@ -206,6 +206,29 @@ k_scan_excl(const Tin *__restrict__ in, Tout *__restrict__ out, u64 n, u64 *__re
     }
     if (threadIdx.x == 0) *total = (u64)running;
 }
+// Same for a handful of tiles (small queries): one warp, no block barriers.
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(32)
+k_scan_excl_warp(const Tin *__restrict__ in, Tout *__restrict__ out, u64 n, u64 *__restrict__ total)
+{
+    Tout running = 0;
+    for (u64 base = 0; base < n; base += 128) {
+        u64 i0 = base + (u64)threadIdx.x * 4;
+        Tout v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[k] = (i0 + k < n) ? (Tout)in[i0 + k] : (Tout)0;
+        Tout s = v[0] + v[1] + v[2] + v[3];
+        Tout incl = warp_scan_incl<Tout>(s);
+        Tout ex = incl - s + running;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (i0 + k < n) out[i0 + k] = ex;
+            ex += v[k];
+        }
+        running += __shfl_sync(QCE_FULL_MASK, incl, 31);
+    }
+    if (threadIdx.x == 0) *total = (u64)running;
+}
 
 // ---- pass 2: mask -> compacted outputs -----------------------------------------
 // MODE  QCE_EMIT_INDEX   out0[r] = position

@@ -28,7 +28,8 @@
 #include "qce_common.cuh"
 
 #define QCE_RADIX_BITS 8
-#define QCE_RADIX_BINS 256
+#define QCE_RADIX_BINS 256  // 8-bit digits: the default
+#define QCE_MAX_BINS 512    // 9-bit digits, when they save a pass
 #define QCE_MAX_PASSES 8
 
 struct RadixShifts {
@@ -104,11 +105,13 @@ k_unpack_lo(const u64 *__restrict__ in, u64 n, u32 *__restrict__ out)
 
 // ---- digit histograms of every pass in one read (build_histogram,
 // src/utilities.c:20-31, hoisted out of the per-bucket loop) ------------------------
+// `bins` = 256 or 512 (8- or 9-bit digits), the same for every pass of a sort.
 __global__ void __launch_bounds__(512)
-k_radix_hist(const u64 *__restrict__ keys, u64 n, RadixShifts rs, u32 *__restrict__ ghist)
+k_radix_hist(const u64 *__restrict__ keys, u64 n, RadixShifts rs, u32 bins, u32 *__restrict__ ghist)
 {
-    __shared__ u32 sh[QCE_MAX_PASSES * QCE_RADIX_BINS];
-    for (int i = threadIdx.x; i < rs.npass * QCE_RADIX_BINS; i += 512) sh[i] = 0;
+    __shared__ u32 sh[QCE_MAX_PASSES * QCE_MAX_BINS];
+    const u32 mask = bins - 1;
+    for (u32 i = threadIdx.x; i < rs.npass * bins; i += 512) sh[i] = 0;
     __syncthreads();
     const u64 stride = (u64)gridDim.x * 1024;
     for (u64 e = ((u64)blockIdx.x * 512 + threadIdx.x) * 2; e < n; e += stride) {
@@ -119,13 +122,13 @@ k_radix_hist(const u64 *__restrict__ keys, u64 n, RadixShifts rs, u32 *__restric
 #pragma unroll
         for (int p = 0; p < QCE_MAX_PASSES; p++) {
             if (p < rs.npass) {
-                atomicAdd(&sh[p * QCE_RADIX_BINS + ((a >> rs.shift[p]) & 255)], 1u);
-                if (two) atomicAdd(&sh[p * QCE_RADIX_BINS + ((b >> rs.shift[p]) & 255)], 1u);
+                atomicAdd(&sh[p * bins + ((u32)(a >> rs.shift[p]) & mask)], 1u);
+                if (two) atomicAdd(&sh[p * bins + ((u32)(b >> rs.shift[p]) & mask)], 1u);
             }
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < rs.npass * QCE_RADIX_BINS; i += 512)
+    for (u32 i = threadIdx.x; i < rs.npass * bins; i += 512)
         if (sh[i]) atomicAdd(&ghist[i], sh[i]);
 }
 
@@ -133,8 +136,8 @@ k_radix_hist(const u64 *__restrict__ keys, u64 n, RadixShifts rs, u32 *__restric
 __global__ void __launch_bounds__(512)
 k_hist_u32(const u32 *__restrict__ keys, u64 n, int shift, u32 *__restrict__ ghist)
 {
-    __shared__ u32 sh[QCE_RADIX_BINS];
-    if (threadIdx.x < QCE_RADIX_BINS) sh[threadIdx.x] = 0;
+    __shared__ u32 sh[256];
+    if (threadIdx.x < 256) sh[threadIdx.x] = 0;
     __syncthreads();
     const u64 stride = (u64)gridDim.x * 2048;
     const u64 n4 = n & ~3ull;
@@ -147,26 +150,42 @@ k_hist_u32(const u32 *__restrict__ keys, u64 n, int shift, u32 *__restrict__ ghi
     }
     if (blockIdx.x == 0 && threadIdx.x < (n - n4)) atomicAdd(&sh[(keys[n4 + threadIdx.x] >> shift) & 255], 1u);
     __syncthreads();
-    if (threadIdx.x < QCE_RADIX_BINS && sh[threadIdx.x]) atomicAdd(&ghist[threadIdx.x], sh[threadIdx.x]);
+    if (threadIdx.x < 256 && sh[threadIdx.x]) atomicAdd(&ghist[threadIdx.x], sh[threadIdx.x]);
 }
 
-// build_psum (src/utilities.c:34-48): exclusive prefix over the 256 bins of
-// each pass.  One CTA of 256 threads per pass.
-__global__ void __launch_bounds__(256) k_radix_bases(const u32 *__restrict__ ghist,
-                                                     u32 *__restrict__ gbase)
+// build_psum (src/utilities.c:34-48): exclusive prefix over the bins of each
+// pass.  One CTA of `bins` (256 or 512) threads per pass.
+__global__ void __launch_bounds__(512) k_radix_bases(const u32 *__restrict__ ghist, u32 *__restrict__ gbase)
 {
     __shared__ u32 scratch[33];
-    u32 v = ghist[blockIdx.x * QCE_RADIX_BINS + threadIdx.x];
-    u32 tot;
-    u32 ex = block_scan_excl<u32, 256>(v, scratch, &tot);
-    gbase[blockIdx.x * QCE_RADIX_BINS + threadIdx.x] = ex;
+    const u32 bins = blockDim.x;
+    u32 v = ghist[blockIdx.x * bins + threadIdx.x];
+    // block_scan_excl is written for a compile-time thread count; 16 warps cover both sizes
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32 incl = warp_scan_incl<u32>(v);
+    if (lane == 31) scratch[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        u32 w = (lane < (int)(bins / 32)) ? scratch[lane] : 0u;
+        u32 wi = warp_scan_incl<u32>(w);
+        scratch[lane] = wi - w;
+    }
+    __syncthreads();
+    gbase[blockIdx.x * bins + threadIdx.x] = scratch[warp] + incl - v;
 }
 
 // ---- digit functors ------------------------------------------------------------
+// A functor returns the digit of a key under a `mask` (bins - 1) the kernel supplies.
 struct DigitShift {
     int shift;
-    __device__ __forceinline__ u32 operator()(u64 k) const { return (u32)(k >> shift) & 255u; }
-    __device__ __forceinline__ u32 operator()(u32 k) const { return (k >> shift) & 255u; }
+    __device__ __forceinline__ u32 operator()(u64 k, u32 mask) const { return (u32)(k >> shift) & mask; }
+    __device__ __forceinline__ u32 operator()(u32 k, u32 mask) const { return (k >> shift) & mask; }
+};
+// Packed words always sort key bits, i.e. word bits >= 32: the digit only needs
+// the high register (no 64-bit funnel shifts).  hi_shift = shift - 32.
+struct DigitShiftHi {
+    int hi_shift;
+    __device__ __forceinline__ u32 operator()(u64 k, u32 mask) const { return ((u32)(k >> 32) >> hi_shift) & mask; }
 };
 // Range partition for the multi-GPU exchange.  Splitters sit on the boundaries of
 // the 256-bin histogram of the top 8 significant key bits, so the destination of
@@ -176,26 +195,37 @@ struct DigitSplit {
                     // kernel-parameter array: lanes index it divergently, which the
                     // constant bank serialises; 256 B in global memory stay in L1.
     int shift;      // 32 + key_bits - 8 (packed word)
-    __device__ __forceinline__ u32 operator()(u64 k) const
+    __device__ __forceinline__ u32 operator()(u64 k, u32) const
     {
         const u32 bin = (u32)(k >> shift) & 255u;
         return (__ldg(lut + (bin >> 2)) >> ((bin & 3u) * 8)) & 255u;
     }
 };
 
-// Lanes of the warp holding the same 8-bit digit.  `match.any` gives this in one
-// instruction, but on sm_100a it runs on the address-divergence unit at about
+// Lanes of the warp holding the same BITS-bit digit.  `match.any` gives this in
+// one instruction, but on sm_100a it runs on the address-divergence unit at about
 // one warp instruction per 60 cycles per SM (ncu: pipe_adu 73 % busy, the pass
-// capped at ~2 TB/s).  Eight ballots -- one per digit bit, intersected -- go
-// through the vote path at two warps per clock instead.
-__device__ __forceinline__ u32 warp_peers_8bit(u32 d)
+// capped at ~2 TB/s).  One ballot per digit bit, intersected, goes through the
+// vote path at two warps per clock instead.
+template <int BITS> __device__ __forceinline__ u32 warp_peers(u32 d)
 {
+    // per bit: test -> predicate, ballot m, then keep the lanes whose bit agrees
+    // with ours: peers &= m ^ (bit ? 0 : ~0).  Hand-written: the compiler's
+    // version of the plain C loop cost ~7 instructions per bit; this is 2-3.
     u32 peers = QCE_FULL_MASK;
 #pragma unroll
-    for (int b = 0; b < QCE_RADIX_BITS; b++) {
-        const bool bit = (d >> b) & 1u;
-        const u32 m = __ballot_sync(QCE_FULL_MASK, bit);
-        peers &= bit ? m : ~m;
+    for (int b = 0; b < BITS; b++) {
+        asm("{\n\t"
+            ".reg .pred p;\n\t"
+            ".reg .b32 t, m, nm;\n\t"
+            "and.b32 t, %1, %2;\n\t"
+            "setp.ne.u32 p, t, 0;\n\t"
+            "vote.sync.ballot.b32 m, p, 0xffffffff;\n\t"
+            "selp.b32 nm, 0, 0xffffffff, p;\n\t"
+            "lop3.b32 %0, %0, m, nm, 0x60;\n\t" // a & (b ^ c)
+            "}"
+            : "+r"(peers)
+            : "r"(d), "r"(1u << b));
     }
     return peers;
 }
@@ -210,11 +240,11 @@ template <typename KeyT> __device__ __forceinline__ KeyT ld_stream_key(const Key
 template <> __device__ __forceinline__ u64 ld_stream_key<u64>(const u64 *p) { return ld_stream_u64(p); }
 template <> __device__ __forceinline__ u32 ld_stream_key<u32>(const u32 *p) { return ld_stream_u32(p); }
 
-template <int THREADS, int ITEMS, typename KeyT = u64> struct OnesweepSmem {
-    u32 warp_hist[(THREADS / 32) * QCE_RADIX_BINS]; // per-warp digit counts -> bases
-    u32 tile_excl[QCE_RADIX_BINS];                  // digit start inside the sorted tile
-    u32 goff[QCE_RADIX_BINS];                       // global start of digit minus tile_excl
-    u32 tile_cnt[QCE_RADIX_BINS];                   // early digit counts of the tile
+template <int THREADS, int ITEMS, int BITS, typename KeyT = u64> struct OnesweepSmem {
+    static constexpr int BINS = 1 << BITS;
+    u32 warp_hist[(THREADS / 32) * BINS]; // per-warp digit counts -> bases
+    u32 tile_excl[BINS];                  // digit start inside the sorted tile
+    u32 goff[BINS];                       // global start of digit minus tile_excl
     u32 scratch[33];
     u32 tile_id;
     KeyT keys[THREADS * ITEMS];
@@ -222,17 +252,22 @@ template <int THREADS, int ITEMS, typename KeyT = u64> struct OnesweepSmem {
 
 // One tile of the pass.  FULL = every slot of the tile holds a real tuple (no
 // bounds checks, no padding logic): all tiles but the last.
-template <int THREADS, int ITEMS, bool HAS_VALS, bool FULL, bool EARLY, int MATCH_EVERY, typename KeyT, typename DigitOp>
+template <int THREADS, int ITEMS, int BITS, bool HAS_VALS, bool FULL, int MATCH_EVERY, typename KeyT,
+          typename DigitOp>
 __device__ __forceinline__ void
-onesweep_tile(OnesweepSmem<THREADS, ITEMS, KeyT> &sm, u32 *svals, const KeyT *__restrict__ keys_in,
+onesweep_tile(OnesweepSmem<THREADS, ITEMS, BITS, KeyT> &sm, u32 *svals, const KeyT *__restrict__ keys_in,
               KeyT *__restrict__ keys_out, const u32 *__restrict__ vals_in, u32 *__restrict__ vals_out, u32 n,
               const DigitOp &digit, const u32 *__restrict__ gbase, u32 *__restrict__ status, u32 tile)
 {
     constexpr int TILE = THREADS * ITEMS;
     constexpr int WARPS = THREADS / 32;
+    constexpr int BINS = 1 << BITS;
+    constexpr u32 DMASK = BINS - 1;
+    constexpr int BPT = (BINS + THREADS - 1) / THREADS; // bins per thread, consecutive
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 tbase = tile * TILE;
     const u32 nvalid = FULL ? (u32)TILE : (n - tbase);
+    const u32 npad = TILE - nvalid; // padding slots of the last tile (digit BINS-1)
 
     // ---- load: warp-striped so that (warp, item, lane) order == input order
     KeyT key[ITEMS];
@@ -250,34 +285,14 @@ onesweep_tile(OnesweepSmem<THREADS, ITEMS, KeyT> &sm, u32 *svals, const KeyT *__
         }
     }
 
-    // ---- early counts (EARLY): tile digit histogram with no-return shared
-    // atomics, so the tile's PARTIAL status is published before the (long)
-    // ranking phase and successors' look-back finds it without spinning.
-    u32 my_count = 0;
-    if (EARLY) {
-#pragma unroll
-        for (int j = 0; j < ITEMS; j++) {
-            const u32 d = (!FULL && (wbase + j * 32) >= n) ? 255u : digit(key[j]);
-            atomicAdd(&sm.tile_cnt[d], 1u);
-        }
-        __syncthreads();
-        if (tid < QCE_RADIX_BINS) {
-            my_count = sm.tile_cnt[tid];
-            // the padding of the last tile is not part of the global count
-            const u32 pub = my_count - ((!FULL && tid == 255) ? (TILE - nvalid) : 0u);
-            st_relaxed_gpu_u32(status + (size_t)tile * QCE_RADIX_BINS + tid,
-                               (tile == 0 ? QCE_ST_INCL : QCE_ST_PART) | pub);
-        }
-    }
-
     // ---- rank inside the warp.  Lanes with the same digit are found with
-    // per-bit ballots (warp_peers_8bit); the lowest of them reserves the group's slots with one shared
-    // atomicAdd (program order within the warp keeps items in input order) and
-    // hands the base to its peers.  Done in chunks of CH items with the three
-    // long-latency steps (ballots, ATOMS, SHFL) each issued back to back, so their
-    // latencies overlap instead of adding up.
+    // per-bit ballots (warp_peers); the lowest of them reserves the group's slots
+    // with one shared atomicAdd (program order within the warp keeps items in
+    // input order) and hands the base to its peers.  Done in chunks of CH items
+    // with the three long-latency steps (ballots, ATOMS, SHFL) each issued back
+    // to back, so their latencies overlap instead of adding up.
     u32 rd[ITEMS]; // digit << 16 | rank inside (warp, digit)
-    u32 *wh = sm.warp_hist + warp * QCE_RADIX_BINS;
+    u32 *wh = sm.warp_hist + warp * BINS;
     const u32 lt = lanemask_lt();
     constexpr int CH = (ITEMS % 4 == 0) ? 4 : ((ITEMS % 3 == 0) ? 3 : 1);
 #pragma unroll
@@ -285,12 +300,13 @@ onesweep_tile(OnesweepSmem<THREADS, ITEMS, KeyT> &sm, u32 *svals, const KeyT *__
         u32 d[CH], peers[CH], old[CH];
 #pragma unroll
         for (int c = 0; c < CH; c++) {
-            d[c] = (!FULL && (wbase + (j0 + c) * 32) >= n) ? 255u : digit(key[j0 + c]);
+            // padding of the last tile must sort behind every real tuple of the tile
+            d[c] = (!FULL && (wbase + (j0 + c) * 32) >= n) ? DMASK : digit(key[j0 + c], DMASK);
             // every MATCH_EVERY-th item goes to match.any: the ADU pipe is idle
             // otherwise, so it takes a share of the ranking off the ALU ballots
             peers[c] = (MATCH_EVERY > 0 && ((j0 + c) % (MATCH_EVERY > 0 ? MATCH_EVERY : 1)) == MATCH_EVERY - 1)
                            ? __match_any_sync(QCE_FULL_MASK, d[c])
-                           : warp_peers_8bit(d[c]);
+                           : warp_peers<BITS>(d[c]);
         }
 #pragma unroll
         for (int c = 0; c < CH; c++) {
@@ -304,44 +320,74 @@ onesweep_tile(OnesweepSmem<THREADS, ITEMS, KeyT> &sm, u32 *svals, const KeyT *__
         }
     }
     __syncthreads(); // all warps have ranked
-    // ---- per digit: exclusive scan of the warp counts
-    if (tid < QCE_RADIX_BINS) {
-        u32 run = 0;
+
+    // ---- per digit (thread t owns bins t*BPT .. t*BPT+BPT-1): exclusive scan of
+    //      the warp counts, tile total, publish the tile-local count
+    u32 cnt[BPT], sum = 0;
 #pragma unroll
-        for (int w = 0; w < WARPS; w++) {
-            const u32 c = sm.warp_hist[w * QCE_RADIX_BINS + tid];
-            sm.warp_hist[w * QCE_RADIX_BINS + tid] = run;
-            run += c;
+    for (int q = 0; q < BPT; q++) {
+        const int b = tid * BPT + q;
+        cnt[q] = 0;
+        if (b < BINS) {
+            u32 run = 0;
+#pragma unroll
+            for (int w = 0; w < WARPS; w++) {
+                const u32 c = sm.warp_hist[w * BINS + b];
+                sm.warp_hist[w * BINS + b] = run;
+                run += c;
+            }
+            cnt[q] = run;
+            // the padding of the last tile is not part of the global count
+            const u32 pub = run - ((!FULL && b == BINS - 1) ? npad : 0u);
+            st_relaxed_gpu_u32(status + (size_t)tile * BINS + b, (tile == 0 ? QCE_ST_INCL : QCE_ST_PART) | pub);
         }
-        if (!EARLY) {
-            my_count = run;
-            const u32 pub = my_count - ((!FULL && tid == 255) ? (TILE - nvalid) : 0u);
-            st_relaxed_gpu_u32(status + (size_t)tile * QCE_RADIX_BINS + tid,
-                               (tile == 0 ? QCE_ST_INCL : QCE_ST_PART) | pub);
-        }
+        sum += cnt[q];
     }
-    // ---- digit starts inside the tile (exclusive scan over the 256 digits)
+    // ---- digit starts inside the tile (exclusive scan over the bins)
     {
         u32 tot;
-        u32 ex = block_scan_excl<u32, THREADS>((tid < QCE_RADIX_BINS) ? my_count : 0u, sm.scratch, &tot);
-        if (tid < QCE_RADIX_BINS) sm.tile_excl[tid] = ex;
-    }
-    if (tid < QCE_RADIX_BINS) {
-        // ---- decoupled look-back: sum the counts of the preceding tiles
-        u32 excl = 0;
-        if (tile > 0) {
-            const u32 pub = my_count - ((!FULL && tid == 255) ? (TILE - nvalid) : 0u);
-            int p = (int)tile - 1;
-            while (true) {
-                const u32 v = ld_relaxed_gpu_u32(status + (size_t)p * QCE_RADIX_BINS + tid);
-                if ((v & ~QCE_ST_MASK) == 0) { __nanosleep(20); continue; }
-                excl += v & QCE_ST_MASK;
-                if (v & QCE_ST_INCL) break;
-                p--;
-            }
-            st_relaxed_gpu_u32(status + (size_t)tile * QCE_RADIX_BINS + tid, QCE_ST_INCL | (excl + pub));
+        u32 ex = block_scan_excl<u32, THREADS>(sum, sm.scratch, &tot);
+#pragma unroll
+        for (int q = 0; q < BPT; q++) {
+            const int b = tid * BPT + q;
+            if (b < BINS) sm.tile_excl[b] = ex;
+            ex += cnt[q];
         }
-        sm.goff[tid] = gbase[tid] + excl - sm.tile_excl[tid];
+    }
+    // ---- decoupled look-back: sum the counts of the preceding tiles.  The status
+    //      words of LB predecessors are fetched together (one L2 round trip).
+#pragma unroll
+    for (int q = 0; q < BPT; q++) {
+        const int b = tid * BPT + q;
+        if (b < BINS) {
+            u32 excl = 0;
+            if (tile > 0) {
+                const u32 pub = cnt[q] - ((!FULL && b == BINS - 1) ? npad : 0u);
+                constexpr int LB = 4;
+                int p = (int)tile - 1;
+                bool done = false;
+                while (!done) {
+                    u32 v[LB];
+#pragma unroll
+                    for (int k = 0; k < LB; k++)
+                        v[k] = (p - k >= 0) ? ld_relaxed_gpu_u32(status + (size_t)(p - k) * BINS + b)
+                                            : QCE_ST_INCL; // before tile 0: inclusive prefix 0
+                    int used = 0;
+#pragma unroll
+                    for (int k = 0; k < LB; k++) {
+                        if (!done && used == k && (v[k] & ~QCE_ST_MASK) != 0) {
+                            excl += v[k] & QCE_ST_MASK;
+                            done = (v[k] & QCE_ST_INCL) != 0;
+                            used = k + 1;
+                        }
+                    }
+                    p -= used; // resume at the first tile that had not published yet
+                    if (!done && used < LB) __nanosleep(20);
+                }
+                st_relaxed_gpu_u32(status + (size_t)tile * BINS + b, QCE_ST_INCL | (excl + pub));
+            }
+            sm.goff[b] = gbase[b] + excl - sm.tile_excl[b];
+        }
     }
     __syncthreads();
 
@@ -362,39 +408,128 @@ onesweep_tile(OnesweepSmem<THREADS, ITEMS, KeyT> &sm, u32 *svals, const KeyT *__
         const u32 p = tid + j * THREADS;
         if (FULL || p < nvalid) {
             const KeyT k = sm.keys[p];
-            const u32 g = sm.goff[digit(k)] + p;
+            const u32 g = sm.goff[digit(k, DMASK)] + p;
             keys_out[g] = k;
             if (HAS_VALS) vals_out[g] = svals[p];
         }
     }
 }
 
-template <int THREADS, int ITEMS, int MIN_CTAS, bool EARLY, int MATCH_EVERY, bool HAS_VALS, typename KeyT, typename DigitOp>
+template <int THREADS, int ITEMS, int MIN_CTAS, int BITS, int MATCH_EVERY, bool HAS_VALS, typename KeyT,
+          typename DigitOp>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 k_onesweep(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out,
            const u32 *__restrict__ vals_in, u32 *__restrict__ vals_out, u32 n, DigitOp digit,
            const u32 *__restrict__ gbase, u32 *__restrict__ status, u32 *__restrict__ tile_counter)
 {
-    static_assert(THREADS >= QCE_RADIX_BINS && THREADS * ITEMS <= 65536, "tile shape");
+    static_assert(THREADS * ITEMS <= 65536 && ITEMS * 32 < 65536, "tile shape");
     constexpr int TILE = THREADS * ITEMS;
     constexpr int WARPS = THREADS / 32;
+    constexpr int BINS = 1 << BITS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    OnesweepSmem<THREADS, ITEMS, KeyT> &sm = *reinterpret_cast<OnesweepSmem<THREADS, ITEMS, KeyT> *>(smem_raw);
-    u32 *svals = reinterpret_cast<u32 *>(smem_raw + sizeof(OnesweepSmem<THREADS, ITEMS, KeyT>));
+    typedef OnesweepSmem<THREADS, ITEMS, BITS, KeyT> Smem;
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    u32 *svals = reinterpret_cast<u32 *>(smem_raw + sizeof(Smem));
 
     // Tiles are claimed in launch order so that every tile a CTA may wait on in
     // the look-back is owned by a CTA that is already resident.
     if (threadIdx.x == 0) sm.tile_id = atomicAdd(tile_counter, 1u);
-    for (int i = threadIdx.x; i < WARPS * QCE_RADIX_BINS; i += THREADS) sm.warp_hist[i] = 0;
-    if (threadIdx.x < QCE_RADIX_BINS) sm.tile_cnt[threadIdx.x] = 0;
+    for (int i = threadIdx.x; i < WARPS * BINS; i += THREADS) sm.warp_hist[i] = 0;
     __syncthreads();
     const u32 tile = sm.tile_id;
     if ((tile + 1) * (u32)TILE <= n)
-        onesweep_tile<THREADS, ITEMS, HAS_VALS, true, EARLY, MATCH_EVERY, KeyT>(sm, svals, keys_in, keys_out, vals_in, vals_out, n, digit,
-                                                      gbase, status, tile);
+        onesweep_tile<THREADS, ITEMS, BITS, HAS_VALS, true, MATCH_EVERY, KeyT>(sm, svals, keys_in, keys_out, vals_in,
+                                                                              vals_out, n, digit, gbase, status, tile);
     else
-        onesweep_tile<THREADS, ITEMS, HAS_VALS, false, EARLY, MATCH_EVERY, KeyT>(sm, svals, keys_in, keys_out, vals_in, vals_out, n, digit,
-                                                       gbase, status, tile);
+        onesweep_tile<THREADS, ITEMS, BITS, HAS_VALS, false, MATCH_EVERY, KeyT>(sm, svals, keys_in, keys_out, vals_in,
+                                                                               vals_out, n, digit, gbase, status, tile);
+}
+
+// ---- small runs: whole sort in one CTA's shared memory --------------------------
+// Replaces the reference's small-bucket sort (random_quicksort, src/quicksort.c:
+// 54-64, used below 4096 tuples -- src/join.c:6,56).  A run of up to THREADS*ITEMS
+// tuples is loaded once, every digit pass ranks it with the same ballot scheme as
+// k_onesweep and permutes it between two shared-memory buffers, and it is written
+// back once: one launch instead of histogram + prefix + one launch per digit (and
+// their look-back arrays), which is what bounds the many-small-queries regime.
+// Stable, like the large path.
+template <int THREADS, int ITEMS, bool HAS_VALS>
+__global__ void __launch_bounds__(THREADS)
+k_block_sort(u64 *__restrict__ keys, u32 *__restrict__ vals, u32 n, RadixShifts rs)
+{
+    constexpr int TILE = THREADS * ITEMS;
+    constexpr int WARPS = THREADS / 32;
+    constexpr int BINS = 256;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64 *skeys = reinterpret_cast<u64 *>(smem_raw);                       // TILE
+    u32 *svals = reinterpret_cast<u32 *>(skeys + TILE);                   // TILE (HAS_VALS)
+    u32 *warp_hist = svals + (HAS_VALS ? TILE : 0);                       // WARPS * BINS
+    u32 *tile_excl = warp_hist + WARPS * BINS;                            // BINS
+    u32 *scratch = tile_excl + BINS;                                      // 33
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 lt = lanemask_lt();
+    const u32 slot0 = warp * (32 * ITEMS) + lane; // warp-striped: (warp, item, lane) == run order
+
+    u64 key[ITEMS];
+    u32 val[HAS_VALS ? ITEMS : 1];
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+        const u32 idx = slot0 + j * 32;
+        key[j] = (idx < n) ? keys[idx] : ~0ull; // padding: digit 255 in every pass, stays last
+        if (HAS_VALS) val[j] = (idx < n) ? vals[idx] : 0u;
+    }
+    for (int p = 0; p < rs.npass; p++) {
+        const int shift = rs.shift[p];
+        for (int i = tid; i < WARPS * BINS; i += THREADS) warp_hist[i] = 0;
+        __syncthreads();
+        u32 rd[ITEMS];
+        u32 *wh = warp_hist + warp * BINS;
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) {
+            const u32 d = (u32)(key[j] >> shift) & 255u;
+            const u32 peers = warp_peers<8>(d);
+            u32 old = 0;
+            if ((peers & lt) == 0) old = atomicAdd(&wh[d], (u32)__popc(peers));
+            old = __shfl_sync(QCE_FULL_MASK, old, __ffs(peers) - 1);
+            rd[j] = (d << 16) | (old + __popc(peers & lt));
+        }
+        __syncthreads();
+        u32 cnt = 0;
+        if (tid < BINS) {
+#pragma unroll
+            for (int w = 0; w < WARPS; w++) {
+                const u32 c = warp_hist[w * BINS + tid];
+                warp_hist[w * BINS + tid] = cnt;
+                cnt += c;
+            }
+        }
+        u32 tot;
+        const u32 ex = block_scan_excl<u32, THREADS>(cnt, scratch, &tot);
+        if (tid < BINS) tile_excl[tid] = ex;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) {
+            const u32 d = rd[j] >> 16;
+            const u32 pos = tile_excl[d] + wh[d] + (rd[j] & 0xffffu);
+            skeys[pos] = key[j];
+            if (HAS_VALS) svals[pos] = val[j];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) {
+            key[j] = skeys[slot0 + j * 32];
+            if (HAS_VALS) val[j] = svals[slot0 + j * 32];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+        const u32 idx = slot0 + j * 32;
+        if (idx < n) {
+            keys[idx] = key[j];
+            if (HAS_VALS) vals[idx] = val[j];
+        }
+    }
 }
 
 // 1 if keys[i-1] > keys[i] anywhere (checks the "already sorted" assumption of

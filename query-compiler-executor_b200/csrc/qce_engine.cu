@@ -292,7 +292,10 @@ int compact_from_mask(int layout, int mode, const u32 *mask, const u32 *tile_cou
 {
     u32 *tile_off = nullptr;
     if (dalloc(&tile_off, ntiles) != 0) return -1;
-    LAUNCH("scan_tiles", (k_scan_excl<u32, u32>), 1, 1024, 0, tile_count, tile_off, ntiles, g.d_scalars);
+    if (ntiles <= 512)
+        LAUNCH("scan_tiles", (k_scan_excl_warp<u32, u32>), 1, 32, 0, tile_count, tile_off, ntiles, g.d_scalars);
+    else
+        LAUNCH("scan_tiles", (k_scan_excl<u32, u32>), 1, 1024, 0, tile_count, tile_off, ntiles, g.d_scalars);
     if (read_scalars(1) != 0) return -1;
     const u64 m = g.h_scalars[0];
     if (new_rowids(m, id_bound0, out0) != 0) return -1;
@@ -322,30 +325,30 @@ int compact_from_mask(int layout, int mode, const u32 *mask, const u32 *tile_cou
 // ---- radix sort driver -------------------------------------------------------
 // Tile shapes of the one-sweep pass.  The default was picked by sweeping them on
 // B200 (tools/sort_bench.py, profiles/); QCE_ONESWEEP_CFG=<index> overrides it.
-struct OnesweepCfg { int threads, items, min_ctas, early, match_every; };
-static const OnesweepCfg kOnesweepCfgs[] = {{256, 16, 4, 1, 0}, {256, 16, 4, 0, 0}, {256, 16, 4, 1, 4}, {256, 16, 4, 0, 4},
-                                            {256, 16, 3, 0, 4}, {384, 12, 3, 0, 4}, {512, 8, 3, 0, 4},  {256, 24, 2, 0, 4},
-                                            {256, 16, 4, 0, 2}, {256, 16, 3, 0, 0}};
+struct OnesweepCfg { int threads, items, min_ctas, match_every; };
+static const OnesweepCfg kOnesweepCfgs[] = {{256, 16, 4, 4}, {256, 16, 3, 4}, {256, 24, 2, 4}, {384, 12, 3, 4},
+                                            {512, 8, 3, 4},  {256, 16, 4, 0}};
 constexpr int kNumOnesweepCfgs = (int)(sizeof(kOnesweepCfgs) / sizeof(kOnesweepCfgs[0]));
 static int g_onesweep_cfg = -1;
 static int onesweep_cfg()
 {
     if (g_onesweep_cfg < 0) {
         const char *e = getenv("QCE_ONESWEEP_CFG");
-        int c = e ? atoi(e) : 3;
+        int c = e ? atoi(e) : 0;
         g_onesweep_cfg = (c >= 0 && c < kNumOnesweepCfgs) ? c : 0;
     }
     return g_onesweep_cfg;
 }
 static int onesweep_tile_size() { const OnesweepCfg &c = kOnesweepCfgs[onesweep_cfg()]; return c.threads * c.items; }
 
-template <int THREADS, int ITEMS, int MIN_CTAS, bool EARLY, int MATCH_EVERY, bool HAS_VALS, typename KeyT, typename DigitOp>
+template <int THREADS, int ITEMS, int MIN_CTAS, int BITS, int MATCH_EVERY, bool HAS_VALS, typename KeyT,
+          typename DigitOp>
 int launch_onesweep_cfg(const KeyT *kin, KeyT *kout, const u32 *vin, u32 *vout, u32 n, DigitOp dop,
                         const u32 *gbase, u32 *status, u32 *counter)
 {
-    auto kern = k_onesweep<THREADS, ITEMS, MIN_CTAS, EARLY, MATCH_EVERY, HAS_VALS, KeyT, DigitOp>;
+    auto kern = k_onesweep<THREADS, ITEMS, MIN_CTAS, BITS, MATCH_EVERY, HAS_VALS, KeyT, DigitOp>;
     constexpr int TILE = THREADS * ITEMS;
-    const size_t smem = sizeof(OnesweepSmem<THREADS, ITEMS, KeyT>) + (HAS_VALS ? TILE * sizeof(u32) : 0);
+    const size_t smem = sizeof(OnesweepSmem<THREADS, ITEMS, BITS, KeyT>) + (HAS_VALS ? TILE * sizeof(u32) : 0);
     static bool attr_set = false; // per instantiation
     if (!attr_set) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -357,57 +360,85 @@ int launch_onesweep_cfg(const KeyT *kin, KeyT *kout, const u32 *vin, u32 *vout, 
     return 0;
 }
 
-template <bool HAS_VALS, typename KeyT, typename DigitOp>
+// BITS = 8 (256 bins) or 9 (512 bins, when it saves a pass)
+template <bool HAS_VALS, int BITS, typename KeyT, typename DigitOp>
 int launch_onesweep(const KeyT *kin, KeyT *kout, const u32 *vin, u32 *vout, u32 n, DigitOp dop,
                     const u32 *gbase, u32 *status, u32 *counter)
 {
-#define QCE_OS_CASE(I, T, IT, MC, EA, ME) \
-    case I: return launch_onesweep_cfg<T, IT, MC, EA, ME, HAS_VALS, KeyT>(kin, kout, vin, vout, n, dop, gbase, status, counter);
+#define QCE_OS_CASE(I, T, IT, MC, ME) \
+    case I: return launch_onesweep_cfg<T, IT, MC, BITS, ME, HAS_VALS, KeyT>(kin, kout, vin, vout, n, dop, gbase, status, counter);
     switch (onesweep_cfg()) {
-        QCE_OS_CASE(0, 256, 16, 4, true, 0)
-        QCE_OS_CASE(1, 256, 16, 4, false, 0)
-        QCE_OS_CASE(2, 256, 16, 4, true, 4)
-        QCE_OS_CASE(3, 256, 16, 4, false, 4)
-        QCE_OS_CASE(4, 256, 16, 3, false, 4)
-        QCE_OS_CASE(5, 384, 12, 3, false, 4)
-        QCE_OS_CASE(6, 512, 8, 3, false, 4)
-        QCE_OS_CASE(7, 256, 24, 2, false, 4)
-        QCE_OS_CASE(8, 256, 16, 4, false, 2)
-        QCE_OS_CASE(9, 256, 16, 3, false, 0)
+        QCE_OS_CASE(0, 256, 16, 4, 4)
+        QCE_OS_CASE(1, 256, 16, 3, 4)
+        QCE_OS_CASE(2, 256, 24, 2, 4)
+        QCE_OS_CASE(3, 384, 12, 3, 4)
+        QCE_OS_CASE(4, 512, 8, 3, 4)
+        QCE_OS_CASE(5, 256, 16, 4, 0)
     }
 #undef QCE_OS_CASE
     return fail("bad one-sweep configuration");
 }
 
+constexpr int BS_THREADS = 512, BS_ITEMS = 8, BS_TILE = BS_THREADS * BS_ITEMS; // block sort: runs <= 4096 tuples
+
 // Sort words (and optional 32-bit values) by the digits listed in rs, least
 // significant first.  *keys / *vals are replaced by the sorted buffers.
-int radix_sort(u64 **keys, u32 **vals, u64 n, const RadixShifts &rs)
+int radix_sort(u64 **keys, u32 **vals, u64 n, const RadixShifts &rs, int digit_bits = QCE_RADIX_BITS)
 {
     if (n <= 1 || rs.npass == 0) return 0;
     if (n >= (1ull << 30)) return fail("sort of %llu tuples exceeds the 2^30 per-run limit", (unsigned long long)n);
+    if (n <= BS_TILE) {
+        // small run: the whole sort in one CTA (k_block_sort), in place
+        const size_t smem = BS_TILE * sizeof(u64) + (vals ? BS_TILE * sizeof(u32) : 0) +
+                            ((BS_THREADS / 32) * 256 + 256 + 33) * sizeof(u32);
+        static bool attr_k = false, attr_kv = false;
+        if (vals) {
+            if (!attr_kv) {
+                CK(cudaFuncSetAttribute(k_block_sort<BS_THREADS, BS_ITEMS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                attr_kv = true;
+            }
+            LAUNCH("block_sort", (k_block_sort<BS_THREADS, BS_ITEMS, true>), 1, BS_THREADS, smem, *keys, *vals, (u32)n, rs);
+        } else {
+            if (!attr_k) {
+                CK(cudaFuncSetAttribute(k_block_sort<BS_THREADS, BS_ITEMS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                attr_k = true;
+            }
+            LAUNCH("block_sort", (k_block_sort<BS_THREADS, BS_ITEMS, false>), 1, BS_THREADS, smem, *keys, (u32 *)nullptr, (u32)n, rs);
+        }
+        return 0;
+    }
+    const u32 bins = 1u << digit_bits;
     const u32 ntiles = (u32)ceil_div(n, onesweep_tile_size());
     u64 *alt_k = nullptr;
     u32 *alt_v = nullptr, *ghist = nullptr, *gbase = nullptr, *status = nullptr, *counters = nullptr;
     if (dalloc(&alt_k, n) != 0) return -1;
     if (vals && dalloc(&alt_v, n) != 0) return -1;
-    if (dalloc(&ghist, (u64)rs.npass * QCE_RADIX_BINS) != 0) return -1;
-    if (dalloc(&gbase, (u64)rs.npass * QCE_RADIX_BINS) != 0) return -1;
-    if (dalloc(&status, (u64)rs.npass * ntiles * QCE_RADIX_BINS) != 0) return -1;
+    if (dalloc(&ghist, (u64)rs.npass * bins) != 0) return -1;
+    if (dalloc(&gbase, (u64)rs.npass * bins) != 0) return -1;
+    if (dalloc(&status, (u64)rs.npass * ntiles * bins) != 0) return -1;
     if (dalloc(&counters, (u64)rs.npass) != 0) return -1;
-    CK(cudaMemsetAsync(ghist, 0, (u64)rs.npass * QCE_RADIX_BINS * sizeof(u32), g.stream));
-    CK(cudaMemsetAsync(status, 0, (u64)rs.npass * ntiles * QCE_RADIX_BINS * sizeof(u32), g.stream));
+    CK(cudaMemsetAsync(ghist, 0, (u64)rs.npass * bins * sizeof(u32), g.stream));
+    CK(cudaMemsetAsync(status, 0, (u64)rs.npass * ntiles * bins * sizeof(u32), g.stream));
     CK(cudaMemsetAsync(counters, 0, (u64)rs.npass * sizeof(u32), g.stream));
-    LAUNCH("radix_hist", k_radix_hist, grid_for(1024, n, 4), 512, 0, *keys, n, rs, ghist);
-    LAUNCH("radix_bases", k_radix_bases, rs.npass, 256, 0, ghist, gbase);
+    LAUNCH("radix_hist", k_radix_hist, grid_for(1024, n, 4), 512, 0, *keys, n, rs, bins, ghist);
+    LAUNCH("radix_bases", k_radix_bases, rs.npass, bins, 0, ghist, gbase);
 
     u64 *kin = *keys, *kout = alt_k;
     u32 *vin = vals ? *vals : nullptr, *vout = alt_v;
     for (int p = 0; p < rs.npass; p++) {
         DigitShift dop{rs.shift[p]};
-        int rc = vals ? launch_onesweep<true, u64>(kin, kout, vin, vout, (u32)n, dop, gbase + p * QCE_RADIX_BINS,
-                                              status + (u64)p * ntiles * QCE_RADIX_BINS, counters + p)
-                      : launch_onesweep<false, u64>(kin, kout, vin, vout, (u32)n, dop, gbase + p * QCE_RADIX_BINS,
-                                               status + (u64)p * ntiles * QCE_RADIX_BINS, counters + p);
+        DigitShiftHi dhi{rs.shift[p] - 32};
+        u32 *gb = gbase + p * bins, *st = status + (u64)p * ntiles * bins;
+        const u32 m = (u32)n;
+        int rc;
+        if (vals)
+            rc = launch_onesweep<true, 8, u64>(kin, kout, vin, vout, m, dop, gb, st, counters + p);
+        else if (digit_bits == 9)
+            rc = rs.shift[p] >= 32 ? launch_onesweep<false, 9, u64>(kin, kout, vin, vout, m, dhi, gb, st, counters + p)
+                                   : launch_onesweep<false, 9, u64>(kin, kout, vin, vout, m, dop, gb, st, counters + p);
+        else
+            rc = rs.shift[p] >= 32 ? launch_onesweep<false, 8, u64>(kin, kout, vin, vout, m, dhi, gb, st, counters + p)
+                                   : launch_onesweep<false, 8, u64>(kin, kout, vin, vout, m, dop, gb, st, counters + p);
         if (rc != 0) return -1;
         std::swap(kin, kout);
         std::swap(vin, vout);
@@ -424,11 +455,28 @@ int radix_sort(u64 **keys, u32 **vals, u64 n, const RadixShifts &rs)
     return 0;
 }
 
-RadixShifts shifts_for(int base_shift, int bits)
+// Digit plan for `bits` significant key bits starting at word bit `base_shift`:
+// 9-bit digits when that saves a whole pass over 8-bit digits (9, 17-18, 25-27,
+// 33-36 ... bits; keys-only runs), otherwise 8-bit.  The digit width is the same
+// for every pass of one sort; the last digit may cover bits above the key, which
+// are zero.
+int digit_bits_for(int bits, bool keys_only)
+{
+    static int force = -1; // QCE_DIGIT_BITS=8|9 overrides
+    if (force < 0) {
+        const char *e = getenv("QCE_DIGIT_BITS");
+        force = e ? atoi(e) : 0;
+    }
+    if (!keys_only) return 8;
+    if (force == 8 || force == 9) return force;
+    (void)bits;
+    return 8; // 9-bit digits measured slower on B200: +35 % per pass outweighs the saved pass (profiles/)
+}
+RadixShifts shifts_for(int base_shift, int bits, int digit_bits = QCE_RADIX_BITS)
 {
     RadixShifts rs;
     rs.npass = 0;
-    for (int b = 0; b < bits && rs.npass < QCE_MAX_PASSES; b += QCE_RADIX_BITS) rs.shift[rs.npass++] = base_shift + b;
+    for (int b = 0; b < bits && rs.npass < QCE_MAX_PASSES; b += digit_bits) rs.shift[rs.npass++] = base_shift + b;
     for (int i = rs.npass; i < QCE_MAX_PASSES; i++) rs.shift[i] = 0;
     return rs;
 }
@@ -476,9 +524,15 @@ int merge_join_t(const qce_tuples *R, const qce_tuples *S, bool want_r, bool wan
         LAUNCH("join_bounds", (k_join_bounds<WR, WS>), (int)ntiles, QCE_JTHREADS, QCE_JSMEM_BYTES, vr, nR, vs, win,
                lb, cnt, tile_total, tile_chunks);
     }
-    LAUNCH("scan_tiles", (k_scan_excl<u64, u64>), 1, 1024, 0, tile_total, tile_off, (u64)ntiles, g.d_scalars);
-    LAUNCH("scan_tiles", (k_scan_excl<u32, u32>), 1, 1024, 0, tile_chunks, chunk_off, (u64)ntiles,
-           g.d_scalars + 1);
+    if (ntiles <= 512) {
+        LAUNCH("scan_tiles", (k_scan_excl_warp<u64, u64>), 1, 32, 0, tile_total, tile_off, (u64)ntiles, g.d_scalars);
+        LAUNCH("scan_tiles", (k_scan_excl_warp<u32, u32>), 1, 32, 0, tile_chunks, chunk_off, (u64)ntiles,
+               g.d_scalars + 1);
+    } else {
+        LAUNCH("scan_tiles", (k_scan_excl<u64, u64>), 1, 1024, 0, tile_total, tile_off, (u64)ntiles, g.d_scalars);
+        LAUNCH("scan_tiles", (k_scan_excl<u32, u32>), 1, 1024, 0, tile_chunks, chunk_off, (u64)ntiles,
+               g.d_scalars + 1);
+    }
     if (read_scalars(2) != 0) return -1;
     const u64 m = g.h_scalars[0], nchunks = g.h_scalars[1];
     if (m >= (1ull << 32)) return fail("join output of %llu pairs exceeds the 2^32 row-id column limit", (unsigned long long)m);
@@ -582,7 +636,7 @@ int partition_ids_by_top_bits(const qce_rowids *ids, u32 **out)
     LAUNCH("hist_u32", k_hist_u32, grid_for(2048, n, 4), 512, 0, ids->d, n, shift, ghist);
     LAUNCH("radix_bases", k_radix_bases, 1, 256, 0, ghist, gbase);
     DigitShift dop{shift};
-    if (launch_onesweep<false, u32>(ids->d, dst, nullptr, nullptr, (u32)n, dop, gbase, status, counter) != 0) return -1;
+    if (launch_onesweep<false, 8, u32>(ids->d, dst, nullptr, nullptr, (u32)n, dop, gbase, status, counter) != 0) return -1;
     dfree(ghist); dfree(gbase); dfree(status); dfree(counter);
     *out = dst;
     return 0;
@@ -920,8 +974,9 @@ int qce_sort_tuples(qce_tuples *t)
 {
     NEED_INIT();
     if (!t) return fail("null tuple run");
-    RadixShifts rs = shifts_for(t->wide ? 0 : 32, t->key_bits);
-    int rc = t->wide ? radix_sort(&t->a, &t->ids, t->n, rs) : radix_sort(&t->a, nullptr, t->n, rs);
+    const int db = digit_bits_for(t->key_bits, !t->wide);
+    RadixShifts rs = shifts_for(t->wide ? 0 : 32, t->key_bits, db);
+    int rc = t->wide ? radix_sort(&t->a, &t->ids, t->n, rs) : radix_sort(&t->a, nullptr, t->n, rs, db);
     if (rc == 0) t->sorted = true;
     return rc;
 }
@@ -1029,8 +1084,9 @@ int qce_rejoin(const qce_rowids *driver, const qce_rowids *last, const qce_rowid
     if (dalloc(&R.a, R.n) || dalloc(&S.a, S.n)) return -1;
     if (R.n) LAUNCH("pack_pairs", k_pack_pairs, grid_for(256, R.n), 256, 0, last->d, edit->d, R.n, R.a);
     if (S.n) LAUNCH("pack_pairs", k_pack_pairs, grid_for(256, S.n), 256, 0, driver->d, (const u32 *)nullptr, S.n, S.a);
-    RadixShifts rs = shifts_for(32, R.key_bits);
-    if (radix_sort(&R.a, nullptr, R.n, rs) != 0 || radix_sort(&S.a, nullptr, S.n, rs) != 0) return -1;
+    const int db = digit_bits_for(R.key_bits, true);
+    RadixShifts rs = shifts_for(32, R.key_bits, db);
+    if (radix_sort(&R.a, nullptr, R.n, rs, db) != 0 || radix_sort(&S.a, nullptr, S.n, rs, db) != 0) return -1;
     int rc = merge_join_any(&R, &S, true, false, out, nullptr);
     dfree(R.a);
     dfree(S.a);
@@ -1205,7 +1261,7 @@ int qce_key_histogram(const qce_tuples *t, uint32_t key_bits, uint64_t *hist)
     rs.npass = 1;
     for (int i = 0; i < QCE_MAX_PASSES; i++) rs.shift[i] = 0;
     rs.shift[0] = 32 + (key_bits > 8 ? (int)key_bits - 8 : 0);
-    if (t->n) LAUNCH("radix_hist", k_radix_hist, grid_for(1024, t->n, 4), 512, 0, t->a, t->n, rs, gh);
+    if (t->n) LAUNCH("radix_hist", k_radix_hist, grid_for(1024, t->n, 4), 512, 0, t->a, t->n, rs, 256u, gh);
     std::vector<u32> tmp(QCE_RADIX_BINS);
     CK(cudaMemcpyAsync(tmp.data(), gh, QCE_RADIX_BINS * sizeof(u32), cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
@@ -1256,14 +1312,14 @@ int qce_partition_tuples(const qce_tuples *t, uint32_t key_bits, const uint64_t 
     rs.shift[0] = ds.shift;
     std::vector<u32> bins(QCE_RADIX_BINS, 0), parts(QCE_RADIX_BINS, 0);
     if (n) {
-        LAUNCH("radix_hist", k_radix_hist, grid_for(1024, n, 4), 512, 0, t->a, n, rs, ghist);
+        LAUNCH("radix_hist", k_radix_hist, grid_for(1024, n, 4), 512, 0, t->a, n, rs, 256u, ghist);
         CK(cudaMemcpyAsync(bins.data(), ghist, QCE_RADIX_BINS * sizeof(u32), cudaMemcpyDeviceToHost, g.stream));
         CK(cudaStreamSynchronize(g.stream));
         for (u32 b = 0; b < 256; b++) parts[lut[b]] += bins[b];
         u32 *part_hist = ghist + QCE_RADIX_BINS;
         CK(cudaMemcpyAsync(part_hist, parts.data(), QCE_RADIX_BINS * sizeof(u32), cudaMemcpyHostToDevice, g.stream));
         LAUNCH("radix_bases", k_radix_bases, 1, 256, 0, part_hist, gbase);
-        if (launch_onesweep<false, u64>((const u64 *)t->a, out, nullptr, nullptr, (u32)n, ds, gbase, status, counter) != 0)
+        if (launch_onesweep<false, 8, u64>((const u64 *)t->a, out, nullptr, nullptr, (u32)n, ds, gbase, status, counter) != 0)
             return -1;
         CK(cudaStreamSynchronize(g.stream)); // the caller hands *sendbuf to another stream
     }

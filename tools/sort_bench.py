@@ -26,7 +26,7 @@ print(json.dumps({"cfg": os.environ.get("QCE_ONESWEEP_CFG"), "ok": ok and srt, "
                   "GBps": 16.0 * n / ms / 1e6, "hist_ms": prof["radix_hist"]["ms"] / 3}))
 ''' % ROOT
 n = sys.argv[1] if len(sys.argv) > 1 else "1e8"
-cfgs = sys.argv[2].split(",") if len(sys.argv) > 2 else [str(i) for i in range(10)]
+cfgs = sys.argv[2].split(",") if len(sys.argv) > 2 else [str(i) for i in range(6)]
 out = []
 for c in cfgs:
     env = dict(os.environ, QCE_ONESWEEP_CFG=c)
