@@ -103,8 +103,9 @@ int qce_build_tuples_base_range(uint32_t rel, uint32_t col, uint64_t row_begin, 
 int qce_build_tuples_rowids(uint32_t rel, uint32_t col, const qce_rowids *ids, qce_tuples **out);
 /* iterative_sort, src/join.c:5-94 (+ build_histogram/build_psum/
  * build_reordered_array, src/utilities.c:20-70; random_quicksort,
- * src/quicksort.c:54-64): ascending by key.  Stable (equal keys keep their
- * input order) -- the reference's tie order is unspecified. */
+ * src/quicksort.c:54-64): ascending by key.  The order among equal keys is
+ * unspecified, as in the reference (its quicksort is rand()-driven): runs below
+ * 2^20 tuples are sorted stably, larger ones may take the MSD partition path. */
 int qce_sort_tuples(qce_tuples *t);
 /* 1 if keys are non-decreasing (the reference never checks; the host layer
  * uses it to refuse JOIN_SORT_* merges over unsorted input). */
@@ -179,9 +180,12 @@ void qce_tuples_free(qce_tuples *t);
 int qce_partition_tuples(const qce_tuples *t, uint32_t key_bits, const uint64_t *splitters,
                          uint32_t nparts, uint64_t *counts, void **sendbuf);
 /* Wrap `n` received packed words (device pointer, copied) as a tuple run.
- * id_bound = exclusive upper bound of the row ids they carry (0 = unknown). */
+ * id_bound = exclusive upper bound of the row ids they carry (0 = unknown);
+ * [key_lo, key_hi] = the key range this rank received (its splitter interval;
+ * key_hi = 0 when unknown) -- it sizes the buckets of the local sort. */
 int qce_tuples_from_device_packed(const void *dev_words, uint64_t n, uint32_t key_bits,
-                                  uint32_t id_bound, qce_tuples **out);
+                                  uint32_t id_bound, uint64_t key_lo, uint64_t key_hi,
+                                  qce_tuples **out);
 int qce_exchange_release(void *sendbuf);
 /* 256-bin histogram of the top 8 significant key bits of a run (for splitter
  * selection from an all-reduced global histogram).  hist = 256 uint64 on host. */

@@ -532,6 +532,337 @@ k_block_sort(u64 *__restrict__ keys, u32 *__restrict__ vals, u32 n, RadixShifts 
     }
 }
 
+// ---- MSD partition + in-shared-memory bucket sort (large, non-skewed runs) -------
+// The reference sorts MSD-first: byte 1, then byte 2 ... per bucket, and hands
+// buckets below 4096 tuples to a small sort (iterative_sort, src/join.c:5-94).
+// The same shape is the cheapest one here, because an MSD partition does not
+// have to be stable: no per-bit ballots, no look-back chain.
+//   pass A   scatter by the top P1 key bits          (k_msd_partition, level 0)
+//   pass B   per bucket, scatter by the next P2 bits (k_msd_partition, level 1)
+//   finish   every sub-bucket (<= 4096 tuples) is sorted on the remaining key
+//            bits inside one CTA's shared memory     (k_msd_local_sort)
+// Inside a tile a key's slot among equal digits comes from a shared-memory
+// cursor (atomicAdd with return); a tile reserves its output range per digit
+// with one global atomicAdd on the bucket's cursor.  Equal keys end up in an
+// unspecified order (as in the reference, whose quicksort is rand()-driven).
+// Skew: if any sub-bucket exceeds the finish kernel's capacity the caller falls
+// back to the LSD one-sweep passes, which do not care about key distribution.
+#define QCE_MSD_THREADS 256
+#define QCE_MSD_ITEMS 16
+#define QCE_MSD_TILE (QCE_MSD_THREADS * QCE_MSD_ITEMS)
+
+// tile_start[b] = first tile of bucket b when every bucket is cut into tiles of
+// QCE_MSD_TILE (one CTA, nbuckets <= 256 threads); tile_start[nbuckets] = total.
+__global__ void __launch_bounds__(256)
+k_msd_tile_starts(const u32 *__restrict__ bucket_size, u32 nbuckets, u32 *__restrict__ tile_start)
+{
+    __shared__ u32 scratch[33];
+    const u32 v = threadIdx.x < nbuckets ? (bucket_size[threadIdx.x] + QCE_MSD_TILE - 1) / QCE_MSD_TILE : 0u;
+    u32 tot;
+    const u32 ex = block_scan_excl<u32, 256>(v, scratch, &tot);
+    if (threadIdx.x < nbuckets) tile_start[threadIdx.x] = ex;
+    if (threadIdx.x == 0) tile_start[nbuckets] = tot;
+}
+
+// Bucket and range of tile `t` (tiles never straddle buckets).
+__device__ __forceinline__ bool msd_locate_tile(u32 t, const u32 *__restrict__ tile_start, const u32 *__restrict__ bucket_off,
+                                                const u32 *__restrict__ bucket_size, u32 nbuckets, u32 &bucket,
+                                                u32 &begin, u32 &count)
+{
+    if (t >= tile_start[nbuckets]) return false;
+    u32 lo = 0, hi = nbuckets; // largest b with tile_start[b] <= t
+    while (hi - lo > 1) {
+        const u32 mid = (lo + hi) >> 1;
+        if (tile_start[mid] <= t) lo = mid; else hi = mid;
+    }
+    // buckets without tiles share their start with the next one: move to the owner
+    while (lo + 1 < nbuckets && tile_start[lo + 1] <= t) lo++;
+    bucket = lo;
+    const u32 local = (t - tile_start[lo]) * QCE_MSD_TILE;
+    begin = bucket_off[lo] + local;
+    count = min((u32)QCE_MSD_TILE, bucket_size[lo] - local);
+    return true;
+}
+
+// Histogram of the level's digit, per bucket: ghist[bucket * bins + digit].
+__global__ void __launch_bounds__(QCE_MSD_THREADS)
+k_msd_hist(const u64 *__restrict__ keys, const u32 *__restrict__ tile_start, const u32 *__restrict__ bucket_off,
+           const u32 *__restrict__ bucket_size, u32 nbuckets, u64 base, int shift, u32 bins, u32 *__restrict__ ghist)
+{
+    __shared__ u32 sh[256];
+    __shared__ u32 s_loc[3];
+    if (threadIdx.x == 0) {
+        u32 b = 0, beg = 0, cnt = 0;
+        if (!msd_locate_tile(blockIdx.x, tile_start, bucket_off, bucket_size, nbuckets, b, beg, cnt)) cnt = 0;
+        s_loc[0] = b; s_loc[1] = beg; s_loc[2] = cnt;
+    }
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    const u32 bucket = s_loc[0], begin = s_loc[1], count = s_loc[2];
+    if (count == 0) return;
+    const u32 mask = bins - 1;
+#pragma unroll 4
+    for (u32 i = threadIdx.x; i < count; i += QCE_MSD_THREADS)
+        atomicAdd(&sh[(u32)((ld_stream_u64(keys + begin + i) - base) >> shift) & mask], 1u);
+    __syncthreads();
+    if (threadIdx.x < bins && sh[threadIdx.x]) atomicAdd(&ghist[bucket * bins + threadIdx.x], sh[threadIdx.x]);
+}
+
+// One unstable partition pass.  cursor[bucket * bins + digit] starts at the
+// global output offset of that (bucket, digit) range and is advanced by the tiles.
+__global__ void __launch_bounds__(QCE_MSD_THREADS)
+k_msd_partition(const u64 *__restrict__ in, u64 *__restrict__ out, const u32 *__restrict__ tile_start,
+                const u32 *__restrict__ bucket_off, const u32 *__restrict__ bucket_size, u32 nbuckets, u64 base,
+                int shift, u32 bins, u32 *__restrict__ cursor)
+{
+    __shared__ u64 skeys[QCE_MSD_TILE];
+    __shared__ u32 cnt[256], excl[256], goff[256];
+    __shared__ u32 scratch[33];
+    __shared__ u32 s_loc[3];
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        u32 b = 0, beg = 0, c = 0;
+        if (!msd_locate_tile(blockIdx.x, tile_start, bucket_off, bucket_size, nbuckets, b, beg, c)) c = 0;
+        s_loc[0] = b; s_loc[1] = beg; s_loc[2] = c;
+    }
+    cnt[tid] = 0;
+    __syncthreads();
+    const u32 bucket = s_loc[0], begin = s_loc[1], count = s_loc[2];
+    if (count == 0) return;
+    const u32 mask = bins - 1;
+
+    u64 key[QCE_MSD_ITEMS];
+    u32 slot[QCE_MSD_ITEMS]; // digit << 16 | slot among the tile's keys with that digit
+#pragma unroll
+    for (int j = 0; j < QCE_MSD_ITEMS; j++) {
+        const u32 i = tid + j * QCE_MSD_THREADS;
+        if (i < count) key[j] = ld_stream_u64(in + begin + i);
+    }
+#pragma unroll
+    for (int j = 0; j < QCE_MSD_ITEMS; j++) {
+        const u32 i = tid + j * QCE_MSD_THREADS;
+        if (i < count) {
+            const u32 d = (u32)((key[j] - base) >> shift) & mask;
+            slot[j] = (d << 16) | atomicAdd(&cnt[d], 1u);
+        }
+    }
+    __syncthreads();
+    {
+        const u32 c = cnt[tid];
+        u32 tot;
+        const u32 ex = block_scan_excl<u32, QCE_MSD_THREADS>(c, scratch, &tot);
+        excl[tid] = ex;
+        // reserve this tile's output range of the (bucket, digit) run
+        goff[tid] = (c ? atomicAdd(&cursor[bucket * bins + tid], c) : 0u) - ex;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < QCE_MSD_ITEMS; j++) {
+        const u32 i = tid + j * QCE_MSD_THREADS;
+        if (i < count) skeys[excl[slot[j] >> 16] + (slot[j] & 0xffffu)] = key[j];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < QCE_MSD_ITEMS; j++) {
+        const u32 p = tid + j * QCE_MSD_THREADS;
+        if (p < count) {
+            const u64 k = skeys[p];
+            out[goff[(u32)((k - base) >> shift) & mask] + p] = k;
+        }
+    }
+}
+
+// Largest segment length (to decide whether every sub-bucket fits the finish kernel).
+__global__ void __launch_bounds__(256) k_max_u32(const u32 *__restrict__ v, u32 n, u32 *__restrict__ out)
+{
+    u32 m = 0;
+    for (u32 i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) m = max(m, v[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(QCE_FULL_MASK, m, o));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// Digit plan of the finish kernel: the remaining key bits split evenly over the
+// passes (11 bits -> 6 + 5), so that no ballots are spent on bits that are zero.
+struct LocalPlan {
+    int npass;
+    int shift[QCE_MAX_PASSES];
+    int bits[QCE_MAX_PASSES];
+};
+__device__ __forceinline__ u32 warp_peers_dyn(u32 d, int bits)
+{
+    u32 peers = QCE_FULL_MASK;
+    for (int b = 0; b < bits; b++) {
+        asm("{\n\t"
+            ".reg .pred p;\n\t"
+            ".reg .b32 t, m, nm;\n\t"
+            "and.b32 t, %1, %2;\n\t"
+            "setp.ne.u32 p, t, 0;\n\t"
+            "vote.sync.ballot.b32 m, p, 0xffffffff;\n\t"
+            "selp.b32 nm, 0, 0xffffffff, p;\n\t"
+            "lop3.b32 %0, %0, m, nm, 0x60;\n\t"
+            "}"
+            : "+r"(peers)
+            : "r"(d), "r"(1u << b));
+    }
+    return peers;
+}
+
+// Finish: CTA s sorts segment s = [seg_off[s], seg_off[s] + seg_size[s]) in place
+// on the planned digits (the key bits below the partition bits), all in shared
+// memory.  Same ranking as k_block_sort; warps whose slots are all past the end
+// of the segment skip the ranking work.  The host picks the smallest THREADS x
+// ITEMS that holds the largest segment.
+template <int THREADS, int ITEMS, int MIN_CTAS>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS)
+k_msd_local_sort(u64 *__restrict__ keys, const u32 *__restrict__ seg_off, const u32 *__restrict__ seg_size,
+                 u64 key_base, LocalPlan plan)
+{
+    constexpr int TILE = THREADS * ITEMS;
+    constexpr int WARPS = THREADS / 32;
+    constexpr int BINS = 256;
+    __shared__ u64 skeys[TILE];
+    __shared__ u32 warp_hist[WARPS * BINS];
+    __shared__ u32 tile_excl[BINS];
+    __shared__ u32 scratch[33];
+    const u32 n = seg_size[blockIdx.x];
+    if (n <= 1) return;
+    u64 *base = keys + seg_off[blockIdx.x];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 lt = lanemask_lt();
+    const u32 slot0 = warp * (32 * ITEMS) + lane;
+    const bool warp_live = (u32)(warp * 32 * ITEMS) < n;
+
+    u64 key[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+        const u32 idx = slot0 + j * 32;
+        key[j] = (idx < n) ? base[idx] : ~0ull;
+    }
+    for (int p = 0; p < plan.npass; p++) {
+        const int shift = plan.shift[p], bits = plan.bits[p];
+        const u32 mask = (1u << bits) - 1, nbins = 1u << bits;
+        for (u32 i = tid; i < WARPS * BINS; i += THREADS) warp_hist[i] = 0;
+        __syncthreads();
+        u32 rd[ITEMS];
+        u32 *wh = warp_hist + warp * BINS;
+        if (warp_live) {
+#pragma unroll
+            for (int j = 0; j < ITEMS; j++) {
+                const u32 idx = slot0 + j * 32;
+                // padding ranks behind every real tuple: top digit, and it comes last in run order
+                const u32 d = (idx < n) ? ((u32)((key[j] - key_base) >> shift) & mask) : mask;
+                const u32 peers = warp_peers_dyn(d, bits);
+                u32 old = 0;
+                if ((peers & lt) == 0) old = atomicAdd(&wh[d], (u32)__popc(peers));
+                old = __shfl_sync(QCE_FULL_MASK, old, __ffs(peers) - 1);
+                rd[j] = (d << 16) | (old + __popc(peers & lt));
+            }
+        }
+        __syncthreads();
+        u32 cnt = 0;
+        if (tid < (int)nbins) {
+#pragma unroll
+            for (int w = 0; w < WARPS; w++) {
+                const u32 c = warp_hist[w * BINS + tid];
+                warp_hist[w * BINS + tid] = cnt;
+                cnt += c;
+            }
+        }
+        u32 tot;
+        const u32 ex = block_scan_excl<u32, THREADS>(cnt, scratch, &tot);
+        if (tid < BINS) tile_excl[tid] = ex;
+        __syncthreads();
+        if (warp_live) {
+#pragma unroll
+            for (int j = 0; j < ITEMS; j++) {
+                const u32 d = rd[j] >> 16;
+                skeys[tile_excl[d] + wh[d] + (rd[j] & 0xffffu)] = key[j];
+            }
+        }
+        __syncthreads();
+        if (warp_live) {
+#pragma unroll
+            for (int j = 0; j < ITEMS; j++) key[j] = skeys[slot0 + j * 32];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+        const u32 idx = slot0 + j * 32;
+        if (idx < n) base[idx] = key[j];
+    }
+}
+
+// Finish, remaining bits R <= 12: one unstable counting sort per sub-bucket on ALL
+// remaining key bits (2^R shared-memory counters).  Equal digits are now equal
+// keys, so no stability is needed: a key's slot inside its digit comes from
+// atomicAdd-with-return on the digit's counter -- no ballots, one pass.
+template <int THREADS, int ITEMS, int MIN_CTAS>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS)
+k_msd_count_sort(u64 *__restrict__ keys, const u32 *__restrict__ seg_off, const u32 *__restrict__ seg_size,
+                 u64 key_base, int rbits)
+{
+    constexpr int TILE = THREADS * ITEMS;
+    constexpr int MAXB = 4096;
+    constexpr int BPT = MAXB / THREADS; // counters per thread in the scan (consecutive)
+    extern __shared__ __align__(16) unsigned char smem_raw[]; // TILE*8 + MAXB*4 + 33*4 bytes
+    u64 *skeys = reinterpret_cast<u64 *>(smem_raw);
+    u32 *cnt = reinterpret_cast<u32 *>(skeys + TILE);
+    u32 *scratch = cnt + MAXB;
+    const u32 n = seg_size[blockIdx.x];
+    if (n <= 1) return;
+    u64 *base = keys + seg_off[blockIdx.x];
+    const int tid = threadIdx.x;
+    const u32 nb = 1u << rbits, mask = nb - 1;
+    for (u32 i = tid; i < nb; i += THREADS) cnt[i] = 0;
+    __syncthreads();
+    u64 key[ITEMS];
+    u32 slot[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+        const u32 i = tid + j * THREADS;
+        if (i < n) key[j] = base[i];
+    }
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+        const u32 i = tid + j * THREADS;
+        if (i < n) slot[j] = atomicAdd(&cnt[(u32)((key[j] - key_base) >> 32) & mask], 1u);
+    }
+    __syncthreads();
+    // exclusive scan of the counters in place (thread t owns nb/THREADS consecutive ones)
+    {
+        const u32 per = (nb + THREADS - 1) / THREADS; // <= BPT
+        u32 c[BPT], sum = 0;
+#pragma unroll
+        for (int q = 0; q < BPT; q++) {
+            const u32 b = tid * per + q;
+            c[q] = (q < (int)per && b < nb) ? cnt[b] : 0u;
+            sum += c[q];
+        }
+        u32 tot;
+        u32 ex = block_scan_excl<u32, THREADS>(sum, scratch, &tot);
+#pragma unroll
+        for (int q = 0; q < BPT; q++) {
+            const u32 b = tid * per + q;
+            if (q < (int)per && b < nb) cnt[b] = ex;
+            ex += c[q];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+        const u32 i = tid + j * THREADS;
+        if (i < n) skeys[cnt[(u32)((key[j] - key_base) >> 32) & mask] + slot[j]] = key[j];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+        const u32 i = tid + j * THREADS;
+        if (i < n) base[i] = skeys[i];
+    }
+}
+
 // 1 if keys[i-1] > keys[i] anywhere (checks the "already sorted" assumption of
 // JOIN_SORT_LHS / JOIN_SORT_RHS, src/join.c:647-658).
 template <bool WIDE>

@@ -39,6 +39,8 @@ struct qce_tuples {
     u64 n;
     bool wide;
     int key_bits;  // significant bits of the largest possible key
+    u64 key_min;   // smallest / largest possible key (column statistics, or the rank's key
+    u64 key_max;   // range after an exchange); they size the MSD buckets
     u32 id_bound;
     bool sorted;
 };
@@ -479,6 +481,116 @@ RadixShifts shifts_for(int base_shift, int bits, int digit_bits = QCE_RADIX_BITS
     for (int b = 0; b < bits && rs.npass < QCE_MAX_PASSES; b += digit_bits) rs.shift[rs.npass++] = base_shift + b;
     for (int i = rs.npass; i < QCE_MAX_PASSES; i++) rs.shift[i] = 0;
     return rs;
+}
+
+// ---- MSD partition + shared-memory finish (k_radix.cuh) --------------------------
+// For large packed runs.  *done = false means "not applicable or skewed": the
+// caller sorts with the LSD passes instead (the run is left untouched).
+constexpr u32 MSD_LOCAL_CAP = 256 * 16; // tuples the largest k_msd_local_sort shape can hold
+int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done)
+{
+    *done = false;
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char *e = getenv("QCE_MSD");
+        enabled = e ? atoi(e) : 1;
+    }
+    if (!enabled || n < (1ull << 20) || n >= (1ull << 30)) return 0;
+    // the kernels work on key - key_min, so a run that covers only a slice of the
+    // key space (a rank's share after the exchange) still spreads over the buckets
+    const u64 base = key_min << 32;
+    key_max -= key_min;
+    const int key_bits = bitlen(key_max);
+    if (key_bits < 9 || key_bits > 32) return 0;
+    // Partition bits P: the smallest count for which a populated sub-bucket holds
+    // at most ~2700 tuples on average (finish capacity 4096), assuming keys spread
+    // over [0, key_max]; anything denser is caught by the max-bucket check below.
+    int P = 9;
+    while (P < 16 && P < key_bits && n / (((key_max >> (key_bits - P)) + 1)) > 2700) P++;
+    if (n / (((key_max >> (key_bits - P)) + 1)) > 2700) return 0; // too dense for 16 partition bits: LSD
+    const int P1 = 8, P2 = P - 8, R = key_bits - P;
+    const int shiftA = 32 + key_bits - P1, shiftB = 32 + key_bits - P;
+    const u32 nbA = 256, nbB = 1u << P2, nsub = nbA * nbB;
+    const u32 ntiles0 = (u32)ceil_div(n, QCE_MSD_TILE);
+
+    u64 *alt = nullptr;
+    u32 *lvl0 = nullptr, *histA = nullptr, *offA = nullptr, *curA = nullptr, *tstart1 = nullptr, *histB = nullptr,
+        *suboff = nullptr, *curB = nullptr;
+    if (dalloc(&alt, n) || dalloc(&lvl0, 4) || dalloc(&histA, nbA) || dalloc(&offA, nbA) || dalloc(&curA, nbA) ||
+        dalloc(&tstart1, nbA + 1) || dalloc(&histB, nsub) || dalloc(&suboff, nsub) || dalloc(&curB, nsub))
+        return -1;
+    // level 0: one bucket = the whole run.  lvl0 = {tile_start[0], tile_start[1], bucket_off, bucket_size}
+    const u32 h_lvl0[4] = {0u, ntiles0, 0u, (u32)n};
+    CK(cudaMemcpyAsync(lvl0, h_lvl0, sizeof h_lvl0, cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemsetAsync(histA, 0, nbA * sizeof(u32), g.stream));
+    CK(cudaMemsetAsync(histB, 0, nsub * sizeof(u32), g.stream));
+    CK(cudaMemsetAsync(g.d_scalars + 10, 0, sizeof(u64), g.stream));
+    LAUNCH("msd_hist", k_msd_hist, ntiles0, QCE_MSD_THREADS, 0, *keys, lvl0, lvl0 + 2, lvl0 + 3, 1u, base, shiftA, nbA,
+           histA);
+    LAUNCH("radix_bases", k_radix_bases, 1, (int)nbA, 0, histA, offA);
+    CK(cudaMemcpyAsync(curA, offA, nbA * sizeof(u32), cudaMemcpyDeviceToDevice, g.stream));
+    LAUNCH("msd_partition", k_msd_partition, ntiles0, QCE_MSD_THREADS, 0, *keys, alt, lvl0, lvl0 + 2, lvl0 + 3, 1u,
+           base, shiftA, nbA, curA);
+    // level 1: the 256 buckets of level 0, each cut into tiles of its own
+    const u32 ntiles1 = ntiles0 + nbA; // upper bound; surplus CTAs exit
+    LAUNCH("msd_tiles", k_msd_tile_starts, 1, 256, 0, histA, nbA, tstart1);
+    LAUNCH("msd_hist", k_msd_hist, ntiles1, QCE_MSD_THREADS, 0, alt, tstart1, offA, histA, nbA, base, shiftB, nbB,
+           histB);
+    LAUNCH("scan_tiles", (k_scan_excl<u32, u32>), 1, 1024, 0, histB, suboff, (u64)nsub, g.d_scalars + 11);
+    LAUNCH("msd_max", k_max_u32, grid_for(256, nsub, 1), 256, 0, histB, nsub, (u32 *)(g.d_scalars + 10));
+    CK(cudaMemcpyAsync(g.h_scalars + 10, g.d_scalars + 10, sizeof(u64), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    const u32 max_sub = (u32)(g.h_scalars[10] & 0xffffffffu);
+    if (max_sub <= MSD_LOCAL_CAP) {
+        CK(cudaMemcpyAsync(curB, suboff, nsub * sizeof(u32), cudaMemcpyDeviceToDevice, g.stream));
+        LAUNCH("msd_partition", k_msd_partition, ntiles1, QCE_MSD_THREADS, 0, alt, *keys, tstart1, offA, histA, nbA,
+               base, shiftB, nbB, curB);
+        if (R > 0 && R <= 12) {
+            const size_t sm8 = 256 * 8 * sizeof(u64) + 4096 * sizeof(u32) + 33 * sizeof(u32);
+            const size_t sm16 = 256 * 16 * sizeof(u64) + 4096 * sizeof(u32) + 33 * sizeof(u32);
+            static bool attr_set = false;
+            if (!attr_set) {
+                CK(cudaFuncSetAttribute(k_msd_count_sort<256, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm8));
+                CK(cudaFuncSetAttribute(k_msd_count_sort<256, 16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16));
+                attr_set = true;
+            }
+            if (max_sub <= 256 * 8)
+                LAUNCH("msd_count_sort", (k_msd_count_sort<256, 8, 4>), nsub, 256, sm8, *keys, suboff, histB, base, R);
+            else
+                LAUNCH("msd_count_sort", (k_msd_count_sort<256, 16, 3>), nsub, 256, sm16, *keys, suboff, histB, base, R);
+        } else if (R > 0) {
+            LocalPlan plan;
+            plan.npass = (R + 7) / 8;
+            int at = 32;
+            for (int p = 0; p < QCE_MAX_PASSES; p++) {
+                const int left = R - (at - 32), passes_left = plan.npass - p;
+                plan.bits[p] = p < plan.npass ? (left + passes_left - 1) / passes_left : 0;
+                plan.shift[p] = at;
+                at += plan.bits[p];
+            }
+            if (max_sub <= 256 * 8)
+                LAUNCH("msd_local_sort", (k_msd_local_sort<256, 8, 5>), nsub, 256, 0, *keys, suboff, histB, base, plan);
+            else
+                LAUNCH("msd_local_sort", (k_msd_local_sort<256, 16, 2>), nsub, 256, 0, *keys, suboff, histB, base, plan);
+        }
+        *done = true;
+    }
+    dfree(alt); dfree(lvl0); dfree(histA); dfree(offA); dfree(curA); dfree(tstart1); dfree(histB); dfree(suboff);
+    dfree(curB);
+    return 0;
+}
+
+// Sort a packed run on its `key_bits` key bits.
+int sort_packed(u64 **a, u64 n, int key_bits, u64 key_min, u64 key_max)
+{
+    bool done = false;
+    if (key_max == 0 || key_max >= (1ull << key_bits)) key_max = (1ull << key_bits) - 1;
+    if (key_min > key_max) key_min = 0;
+    if (msd_sort(a, n, key_min, key_max, &done) != 0) return -1;
+    if (done) return 0;
+    const int db = digit_bits_for(key_bits, true);
+    RadixShifts rs = shifts_for(32, key_bits, db);
+    return radix_sort(a, nullptr, n, rs, db);
 }
 
 TupleView view_of(const qce_tuples *t)
@@ -927,6 +1039,8 @@ static int build_tuples(const Column *cl, const qce_rowids *ids, qce_tuples **ou
     qce_tuples *t = new qce_tuples();
     t->n = n;
     t->key_bits = bitlen(cl->maxv) ? bitlen(cl->maxv) : 1;
+    t->key_min = 0;
+    t->key_max = cl->maxv;
     t->wide = t->key_bits > 32;
     t->id_bound = (u32)cl->n;
     t->sorted = false;
@@ -974,9 +1088,13 @@ int qce_sort_tuples(qce_tuples *t)
 {
     NEED_INIT();
     if (!t) return fail("null tuple run");
-    const int db = digit_bits_for(t->key_bits, !t->wide);
-    RadixShifts rs = shifts_for(t->wide ? 0 : 32, t->key_bits, db);
-    int rc = t->wide ? radix_sort(&t->a, &t->ids, t->n, rs) : radix_sort(&t->a, nullptr, t->n, rs, db);
+    int rc;
+    if (t->wide) {
+        RadixShifts rs = shifts_for(0, t->key_bits, 8);
+        rc = radix_sort(&t->a, &t->ids, t->n, rs);
+    } else {
+        rc = sort_packed(&t->a, t->n, t->key_bits, t->key_min, t->key_max);
+    }
     if (rc == 0) t->sorted = true;
     return rc;
 }
@@ -1079,14 +1197,13 @@ int qce_rejoin(const qce_rowids *driver, const qce_rowids *last, const qce_rowid
                     (unsigned long long)edit->n, (unsigned long long)last->n);
     const int bits = last->id_bound ? bitlen(last->id_bound - 1) : 32;
     qce_tuples R, S;
-    R.n = last->n; R.wide = false; R.ids = nullptr; R.key_bits = bits ? bits : 1; R.id_bound = edit->id_bound; R.sorted = false; R.a = nullptr;
+    R.n = last->n; R.key_min = 0; S.key_min = 0; R.key_max = 0; S.key_max = 0; R.wide = false; R.ids = nullptr; R.key_bits = bits ? bits : 1; R.id_bound = edit->id_bound; R.sorted = false; R.a = nullptr;
     S.n = driver->n; S.wide = false; S.ids = nullptr; S.key_bits = R.key_bits; S.id_bound = 0; S.sorted = false; S.a = nullptr;
     if (dalloc(&R.a, R.n) || dalloc(&S.a, S.n)) return -1;
     if (R.n) LAUNCH("pack_pairs", k_pack_pairs, grid_for(256, R.n), 256, 0, last->d, edit->d, R.n, R.a);
     if (S.n) LAUNCH("pack_pairs", k_pack_pairs, grid_for(256, S.n), 256, 0, driver->d, (const u32 *)nullptr, S.n, S.a);
-    const int db = digit_bits_for(R.key_bits, true);
-    RadixShifts rs = shifts_for(32, R.key_bits, db);
-    if (radix_sort(&R.a, nullptr, R.n, rs, db) != 0 || radix_sort(&S.a, nullptr, S.n, rs, db) != 0) return -1;
+    const u64 id_max = last->id_bound ? last->id_bound - 1 : 0;
+    if (sort_packed(&R.a, R.n, R.key_bits, 0, id_max) != 0 || sort_packed(&S.a, S.n, S.key_bits, 0, id_max) != 0) return -1;
     int rc = merge_join_any(&R, &S, true, false, out, nullptr);
     dfree(R.a);
     dfree(S.a);
@@ -1197,6 +1314,8 @@ int qce_tuples_from_host(const uint64_t *keys, const uint64_t *rowids, uint64_t 
     qce_tuples *t = new qce_tuples();
     t->n = n;
     t->key_bits = bitlen(mk) ? bitlen(mk) : 1;
+    t->key_min = 0;
+    t->key_max = mk;
     t->wide = t->key_bits > 32;
     t->id_bound = (mi + 1 >= (1ull << 32)) ? 0 : (u32)(mi + 1);
     t->sorted = false;
@@ -1335,7 +1454,7 @@ int qce_exchange_release(void *sendbuf)
     return 0;
 }
 int qce_tuples_from_device_packed(const void *dev_words, uint64_t n, uint32_t key_bits, uint32_t id_bound,
-                                  qce_tuples **out)
+                                  uint64_t key_lo, uint64_t key_hi, qce_tuples **out)
 {
     NEED_INIT();
     if (!out) return fail("null argument");
@@ -1343,6 +1462,8 @@ int qce_tuples_from_device_packed(const void *dev_words, uint64_t n, uint32_t ke
     qce_tuples *t = new qce_tuples();
     t->n = n;
     t->key_bits = (int)key_bits;
+    t->key_min = key_lo;
+    t->key_max = key_hi; // 0 = unknown: the sort assumes the whole 2^key_bits range
     t->wide = false;
     t->id_bound = id_bound;
     t->sorted = false;

@@ -67,7 +67,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "qce_rowids_free": (None, [vp]), "qce_tuples_count": (u64, [vp]),
         "qce_tuples_from_host": (i32, [vp, vp, u64, P(vp)]), "qce_tuples_to_host": (i32, [vp, vp, vp]),
         "qce_tuples_free": (None, [vp]), "qce_partition_tuples": (i32, [vp, u32, vp, u32, P(u64), P(vp)]),
-        "qce_tuples_from_device_packed": (i32, [vp, u64, u32, u32, P(vp)]), "qce_exchange_release": (i32, [vp]),
+        "qce_tuples_from_device_packed": (i32, [vp, u64, u32, u32, u64, u64, P(vp)]), "qce_exchange_release": (i32, [vp]),
         "qce_key_histogram": (i32, [vp, u32, P(u64)]),
     }
     for name, (res, args) in sig.items():
@@ -258,9 +258,10 @@ class Engine:
         self._ck(self.lib.qce_partition_tuples(t, key_bits, sp.ctypes.data, nparts, counts, C.byref(buf)))
         return [int(x) for x in counts], buf.value
 
-    def tuples_from_device_packed(self, dev_ptr: int, n: int, key_bits: int, id_bound: int = 0) -> int:
+    def tuples_from_device_packed(self, dev_ptr: int, n: int, key_bits: int, id_bound: int = 0,
+                                  key_lo: int = 0, key_hi: int = 0) -> int:
         h = C.c_void_p()
-        self._ck(self.lib.qce_tuples_from_device_packed(dev_ptr, n, key_bits, id_bound, C.byref(h)))
+        self._ck(self.lib.qce_tuples_from_device_packed(dev_ptr, n, key_bits, id_bound, key_lo, key_hi, C.byref(h)))
         return h.value
 
     def exchange_release(self, buf: Optional[int]) -> None:

@@ -105,10 +105,10 @@ class EngineOps:
     def release_partition(self, buf):
         self.e.exchange_release(buf)
 
-    def from_exchange(self, recv, key_bits, id_bound=0):
+    def from_exchange(self, recv, key_bits, id_bound=0, key_range=(0, 0)):
         self.torch.cuda.current_stream().synchronize()
         return self.e.tuples_from_device_packed(recv.data_ptr() if recv.numel() else 0, recv.numel(), key_bits,
-                                                id_bound)
+                                                id_bound, key_range[0], key_range[1])
 
     def sort(self, t):
         self.e.sort_tuples(t)
@@ -174,6 +174,10 @@ class ShardedJoin:
         # 2. splitters from the global key histogram
         hist = self._allreduce_u64(ops.histogram(L, key_bits) + ops.histogram(R, key_bits))
         splitters = choose_splitters(hist, key_bits, world)
+        # this rank's key interval (sizes the buckets of its local sort)
+        lo = splitters[rank - 1] if rank > 0 else 0
+        hi = (splitters[rank] - 1) if rank < world - 1 else (1 << key_bits) - 1
+        my_range = (lo, max(lo, hi))
         # 3+4. group by destination, exchange
         t1 = time.perf_counter()
         sent = 0
@@ -182,7 +186,7 @@ class ShardedJoin:
             counts, send, buf = ops.partition(run, key_bits, splitters, world)
             sent += sum(counts) - counts[rank]
             recv, _ = self._exchange(counts, send)
-            recv_runs.append(ops.from_exchange(recv, key_bits, nrows))
+            recv_runs.append(ops.from_exchange(recv, key_bits, nrows, my_range))
             ops.release_partition(buf)
             ops.free_tuples(run)
             del recv, send

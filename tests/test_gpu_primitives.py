@@ -16,6 +16,17 @@ def _col(rng, n, domain):
     return rng.integers(0, max(1, domain), n, dtype=np.uint64)
 
 
+def _assert_sorted_run(k, p, keys, payloads):
+    """The run is sorted by key and is a permutation of the input tuples.  The
+    order among EQUAL keys is unspecified (large runs take the MSD partition path,
+    which is not stable -- neither is the reference's rand()-driven quicksort)."""
+    order = np.argsort(keys, kind="stable")
+    np.testing.assert_array_equal(k, keys[order])
+    got = np.lexsort((p, k))
+    want = np.lexsort((payloads[order], keys[order]))
+    np.testing.assert_array_equal(p[got], payloads[order][want])
+
+
 # ------------------------------------------------------------------ filter scan
 @pytest.mark.parametrize("n", SIZES)
 @pytest.mark.parametrize("op", ["<", ">", "="])
@@ -81,9 +92,10 @@ def test_build_and_sort_base(engine, n, domain):
     engine.sort_tuples(t)
     assert engine.is_sorted(t)
     k, p = engine.tuples_to_host(t)
-    sk, sp = orc.sort_tuples(wk, wp)
-    np.testing.assert_array_equal(k, sk)
-    np.testing.assert_array_equal(p, sp)  # stable: ties in input order
+    _assert_sorted_run(k, p, wk, wp)
+    if n < (1 << 20):  # below the MSD threshold the LSD passes keep ties in input order
+        sk, sp = orc.sort_tuples(wk, wp)
+        np.testing.assert_array_equal(p, sp)
     engine.tuples_free(t)
 
 
@@ -321,4 +333,31 @@ def test_row_window_scan_and_build(engine, begin, count):
     k, p = engine.tuples_to_host(t)
     np.testing.assert_array_equal(k, col[begin:begin + count])
     np.testing.assert_array_equal(p, np.arange(begin, begin + count, dtype=U64))
+    engine.tuples_free(t)
+
+
+@pytest.mark.parametrize("n,kind", [(3_000_000, "uniform27"), (2_500_001, "uniform20"), (3_000_000, "zipf"),
+                                    (2_000_000, "few_keys"), (1_048_576, "dense"), (5_000_000, "uniform32")])
+def test_large_sort_msd_and_fallback(engine, n, kind):
+    """Large packed runs: MSD partition + shared-memory finish for non-skewed keys,
+    LSD fallback for skewed ones (a sub-bucket over the finish kernel's capacity)."""
+    rng = np.random.default_rng(n)
+    if kind == "uniform27":
+        keys = rng.integers(0, 1 << 27, n, dtype=np.uint64)
+    elif kind == "uniform20":
+        keys = rng.integers(0, 1 << 20, n, dtype=np.uint64)
+    elif kind == "uniform32":
+        keys = rng.integers(0, (1 << 32) - 1, n, dtype=np.uint64)
+    elif kind == "zipf":
+        keys = (rng.zipf(1.2, n) % (1 << 27)).astype(np.uint64)
+    elif kind == "few_keys":
+        keys = rng.integers(0, 100, n, dtype=np.uint64)
+    else:
+        keys = rng.permutation(n).astype(np.uint64)
+    ids = np.arange(n, dtype=U64)
+    t = engine.tuples_from_host(keys, ids)
+    engine.sort_tuples(t)
+    assert engine.is_sorted(t)
+    k, p = engine.tuples_to_host(t)
+    _assert_sorted_run(k, p, keys, ids)
     engine.tuples_free(t)

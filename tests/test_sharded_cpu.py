@@ -52,7 +52,7 @@ class NumpyOps:
     def release_partition(self, buf):
         pass
 
-    def from_exchange(self, recv, key_bits, id_bound=0):
+    def from_exchange(self, recv, key_bits, id_bound=0, key_range=(0, 0)):
         return recv.numpy().view(np.uint64).copy()
 
     def sort(self, t):
