@@ -292,7 +292,6 @@ def main():
     # ---- roofline of the dominant kernel: the one-sweep radix pass on packed
     # 8-byte tuples: 8 B read + 8 B written per tuple per launch;
     # tuples per step = 4 passes x (filtered lhs run + 100M-row rhs run)
-    os_prof = prof.get("onesweep_k", {"launches": 0, "ms": 0.0})
     # sizes of the intermediate runs (one untimed pass over the primitives)
     ids = eng.filter_scan(0, 2, ">", 500000)
     lhs = eng.rowids_count(ids)
@@ -305,28 +304,46 @@ def main():
     eng.tuples_free(tl); eng.tuples_free(tr)
     _, key_max = eng.column_info(1, 1)
     passes = (max(1, int(key_max).bit_length()) + 7) // 8
-    alg_bytes = 16.0 * passes * (lhs + rows) * args.steps
-    achieved = alg_bytes / (os_prof["ms"] / 1e3) / 1e9 if os_prof["ms"] else 0.0
-    traffic = None  # DRAM bytes per launch from the committed ncu --set full capture (per tuple x tuples/launch)
+    sort_tuples = lhs + rows
+    # algorithmic HBM bytes per STEP of every kernel that can dominate:
+    # packed 8-byte tuples, 4-byte row ids, 8-byte column values
+    models = {
+        "msd_partition": (16.0 * sort_tuples * 2, "16 B per tuple per launch (8 read + 8 written), two partition levels"),
+        "msd_count_sort": (16.0 * sort_tuples, "16 B per tuple (8 read + 8 written)"),
+        "msd_hist": (8.0 * sort_tuples * 2, "8 B per tuple per level"),
+        "onesweep_k": (16.0 * sort_tuples * passes, "16 B per tuple per pass (8 read + 8 written; the reference's 16-byte tuples would be 32 B)"),
+        "checksum": (12.0 * pairs * 3, "4 B row id + 8 B value per row per projected column"),
+        "join_bounds": (8.0 * sort_tuples + 8.0 * lhs, "8 B per input tuple + 8 B (lb,cnt) per lhs tuple"),
+        "join_write": (8.0 * lhs + 8.0 * pairs + 4.0 * pairs, "8 B (lb,cnt) per lhs tuple + 8 B per pair written + 4 B rhs id per pair"),
+        "build_tuples": (8.0 * rows + 12.0 * lhs + 8.0 * sort_tuples, "8 B key (+4 B id) in, 8 B packed tuple out"),
+    }
+    total_kernel_ms = sum(v["ms"] for v in prof.values())
+    dom = max((k for k in prof if k in models), key=lambda k: prof[k]["ms"])
+    dprof = prof[dom]
+    alg_bytes = models[dom][0] * args.steps
+    achieved = alg_bytes / (dprof["ms"] / 1e3) / 1e9 if dprof["ms"] else 0.0
+    traffic = None  # DRAM bytes per launch from the committed ncu --set full capture of this kernel
     try:
-        per_tuple = json.load(open(os.path.join(ROOT, "profiles", "onesweep_traffic.json")))["dram_bytes_per_tuple"]
-        traffic = per_tuple * passes * (lhs + rows) / max(1, os_prof["launches"] // args.steps)
+        tr_db = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json")))
+        if dom in tr_db:
+            traffic = tr_db[dom]["dram_bytes_per_tuple"] * models[dom][0] / tr_db[dom]["algorithmic_bytes_per_tuple"] \
+                / max(1, dprof["launches"] // args.steps)
     except Exception:
         pass
-    total_kernel_ms = sum(v["ms"] for v in prof.values())
     # whole-query algorithmic bytes in SURVEY 8d's terms (uint64 SoA, 16-byte tuples)
     alg_query = (8 * rows + 8 * lhs) + (32 * lhs + 24 * rows) + (lhs + rows) * (8 + passes * 32) \
         + 16 * (lhs + rows) + 16 * pairs + 3 * 16 * pairs
-    roofline = {"bound": "hbm", "kernel": "k_onesweep (radix pass over packed 8-byte tuples)", "achieved": achieved,
-                "peak": pk["hbm_gbs"], "peak_source": pk_src, "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes / max(1, os_prof["launches"]),
-                "launches": os_prof["launches"],
-                "avg_launch_ms": os_prof["ms"] / max(1, os_prof["launches"]),
-                "share_of_kernel_time": os_prof["ms"] / total_kernel_ms if total_kernel_ms else None,
-                "algorithmic_bytes": "16 B per tuple per pass (8 read + 8 written; the reference's 16-byte tuples would be 32 B)",
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": pk["hbm_gbs"], "peak_source": pk_src,
+                "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
+                "algorithmic_bytes_per_launch": alg_bytes / max(1, dprof["launches"]), "launches": dprof["launches"],
+                "avg_launch_ms": dprof["ms"] / max(1, dprof["launches"]),
+                "share_of_kernel_time": dprof["ms"] / total_kernel_ms if total_kernel_ms else None,
+                "algorithmic_bytes": models[dom][1],
                 "kernels_ms_per_step": {k: round(v["ms"] / args.steps, 4) for k, v in prof.items()},
+                "kernels_frac_of_peak": {k: round(models[k][0] * args.steps / (prof[k]["ms"] / 1e3) / 1e9 / pk["hbm_gbs"], 3)
+                                         for k in prof if k in models and prof[k]["ms"]},
                 "whole_query": {"algorithmic_gb_survey_8d": alg_query / 1e9, "lhs_rows": lhs, "pairs": pairs,
-                                "sort_passes": passes,
+                                "lsd_passes_for_these_keys": passes,
                                 "frac_of_peak": (alg_query / 1e9) / (ms_per_step / 1e3) / pk["hbm_gbs"]}}
 
     cpu = None

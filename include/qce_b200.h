@@ -175,7 +175,7 @@ void qce_tuples_free(qce_tuples *t);
  * qce_key_histogram returns).  counts[p] = tuples for rank p.  The packed 8-byte
  * words of part p are contiguous in *sendbuf (device pointer owned by the
  * engine until qce_exchange_release) at element offset sum(counts[0..p)); the
- * grouping is stable.  The collective itself (all-to-all over NVLink) is done
+ * order inside a part is unspecified (the receiver sorts it).  The collective itself (all-to-all over NVLink) is done
  * by the caller's communicator (torch.distributed / NCCL) on those pointers. */
 int qce_partition_tuples(const qce_tuples *t, uint32_t key_bits, const uint64_t *splitters,
                          uint32_t nparts, uint64_t *counts, void **sendbuf);
@@ -186,6 +186,11 @@ int qce_partition_tuples(const qce_tuples *t, uint32_t key_bits, const uint64_t 
 int qce_tuples_from_device_packed(const void *dev_words, uint64_t n, uint32_t key_bits,
                                   uint32_t id_bound, uint64_t key_lo, uint64_t key_hi,
                                   qce_tuples **out);
+/* Same without the copy: the run is sorted/joined in the caller's buffer, which
+ * must be complete (its stream synchronised), 16-byte aligned and outlive the run. */
+int qce_tuples_adopt_device_packed(void *dev_words, uint64_t n, uint32_t key_bits,
+                                   uint32_t id_bound, uint64_t key_lo, uint64_t key_hi,
+                                   qce_tuples **out);
 int qce_exchange_release(void *sendbuf);
 /* 256-bin histogram of the top 8 significant key bits of a run (for splitter
  * selection from an all-reduced global histogram).  hist = 256 uint64 on host. */

@@ -610,11 +610,13 @@ k_msd_hist(const u64 *__restrict__ keys, const u32 *__restrict__ tile_start, con
 
 // One unstable partition pass.  cursor[bucket * bins + digit] starts at the
 // global output offset of that (bucket, digit) range and is advanced by the tiles.
-__global__ void __launch_bounds__(QCE_MSD_THREADS)
+template <int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS)
 k_msd_partition(const u64 *__restrict__ in, u64 *__restrict__ out, const u32 *__restrict__ tile_start,
                 const u32 *__restrict__ bucket_off, const u32 *__restrict__ bucket_size, u32 nbuckets, u64 base,
-                int shift, u32 bins, u32 *__restrict__ cursor)
+                int shift, u32 bins, u32 *__restrict__ cursor, const u32 *__restrict__ lut)
 {
+    static_assert(THREADS * ITEMS == QCE_MSD_TILE && THREADS >= 256, "tile shape");
     __shared__ u64 skeys[QCE_MSD_TILE];
     __shared__ u32 cnt[256], excl[256], goff[256];
     __shared__ u32 scratch[33];
@@ -625,49 +627,55 @@ k_msd_partition(const u64 *__restrict__ in, u64 *__restrict__ out, const u32 *__
         if (!msd_locate_tile(blockIdx.x, tile_start, bucket_off, bucket_size, nbuckets, b, beg, c)) c = 0;
         s_loc[0] = b; s_loc[1] = beg; s_loc[2] = c;
     }
-    cnt[tid] = 0;
+    if (tid < 256) cnt[tid] = 0;
     __syncthreads();
     const u32 bucket = s_loc[0], begin = s_loc[1], count = s_loc[2];
     if (count == 0) return;
-    const u32 mask = bins - 1;
+    const u32 mask = lut ? 255u : bins - 1;
 
-    u64 key[QCE_MSD_ITEMS];
-    u32 slot[QCE_MSD_ITEMS]; // digit << 16 | slot among the tile's keys with that digit
+    u64 key[ITEMS];
+    u32 slot[ITEMS]; // digit << 16 | slot among the tile's keys with that digit
 #pragma unroll
-    for (int j = 0; j < QCE_MSD_ITEMS; j++) {
-        const u32 i = tid + j * QCE_MSD_THREADS;
+    for (int j = 0; j < ITEMS; j++) {
+        const u32 i = tid + j * THREADS;
         if (i < count) key[j] = ld_stream_u64(in + begin + i);
     }
 #pragma unroll
-    for (int j = 0; j < QCE_MSD_ITEMS; j++) {
-        const u32 i = tid + j * QCE_MSD_THREADS;
+    for (int j = 0; j < ITEMS; j++) {
+        const u32 i = tid + j * THREADS;
         if (i < count) {
-            const u32 d = (u32)((key[j] - base) >> shift) & mask;
+            u32 d = (u32)((key[j] - base) >> shift) & mask;
+            // exchange partition: the digit is a histogram bin, its destination rank comes from a table
+            if (lut) d = (__ldg(lut + (d >> 2)) >> ((d & 3u) * 8)) & 255u;
             slot[j] = (d << 16) | atomicAdd(&cnt[d], 1u);
         }
     }
     __syncthreads();
     {
-        const u32 c = cnt[tid];
+        const u32 c = tid < 256 ? cnt[tid] : 0u;
         u32 tot;
-        const u32 ex = block_scan_excl<u32, QCE_MSD_THREADS>(c, scratch, &tot);
-        excl[tid] = ex;
-        // reserve this tile's output range of the (bucket, digit) run
-        goff[tid] = (c ? atomicAdd(&cursor[bucket * bins + tid], c) : 0u) - ex;
+        const u32 ex = block_scan_excl<u32, THREADS>(c, scratch, &tot);
+        if (tid < 256) {
+            excl[tid] = ex;
+            // reserve this tile's output range of the (bucket, digit) run
+            goff[tid] = (c ? atomicAdd(&cursor[bucket * bins + tid], c) : 0u) - ex;
+        }
     }
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < QCE_MSD_ITEMS; j++) {
-        const u32 i = tid + j * QCE_MSD_THREADS;
+    for (int j = 0; j < ITEMS; j++) {
+        const u32 i = tid + j * THREADS;
         if (i < count) skeys[excl[slot[j] >> 16] + (slot[j] & 0xffffu)] = key[j];
     }
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < QCE_MSD_ITEMS; j++) {
-        const u32 p = tid + j * QCE_MSD_THREADS;
+    for (int j = 0; j < ITEMS; j++) {
+        const u32 p = tid + j * THREADS;
         if (p < count) {
             const u64 k = skeys[p];
-            out[goff[(u32)((k - base) >> shift) & mask] + p] = k;
+            u32 d = (u32)((k - base) >> shift) & mask;
+            if (lut) d = (__ldg(lut + (d >> 2)) >> ((d & 3u) * 8)) & 255u;
+            out[goff[d] + p] = k;
         }
     }
 }

@@ -43,6 +43,9 @@ struct qce_tuples {
     u64 key_max;   // range after an exchange); they size the MSD buckets
     u32 id_bound;
     bool sorted;
+    u32 *hist256;     // device, cached by qce_key_histogram for qce_partition_tuples
+    int hist_key_bits;
+    std::vector<unsigned int> hist_host; // the same 256 counts on the host
 };
 
 namespace {
@@ -529,8 +532,17 @@ int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done)
            histA);
     LAUNCH("radix_bases", k_radix_bases, 1, (int)nbA, 0, histA, offA);
     CK(cudaMemcpyAsync(curA, offA, nbA * sizeof(u32), cudaMemcpyDeviceToDevice, g.stream));
-    LAUNCH("msd_partition", k_msd_partition, ntiles0, QCE_MSD_THREADS, 0, *keys, alt, lvl0, lvl0 + 2, lvl0 + 3, 1u,
-           base, shiftA, nbA, curA);
+    static int shape = -1; // QCE_MSD_SHAPE: 0 = 256 threads x 16 tuples, 1 = 512 x 8
+    if (shape < 0) {
+        const char *e = getenv("QCE_MSD_SHAPE");
+        shape = e ? atoi(e) : 1;
+    }
+    if (shape == 1)
+        LAUNCH("msd_partition", (k_msd_partition<512, 8>), ntiles0, 512, 0, *keys, alt, lvl0, lvl0 + 2, lvl0 + 3, 1u,
+               base, shiftA, nbA, curA, (const u32 *)nullptr);
+    else
+        LAUNCH("msd_partition", (k_msd_partition<256, 16>), ntiles0, 256, 0, *keys, alt, lvl0, lvl0 + 2, lvl0 + 3, 1u,
+               base, shiftA, nbA, curA, (const u32 *)nullptr);
     // level 1: the 256 buckets of level 0, each cut into tiles of its own
     const u32 ntiles1 = ntiles0 + nbA; // upper bound; surplus CTAs exit
     LAUNCH("msd_tiles", k_msd_tile_starts, 1, 256, 0, histA, nbA, tstart1);
@@ -543,8 +555,12 @@ int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done)
     const u32 max_sub = (u32)(g.h_scalars[10] & 0xffffffffu);
     if (max_sub <= MSD_LOCAL_CAP) {
         CK(cudaMemcpyAsync(curB, suboff, nsub * sizeof(u32), cudaMemcpyDeviceToDevice, g.stream));
-        LAUNCH("msd_partition", k_msd_partition, ntiles1, QCE_MSD_THREADS, 0, alt, *keys, tstart1, offA, histA, nbA,
-               base, shiftB, nbB, curB);
+        if (shape == 1)
+            LAUNCH("msd_partition", (k_msd_partition<512, 8>), ntiles1, 512, 0, alt, *keys, tstart1, offA, histA, nbA,
+                   base, shiftB, nbB, curB, (const u32 *)nullptr);
+        else
+            LAUNCH("msd_partition", (k_msd_partition<256, 16>), ntiles1, 256, 0, alt, *keys, tstart1, offA, histA, nbA,
+                   base, shiftB, nbB, curB, (const u32 *)nullptr);
         if (R > 0 && R <= 12) {
             const size_t sm8 = 256 * 8 * sizeof(u64) + 4096 * sizeof(u32) + 33 * sizeof(u32);
             const size_t sm16 = 256 * 16 * sizeof(u64) + 4096 * sizeof(u32) + 33 * sizeof(u32);
@@ -552,10 +568,13 @@ int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done)
             if (!attr_set) {
                 CK(cudaFuncSetAttribute(k_msd_count_sort<256, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm8));
                 CK(cudaFuncSetAttribute(k_msd_count_sort<256, 16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16));
+                CK(cudaFuncSetAttribute(k_msd_count_sort<512, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16));
                 attr_set = true;
             }
             if (max_sub <= 256 * 8)
                 LAUNCH("msd_count_sort", (k_msd_count_sort<256, 8, 4>), nsub, 256, sm8, *keys, suboff, histB, base, R);
+            else if (shape == 1)
+                LAUNCH("msd_count_sort", (k_msd_count_sort<512, 8, 2>), nsub, 512, sm16, *keys, suboff, histB, base, R);
             else
                 LAUNCH("msd_count_sort", (k_msd_count_sort<256, 16, 3>), nsub, 256, sm16, *keys, suboff, histB, base, R);
         } else if (R > 0) {
@@ -1197,7 +1216,7 @@ int qce_rejoin(const qce_rowids *driver, const qce_rowids *last, const qce_rowid
                     (unsigned long long)edit->n, (unsigned long long)last->n);
     const int bits = last->id_bound ? bitlen(last->id_bound - 1) : 32;
     qce_tuples R, S;
-    R.n = last->n; R.key_min = 0; S.key_min = 0; R.key_max = 0; S.key_max = 0; R.wide = false; R.ids = nullptr; R.key_bits = bits ? bits : 1; R.id_bound = edit->id_bound; R.sorted = false; R.a = nullptr;
+    R.n = last->n; R.key_min = 0; S.key_min = 0; R.key_max = 0; S.key_max = 0; R.hist256 = nullptr; S.hist256 = nullptr; R.wide = false; R.ids = nullptr; R.key_bits = bits ? bits : 1; R.id_bound = edit->id_bound; R.sorted = false; R.a = nullptr;
     S.n = driver->n; S.wide = false; S.ids = nullptr; S.key_bits = R.key_bits; S.id_bound = 0; S.sorted = false; S.a = nullptr;
     if (dalloc(&R.a, R.n) || dalloc(&S.a, S.n)) return -1;
     if (R.n) LAUNCH("pack_pairs", k_pack_pairs, grid_for(256, R.n), 256, 0, last->d, edit->d, R.n, R.a);
@@ -1363,7 +1382,7 @@ int qce_tuples_to_host(const qce_tuples *t, uint64_t *keys, uint64_t *rowids)
 void qce_tuples_free(qce_tuples *t)
 {
     if (!t) return;
-    if (g.inited) { dfree(t->a); dfree(t->ids); }
+    if (g.inited) { dfree(t->a); dfree(t->ids); dfree(t->hist256); }
     delete t;
 }
 
@@ -1373,8 +1392,9 @@ int qce_key_histogram(const qce_tuples *t, uint32_t key_bits, uint64_t *hist)
     NEED_INIT();
     if (!t || !hist) return fail("null argument");
     if (t->wide) return fail("the sharded exchange supports packed (key < 2^32) runs only");
-    u32 *gh = nullptr;
-    if (dalloc(&gh, QCE_RADIX_BINS) != 0) return -1;
+    qce_tuples *mt = const_cast<qce_tuples *>(t); // the device histogram is cached on the run
+    if (!mt->hist256 && dalloc(&mt->hist256, QCE_RADIX_BINS) != 0) return -1;
+    u32 *gh = mt->hist256;
     CK(cudaMemsetAsync(gh, 0, QCE_RADIX_BINS * sizeof(u32), g.stream));
     RadixShifts rs;
     rs.npass = 1;
@@ -1385,7 +1405,8 @@ int qce_key_histogram(const qce_tuples *t, uint32_t key_bits, uint64_t *hist)
     CK(cudaMemcpyAsync(tmp.data(), gh, QCE_RADIX_BINS * sizeof(u32), cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
     for (int i = 0; i < QCE_RADIX_BINS; i++) hist[i] = tmp[i];
-    dfree(gh);
+    mt->hist_key_bits = (int)key_bits;
+    mt->hist_host.assign(tmp.begin(), tmp.end());
     return 0;
 }
 
@@ -1413,37 +1434,31 @@ int qce_partition_tuples(const qce_tuples *t, uint32_t key_bits, const uint64_t 
     }
     const u64 n = t->n;
     u64 *out = nullptr;
-    u32 *ghist = nullptr, *gbase = nullptr, *status = nullptr, *counter = nullptr, *dlut = nullptr;
-    if (dalloc(&dlut, 64) != 0) return -1;
-    CK(cudaMemcpyAsync(dlut, lut, sizeof lut, cudaMemcpyHostToDevice, g.stream));
-    ds.lut = dlut;
-    const u32 ntiles = (u32)ceil_div(n ? n : 1, onesweep_tile_size());
-    if (dalloc(&out, n) || dalloc(&ghist, 2 * QCE_RADIX_BINS) || dalloc(&gbase, QCE_RADIX_BINS) ||
-        dalloc(&status, (u64)ntiles * QCE_RADIX_BINS) || dalloc(&counter, 1))
-        return -1;
-    CK(cudaMemsetAsync(ghist, 0, 2 * QCE_RADIX_BINS * sizeof(u32), g.stream));
-    CK(cudaMemsetAsync(status, 0, (u64)ntiles * QCE_RADIX_BINS * sizeof(u32), g.stream));
-    CK(cudaMemsetAsync(counter, 0, sizeof(u32), g.stream));
-    // per-destination counts = the bin histogram folded through the table (host, 256 adds)
-    RadixShifts rs;
-    rs.npass = 1;
-    for (int i = 0; i < QCE_MAX_PASSES; i++) rs.shift[i] = 0;
-    rs.shift[0] = ds.shift;
-    std::vector<u32> bins(QCE_RADIX_BINS, 0), parts(QCE_RADIX_BINS, 0);
+    u32 *dlut = nullptr, *lvl0 = nullptr, *cursor = nullptr;
+    if (dalloc(&out, n) || dalloc(&dlut, 64) || dalloc(&lvl0, 4) || dalloc(&cursor, QCE_RADIX_BINS)) return -1;
+    // per-destination counts = the 256-bin key histogram folded through the table.  The
+    // histogram is the one qce_key_histogram left on the run (splitter selection needs it anyway).
+    std::vector<u32> bins(QCE_RADIX_BINS, 0), parts(QCE_RADIX_BINS, 0), offs(QCE_RADIX_BINS, 0);
     if (n) {
-        LAUNCH("radix_hist", k_radix_hist, grid_for(1024, n, 4), 512, 0, t->a, n, rs, 256u, ghist);
-        CK(cudaMemcpyAsync(bins.data(), ghist, QCE_RADIX_BINS * sizeof(u32), cudaMemcpyDeviceToHost, g.stream));
-        CK(cudaStreamSynchronize(g.stream));
-        for (u32 b = 0; b < 256; b++) parts[lut[b]] += bins[b];
-        u32 *part_hist = ghist + QCE_RADIX_BINS;
-        CK(cudaMemcpyAsync(part_hist, parts.data(), QCE_RADIX_BINS * sizeof(u32), cudaMemcpyHostToDevice, g.stream));
-        LAUNCH("radix_bases", k_radix_bases, 1, 256, 0, part_hist, gbase);
-        if (launch_onesweep<false, 8, u64>((const u64 *)t->a, out, nullptr, nullptr, (u32)n, ds, gbase, status, counter) != 0)
-            return -1;
+        if (!(t->hist256 && t->hist_key_bits == (int)key_bits && t->hist_host.size() == QCE_RADIX_BINS)) {
+            uint64_t h[QCE_RADIX_BINS];
+            if (qce_key_histogram(t, key_bits, h) != 0) return -1;
+        }
+        for (u32 b = 0; b < 256; b++) parts[lut[b]] += t->hist_host[b];
+        for (u32 p = 1; p < 256; p++) offs[p] = offs[p - 1] + parts[p - 1];
+        const u32 ntiles = (u32)ceil_div(n, QCE_MSD_TILE);
+        const u32 h_lvl0[4] = {0u, ntiles, 0u, (u32)n};
+        CK(cudaMemcpyAsync(lvl0, h_lvl0, sizeof h_lvl0, cudaMemcpyHostToDevice, g.stream));
+        CK(cudaMemcpyAsync(dlut, lut, sizeof lut, cudaMemcpyHostToDevice, g.stream));
+        CK(cudaMemcpyAsync(cursor, offs.data(), QCE_RADIX_BINS * sizeof(u32), cudaMemcpyHostToDevice, g.stream));
+        // the unstable MSD partition kernel with the destination table as digit: no ranking
+        // ballots, no look-back (the order inside a destination does not matter, it is sorted next)
+        LAUNCH("exchange_partition", (k_msd_partition<512, 8>), ntiles, 512, 0, (const u64 *)t->a, out, lvl0, lvl0 + 2,
+               lvl0 + 3, 1u, 0ull, ds.shift, 256u, cursor, (const u32 *)dlut);
         CK(cudaStreamSynchronize(g.stream)); // the caller hands *sendbuf to another stream
     }
     for (u32 p = 0; p < nparts; p++) counts[p] = parts[p];
-    dfree(ghist); dfree(gbase); dfree(status); dfree(counter); dfree(dlut);
+    dfree(dlut); dfree(lvl0); dfree(cursor);
     *sendbuf = out;
     return 0;
 }
@@ -1453,8 +1468,20 @@ int qce_exchange_release(void *sendbuf)
     dfree((u64 *)sendbuf);
     return 0;
 }
+static int tuples_from_device(const void *dev_words, uint64_t n, uint32_t key_bits, uint32_t id_bound, uint64_t key_lo,
+                              uint64_t key_hi, bool adopt, qce_tuples **out);
 int qce_tuples_from_device_packed(const void *dev_words, uint64_t n, uint32_t key_bits, uint32_t id_bound,
                                   uint64_t key_lo, uint64_t key_hi, qce_tuples **out)
+{
+    return tuples_from_device(dev_words, n, key_bits, id_bound, key_lo, key_hi, false, out);
+}
+int qce_tuples_adopt_device_packed(void *dev_words, uint64_t n, uint32_t key_bits, uint32_t id_bound, uint64_t key_lo,
+                                   uint64_t key_hi, qce_tuples **out)
+{
+    return tuples_from_device(dev_words, n, key_bits, id_bound, key_lo, key_hi, true, out);
+}
+static int tuples_from_device(const void *dev_words, uint64_t n, uint32_t key_bits, uint32_t id_bound, uint64_t key_lo,
+                              uint64_t key_hi, bool adopt, qce_tuples **out)
 {
     NEED_INIT();
     if (!out) return fail("null argument");
@@ -1468,10 +1495,19 @@ int qce_tuples_from_device_packed(const void *dev_words, uint64_t n, uint32_t ke
     t->id_bound = id_bound;
     t->sorted = false;
     t->ids = nullptr;
-    if (dalloc(&t->a, n) != 0) { delete t; return -1; }
-    // the caller's buffer may live on another stream (torch): order by a full device sync
-    CK(cudaDeviceSynchronize());
-    if (n) CK(cudaMemcpyAsync(t->a, dev_words, n * sizeof(u64), cudaMemcpyDeviceToDevice, g.stream));
+    if (adopt) {
+        // no copy: the run lives in the caller's buffer (it must stay alive and must be
+        // complete, i.e. the caller has synchronised the stream that filled it).  The arena
+        // ignores pointers it did not hand out, so freeing the run leaves the buffer alone.
+        if (n && ((uintptr_t)dev_words & 15) != 0) { delete t; return fail("adopted buffer must be 16-byte aligned"); }
+        t->a = (u64 *)dev_words;
+        if (n == 0 && dalloc(&t->a, 1) != 0) { delete t; return -1; }
+    } else {
+        if (dalloc(&t->a, n) != 0) { delete t; return -1; }
+        // the caller's buffer may live on another stream (torch): order by a full device sync
+        CK(cudaDeviceSynchronize());
+        if (n) CK(cudaMemcpyAsync(t->a, dev_words, n * sizeof(u64), cudaMemcpyDeviceToDevice, g.stream));
+    }
     *out = t;
     return 0;
 }

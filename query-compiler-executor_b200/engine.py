@@ -27,7 +27,7 @@ SYMBOLS = [
     "qce_merge_join", "qce_merge_join_walk", "qce_distinct_pairs", "qce_scan_join", "qce_scan_join_base", "qce_rejoin", "qce_checksum", "qce_rowids_count",
     "qce_rowids_from_host", "qce_rowids_to_host", "qce_rowids_clone", "qce_rowids_free", "qce_tuples_count",
     "qce_tuples_from_host", "qce_tuples_to_host", "qce_tuples_free", "qce_partition_tuples",
-    "qce_tuples_from_device_packed", "qce_exchange_release", "qce_key_histogram",
+    "qce_tuples_from_device_packed", "qce_tuples_adopt_device_packed", "qce_exchange_release", "qce_key_histogram",
 ]
 
 
@@ -67,7 +67,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "qce_rowids_free": (None, [vp]), "qce_tuples_count": (u64, [vp]),
         "qce_tuples_from_host": (i32, [vp, vp, u64, P(vp)]), "qce_tuples_to_host": (i32, [vp, vp, vp]),
         "qce_tuples_free": (None, [vp]), "qce_partition_tuples": (i32, [vp, u32, vp, u32, P(u64), P(vp)]),
-        "qce_tuples_from_device_packed": (i32, [vp, u64, u32, u32, u64, u64, P(vp)]), "qce_exchange_release": (i32, [vp]),
+        "qce_tuples_from_device_packed": (i32, [vp, u64, u32, u32, u64, u64, P(vp)]),
+        "qce_tuples_adopt_device_packed": (i32, [vp, u64, u32, u32, u64, u64, P(vp)]), "qce_exchange_release": (i32, [vp]),
         "qce_key_histogram": (i32, [vp, u32, P(u64)]),
     }
     for name, (res, args) in sig.items():
@@ -259,9 +260,10 @@ class Engine:
         return [int(x) for x in counts], buf.value
 
     def tuples_from_device_packed(self, dev_ptr: int, n: int, key_bits: int, id_bound: int = 0,
-                                  key_lo: int = 0, key_hi: int = 0) -> int:
+                                  key_lo: int = 0, key_hi: int = 0, adopt: bool = False) -> int:
         h = C.c_void_p()
-        self._ck(self.lib.qce_tuples_from_device_packed(dev_ptr, n, key_bits, id_bound, key_lo, key_hi, C.byref(h)))
+        fn = self.lib.qce_tuples_adopt_device_packed if adopt else self.lib.qce_tuples_from_device_packed
+        self._ck(fn(dev_ptr, n, key_bits, id_bound, key_lo, key_hi, C.byref(h)))
         return h.value
 
     def exchange_release(self, buf: Optional[int]) -> None:

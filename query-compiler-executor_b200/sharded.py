@@ -106,9 +106,11 @@ class EngineOps:
         self.e.exchange_release(buf)
 
     def from_exchange(self, recv, key_bits, id_bound=0, key_range=(0, 0)):
+        # the run is sorted and joined in place in the receive buffer (no copy); the caller
+        # keeps `recv` alive until the run is freed and has waited for the all-to-all
         self.torch.cuda.current_stream().synchronize()
         return self.e.tuples_from_device_packed(recv.data_ptr() if recv.numel() else 0, recv.numel(), key_bits,
-                                                id_bound, key_range[0], key_range[1])
+                                                id_bound, key_range[0], key_range[1], adopt=recv.numel() > 0)
 
     def sort(self, t):
         self.e.sort_tuples(t)
@@ -144,15 +146,17 @@ class ShardedJoin:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
         return t.cpu().numpy().view(np.uint64)
 
-    def _exchange(self, counts: List[int], send):
+    def _exchange_start(self, counts: List[int], send):
+        """Counts first (small, blocking), then the payload all-to-all as an async
+        op so that the next run's partition kernel overlaps the transfer."""
         torch, dist = self.torch, self.dist
         sc = torch.tensor(counts, dtype=torch.int64, device=self.dev)
         rc = torch.empty_like(sc)
         dist.all_to_all_single(rc, sc)
         rcounts = [int(x) for x in rc.cpu().tolist()]
         recv = torch.empty(sum(rcounts), dtype=torch.int64, device=self.dev)
-        dist.all_to_all_single(recv, send, output_split_sizes=rcounts, input_split_sizes=counts)
-        return recv, rcounts
+        work = dist.all_to_all_single(recv, send, output_split_sizes=rcounts, input_split_sizes=counts, async_op=True)
+        return recv, work
 
     def run(self, spec: JoinSpec, rows_lhs: int, rows_rhs: int) -> dict:
         ops, world, rank = self.ops, self.world, self.rank
@@ -181,15 +185,20 @@ class ShardedJoin:
         # 3+4. group by destination, exchange
         t1 = time.perf_counter()
         sent = 0
-        recv_runs = []
+        pending = []
         for run, nrows in ((L, rows_lhs), (R, rows_rhs)):
             counts, send, buf = ops.partition(run, key_bits, splitters, world)
             sent += sum(counts) - counts[rank]
-            recv, _ = self._exchange(counts, send)
+            recv, work = self._exchange_start(counts, send)
+            pending.append((recv, work, send, buf, nrows))
+            ops.free_tuples(run)
+        recv_runs, keep_alive = [], []
+        for recv, work, send, buf, nrows in pending:
+            work.wait()
             recv_runs.append(ops.from_exchange(recv, key_bits, nrows, my_range))
             ops.release_partition(buf)
-            ops.free_tuples(run)
-            del recv, send
+            keep_alive.append(recv)  # the runs live in these buffers until they are freed
+            del send
         t2 = time.perf_counter()
         # 5. local sort + merge + checksums of this rank's key range
         L2, R2 = recv_runs
@@ -203,6 +212,7 @@ class ShardedJoin:
             ops.free_ids(h)
         ops.free_tuples(L2)
         ops.free_tuples(R2)
+        del keep_alive
         # 6. reduce
         red = self._allreduce_u64(np.array(sums + [pairs, local_in], dtype=np.uint64))
         t3 = time.perf_counter()
