@@ -84,49 +84,104 @@ template <bool LT> __device__ __forceinline__ u32 bound_s(const u64 *skeys, u32 
     return lo;
 }
 
+// Per R tile (2048 sorted tuples, S window [w.x, w.y)):
+//  * table path -- the tile's keys span at most QCE_JTAB integer values (both runs
+//    are sorted, so this is the common case: consecutive tuples have close keys):
+//    the S window is histogrammed by key offset with shared-memory atomics, the
+//    histogram is exclusive-scanned in place, and each R tuple's lower bound and
+//    match count are two table lookups (tab[v], tab[v+1]) instead of two 12-step
+//    binary searches;
+//  * search path -- sparse keys: the S window (<= QCE_JWIN keys) is staged in shared
+//    memory and searched; beyond that, binary search in global memory.
+#define QCE_JTAB 8192
 template <bool WR, bool WS>
 __global__ void __launch_bounds__(QCE_JTHREADS)
 k_join_bounds(TupleView R, u32 nR, TupleView S, const uint2 *__restrict__ win,
               u32 *__restrict__ lb_out, u32 *__restrict__ cnt_out, u64 *__restrict__ tile_total,
               u32 *__restrict__ tile_chunks)
 {
-    extern __shared__ __align__(16) u64 skeys[]; // QCE_JSMEM_BYTES
+    extern __shared__ __align__(16) u64 skeys[]; // QCE_JSMEM_BYTES: S keys (search path) or the count table
     __shared__ u64 scratch[33];
     const int tid = threadIdx.x;
     const u32 tbase = blockIdx.x * QCE_JTILE;
     const uint2 w = win[blockIdx.x];
     const u32 wn = w.y - w.x;
-    const bool staged = wn <= QCE_JWIN;
-    if (staged) {
-        for (u32 i = tid; i < wn; i += QCE_JTHREADS) skeys[i] = tv_key<WS>(S, w.x + i);
-    }
-    // consecutive lanes take consecutive R tuples: their probes into the staged
-    // window are a few slots apart (few bank conflicts) and the 8 searches of a
-    // thread are independent (they overlap)
+    // consecutive lanes take consecutive R tuples; the 8 tuples of a thread are independent
     u64 key[QCE_JTILE / QCE_JTHREADS];
 #pragma unroll
     for (int k = 0; k < QCE_JTILE / QCE_JTHREADS; k++) {
         const u32 i = tbase + k * QCE_JTHREADS + tid;
         key[k] = (i < nR) ? tv_key<WR>(R, i) : ~0ull;
     }
-    __syncthreads();
+    const u32 last = min(tbase + QCE_JTILE, nR) - 1;
+    const u64 klo = tv_key<WR>(R, tbase), khi = tv_key<WR>(R, last);
     u64 sum = 0;
+    if (wn == 0) {
 #pragma unroll
-    for (int k = 0; k < QCE_JTILE / QCE_JTHREADS; k++) {
-        const u32 i = tbase + k * QCE_JTHREADS + tid;
-        if (i < nR) {
-            u32 lb, ub;
-            if (staged) {
-                lb = bound_s<true>(skeys, wn, key[k]) + w.x;
-                ub = bound_s<false>(skeys, wn, key[k]) + w.x;
-            } else {
-                // S is much denser than R here (or one key is very heavy)
-                lb = lower_bound_g<WS>(S, w.x, w.y, key[k]);
-                ub = upper_bound_g<WS>(S, lb, w.y, key[k]);
+        for (int k = 0; k < QCE_JTILE / QCE_JTHREADS; k++) {
+            const u32 i = tbase + k * QCE_JTHREADS + tid;
+            if (i < nR) { lb_out[i] = w.x; cnt_out[i] = 0; }
+        }
+    } else if (khi - klo < QCE_JTAB) {
+        // ---- table path
+        u32 *tab = reinterpret_cast<u32 *>(skeys); // range + 1 entries
+        const u32 range = (u32)(khi - klo) + 1;
+        for (u32 v = tid; v <= range; v += QCE_JTHREADS) tab[v] = 0;
+        __syncthreads();
+        // every key of the window lies in [klo, khi] (the window is lower_bound(klo) .. upper_bound(khi))
+        for (u32 i = tid; i < wn; i += QCE_JTHREADS) atomicAdd(&tab[(u32)(tv_key<WS>(S, w.x + i) - klo)], 1u);
+        __syncthreads();
+        {   // exclusive scan in place; thread t owns `per` consecutive entries
+            const u32 per = (range + 1 + QCE_JTHREADS - 1) / QCE_JTHREADS; // <= 33
+            const u32 b0 = tid * per;
+            u32 local = 0;
+            for (u32 q = 0; q < per; q++)
+                if (b0 + q <= range) local += tab[b0 + q];
+            u32 tot32;
+            u32 ex = block_scan_excl<u32, QCE_JTHREADS>(local, reinterpret_cast<u32 *>(scratch), &tot32);
+            for (u32 q = 0; q < per; q++) {
+                if (b0 + q <= range) {
+                    const u32 c = tab[b0 + q];
+                    tab[b0 + q] = ex;
+                    ex += c;
+                }
             }
-            lb_out[i] = lb;
-            cnt_out[i] = ub - lb;
-            sum += ub - lb;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < QCE_JTILE / QCE_JTHREADS; k++) {
+            const u32 i = tbase + k * QCE_JTHREADS + tid;
+            if (i < nR) {
+                const u32 v = (u32)(key[k] - klo);
+                const u32 lo = tab[v], c = tab[v + 1] - lo;
+                lb_out[i] = w.x + lo;
+                cnt_out[i] = c;
+                sum += c;
+            }
+        }
+    } else {
+        const bool staged = wn <= QCE_JWIN;
+        if (staged) {
+            for (u32 i = tid; i < wn; i += QCE_JTHREADS) skeys[i] = tv_key<WS>(S, w.x + i);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < QCE_JTILE / QCE_JTHREADS; k++) {
+            const u32 i = tbase + k * QCE_JTHREADS + tid;
+            if (i < nR) {
+                u32 lb, ub;
+                if (staged) {
+                    lb = bound_s<true>(skeys, wn, key[k]) + w.x;
+                    ub = bound_s<false>(skeys, wn, key[k]) + w.x;
+                } else {
+                    // S is much denser than R here (or one key is very heavy)
+                    lb = lower_bound_g<WS>(S, w.x, w.y, key[k]);
+                    ub = upper_bound_g<WS>(S, lb, w.y, key[k]);
+                }
+                lb_out[i] = lb;
+                cnt_out[i] = ub - lb;
+                sum += ub - lb;
+            }
         }
     }
     u64 tot = block_sum<u64, QCE_JTHREADS>(sum, scratch);

@@ -32,6 +32,10 @@
 #define QCE_MAX_BINS 512    // 9-bit digits, when they save a pass
 #define QCE_MAX_PASSES 8
 
+template <typename KeyT> __device__ __forceinline__ KeyT ld_stream_key(const KeyT *p);
+template <> __device__ __forceinline__ u64 ld_stream_key<u64>(const u64 *p) { return ld_stream_u64(p); }
+template <> __device__ __forceinline__ u32 ld_stream_key<u32>(const u32 *p) { return ld_stream_u32(p); }
+
 struct RadixShifts {
     int npass;
     int shift[QCE_MAX_PASSES];
@@ -235,10 +239,6 @@ template <int BITS> __device__ __forceinline__ u32 warp_peers(u32 d)
 #define QCE_ST_PART 0x40000000u
 #define QCE_ST_INCL 0x80000000u
 #define QCE_ST_MASK 0x3fffffffu
-
-template <typename KeyT> __device__ __forceinline__ KeyT ld_stream_key(const KeyT *p);
-template <> __device__ __forceinline__ u64 ld_stream_key<u64>(const u64 *p) { return ld_stream_u64(p); }
-template <> __device__ __forceinline__ u32 ld_stream_key<u32>(const u32 *p) { return ld_stream_u32(p); }
 
 template <int THREADS, int ITEMS, int BITS, typename KeyT = u64> struct OnesweepSmem {
     static constexpr int BINS = 1 << BITS;
@@ -610,14 +610,14 @@ k_msd_hist(const u64 *__restrict__ keys, const u32 *__restrict__ tile_start, con
 
 // One unstable partition pass.  cursor[bucket * bins + digit] starts at the
 // global output offset of that (bucket, digit) range and is advanced by the tiles.
-template <int THREADS, int ITEMS>
+template <int THREADS, int ITEMS, typename KeyT = u64>
 __global__ void __launch_bounds__(THREADS)
-k_msd_partition(const u64 *__restrict__ in, u64 *__restrict__ out, const u32 *__restrict__ tile_start,
-                const u32 *__restrict__ bucket_off, const u32 *__restrict__ bucket_size, u32 nbuckets, u64 base,
+k_msd_partition(const KeyT *__restrict__ in, KeyT *__restrict__ out, const u32 *__restrict__ tile_start,
+                const u32 *__restrict__ bucket_off, const u32 *__restrict__ bucket_size, u32 nbuckets, KeyT base,
                 int shift, u32 bins, u32 *__restrict__ cursor, const u32 *__restrict__ lut)
 {
     static_assert(THREADS * ITEMS == QCE_MSD_TILE && THREADS >= 256, "tile shape");
-    __shared__ u64 skeys[QCE_MSD_TILE];
+    __shared__ KeyT skeys[QCE_MSD_TILE];
     __shared__ u32 cnt[256], excl[256], goff[256];
     __shared__ u32 scratch[33];
     __shared__ u32 s_loc[3];
@@ -633,12 +633,12 @@ k_msd_partition(const u64 *__restrict__ in, u64 *__restrict__ out, const u32 *__
     if (count == 0) return;
     const u32 mask = lut ? 255u : bins - 1;
 
-    u64 key[ITEMS];
+    KeyT key[ITEMS];
     u32 slot[ITEMS]; // digit << 16 | slot among the tile's keys with that digit
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
         const u32 i = tid + j * THREADS;
-        if (i < count) key[j] = ld_stream_u64(in + begin + i);
+        if (i < count) key[j] = ld_stream_key<KeyT>(in + begin + i);
     }
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
@@ -672,7 +672,7 @@ k_msd_partition(const u64 *__restrict__ in, u64 *__restrict__ out, const u32 *__
     for (int j = 0; j < ITEMS; j++) {
         const u32 p = tid + j * THREADS;
         if (p < count) {
-            const u64 k = skeys[p];
+            const KeyT k = skeys[p];
             u32 d = (u32)((k - base) >> shift) & mask;
             if (lut) d = (__ldg(lut + (d >> 2)) >> ((d & 3u) * 8)) & 255u;
             out[goff[d] + p] = k;

@@ -535,9 +535,9 @@ int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done)
     static int shape = -1; // QCE_MSD_SHAPE: 0 = 256 threads x 16 tuples, 1 = 512 x 8
     if (shape < 0) {
         const char *e = getenv("QCE_MSD_SHAPE");
-        shape = e ? atoi(e) : 1;
+        shape = e ? atoi(e) : 2;
     }
-    if (shape == 1)
+    if (shape >= 1)
         LAUNCH("msd_partition", (k_msd_partition<512, 8>), ntiles0, 512, 0, *keys, alt, lvl0, lvl0 + 2, lvl0 + 3, 1u,
                base, shiftA, nbA, curA, (const u32 *)nullptr);
     else
@@ -555,7 +555,7 @@ int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done)
     const u32 max_sub = (u32)(g.h_scalars[10] & 0xffffffffu);
     if (max_sub <= MSD_LOCAL_CAP) {
         CK(cudaMemcpyAsync(curB, suboff, nsub * sizeof(u32), cudaMemcpyDeviceToDevice, g.stream));
-        if (shape == 1)
+        if (shape >= 1)
             LAUNCH("msd_partition", (k_msd_partition<512, 8>), ntiles1, 512, 0, alt, *keys, tstart1, offA, histA, nbA,
                    base, shiftB, nbB, curB, (const u32 *)nullptr);
         else
@@ -569,12 +569,18 @@ int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done)
                 CK(cudaFuncSetAttribute(k_msd_count_sort<256, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm8));
                 CK(cudaFuncSetAttribute(k_msd_count_sort<256, 16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16));
                 CK(cudaFuncSetAttribute(k_msd_count_sort<512, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16));
+                CK(cudaFuncSetAttribute(k_msd_count_sort<512, 8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16));
+                CK(cudaFuncSetAttribute(k_msd_count_sort<512, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16));
                 attr_set = true;
             }
             if (max_sub <= 256 * 8)
                 LAUNCH("msd_count_sort", (k_msd_count_sort<256, 8, 4>), nsub, 256, sm8, *keys, suboff, histB, base, R);
             else if (shape == 1)
                 LAUNCH("msd_count_sort", (k_msd_count_sort<512, 8, 2>), nsub, 512, sm16, *keys, suboff, histB, base, R);
+            else if (shape == 2)
+                LAUNCH("msd_count_sort", (k_msd_count_sort<512, 8, 3>), nsub, 512, sm16, *keys, suboff, histB, base, R);
+            else if (shape == 3)
+                LAUNCH("msd_count_sort", (k_msd_count_sort<512, 8, 4>), nsub, 512, sm16, *keys, suboff, histB, base, R);
             else
                 LAUNCH("msd_count_sort", (k_msd_count_sort<256, 16, 3>), nsub, 256, sm16, *keys, suboff, histB, base, R);
         } else if (R > 0) {
@@ -753,22 +759,22 @@ bool bucketed_checksum_pays(const qce_rowids *ids, u64 col_rows)
 
 int partition_ids_by_top_bits(const qce_rowids *ids, u32 **out)
 {
+    // unstable MSD partition of the 4-byte ids by their top 8 bits (the order inside
+    // a bucket is irrelevant for a sum): histogram, prefix, one scatter pass
     const u64 n = ids->n;
     const int bits = ids->id_bound ? bitlen(ids->id_bound - 1) : 32;
     const int shift = bits > 8 ? bits - 8 : 0;
-    const u32 ntiles = (u32)ceil_div(n, onesweep_tile_size());
-    u32 *ghist = nullptr, *gbase = nullptr, *status = nullptr, *counter = nullptr, *dst = nullptr;
-    if (dalloc(&dst, n) || dalloc(&ghist, QCE_RADIX_BINS) || dalloc(&gbase, QCE_RADIX_BINS) ||
-        dalloc(&status, (u64)ntiles * QCE_RADIX_BINS) || dalloc(&counter, 1))
-        return -1;
+    const u32 ntiles = (u32)ceil_div(n, QCE_MSD_TILE);
+    u32 *ghist = nullptr, *cursor = nullptr, *lvl0 = nullptr, *dst = nullptr;
+    if (dalloc(&dst, n) || dalloc(&ghist, QCE_RADIX_BINS) || dalloc(&cursor, QCE_RADIX_BINS) || dalloc(&lvl0, 4)) return -1;
+    const u32 h_lvl0[4] = {0u, ntiles, 0u, (u32)n};
+    CK(cudaMemcpyAsync(lvl0, h_lvl0, sizeof h_lvl0, cudaMemcpyHostToDevice, g.stream));
     CK(cudaMemsetAsync(ghist, 0, QCE_RADIX_BINS * sizeof(u32), g.stream));
-    CK(cudaMemsetAsync(status, 0, (u64)ntiles * QCE_RADIX_BINS * sizeof(u32), g.stream));
-    CK(cudaMemsetAsync(counter, 0, sizeof(u32), g.stream));
     LAUNCH("hist_u32", k_hist_u32, grid_for(2048, n, 4), 512, 0, ids->d, n, shift, ghist);
-    LAUNCH("radix_bases", k_radix_bases, 1, 256, 0, ghist, gbase);
-    DigitShift dop{shift};
-    if (launch_onesweep<false, 8, u32>(ids->d, dst, nullptr, nullptr, (u32)n, dop, gbase, status, counter) != 0) return -1;
-    dfree(ghist); dfree(gbase); dfree(status); dfree(counter);
+    LAUNCH("radix_bases", k_radix_bases, 1, 256, 0, ghist, cursor);
+    LAUNCH("partition_u32", (k_msd_partition<512, 8, u32>), ntiles, 512, 0, (const u32 *)ids->d, dst, lvl0, lvl0 + 2,
+           lvl0 + 3, 1u, 0u, shift, 256u, cursor, (const u32 *)nullptr);
+    dfree(ghist); dfree(cursor); dfree(lvl0);
     *out = dst;
     return 0;
 }
