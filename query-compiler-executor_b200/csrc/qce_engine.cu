@@ -936,6 +936,10 @@ static int register_column(u32 rel, u32 col, const u64 *d, u64 n, bool owned)
     return 0;
 }
 
+// A threaded pinned-staging pipeline (4 host threads, 2 x 16 MB pinned buffers and a stream
+// each) was measured here: 0.9-1.0 s for 4.8 GB of page-cache-resident relation files
+// against 0.45-0.55 s for the plain copy below (the driver's own bounce path already reaches
+// 9-10 GB/s; per-column pinned allocations and thread set-up cost more than the overlap gains).
 int qce_upload_column(uint32_t rel, uint32_t col, const uint64_t *host, uint64_t n)
 {
     NEED_INIT();
