@@ -35,7 +35,7 @@ def timed(name, fn):
 for name in ["filter_window", "build_from_ids", "build_window", "histogram", "partition", "from_exchange", "sort", "merge_join", "checksum", "release_partition"]:
     setattr(ops, name, timed(name, getattr(ops, name)))
 sj = sharded.ShardedJoin(ops, dist, torch, rank, world)
-sj._exchange = timed("exchange(all_to_all)", sj._exchange)
+sj._exchange_start = timed("exchange_start(counts + async all_to_all)", sj._exchange_start)
 sj._allreduce_u64 = timed("allreduce", sj._allreduce_u64)
 spec = sharded.JoinSpec(lhs=(0, 1), rhs=(1, 1), lhs_filter=(2, ">", 500000), lhs_selects=[0], rhs_selects=[0, 2])
 for _ in range(3): sj.run(spec, n, n)
