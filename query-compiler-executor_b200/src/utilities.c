@@ -120,23 +120,29 @@ static int print_sums(DArray *entities, const query *q, FILE *out)
     uint64_t sums[MAX_SELECTS];
     int is_null[MAX_SELECTS], done[MAX_SELECTS];
     mid_result *entry[MAX_SELECTS];
-    const size_t ns = q->select_size;
+    size_t ns = q->select_size;
     if (ns > MAX_SELECTS) {
         log_err("too many selects");
         return -1;
     }
+    /* The reference resolves and prints select by select and exits at the first
+     * binding without a mid result (src/utilities.c:203-207), i.e. AFTER the earlier
+     * tokens were written: `limit` keeps that observable behaviour. */
+    size_t limit = ns;
     for (size_t i = 0; i < ns; i++) {
         const uint64_t binding = q->selects[i].relation;
         exists_info where = relation_exists(entities, q->relations[binding], binding);
         if (where.index == -1) {
-            log_err("Something went really wrong...");
-            exit(EXIT_FAILURE); /* src/utilities.c:204-207 */
+            limit = i;
+            break;
         }
         DArray *entity = *(DArray **)DArray_get(entities, where.mid_result);
         entry[i] = (mid_result *)DArray_get(entity, where.index);
         is_null[i] = qce_rowids_count(entry[i]->payloads) == 0;
         done[i] = is_null[i];
     }
+    const size_t ns_all = ns;
+    ns = limit;
     /* every selected column of one binding in a single pass over its row ids */
     for (size_t i = 0; i < ns; i++) {
         if (done[i]) continue;
@@ -162,6 +168,12 @@ static int print_sums(DArray *entities, const query *q, FILE *out)
     for (size_t i = 0; i < ns; i++) {
         if (is_null[i]) fputs("NULL ", out);
         else fprintf(out, "%lu ", (unsigned long)sums[i]);
+    }
+    if (limit < ns_all) {
+        log_err("Something went really wrong...");
+        fflush(out);
+        if (out != stdout) { /* batch mode: hand the partial line to the caller's stream owner */ }
+        exit(EXIT_FAILURE); /* src/utilities.c:204-207 */
     }
     fputc('\n', out);
     return 0;

@@ -110,8 +110,32 @@ def golden_ops():
     classify_batch(db, qs, "ops.json")
 
 
+def golden_edge():
+    """Empty / one-row / duplicate-heavy / tile-boundary relations, repeated bindings."""
+    rng = np.random.default_rng(5)
+    db = [
+        [np.zeros(0, dtype=np.uint64), np.zeros(0, dtype=np.uint64)],                                   # r0: no rows
+        [np.array([7], dtype=np.uint64), np.array([3], dtype=np.uint64), np.array([9], dtype=np.uint64)],  # r1: one row
+        [np.array([1, 1, 1, 2, 2], dtype=np.uint64), np.array([3, 3, 3, 3, 7], dtype=np.uint64),
+         np.array([5, 6, 7, 8, 9], dtype=np.uint64)],                                                   # r2: duplicates
+        [np.arange(4097, dtype=np.uint64), rng.integers(0, 8, 4097, dtype=np.uint64)],                  # r3: 4097 rows
+        [rng.integers(0, 8, 4096, dtype=np.uint64), np.arange(4096, dtype=np.uint64),
+         rng.integers(0, 3, 4096, dtype=np.uint64)],                                                    # r4: 4096 rows
+    ]
+    save_db(os.path.join(HERE, "edge_db.npz"), db)
+    qs = [
+        "0|0.0<5|0.0", "0 1|0.0=1.0|0.1 1.1", "1 0|0.0=1.0|0.1", "1|0.0=7|0.0 0.1 0.2", "1|0.0>7|0.0", "1|0.1<4&0.2>8|0.2",
+        "1 2|0.1=1.1|0.0 1.2", "2 2|0.0=1.1|0.2 1.2", "2 2|0.1=1.1|0.2 1.2", "2 2|0.0=1.0&0.2<8|0.2 1.2",
+        "2 3|0.1=1.1|0.2 1.0", "3 4|0.1=1.0|0.0 1.1", "3 4|0.1=1.0&0.0<100|0.0 1.1 1.2", "3 4|0.1=1.0&1.2=1|0.0 1.1",
+        "4 3|0.0=1.1&0.2=0&0.1>4000|0.1 1.0", "3 4 2|0.1=1.0&1.2=2.0|0.0 1.1 2.2", "3|0.1=3|0.0 0.1", "3|0.0>4095|0.0",
+        "3|0.0<1&0.1<100|0.1", "4 4|0.2=1.2&0.1<40&0.0=5|0.1 1.1", "3 3|0.0=1.0|0.1 1.1", "2|0.0=0.1|0.2", "2|0.1<5&0.0=0.1|0.2",
+    ]
+    classify_batch(db, qs, "edge.json")
+
+
 if __name__ == "__main__":
     assert wl.have_reference(), "build oracle/_ref first: make -C oracle"
     golden_arrange()
     golden_ops()
     golden_small()
+    golden_edge()

@@ -25,7 +25,8 @@ def _paths(db):
     return wl.write_db(tempfile.mkdtemp(), db)
 
 
-@pytest.mark.parametrize("db_name,batch", [("ops_db.npz", "ops.json"), ("small_db.npz", "small_batch.json")])
+@pytest.mark.parametrize("db_name,batch", [("ops_db.npz", "ops.json"), ("small_db.npz", "small_batch.json"),
+                                           ("edge_db.npz", "edge.json")])
 def test_golden_stdout_byte_exact(binaries, db_name, batch):
     """Every PDQ query of the golden batches, one process per query (like the
     fixture was recorded).  PDQ-T must match; PDQ-D must match or be refused
@@ -49,6 +50,12 @@ def test_reference_abort_is_mirrored(binaries):
     db = load_db("ops_db.npz")
     out, err, rc = run_queries_bin(binaries[0], _paths(db), "0|0.1=0.2|0.0\n")
     assert rc != 0 and out == "" and "Something went really wrong" in err  # src/join.c:608-611
+    # a projected binding without a mid result: the reference has already printed the earlier
+    # checksums when it exits (src/utilities.c:203-207) -- same bytes here
+    edge = load_db("edge_db.npz")
+    rec = [r for r in load_json("edge.json") if r["query"] == "2 2|0.0=1.0&0.2<8|0.2 1.2"][0]
+    out, err, rc = run_queries_bin(binaries[0], _paths(edge), rec["query"] + "\n")
+    assert rc != 0 and out == rec["stdout"] == "18 " and "Something went really wrong" in err
 
 
 def test_batch_order_and_count_lines(binaries):
