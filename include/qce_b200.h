@@ -196,6 +196,69 @@ int qce_exchange_release(void *sendbuf);
  * selection from an all-reduced global histogram).  hist = 256 uint64 on host. */
 int qce_key_histogram(const qce_tuples *t, uint32_t key_bits, uint64_t *hist);
 
+/* ---- peer-memory exchange: partition + push over NVLink --------
+ * The multi-GPU half of the reference's radix partitioning (build_histogram /
+ * build_psum / build_reordered_array, src/utilities.c:20-70): the scatter pass of
+ * the top digit stores every tuple directly into the receive window of the GPU
+ * that owns its key range (P2P stores through CUDA-IPC-mapped windows), so the
+ * partition pass IS the transfer -- no send buffer, no separate all-to-all.
+ * One process per GPU; the caller (any communicator: torch.distributed here)
+ * only all-gathers the 64-byte IPC handles once and the 256-bin histograms per
+ * exchange, and provides a barrier after the pushing kernels have completed. */
+int qce_xwin_create(uint64_t bytes, unsigned char *ipc_handle_out /* 64 bytes, may be NULL */);
+int qce_xwin_attach(uint32_t world, uint32_t rank, const unsigned char *handles /* world x 64 bytes */);
+/* single process: present the local window as `world` ranks (rank r = bytes from r * window/world) */
+int qce_xwin_loopback(uint32_t world);
+int qce_xwin_info(uint64_t *bytes, void **local_base);
+int qce_xwin_destroy(void);
+/* Scatter a packed run by key range (same splitter rules as qce_partition_tuples) into
+ * the destination windows: the tuples for rank p are stored from 8-byte word offset
+ * dst_word_offset[p] of p's window on (order inside unspecified).  Asynchronous on the
+ * engine stream.  dst_run_index != NULL: the payload of every tuple is replaced by
+ * dst_run_index[p] + its position inside this rank's segment, i.e. its index in the
+ * receiver's run when the caller lays the segments out in that order; slots_out != NULL
+ * receives, per input tuple, (p << 28 | position inside the segment) for
+ * qce_push_u32_by_slot (bystander columns of the same entity, join.c:486-505). */
+int qce_push_tuples(const qce_tuples *t, uint32_t key_bits, const uint64_t *splitters, uint32_t nparts,
+                    const uint64_t *dst_word_offset, const uint32_t *dst_run_index, qce_rowids **slots_out);
+/* vals[i] -> 4-byte element dst_u32_offset[p] + position of rank p's window, (p, position) = slots[i] */
+int qce_push_u32_by_slot(const qce_rowids *vals, const qce_rowids *slots, uint32_t nparts,
+                         const uint64_t *dst_u32_offset);
+/* Row ids by owner: owner(id) = min(id / rows_per_rank, nranks-1); inside the owner's rows
+ * bins_per_rank equal-width bins (bin_width rows each, the last one open-ended);
+ * bin(id) = owner * bins_per_rank + local bin.  hist = nranks * bins_per_rank uint64 on the
+ * host.  qce_push_rowids stores the ids of bin b from 4-byte element offset
+ * bin_u32_offset[b] of the owner's window on: the owner receives its ids grouped by row
+ * region, which is what print_sums' gathers (src/utilities.c:215-219) want. */
+int qce_rowids_bin_histogram(const qce_rowids *ids, uint32_t rows_per_rank, uint32_t bin_width,
+                             uint32_t bins_per_rank, uint32_t nranks, uint64_t *hist);
+int qce_push_rowids(const qce_rowids *ids, uint32_t rows_per_rank, uint32_t bin_width,
+                    uint32_t bins_per_rank, uint32_t nranks, const uint64_t *bin_u32_offset);
+/* Carried join-key columns of the sharded executor: the low 32 bits of a base column's row
+ * window as a 4-byte device column; row ids begin..begin+count-1; a packed run
+ * (keys[i] << 32 | i) over such a column (allocate_relation_mid_results, src/join.c:96-120,
+ * with the key already at hand). */
+int qce_column_window_u32(uint32_t rel, uint32_t col, uint64_t row_begin, uint64_t row_count,
+                          qce_rowids **out);
+int qce_column_gather_u32(uint32_t rel, uint32_t col, const qce_rowids *ids, qce_rowids **out);
+int qce_rowids_iota(uint64_t begin, uint64_t count, uint32_t id_bound, qce_rowids **out);
+int qce_tuples_from_u32(const qce_rowids *keys, uint32_t key_bits, qce_tuples **out);
+/* Views into this rank's own window (no copy; valid until the window is reused). */
+int qce_tuples_from_window(uint64_t word_offset, uint64_t n, uint32_t key_bits, uint32_t id_bound,
+                           uint64_t key_lo, uint64_t key_hi, qce_tuples **out);
+int qce_rowids_from_window(uint64_t u32_offset, uint64_t n, uint32_t id_bound, int bucketed,
+                           qce_rowids **out);
+/* out[i] = src[index[i]] (re-align a bystander row-id column with a join output whose
+ * payloads are positions; SURVEY 8f-2, replaces join_payloads src/join.c:426-484 inside PDQ-T). */
+int qce_rowids_gather(const qce_rowids *src, const qce_rowids *index, qce_rowids **out);
+/* Row-sharded base column: this rank holds rows [row_begin, row_begin + row_count) of a
+ * relation of rows_global rows (device buffer of row_count uint64, adopted).  Row ids stay
+ * relation-global everywhere; operators may only touch resident rows (checked for windows,
+ * by construction for gathers: ids are routed to their owner with qce_push_rowids). */
+int qce_adopt_column_window(uint32_t rel, uint32_t col, const void *dev, uint64_t row_begin,
+                            uint64_t row_count, uint64_t rows_global, uint64_t max_value_global);
+int qce_column_max_device(const void *dev, uint64_t n, uint64_t *max_value);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,6 +24,7 @@
 #include "k_filter.cuh"
 #include "k_join.cuh"
 #include "k_radix.cuh"
+#include "k_exchange.cuh"
 
 #define QCE_ABI_VERSION 1
 
@@ -32,6 +33,7 @@ struct qce_rowids {
     u32 *d;        // device row ids
     u64 n;
     u32 id_bound;  // exclusive upper bound of the ids (rows of the source relation), 0 = unknown
+    bool bucketed = false; // already grouped by row region (received through qce_push_rowids)
 };
 struct qce_tuples {
     u64 *a;        // packed words (key << 32 | rowid), or keys when wide
@@ -51,10 +53,12 @@ struct qce_tuples {
 namespace {
 
 struct Column {
-    const u64 *d = nullptr;
-    u64 n = 0;
+    const u64 *d = nullptr; // row-sharded column: VIRTUAL base (window pointer - win_begin), rows outside the
+    u64 n = 0;              // window are not resident; n stays the relation's global row count
     u64 maxv = 0;
     bool owned = false;
+    bool windowed = false;
+    u64 win_begin = 0, win_count = 0;
 };
 
 struct ProfRec {
@@ -76,6 +80,12 @@ struct Engine {
     std::vector<ProfRec> prof;
     std::vector<cudaEvent_t> ev_pool; // recycled profiling events
     std::string prof_json;
+    // peer-memory exchange: this rank's receive window + the peers' windows mapped through CUDA IPC
+    unsigned char *xwin = nullptr;
+    u64 xwin_bytes = 0;
+    u32 xworld = 0, xrank = 0;
+    PeerWindows peers;
+    std::vector<void *> xopened;
 };
 Engine g;
 thread_local char g_err[512] = "";
@@ -255,12 +265,20 @@ int read_scalars(int k)
     return 0;
 }
 
+// Row-sharded columns hold only [win_begin, win_begin + win_count) of the relation.
+bool window_resident(const struct Column *cl, u64 begin, u64 count);
 int get_column(u32 rel, u32 col, const Column **out)
 {
     auto it = g.cols.find(col_key(rel, col));
     if (it == g.cols.end()) return fail("relation %u column %u was never uploaded", rel, col);
     *out = &it->second;
     return 0;
+}
+
+bool window_resident(const Column *cl, u64 begin, u64 count)
+{
+    if (!cl->windowed || count == 0) return true;
+    return begin >= cl->win_begin && begin + count <= cl->win_begin + cl->win_count;
 }
 
 int op_code(char op, int *code)
@@ -965,6 +983,37 @@ int qce_adopt_column_device(uint32_t rel, uint32_t col, const void *dev, uint64_
     if (((uintptr_t)dev & 15) != 0) return fail("adopted column must be 16-byte aligned");
     return register_column(rel, col, (const u64 *)dev, n, false);
 }
+int qce_adopt_column_window(uint32_t rel, uint32_t col, const void *dev, uint64_t row_begin, uint64_t row_count,
+                            uint64_t rows_global, uint64_t max_value_global)
+{
+    NEED_INIT();
+    if (rows_global >= (1ull << 32)) return fail("relation %u has %llu rows; device row ids are 32-bit", rel, (unsigned long long)rows_global);
+    if (row_begin > rows_global || row_count > rows_global - row_begin) return fail("row window outside the relation");
+    if (((uintptr_t)dev & 15) != 0 || (row_begin & 1)) return fail("window must be 16-byte aligned and start on an even row");
+    Column c;
+    c.d = (const u64 *)dev - row_begin; // virtual base: row id r of the window lives at c.d[r]
+    c.n = rows_global;
+    c.maxv = max_value_global;
+    c.owned = false;
+    c.windowed = true;
+    c.win_begin = row_begin;
+    c.win_count = row_count;
+    auto it = g.cols.find(col_key(rel, col));
+    if (it != g.cols.end() && it->second.owned) cudaFree((void *)it->second.d);
+    g.cols[col_key(rel, col)] = c;
+    return 0;
+}
+int qce_column_max_device(const void *dev, uint64_t n, uint64_t *max_value)
+{
+    NEED_INIT();
+    if (!max_value) return fail("null argument");
+    CK(cudaMemsetAsync(g.d_scalars + 8, 0, sizeof(u64), g.stream));
+    if (n > 0) LAUNCH("column_stats", k_column_stats, grid_for(512, n, 4), 256, 0, (const u64 *)dev, n, g.d_scalars + 8);
+    CK(cudaMemcpyAsync(g.h_scalars + 8, g.d_scalars + 8, sizeof(u64), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    *max_value = g.h_scalars[8];
+    return 0;
+}
 int qce_column_info(uint32_t rel, uint32_t col, uint64_t *n, uint64_t *max_value)
 {
     NEED_INIT();
@@ -996,6 +1045,8 @@ static int filter_scan_window(uint32_t rel, uint32_t col, char op, uint64_t c, u
                                                            (unsigned long long)begin, (unsigned long long)count, rel,
                                                            (unsigned long long)cl->n);
     if (begin & 1) return fail("row window must start on an even row (128-bit loads)");
+    if (!window_resident(cl, begin, count)) return fail("rows [%llu, +%llu) of relation %u are not resident on this rank",
+                                                        (unsigned long long)begin, (unsigned long long)count, rel);
     const u64 n = count;
     if (n == 0) return new_rowids(0, (u32)cl->n, out);
     const u64 *d = cl->d + begin;
@@ -1064,6 +1115,8 @@ static int build_tuples(const Column *cl, const qce_rowids *ids, qce_tuples **ou
                         u64 count = ~0ull)
 {
     if (count == ~0ull) count = cl->n - begin;
+    if (!ids && !window_resident(cl, begin, count)) return fail("rows [%llu, +%llu) are not resident on this rank",
+                                                                (unsigned long long)begin, (unsigned long long)count);
     const u64 n = ids ? ids->n : count;
     qce_tuples *t = new qce_tuples();
     t->n = n;
@@ -1264,7 +1317,7 @@ int qce_checksum(const qce_rowids *ids, uint32_t rel, const uint32_t *cols, uint
         // column region by region and are served from L2.
         const u32 *src = ids->d;
         u32 *bucketed = nullptr;
-        if (bucketed_checksum_pays(ids, col_rows)) {
+        if (!ids->bucketed && bucketed_checksum_pays(ids, col_rows)) {
             if (partition_ids_by_top_bits(ids, &bucketed) != 0) return -1;
             src = bucketed;
         }
@@ -1519,6 +1572,302 @@ static int tuples_from_device(const void *dev_words, uint64_t n, uint32_t key_bi
         if (n) CK(cudaMemcpyAsync(t->a, dev_words, n * sizeof(u64), cudaMemcpyDeviceToDevice, g.stream));
     }
     *out = t;
+    return 0;
+}
+
+// ------------------------------------------------- peer-memory exchange (NVLink)
+// One receive window per rank (plain cudaMalloc so that it can be exported with
+// CUDA IPC); the peers map it once.  The orchestrator carves regions out of the
+// window deterministically from the all-gathered histograms, so no offsets are
+// ever communicated per transfer.
+int qce_xwin_create(uint64_t bytes, unsigned char *ipc_handle_out)
+{
+    NEED_INIT();
+    if (g.xwin) return fail("exchange window already exists");
+    if (bytes == 0) return fail("empty exchange window");
+    bytes = (bytes + 4095) / 4096 * 4096;
+    void *p = nullptr;
+    CK(cudaMalloc(&p, bytes));
+    g.xwin = (unsigned char *)p;
+    g.xwin_bytes = bytes;
+    g.xworld = 1;
+    g.xrank = 0;
+    for (int r = 0; r < QCE_MAX_RANKS; r++) g.peers.base[r] = nullptr;
+    g.peers.base[0] = g.xwin;
+    if (ipc_handle_out) {
+        cudaIpcMemHandle_t h;
+        CK(cudaIpcGetMemHandle(&h, p));
+        static_assert(sizeof(h) == 64, "IPC handle size");
+        memcpy(ipc_handle_out, &h, sizeof h);
+    }
+    return 0;
+}
+int qce_xwin_attach(uint32_t world, uint32_t rank, const unsigned char *handles)
+{
+    NEED_INIT();
+    if (!g.xwin) return fail("create the exchange window first");
+    if (world < 1 || world > QCE_MAX_RANKS || rank >= world) return fail("world size must be 1..%d", QCE_MAX_RANKS);
+    if (world > 1 && !handles) return fail("null argument");
+    for (int r = 0; r < QCE_MAX_RANKS; r++) g.peers.base[r] = nullptr;
+    for (u32 r = 0; r < world; r++) {
+        if (r == rank) { g.peers.base[r] = g.xwin; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + 64 * (size_t)r, sizeof h);
+        void *p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        g.xopened.push_back(p);
+        g.peers.base[r] = (unsigned char *)p;
+    }
+    g.xworld = world;
+    g.xrank = rank;
+    return 0;
+}
+// Single-process testing: present this rank's window as `world` ranks, rank r
+// owning the bytes from r * (window / world) on.
+int qce_xwin_loopback(uint32_t world)
+{
+    NEED_INIT();
+    if (!g.xwin) return fail("create the exchange window first");
+    if (world < 1 || world > QCE_MAX_RANKS) return fail("world size must be 1..%d", QCE_MAX_RANKS);
+    const u64 per = g.xwin_bytes / world / 4096 * 4096;
+    for (int r = 0; r < QCE_MAX_RANKS; r++) g.peers.base[r] = (u32)r < world ? g.xwin + per * r : nullptr;
+    g.xworld = world;
+    g.xrank = 0;
+    return 0;
+}
+int qce_xwin_info(uint64_t *bytes, void **local_base)
+{
+    NEED_INIT();
+    if (bytes) *bytes = g.xwin_bytes;
+    if (local_base) *local_base = g.xwin;
+    return 0;
+}
+int qce_xwin_destroy(void)
+{
+    if (!g.inited) return 0;
+    cudaStreamSynchronize(g.stream);
+    for (void *p : g.xopened) cudaIpcCloseMemHandle(p);
+    g.xopened.clear();
+    if (g.xwin) cudaFree(g.xwin);
+    g.xwin = nullptr;
+    g.xwin_bytes = 0;
+    g.xworld = 0;
+    return 0;
+}
+
+static int push_scratch(u32 ndigits, const uint64_t *seg_start, const u32 *run_base, unsigned long long **d_seg,
+                        u32 **d_run, unsigned long long **d_cur)
+{
+    // seg_start | cursor (same values) | run_base, one small upload each
+    if (dalloc(d_seg, 256) || dalloc(d_cur, 256) || dalloc(d_run, 256)) return -1;
+    std::vector<unsigned long long> seg(256, 0);
+    std::vector<u32> run(256, 0);
+    for (u32 d = 0; d < ndigits; d++) { seg[d] = seg_start[d]; run[d] = run_base ? run_base[d] : 0u; }
+    CK(cudaMemcpyAsync(*d_seg, seg.data(), 256 * sizeof(unsigned long long), cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(*d_cur, seg.data(), 256 * sizeof(unsigned long long), cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(*d_run, run.data(), 256 * sizeof(u32), cudaMemcpyHostToDevice, g.stream));
+    return 0;
+}
+
+int qce_push_tuples(const qce_tuples *t, uint32_t key_bits, const uint64_t *splitters, uint32_t nparts,
+                    const uint64_t *dst_word_offset, const uint32_t *dst_run_index, qce_rowids **slots_out)
+{
+    NEED_INIT();
+    if (!t || !dst_word_offset) return fail("null argument");
+    if (!g.xwin) return fail("no exchange window (qce_xwin_create)");
+    if (t->wide) return fail("the sharded exchange supports packed (key < 2^32) runs only");
+    if (nparts != g.xworld) return fail("nparts (%u) differs from the attached world size (%u)", nparts, g.xworld);
+    if (key_bits == 0 || key_bits > 32) return fail("packed runs carry keys of 1..32 bits");
+    if (t->n >= (1ull << 28)) return fail("push of %llu tuples exceeds the 2^28 per-run limit", (unsigned long long)t->n);
+    if (nparts > 1 && !splitters) return fail("null argument");
+    const int bin_shift = key_bits > 8 ? (int)key_bits - 8 : 0;
+    unsigned char lut[256];
+    for (u32 b = 0; b < 256; b++) {
+        u32 part = 0;
+        for (u32 k = 0; k + 1 < nparts; k++) {
+            if ((splitters[k] & ((1ull << bin_shift) - 1)) != 0)
+                return fail("splitter %llu is not on a boundary of the top-8-bit histogram bins", (unsigned long long)splitters[k]);
+            if (((u64)b << bin_shift) >= splitters[k]) part++;
+        }
+        lut[b] = (unsigned char)part;
+    }
+    if (slots_out && new_rowids(t->n, 0, slots_out) != 0) return -1;
+    if (t->n == 0) return 0;
+    unsigned long long *d_seg = nullptr, *d_cur = nullptr;
+    u32 *d_run = nullptr, *dlut = nullptr;
+    if (push_scratch(nparts, dst_word_offset, dst_run_index, &d_seg, &d_run, &d_cur) != 0 || dalloc(&dlut, 64)) return -1;
+    CK(cudaMemcpyAsync(dlut, lut, sizeof lut, cudaMemcpyHostToDevice, g.stream));
+    PushDigit<u64> dg;
+    dg.shift = 32 + bin_shift;
+    dg.lut = dlut;
+    PushPlan plan{d_seg, d_run, d_cur, nparts, 1u};
+    const u32 n = (u32)t->n, grid = (u32)ceil_div(n, QCE_PUSH_TILE);
+    const int dbits = bitlen(nparts - 1);
+    u32 *so = slots_out ? (*slots_out)->d : nullptr;
+    if (dst_run_index)
+        LAUNCH("push_tuples", (k_push<u64, true, true>), grid, QCE_PUSH_THREADS, 0, (const u64 *)t->a, n, dg, plan, g.peers, dbits, so);
+    else
+        LAUNCH("push_tuples", (k_push<u64, true, false>), grid, QCE_PUSH_THREADS, 0, (const u64 *)t->a, n, dg, plan, g.peers, dbits, so);
+    dfree(d_seg); dfree(d_cur); dfree(d_run); dfree(dlut);
+    return 0;
+}
+
+int qce_push_u32_by_slot(const qce_rowids *vals, const qce_rowids *slots, uint32_t nparts, const uint64_t *dst_u32_offset)
+{
+    NEED_INIT();
+    if (!vals || !slots || !dst_u32_offset) return fail("null argument");
+    if (!g.xwin) return fail("no exchange window (qce_xwin_create)");
+    if (vals->n != slots->n) return fail("column (%llu) and slot (%llu) lengths differ", (unsigned long long)vals->n, (unsigned long long)slots->n);
+    if (nparts != g.xworld) return fail("nparts (%u) differs from the attached world size (%u)", nparts, g.xworld);
+    if (vals->n == 0) return 0;
+    SlotRegions reg;
+    for (u32 r = 0; r < QCE_MAX_RANKS; r++) reg.region[r] = r < nparts ? dst_u32_offset[r] : 0;
+    LAUNCH("push_by_slot", k_push_u32_by_slot, grid_for(2048, vals->n), 256, 0, vals->d, slots->d, vals->n, reg, g.peers);
+    return 0;
+}
+
+static int row_bins(uint32_t rows_per_rank, uint32_t bin_width, uint32_t bins_per_rank, uint32_t nranks, RowBins *rb)
+{
+    if (rows_per_rank == 0 || bin_width == 0 || bins_per_rank == 0 || nranks == 0 || (u64)bins_per_rank * nranks > 256)
+        return fail("row bins: rows_per_rank, bin_width > 0 and bins_per_rank * nranks in 1..256");
+    rb->rows_per_rank = rows_per_rank;
+    rb->last_rank = nranks - 1;
+    rb->width = bin_width;
+    rb->bins_per_rank = bins_per_rank;
+    return 0;
+}
+int qce_rowids_bin_histogram(const qce_rowids *ids, uint32_t rows_per_rank, uint32_t bin_width, uint32_t bins_per_rank,
+                             uint32_t nranks, uint64_t *hist)
+{
+    NEED_INIT();
+    if (!ids || !hist) return fail("null argument");
+    RowBins rb;
+    if (row_bins(rows_per_rank, bin_width, bins_per_rank, nranks, &rb) != 0) return -1;
+    u32 *gh = nullptr;
+    if (dalloc(&gh, 256) != 0) return -1;
+    CK(cudaMemsetAsync(gh, 0, 256 * sizeof(u32), g.stream));
+    if (ids->n) LAUNCH("hist_ids", k_hist_u32_div, grid_for(4096, ids->n, 4), 512, 0, ids->d, ids->n, rb, gh);
+    u32 tmp[256];
+    CK(cudaMemcpyAsync(tmp, gh, sizeof tmp, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    for (u32 b = 0; b < bins_per_rank * nranks; b++) hist[b] = tmp[b];
+    dfree(gh);
+    return 0;
+}
+
+int qce_push_rowids(const qce_rowids *ids, uint32_t rows_per_rank, uint32_t bin_width, uint32_t bins_per_rank,
+                    uint32_t nranks, const uint64_t *bin_u32_offset)
+{
+    NEED_INIT();
+    if (!ids || !bin_u32_offset) return fail("null argument");
+    if (!g.xwin) return fail("no exchange window (qce_xwin_create)");
+    RowBins rb;
+    if (row_bins(rows_per_rank, bin_width, bins_per_rank, nranks, &rb) != 0) return -1;
+    if (nranks != g.xworld) return fail("nranks (%u) differs from the attached world size (%u)", nranks, g.xworld);
+    if (ids->n >= (1ull << 32)) return fail("row-id column too long");
+    if (ids->n == 0) return 0;
+    const u32 nbins = bins_per_rank * nranks;
+    unsigned long long *d_seg = nullptr, *d_cur = nullptr;
+    u32 *d_run = nullptr;
+    if (push_scratch(nbins, bin_u32_offset, nullptr, &d_seg, &d_run, &d_cur) != 0) return -1;
+    PushDigit<u32> dg;
+    dg.bins = rb;
+    PushPlan plan{d_seg, d_run, d_cur, nbins, bins_per_rank};
+    const u32 n = (u32)ids->n, grid = (u32)ceil_div(n, QCE_PUSH_TILE);
+    LAUNCH("push_rowids", (k_push<u32, false, false>), grid, QCE_PUSH_THREADS, 0, (const u32 *)ids->d, n, dg, plan, g.peers, 0,
+           (u32 *)nullptr);
+    dfree(d_seg); dfree(d_cur); dfree(d_run);
+    return 0;
+}
+
+// Carried columns of the sharded executor (sharded.py): join keys travel with the rows.
+int qce_column_window_u32(uint32_t rel, uint32_t col, uint64_t row_begin, uint64_t row_count, qce_rowids **out)
+{
+    NEED_INIT();
+    const Column *cl;
+    if (!out) return fail("null argument");
+    if (get_column(rel, col, &cl) != 0) return -1;
+    if (row_begin > cl->n || row_count > cl->n - row_begin) return fail("row window outside relation %u", rel);
+    if (!window_resident(cl, row_begin, row_count)) return fail("rows are not resident on this rank");
+    if (cl->maxv >> 32) return fail("column %u.%u holds values >= 2^32: cannot be carried as 4-byte keys", rel, col);
+    if (new_rowids(row_count, 0, out) != 0) return -1;
+    if (row_count) LAUNCH("narrow_col", k_narrow_u64, grid_for(2048, row_count), 256, 0, cl->d + row_begin, row_count, (*out)->d);
+    return 0;
+}
+int qce_column_gather_u32(uint32_t rel, uint32_t col, const qce_rowids *ids, qce_rowids **out)
+{
+    NEED_INIT();
+    const Column *cl;
+    if (!ids || !out) return fail("null argument");
+    if (get_column(rel, col, &cl) != 0) return -1;
+    if (cl->maxv >> 32) return fail("column %u.%u holds values >= 2^32: cannot be carried as 4-byte keys", rel, col);
+    if (new_rowids(ids->n, 0, out) != 0) return -1;
+    if (ids->n) LAUNCH("gather_col", k_gather_u64_narrow, grid_for(2048, ids->n), 256, 0, cl->d, ids->d, ids->n, (*out)->d);
+    return 0;
+}
+int qce_rowids_iota(uint64_t begin, uint64_t count, uint32_t id_bound, qce_rowids **out)
+{
+    NEED_INIT();
+    if (!out) return fail("null argument");
+    if (begin + count > (1ull << 32)) return fail("row ids are 32-bit");
+    if (new_rowids(count, id_bound, out) != 0) return -1;
+    if (count) LAUNCH("iota_ids", k_iota_u32, grid_for(2048, count), 256, 0, (u32)begin, count, (*out)->d);
+    return 0;
+}
+int qce_tuples_from_u32(const qce_rowids *keys, uint32_t key_bits, qce_tuples **out)
+{
+    NEED_INIT();
+    if (!keys || !out) return fail("null argument");
+    if (key_bits == 0 || key_bits > 32) return fail("packed runs carry keys of 1..32 bits");
+    if (keys->n >= (1ull << 32)) return fail("run too long");
+    qce_tuples *t = new qce_tuples();
+    t->n = keys->n;
+    t->key_bits = (int)key_bits;
+    t->key_min = 0;
+    t->key_max = key_bits >= 32 ? 0xffffffffull : ((1ull << key_bits) - 1);
+    t->wide = false;
+    t->id_bound = (u32)keys->n;
+    t->sorted = false;
+    t->ids = nullptr;
+    if (dalloc(&t->a, t->n) != 0) { delete t; return -1; }
+    if (t->n) LAUNCH("pack_keys", k_pack_u32_index, grid_for(2048, t->n), 256, 0, keys->d, t->n, t->a);
+    *out = t;
+    return 0;
+}
+
+// Views of this rank's window after the peers' pushes have landed (the caller
+// has synchronised every pushing rank: qce_sync on each + a barrier).
+int qce_tuples_from_window(uint64_t word_offset, uint64_t n, uint32_t key_bits, uint32_t id_bound, uint64_t key_lo,
+                           uint64_t key_hi, qce_tuples **out)
+{
+    NEED_INIT();
+    if (!g.xwin) return fail("no exchange window (qce_xwin_create)");
+    if ((word_offset + n) * 8 > g.xwin_bytes) return fail("run [%llu, +%llu) words exceeds the exchange window", (unsigned long long)word_offset, (unsigned long long)n);
+    if (word_offset & 1) return fail("runs in the window start on 16-byte boundaries");
+    return tuples_from_device(g.peers.base[g.xrank] + word_offset * 8, n, key_bits, id_bound, key_lo, key_hi, true, out);
+}
+int qce_rowids_from_window(uint64_t u32_offset, uint64_t n, uint32_t id_bound, int bucketed, qce_rowids **out)
+{
+    NEED_INIT();
+    if (!g.xwin) return fail("no exchange window (qce_xwin_create)");
+    if (!out) return fail("null argument");
+    if ((u32_offset + n) * 4 > g.xwin_bytes) return fail("row-id column exceeds the exchange window");
+    qce_rowids *r = new qce_rowids();
+    r->d = (u32 *)(g.peers.base[g.xrank] + u32_offset * 4); // not from the arena: freeing the handle leaves it alone
+    r->n = n;
+    r->id_bound = id_bound;
+    r->bucketed = bucketed != 0;
+    *out = r;
+    return 0;
+}
+// out[i] = ids[index[i]]: a bystander column re-aligned with a join output whose
+// payloads are positions in the (received) entity.
+int qce_rowids_gather(const qce_rowids *src, const qce_rowids *index, qce_rowids **out)
+{
+    NEED_INIT();
+    if (!src || !index || !out) return fail("null argument");
+    if (new_rowids(index->n, src->id_bound, out) != 0) return -1;
+    if (index->n) LAUNCH("gather_ids", k_gather_u32, grid_for(2048, index->n), 256, 0, src->d, index->d, index->n, (*out)->d);
     return 0;
 }
 

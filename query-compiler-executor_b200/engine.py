@@ -28,6 +28,10 @@ SYMBOLS = [
     "qce_rowids_from_host", "qce_rowids_to_host", "qce_rowids_clone", "qce_rowids_free", "qce_tuples_count",
     "qce_tuples_from_host", "qce_tuples_to_host", "qce_tuples_free", "qce_partition_tuples",
     "qce_tuples_from_device_packed", "qce_tuples_adopt_device_packed", "qce_exchange_release", "qce_key_histogram",
+    "qce_xwin_create", "qce_xwin_attach", "qce_xwin_loopback", "qce_xwin_info", "qce_xwin_destroy", "qce_push_tuples",
+    "qce_push_u32_by_slot", "qce_rowids_bin_histogram", "qce_push_rowids", "qce_tuples_from_window", "qce_rowids_from_window",
+    "qce_rowids_gather", "qce_adopt_column_window", "qce_column_max_device", "qce_column_window_u32", "qce_rowids_iota",
+    "qce_tuples_from_u32", "qce_column_gather_u32",
 ]
 
 
@@ -70,6 +74,18 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "qce_tuples_from_device_packed": (i32, [vp, u64, u32, u32, u64, u64, P(vp)]),
         "qce_tuples_adopt_device_packed": (i32, [vp, u64, u32, u32, u64, u64, P(vp)]), "qce_exchange_release": (i32, [vp]),
         "qce_key_histogram": (i32, [vp, u32, P(u64)]),
+        "qce_xwin_create": (i32, [u64, vp]), "qce_xwin_attach": (i32, [u32, u32, vp]), "qce_xwin_loopback": (i32, [u32]),
+        "qce_xwin_info": (i32, [P(u64), P(vp)]), "qce_xwin_destroy": (i32, []),
+        "qce_push_tuples": (i32, [vp, u32, vp, u32, vp, vp, P(vp)]),
+        "qce_push_u32_by_slot": (i32, [vp, vp, u32, vp]),
+        "qce_rowids_bin_histogram": (i32, [vp, u32, u32, u32, u32, vp]),
+        "qce_push_rowids": (i32, [vp, u32, u32, u32, u32, vp]),
+        "qce_column_window_u32": (i32, [u32, u32, u64, u64, P(vp)]), "qce_rowids_iota": (i32, [u64, u64, u32, P(vp)]),
+        "qce_tuples_from_u32": (i32, [vp, u32, P(vp)]), "qce_column_gather_u32": (i32, [u32, u32, vp, P(vp)]),
+        "qce_tuples_from_window": (i32, [u64, u64, u32, u32, u64, u64, P(vp)]),
+        "qce_rowids_from_window": (i32, [u64, u64, u32, i32, P(vp)]), "qce_rowids_gather": (i32, [vp, vp, P(vp)]),
+        "qce_adopt_column_window": (i32, [u32, u32, vp, u64, u64, u64, u64]),
+        "qce_column_max_device": (i32, [vp, u64, P(u64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -269,3 +285,94 @@ class Engine:
     def exchange_release(self, buf: Optional[int]) -> None:
         if buf:
             self._ck(self.lib.qce_exchange_release(buf))
+
+    # ---- peer-memory exchange (partition + push over NVLink)
+    def xwin_create(self, nbytes: int) -> bytes:
+        h = (C.c_ubyte * 64)()
+        self._ck(self.lib.qce_xwin_create(nbytes, h))
+        return bytes(h)
+
+    def xwin_attach(self, world: int, rank: int, handles: bytes) -> None:
+        buf = (C.c_ubyte * (64 * world)).from_buffer_copy(handles)
+        self._ck(self.lib.qce_xwin_attach(world, rank, buf))
+
+    def xwin_loopback(self, world: int) -> None:
+        self._ck(self.lib.qce_xwin_loopback(world))
+
+    def xwin_info(self) -> Tuple[int, int]:
+        n, p = C.c_uint64(), C.c_void_p()
+        self._ck(self.lib.qce_xwin_info(C.byref(n), C.byref(p)))
+        return n.value, p.value or 0
+
+    def xwin_destroy(self) -> None:
+        self._ck(self.lib.qce_xwin_destroy())
+
+    def push_tuples(self, t: int, key_bits: int, splitters, nparts: int, dst_word_offset,
+                    dst_run_index=None, want_slots: bool = False) -> Optional[int]:
+        sp = _u64(splitters if len(splitters) else [0])
+        off = _u64(dst_word_offset)
+        ri = np.ascontiguousarray(dst_run_index, dtype=np.uint32) if dst_run_index is not None else None
+        slots = C.c_void_p()
+        self._ck(self.lib.qce_push_tuples(t, key_bits, sp.ctypes.data, nparts, off.ctypes.data,
+                                          ri.ctypes.data if ri is not None else None,
+                                          C.byref(slots) if want_slots else None))
+        return slots.value if want_slots else None
+
+    def push_u32_by_slot(self, vals: int, slots: int, nparts: int, dst_u32_offset) -> None:
+        off = _u64(dst_u32_offset)
+        self._ck(self.lib.qce_push_u32_by_slot(vals, slots, nparts, off.ctypes.data))
+
+    def rowids_bin_histogram(self, ids: int, rows_per_rank: int, bin_width: int, bins_per_rank: int, nranks: int) -> np.ndarray:
+        out = np.zeros(bins_per_rank * nranks, dtype=np.uint64)
+        self._ck(self.lib.qce_rowids_bin_histogram(ids, rows_per_rank, bin_width, bins_per_rank, nranks, out.ctypes.data))
+        return out
+
+    def push_rowids(self, ids: int, rows_per_rank: int, bin_width: int, bins_per_rank: int, nranks: int,
+                    bin_u32_offset) -> None:
+        off = _u64(bin_u32_offset)
+        self._ck(self.lib.qce_push_rowids(ids, rows_per_rank, bin_width, bins_per_rank, nranks, off.ctypes.data))
+
+    def column_window_u32(self, rel: int, col: int, begin: int, count: int) -> int:
+        h = C.c_void_p()
+        self._ck(self.lib.qce_column_window_u32(rel, col, begin, count, C.byref(h)))
+        return h.value
+
+    def column_gather_u32(self, rel: int, col: int, ids: int) -> int:
+        h = C.c_void_p()
+        self._ck(self.lib.qce_column_gather_u32(rel, col, ids, C.byref(h)))
+        return h.value
+
+    def rowids_iota(self, begin: int, count: int, id_bound: int = 0) -> int:
+        h = C.c_void_p()
+        self._ck(self.lib.qce_rowids_iota(begin, count, id_bound, C.byref(h)))
+        return h.value
+
+    def tuples_from_u32(self, keys: int, key_bits: int) -> int:
+        h = C.c_void_p()
+        self._ck(self.lib.qce_tuples_from_u32(keys, key_bits, C.byref(h)))
+        return h.value
+
+    def tuples_from_window(self, word_offset: int, n: int, key_bits: int, id_bound: int = 0,
+                           key_lo: int = 0, key_hi: int = 0) -> int:
+        h = C.c_void_p()
+        self._ck(self.lib.qce_tuples_from_window(word_offset, n, key_bits, id_bound, key_lo, key_hi, C.byref(h)))
+        return h.value
+
+    def rowids_from_window(self, u32_offset: int, n: int, id_bound: int = 0, bucketed: bool = False) -> int:
+        h = C.c_void_p()
+        self._ck(self.lib.qce_rowids_from_window(u32_offset, n, id_bound, 1 if bucketed else 0, C.byref(h)))
+        return h.value
+
+    def rowids_gather(self, src: int, index: int) -> int:
+        h = C.c_void_p()
+        self._ck(self.lib.qce_rowids_gather(src, index, C.byref(h)))
+        return h.value
+
+    def adopt_column_window(self, rel: int, col: int, dev_ptr: int, row_begin: int, row_count: int,
+                            rows_global: int, max_value_global: int) -> None:
+        self._ck(self.lib.qce_adopt_column_window(rel, col, dev_ptr, row_begin, row_count, rows_global, max_value_global))
+
+    def column_max_device(self, dev_ptr: int, n: int) -> int:
+        m = C.c_uint64()
+        self._ck(self.lib.qce_column_max_device(dev_ptr, n, C.byref(m)))
+        return m.value

@@ -1,0 +1,509 @@
+"""Sharded execution of one query over N GPUs with peer-memory exchanges
+(BASELINE.json north_star: "Large joins shard across the 8 GPUs by
+radix high bits ... over NVLink and a final checksum reduce").
+
+One process per GPU.  Base columns are ROW-SHARDED (each rank holds one row
+window of every relation; nothing is replicated), intermediate results are
+sharded by the key range of the last join.  Per join:
+
+  1. every rank builds the tuple runs of its share: the entity side from its
+     slice of the intermediate result (or a filter output / base window), the new
+     relation from its base row window                     (C-ABI build calls)
+  2. 256-bin histograms of the top key bits, ONE all-gather of both -> every rank
+     derives the same splitters (bytes balanced per rank) and the whole
+     count matrix [src][dst], hence every segment offset in every window
+  3. qce_push_tuples: the partition pass stores each tuple directly into the
+     owner's receive window over NVLink (P2P stores; no send buffer, no
+     all-to-all).  Row-id columns of the other bindings of the entity and join
+     keys needed later follow their tuple with qce_push_u32_by_slot
+  4. barrier; local sort + merge join of the received key range; bystander
+     columns re-aligned by position (qce_rowids_gather)
+Projection (print_sums, src/utilities.c:197-224): the row ids of each projected
+binding are pushed to the rank that owns the rows (grouped by row region on
+arrival), gathered and summed there, and the uint64 sums are all-reduced (exact:
+addition mod 2^64 is associative and commutative).
+
+Query class: left-deep join trees -- filters on at most one binding, self-join
+predicates on that binding, then joins that each add one fresh base relation.
+Inside this class the reference is tie-invariant and equals relational truth
+(PDQ-T); everything else is refused with UnsupportedQuery (never
+answered differently from the reference).  Keys must be < 2^32 (packed runs).
+
+The engine is reached through an `ops` object so that the orchestration runs on
+CPU under gloo with a numpy stand-in (tests/test_sharded_cpu.py).
+"""
+from __future__ import annotations
+
+import re
+import time
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .sharded import choose_splitters, row_window
+
+
+class UnsupportedQuery(NotImplementedError):
+    pass
+
+
+# ------------------------------------------------------------------ query text
+def parse_query(text: str):
+    """`r r r|p&p&p|s s` (src/parsing.c:4-148): relations, predicates, selects."""
+    rels_s, preds_s, sels_s = text.strip().split("|")
+    relations = [int(x) for x in rels_s.split()]
+    filters, joins = [], []
+    for p in preds_s.split("&"):
+        m = re.fullmatch(r"\s*(\d+)\.(\d+)\s*([=<>])\s*(\d+)(?:\.(\d+))?\s*", p)
+        if not m:
+            raise ValueError(f"bad predicate {p!r}")
+        b, c, op, x, y = int(m[1]), int(m[2]), m[3], int(m[4]), m[5]
+        if y is None:
+            filters.append((b, c, op, x))
+        else:
+            if op != "=":
+                raise ValueError("joins are equi-joins")
+            joins.append(((b, c), (x, int(y))))
+    selects = []
+    for s in sels_s.split():
+        b, c = s.split(".")
+        selects.append((int(b), int(c)))
+    return relations, filters, joins, selects
+
+
+# ------------------------------------------------------------------ collectives
+class Comm:
+    """Small host-vector collectives on torch.distributed (NCCL on GPUs, gloo on CPU)."""
+
+    def __init__(self, dist, torch, device, rank: int, world: int):
+        self.dist, self.torch, self.dev, self.rank, self.world = dist, torch, device, rank, world
+        self.n_collectives = 0
+
+    def all_gather_u64(self, v: np.ndarray) -> np.ndarray:
+        t = self.torch.from_numpy(np.ascontiguousarray(v, dtype=np.uint64).view(np.int64).copy()).to(self.dev)
+        out = self.torch.empty(self.world * t.numel(), dtype=self.torch.int64, device=self.dev)
+        self.dist.all_gather_into_tensor(out, t)
+        self.n_collectives += 1
+        return out.cpu().numpy().view(np.uint64).reshape(self.world, -1)
+
+    def allreduce_u64(self, v: np.ndarray) -> np.ndarray:
+        t = self.torch.from_numpy(np.ascontiguousarray(v, dtype=np.uint64).view(np.int64).copy()).to(self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        self.n_collectives += 1
+        return t.cpu().numpy().view(np.uint64)
+
+    def allreduce_max(self, v: int) -> int:
+        t = self.torch.tensor([v], dtype=self.torch.int64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return int(t.cpu()[0])
+
+    def barrier(self) -> None:
+        t = self.torch.zeros(1, dtype=self.torch.int64, device=self.dev)
+        self.dist.all_reduce(t)
+        self.n_collectives += 1
+        t.cpu()
+
+    def all_gather_bytes(self, b: bytes) -> List[bytes]:
+        t = self.torch.frombuffer(bytearray(b), dtype=self.torch.uint8).to(self.dev)
+        out = self.torch.empty(self.world * len(b), dtype=self.torch.uint8, device=self.dev)
+        self.dist.all_gather_into_tensor(out, t)
+        raw = bytes(out.cpu().numpy().tobytes())
+        return [raw[i * len(b):(i + 1) * len(b)] for i in range(self.world)]
+
+
+# ------------------------------------------------------------------ GPU backend
+class EngineOps:
+    """qce_b200.Engine behind the executor's op interface: one C-ABI call each."""
+
+    def __init__(self, engine):
+        self.e = engine
+
+    def key_bits(self, rel, col):
+        return max(1, int(self.e.column_info(rel, col)[1]).bit_length())
+
+    def rows(self, rel, col=0):
+        return int(self.e.column_info(rel, col)[0])
+
+    def filter_window(self, rel, col, op, c, begin, count):
+        return self.e.filter_scan(rel, col, op, c, rows=(begin, count))
+
+    def filter_refine(self, ids, rel, col, op, c):
+        self.e.filter_refine(ids, rel, col, op, c)
+        return ids
+
+    def self_join(self, rel, c1, c2, ids):
+        a, b = self.e.scan_join(rel, c1, ids, rel, c2, ids)
+        self.e.rowids_free(b)
+        return a
+
+    def build_from_ids(self, rel, col, ids):
+        return self.e.build_tuples(rel, col, ids)
+
+    def build_window(self, rel, col, begin, count):
+        return self.e.build_tuples(rel, col, rows=(begin, count))
+
+    def narrow_window(self, rel, col, begin, count):
+        return self.e.column_window_u32(rel, col, begin, count)
+
+    def gather_column(self, rel, col, ids):
+        return self.e.column_gather_u32(rel, col, ids)
+
+    def iota(self, begin, count, bound):
+        return self.e.rowids_iota(begin, count, bound)
+
+    def tuples_from_u32(self, keys, key_bits):
+        return self.e.tuples_from_u32(keys, key_bits)
+
+    def histogram(self, t, key_bits):
+        return self.e.key_histogram(t, key_bits)
+
+    def push_tuples(self, t, key_bits, splitters, nparts, dst_word_offset, dst_run_index, want_slots):
+        return self.e.push_tuples(t, key_bits, splitters, nparts, dst_word_offset, dst_run_index, want_slots)
+
+    def push_col(self, col, slots, nparts, dst_u32_offset):
+        self.e.push_u32_by_slot(col, slots, nparts, dst_u32_offset)
+
+    def ids_hist(self, ids, per, width, bpr, world):
+        return self.e.rowids_bin_histogram(ids, per, width, bpr, world)
+
+    def push_ids(self, ids, per, width, bpr, world, bin_u32_offset):
+        self.e.push_rowids(ids, per, width, bpr, world, bin_u32_offset)
+
+    def fence(self):
+        self.e.sync()
+
+    def tuples_view(self, word_offset, n, key_bits, id_bound, key_range):
+        return self.e.tuples_from_window(word_offset, n, key_bits, id_bound, key_range[0], key_range[1])
+
+    def col_view(self, u32_offset, n, id_bound=0, bucketed=False):
+        return self.e.rowids_from_window(u32_offset, n, id_bound, bucketed)
+
+    def sort(self, t):
+        self.e.sort_tuples(t)
+
+    def merge_join(self, L, R):
+        return self.e.merge_join(L, R)
+
+    def gather(self, col, index):
+        return self.e.rowids_gather(col, index)
+
+    def checksum(self, ids, rel, cols):
+        return self.e.checksum(ids, rel, list(cols)) if cols else []
+
+    def count(self, ids):
+        return self.e.rowids_count(ids)
+
+    def tuples_count(self, t):
+        return self.e.tuples_count(t)
+
+    def free_ids(self, h):
+        self.e.rowids_free(h)
+
+    def free_tuples(self, h):
+        self.e.tuples_free(h)
+
+    def window_bytes(self):
+        return self.e.xwin_info()[0]
+
+
+def open_windows(engine, comm: Comm, nbytes: int) -> None:
+    """Create this rank's receive window and map every peer's (CUDA IPC handles
+    all-gathered once).  world == 1: the window is only ever addressed locally."""
+    handle = engine.xwin_create(nbytes)
+    if comm.world > 1:
+        handles = comm.all_gather_bytes(handle)
+        engine.xwin_attach(comm.world, comm.rank, b"".join(handles))
+    comm.barrier()
+
+
+def load_sharded_columns(engine, torch, comm: Comm, db: Sequence[Sequence[np.ndarray]], keep: list) -> None:
+    """Each rank uploads only its row window of every column (global row ids);
+    the column maximum (sort statistics) is all-reduced."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    for r, cols in enumerate(db):
+        n = len(cols[0])
+        begin, count = row_window(n, comm.rank, comm.world)
+        for c, v in enumerate(cols):
+            t = torch.from_numpy(np.ascontiguousarray(v[begin:begin + count], dtype=np.uint64).view(np.int64).copy()).to(dev)
+            keep.append(t)
+            mx = comm.allreduce_max(int(v[begin:begin + count].max()) if count else 0)
+            engine.adopt_column_window(r, c, t.data_ptr() if count else 0, begin, count, n, mx)
+
+
+# ------------------------------------------------------------------ executor
+def _align(x: int, a: int = 16) -> int:
+    return -(-x // a) * a
+
+
+class ShardedExecutor:
+    def __init__(self, ops, comm: Comm, replicated: bool = False):
+        self.ops, self.comm, self.rank, self.world = ops, comm, comm.rank, comm.world
+        self.replicated = replicated  # base columns replicated on every rank: projections gather locally
+        self.stats: Dict[str, float] = {}
+
+    # ---- one exchange of the two inputs of a join -----------------------------
+    def _exchange_pair(self, sides, key_bits: int):
+        """sides = [(run, [u32 columns...]), (run, [...])].  Returns, per side, the
+        received run (a view of this rank's window) and the received columns."""
+        ops, world, me = self.ops, self.world, self.rank
+        t0 = time.perf_counter()
+        hists = np.concatenate([ops.histogram(run, key_bits) for run, _ in sides])
+        H = self.comm.all_gather_u64(hists).reshape(world, len(sides), 256)
+        splitters = choose_splitters(H.sum(axis=(0, 1)), key_bits, world)
+        shift = max(key_bits - 8, 0)
+        part_of_bin = np.searchsorted(np.array(splitters, dtype=np.uint64),
+                                      np.arange(256, dtype=np.uint64) << np.uint64(shift), side="right") \
+            if world > 1 else np.zeros(256, dtype=np.int64)
+        # C[k][s][d]: tuples of side k that rank s sends to rank d
+        C = np.zeros((len(sides), world, world), dtype=np.int64)
+        for d in range(world):
+            C[:, :, d] = H[:, :, part_of_bin == d].sum(axis=2).T.astype(np.int64)
+        recv = C.sum(axis=1)                        # [k][d]
+        before = np.cumsum(C, axis=1) - C           # [k][s][d]: tuples of earlier ranks in d's segment order
+        # window layout of every destination (bytes): per side the run, then its columns
+        run_off = np.zeros((len(sides), world), dtype=np.int64)
+        col_off = [np.zeros((len(cols), world), dtype=np.int64) for _, cols in sides]
+        top = np.zeros(world, dtype=np.int64)
+        for k, (_, cols) in enumerate(sides):
+            run_off[k] = top
+            top = top + 8 * recv[k]
+            top = (top + 15) // 16 * 16
+            for j in range(len(cols)):
+                col_off[k][j] = top
+                top = (top + 4 * recv[k] + 15) // 16 * 16
+        cap = ops.window_bytes()
+        if int(top.max()) > cap:
+            raise MemoryError(f"exchange needs {int(top.max())} bytes of receive window, {cap} available")
+        sent = 0
+        for k, (run, cols) in enumerate(sides):
+            dst_words = run_off[k] // 8 + before[k, me]
+            rewrite = len(cols) > 0
+            slots = ops.push_tuples(run, key_bits, splitters, world, dst_words.astype(np.uint64),
+                                    before[k, me].astype(np.uint32) if rewrite else None, rewrite)
+            for j, col in enumerate(cols):
+                ops.push_col(col, slots, world, (col_off[k][j] // 4 + before[k, me]).astype(np.uint64))
+            if slots is not None:
+                ops.free_ids(slots)
+            sent += int(C[k, me].sum() - C[k, me, me]) * (8 + 4 * len(cols))
+        ops.fence()
+        self.comm.barrier()  # every peer's stores into this rank's window have completed
+        lo = splitters[me - 1] if me > 0 else 0
+        hi = (splitters[me] - 1) if me < world - 1 else (1 << key_bits) - 1
+        out = []
+        for k, (_, cols) in enumerate(sides):
+            n = int(recv[k, me])
+            run = ops.tuples_view(int(run_off[k, me]) // 8, n, key_bits, 0, (lo, max(lo, hi)))
+            views = [ops.col_view(int(col_off[k][j, me]) // 4, n) for j in range(len(cols))]
+            out.append((run, views))
+        self.stats["exchange_s"] = self.stats.get("exchange_s", 0.0) + time.perf_counter() - t0
+        self.stats["bytes_sent_off_rank"] = self.stats.get("bytes_sent_off_rank", 0) + sent
+        self.stats["splitters"] = splitters
+        return out
+
+    # ---- projection -------------------------------------------------------------
+    def _project(self, relations, ent: Dict[int, int], selects, nrows: int):
+        ops, world, me = self.ops, self.world, self.rank
+        by_binding: Dict[int, List[int]] = {}
+        for b, c in selects:
+            by_binding.setdefault(b, [])
+            if c not in by_binding[b]:
+                by_binding[b].append(c)
+        for b in by_binding:
+            if b not in ent:
+                raise UnsupportedQuery(f"projected binding {b} takes part in no predicate")
+        sums: Dict[Tuple[int, int], int] = {}
+        if self.replicated or nrows < 0:
+            for b, cols in by_binding.items():
+                for c, s in zip(cols, ops.checksum(ent[b], relations[b], cols)):
+                    sums[(b, c)] = s
+            return sums
+        t0 = time.perf_counter()
+        bpr = max(1, 256 // world)
+        geo, hists = {}, []
+        for b in by_binding:
+            rows = ops.rows(relations[b])
+            per = max(row_window(rows, 0, world)[1], 1)
+            width = max(1, -(-per // bpr))
+            geo[b] = (per, width, rows)
+            hists.append(ops.ids_hist(ent[b], per, width, bpr, world))
+        nb = bpr * world
+        H = self.comm.all_gather_u64(np.concatenate(hists)).reshape(world, len(by_binding), nb).astype(np.int64)
+        top = np.zeros(world, dtype=np.int64)
+        views = {}
+        sent = 0
+        for k, b in enumerate(by_binding):
+            per, width, rows = geo[b]
+            Hk = H[:, k, :]                                    # [src][bin]
+            bin_tot = Hk.sum(axis=0)                           # [bin]
+            owner = np.arange(nb) // bpr
+            # bin-major inside each owner: offset of (bin, src) relative to the owner's region
+            bin_start = np.zeros(nb, dtype=np.int64)
+            for d in range(world):
+                sel = owner == d
+                bin_start[sel] = np.cumsum(bin_tot[sel]) - bin_tot[sel]
+            src_before = (np.cumsum(Hk, axis=0) - Hk)[me]      # ids of earlier ranks in the same bin
+            region = top.copy()                                 # bytes, per owner
+            total = np.array([bin_tot[owner == d].sum() for d in range(world)], dtype=np.int64)
+            top = (top + 4 * total + 15) // 16 * 16
+            if int(top.max()) > ops.window_bytes():
+                raise MemoryError("projection needs more receive window than is available")
+            offs = region[owner] // 4 + bin_start + src_before
+            ops.push_ids(ent[b], per, width, bpr, world, offs.astype(np.uint64))
+            views[b] = (int(region[me]) // 4, int(total[me]), rows)
+            sent += 4 * int(Hk[me].sum() - Hk[me][owner == me].sum())
+        ops.fence()
+        self.comm.barrier()
+        for b, cols in by_binding.items():
+            off, n, rows = views[b]
+            v = ops.col_view(off, n, rows, True)
+            for c, s in zip(cols, ops.checksum(v, relations[b], cols)):
+                sums[(b, c)] = s
+            ops.free_ids(v)
+        self.stats["project_exchange_s"] = self.stats.get("project_exchange_s", 0.0) + time.perf_counter() - t0
+        self.stats["bytes_sent_off_rank"] = self.stats.get("bytes_sent_off_rank", 0) + sent
+        return sums
+
+    # ---- the query ----------------------------------------------------------------
+    def run_query(self, text: str) -> dict:
+        ops, world, me = self.ops, self.world, self.rank
+        self.stats = {}
+        relations, filters, joins, selects = parse_query(text)
+        fbind = sorted({f[0] for f in filters})
+        if len(fbind) > 1:
+            raise UnsupportedQuery("filters on more than one binding (reference: positional scan join, SURVEY 8c-ii)")
+        self_joins = [j for j in joins if j[0][0] == j[1][0]]
+        chain = [j for j in joins if j[0][0] != j[1][0]]
+        for (b1, c1), (b2, c2) in chain:
+            if relations[b1] == relations[b2] and c1 == c2:
+                raise UnsupportedQuery("same relation and column on both sides: the reference skips this join (8c-v)")
+
+        ent: Dict[int, int] = {}          # binding -> row-id column (aligned, this rank's slice)
+        carried: Dict[Tuple[int, int], int] = {}  # (binding, column) -> 4-byte key column, aligned with ent
+        own_rows: Optional[int] = None    # binding whose ids are rows of this rank's own window
+
+        def window(b):
+            return row_window(ops.rows(relations[b]), me, world)
+
+        if filters:
+            b0 = fbind[0]
+            begin, count = window(b0)
+            _, c, op, x = filters[0]
+            ids = ops.filter_window(relations[b0], c, op, x, begin, count)
+            for _, c, op, x in filters[1:]:
+                ids = ops.filter_refine(ids, relations[b0], c, op, x)
+            ent[b0] = ids
+            own_rows = b0
+        for (b, c1), (_, c2) in self_joins:
+            if b not in ent or own_rows != b:
+                raise UnsupportedQuery("self-join predicate on a binding without a prior filter (reference exits, 8c-iii)")
+            new = ops.self_join(relations[b], c1, c2, ent[b])
+            ops.free_ids(ent[b])
+            ent[b] = new
+
+        remaining = list(chain)
+        while remaining:
+            pick = None
+            for j in remaining:
+                ins = [(j[0][0] in ent), (j[1][0] in ent)]
+                if not ent or ins[0] != ins[1]:
+                    pick = j
+                    break
+            if pick is None:
+                raise UnsupportedQuery("join between two bindings that are both (or neither) in the intermediate result")
+            remaining.remove(pick)
+            (eb, ec), (nb_, nc) = pick if (not ent or pick[0][0] in ent) else (pick[1], pick[0])
+            future = {(b, c) for j in remaining for (b, c) in j}
+            key_bits = max(ops.key_bits(relations[eb], ec), ops.key_bits(relations[nb_], nc))
+            if key_bits > 32:
+                raise UnsupportedQuery("join keys >= 2^32: the exchange carries packed runs only")
+            # ---- entity side
+            Lcols: List[Tuple[tuple, int]] = []
+            temp: List[int] = []
+            if not ent or own_rows == eb:
+                if not ent:
+                    begin, count = window(eb)
+                    L = ops.build_window(relations[eb], ec, begin, count)
+                    need = sorted(c for (b, c) in future if b == eb)
+                    if need:
+                        idcol = ops.iota(begin, count, ops.rows(relations[eb]))
+                        Lcols.append((("id", eb), idcol))
+                        temp.append(idcol)
+                        for c in need:
+                            h = ops.narrow_window(relations[eb], c, begin, count)
+                            Lcols.append((("key", eb, c), h))
+                            temp.append(h)
+                else:
+                    L = ops.build_from_ids(relations[eb], ec, ent[eb])
+                    need = sorted(c for (b, c) in future if b == eb)
+                    if need:
+                        Lcols.append((("id", eb), ent[eb]))
+                        for c in need:
+                            h = ops.gather_column(relations[eb], c, ent[eb])
+                            Lcols.append((("key", eb, c), h))
+                            temp.append(h)
+            else:
+                if (eb, ec) not in carried:
+                    raise UnsupportedQuery(f"join key {eb}.{ec} was not carried")
+                L = ops.tuples_from_u32(carried[(eb, ec)], key_bits)
+                for b, h in ent.items():
+                    Lcols.append((("id", b), h))
+                for (b, c), h in carried.items():
+                    if (b, c) in future:
+                        Lcols.append((("key", b, c), h))
+            # ---- new base relation
+            begin, count = window(nb_)
+            R = ops.build_window(relations[nb_], nc, begin, count)
+            Rcols: List[Tuple[tuple, int]] = []
+            need = sorted(c for (b, c) in future if b == nb_)
+            if need:
+                idcol = ops.iota(begin, count, ops.rows(relations[nb_]))
+                Rcols.append((("id", nb_), idcol))
+                temp.append(idcol)
+                for c in need:
+                    h = ops.narrow_window(relations[nb_], c, begin, count)
+                    Rcols.append((("key", nb_, c), h))
+                    temp.append(h)
+            (L2, Lv), (R2, Rv) = self._exchange_pair([(L, [h for _, h in Lcols]), (R, [h for _, h in Rcols])], key_bits)
+            ops.free_tuples(L)
+            ops.free_tuples(R)
+            for h in temp:
+                ops.free_ids(h)
+            for h in list(ent.values()) + list(carried.values()):
+                ops.free_ids(h)
+            ent, carried, own_rows = {}, {}, None
+            # ---- local join of this rank's key range
+            ops.sort(L2)
+            ops.sort(R2)
+            pL, pR = ops.merge_join(L2, R2)
+            self.stats["local_join_input"] = self.stats.get("local_join_input", 0) + ops.tuples_count(L2) + ops.tuples_count(R2)
+            ops.free_tuples(L2)
+            ops.free_tuples(R2)
+            for names, views, pos, binding in ((Lcols, Lv, pL, eb), (Rcols, Rv, pR, nb_)):
+                if not names:
+                    ent[binding] = pos       # payloads were row ids
+                    continue
+                for (name, _), v in zip(names, views):
+                    g = ops.gather(v, pos)
+                    if name[0] == "id":
+                        ent[name[1]] = g
+                    else:
+                        carried[(name[1], name[2])] = g
+                    ops.free_ids(v)
+                ops.free_ids(pos)
+
+        if not ent:
+            raise UnsupportedQuery("query without predicates")
+        nrows = ops.count(next(iter(ent.values())))
+        sums = self._project(relations, ent, selects, nrows)
+        for h in list(ent.values()) + list(carried.values()):
+            ops.free_ids(h)
+        vec = np.array([sums[s] for s in selects] + [nrows, self.stats.get("local_join_input", 0)], dtype=np.uint64)
+        red = self.comm.allreduce_u64(vec)
+        return {"sums": [int(x) for x in red[:len(selects)]], "pairs": int(red[len(selects)]),
+                "join_input_tuples": int(red[len(selects) + 1])}
+
+
+def format_result(res: dict) -> str:
+    """The line the reference prints for the same query (print_sums,
+    /root/reference/src/utilities.c:212-223)."""
+    return "".join("NULL " if res["pairs"] == 0 else f"{s} " for s in res["sums"]) + "\n"

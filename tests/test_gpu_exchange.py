@@ -1,0 +1,230 @@
+"""GPU parity of the peer-memory exchange primitives (k_exchange.cuh) on ONE GPU:
+the local window is presented as `world` ranks (qce_xwin_loopback), so every
+store of the push kernels lands where a multi-GPU run would put it, and the
+sharded executor at world size 1 (same code path as N GPUs, all stores local)
+against the relational truth / the oracle."""
+import numpy as np
+import pytest
+
+from oracle import qce_oracle as orc
+from oracle import workload as wl
+
+pytestmark = pytest.mark.gpu
+U64 = np.uint64
+WIN = 64 << 20
+
+
+@pytest.fixture(scope="module")
+def xeng(engine):
+    engine.xwin_create(WIN)
+    yield engine
+    engine.xwin_destroy()
+
+
+def _read_words(e, byte_off, n, key_bits):
+    t = e.tuples_from_window(byte_off // 8, n, key_bits)
+    k, p = e.tuples_to_host(t)
+    e.tuples_free(t)
+    return k, p
+
+
+def _read_u32(e, byte_off, n):
+    h = e.rowids_from_window(byte_off // 4, n)
+    v = e.rowids_to_host(h)
+    e.rowids_free(h)
+    return v
+
+
+@pytest.mark.parametrize("n", [0, 1, 33, 4095, 4096, 4097, 100003, 1 << 20])
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+@pytest.mark.parametrize("rewrite", [False, True])
+def test_push_tuples_loopback(xeng, n, world, rewrite):
+    e = xeng
+    e.xwin_loopback(world)
+    per = WIN // world // 4096 * 4096
+    rng = np.random.default_rng(n + world)
+    key_bits = 20
+    keys = rng.integers(0, 1 << key_bits, n, dtype=np.uint64)
+    ids = rng.permutation(n).astype(U64)
+    t = e.tuples_from_host(keys, ids)
+    hist = e.key_histogram(t, key_bits)
+    import qce_b200
+    from qce_b200 import sharded
+    splitters = sharded.choose_splitters(hist, key_bits, world)
+    part = np.searchsorted(np.array(splitters, dtype=U64), keys, side="right") if world > 1 else np.zeros(n, dtype=np.int64)
+    counts = np.bincount(part, minlength=world)
+    seg_words = np.array([64 + 2 * d for d in range(world)], dtype=U64)     # where "this rank's" segment starts
+    run_index = np.array([1000 * (d + 1) for d in range(world)], dtype=np.uint32)
+    slots_h = e.push_tuples(t, key_bits, splitters, world, seg_words, run_index if rewrite else None, rewrite)
+    col = rng.integers(0, 1 << 32, n, dtype=np.uint64)
+    col_off = np.array([(per // 2) // 4 + 16 * d for d in range(world)], dtype=U64)
+    if rewrite:
+        ch = e.rowids_from_host(col)
+        e.push_u32_by_slot(ch, slots_h, world, col_off)
+        slots = e.rowids_to_host(slots_h)
+        e.rowids_free(ch)
+        e.rowids_free(slots_h)
+        assert np.array_equal(slots >> U64(28), part.astype(U64))
+    e.sync()
+    for d in range(world):
+        k, p = _read_words(e, per * d + int(seg_words[d]) * 8, int(counts[d]), key_bits)
+        want = part == d
+        if not rewrite:
+            got = np.lexsort((p, k))
+            exp = np.lexsort((ids[want], keys[want]))
+            np.testing.assert_array_equal(k[got], keys[want][exp])
+            np.testing.assert_array_equal(p[got], ids[want][exp])
+        else:
+            # payload = index in the receiver's run; the bystander column sits at the same index
+            np.testing.assert_array_equal(np.sort(p), run_index[d] + np.arange(counts[d], dtype=U64))
+            got_col = _read_u32(e, per * d + int(col_off[d]) * 4, int(counts[d]))
+            pos = (p - run_index[d]).astype(np.int64)
+            pairs_got = sorted(zip(k.tolist(), got_col[pos].tolist()))
+            pairs_exp = sorted(zip(keys[want].tolist(), col[want].tolist()))
+            assert pairs_got == pairs_exp
+            # slots say where each input tuple went
+            idx = np.nonzero(want)[0]
+            np.testing.assert_array_equal(k[np.argsort(pos)][(slots[idx] & U64(0x0FFFFFFF)).astype(np.int64)], keys[idx])
+
+
+@pytest.mark.parametrize("n", [0, 5, 4097, 300001])
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_push_rowids_loopback(xeng, n, world):
+    e = xeng
+    e.xwin_loopback(world)
+    per_bytes = WIN // world // 4096 * 4096
+    rng = np.random.default_rng(7 * n + world)
+    rows = 1_000_003
+    rows_per_rank = -(-(-(-rows // world)) // 4096) * 4096
+    bpr = 256 // world
+    width = -(-rows_per_rank // bpr)
+    ids = rng.integers(0, rows, n, dtype=np.uint64)
+    h = e.rowids_from_host(ids)
+    hist = e.rowids_bin_histogram(h, rows_per_rank, width, bpr, world)
+    r = np.minimum(ids // U64(rows_per_rank), U64(world - 1))
+    bins = (r * U64(bpr) + np.minimum((ids - r * U64(rows_per_rank)) // U64(width), U64(bpr - 1))).astype(np.int64)
+    np.testing.assert_array_equal(hist, np.bincount(bins, minlength=bpr * world).astype(U64))
+    # bin-major layout inside each owner, 8 ids of slack before every bin (a stand-in for other senders' segments)
+    offs = np.zeros(bpr * world, dtype=U64)
+    for d in range(world):
+        at = 32
+        for b in range(d * bpr, (d + 1) * bpr):
+            offs[b] = at + 8
+            at += 8 + int(hist[b])
+    e.push_rowids(h, rows_per_rank, width, bpr, world, offs)
+    e.sync()
+    for b in range(bpr * world):
+        got = _read_u32(e, per_bytes * (b // bpr) + int(offs[b]) * 4, int(hist[b]))
+        np.testing.assert_array_equal(np.sort(got), np.sort(ids[bins == b]))
+    e.rowids_free(h)
+
+
+def test_window_overflow_and_misuse_are_reported(xeng):
+    import qce_b200
+    e = xeng
+    e.xwin_loopback(2)
+    with pytest.raises(qce_b200.EngineError, match="exceeds the exchange window"):
+        e.tuples_from_window(WIN // 8, 16, 20)
+    t = e.tuples_from_host(np.arange(10, dtype=U64), np.arange(10, dtype=U64))
+    with pytest.raises(qce_b200.EngineError, match="differs from the attached world size"):
+        e.push_tuples(t, 8, [128, 192], 3, np.zeros(3, dtype=U64))
+    with pytest.raises(qce_b200.EngineError, match="not on a boundary"):
+        e.push_tuples(t, 20, [5], 2, np.zeros(2, dtype=U64))
+    e.tuples_free(t)
+
+
+def test_gather_and_carried_columns(engine):
+    rng = np.random.default_rng(3)
+    n = 100_003
+    col = rng.integers(0, 1 << 30, n, dtype=np.uint64)
+    engine.upload_column(120, 0, col)
+    w = engine.column_window_u32(120, 0, 4096, 50_000)
+    np.testing.assert_array_equal(engine.rowids_to_host(w), col[4096:54096])
+    ids = rng.integers(0, n, 70_001, dtype=np.uint64)
+    hi = engine.rowids_from_host(ids)
+    g = engine.column_gather_u32(120, 0, hi)
+    np.testing.assert_array_equal(engine.rowids_to_host(g), col[ids])
+    idx = rng.integers(0, 50_000, 33_333, dtype=np.uint64)
+    hx = engine.rowids_from_host(idx)
+    gg = engine.rowids_gather(w, hx)
+    np.testing.assert_array_equal(engine.rowids_to_host(gg), col[4096:54096][idx])
+    it = engine.rowids_iota(4096, 1000, n)
+    np.testing.assert_array_equal(engine.rowids_to_host(it), np.arange(4096, 5096, dtype=U64))
+    t = engine.tuples_from_u32(w, 30)
+    k, p = engine.tuples_to_host(t)
+    np.testing.assert_array_equal(k, col[4096:54096])
+    np.testing.assert_array_equal(p, np.arange(50_000, dtype=U64))
+    engine.tuples_free(t)
+    for h in (w, hi, g, hx, gg, it):
+        engine.rowids_free(h)
+    import qce_b200
+    engine.upload_column(120, 1, np.array([1 << 40, 3], dtype=U64))
+    with pytest.raises(qce_b200.EngineError, match="cannot be carried"):
+        engine.column_window_u32(120, 1, 0, 2)
+
+
+def test_windowed_column_refuses_non_resident_rows(engine):
+    import qce_b200
+    import torch
+    v = torch.arange(8192, dtype=torch.int64, device="cuda")
+    engine.adopt_column_window(121, 0, v.data_ptr(), 4096, 8192, 20000, 20000)
+    h = engine.filter_scan(121, 0, "<", 6, rows=(4096, 8192))   # values are 0..8191 at rows 4096..12287
+    np.testing.assert_array_equal(engine.rowids_to_host(h), np.arange(4096, 4102, dtype=U64))
+    engine.rowids_free(h)
+    with pytest.raises(qce_b200.EngineError, match="not resident"):
+        engine.filter_scan(121, 0, "<", 6)
+    with pytest.raises(qce_b200.EngineError, match="not resident"):
+        engine.build_tuples(121, 0, rows=(0, 4096))
+
+
+# ---------------------------------------------------------------- executor, world size 1
+EXEC = {
+    "pair": ["0 1|0.1=1.1&0.2>500|0.0 1.0 1.2", "0 1|0.1=1.1|0.0 1.2", "0|0.2<100&0.1>3000|0.2", "0 1|0.1=1.1&0.2>999999|0.0 1.0"],
+    "chain": ["0 1 2 3|0.1=0.2&0.1=1.0&1.1=2.0&2.1=3.0&0.3<900|0.3 1.3 2.3 3.3", "0 1 2|0.1=1.0&0.2=2.0&0.3<200|1.1 2.1 0.0",
+              "0 1 2 3|0.1=1.0&1.1=2.0&2.1=3.0|0.3 3.3"],
+    "zipf": ["0 1 2|0.1=1.0&1.1=2.0|0.2 1.2 2.2"],
+}
+
+
+@pytest.mark.parametrize("kind,rows", [("pair", 300_007), ("chain", 200_000), ("zipf", 150_000), ("chain", 2_000_000)])
+def test_sharded_executor_world1(kind, rows):
+    """One rank: the same orchestration and kernels as N GPUs (windowed columns, push
+    kernels, by-slot columns, id push, bucketed checksum) with every store local."""
+    import subprocess, sys, os, json, tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    child = r'''
+import os, sys, json
+sys.path.insert(0, %r)
+import numpy as np, torch, torch.distributed as dist
+import qce_b200
+from qce_b200 import shardexec
+from oracle import workload as wl, qce_oracle as orc
+os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT="29655", RANK="0", WORLD_SIZE="1")
+torch.cuda.set_device(0)
+dist.init_process_group("nccl", device_id=torch.device("cuda", 0))
+eng = qce_b200.Engine(0)
+kind, rows = %r, %d
+db = {"pair": lambda: wl.gen_pair_db(rows, rows // 3, filt_domain=1000), "chain": lambda: wl.gen_chain_db(rows),
+      "zipf": lambda: wl.gen_zipf_db(rows)}[kind]()
+comm = shardexec.Comm(dist, torch, torch.device("cuda", 0), 0, 1)
+keep = []
+shardexec.load_sharded_columns(eng, torch, comm, db, keep)
+shardexec.open_windows(eng, comm, 1 << 30)
+ex = shardexec.ShardedExecutor(shardexec.EngineOps(eng), comm)
+ok = True
+for q in %r:
+    got = shardexec.format_result(ex.run_query(q))
+    got2 = shardexec.format_result(ex.run_query(q))
+    want = wl.truth_query(orc.parse_query(q), db)
+    if got != want or got2 != want:
+        ok = False
+        print("MISMATCH", q, got, want)
+print("RESULT " + json.dumps({"ok": ok}))
+dist.destroy_process_group()
+''' % (root, kind, rows, EXEC[kind])
+    script = os.path.join(tempfile.mkdtemp(), "exec_child.py")
+    open(script, "w").write(child)
+    p = subprocess.run([sys.executable, script], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    lines = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
+    assert p.returncode == 0 and lines, (p.stdout[-2000:], p.stderr[-3000:])
+    assert json.loads(lines[-1][7:])["ok"], p.stdout[-2000:]

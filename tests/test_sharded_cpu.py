@@ -123,3 +123,69 @@ def test_choose_splitters_balances():
     sp = sharded.choose_splitters(hist, 16, 4)
     assert sp == sorted(sp) and all(s >= (8 << 8) for s in sp)
     assert sharded.row_window(10_000, 1, 4) == (4096, 4096) and sharded.row_window(10_000, 3, 4) == (10_000, 0)
+
+
+# ---------------------------------------------------------------- peer-push executor (shardexec)
+EXEC_QUERIES = {
+    "pair": ["0 1|0.1=1.1&0.2>500|0.0 1.0 1.2", "0 1|0.1=1.1|0.0 1.2", "0|0.2<100|0.0 0.1", "0|0.2<100&0.1>3000|0.2",
+             "0 1|0.1=1.1&0.2>999999|0.0 1.0", "1 0|0.1=1.1&1.2<300|0.2 1.0"],
+    "chain": ["0 1 2 3|0.1=0.2&0.1=1.0&1.1=2.0&2.1=3.0&0.3<900|0.3 1.3 2.3 3.3",
+              "0 1 2|0.1=1.0&1.1=2.0&0.3<500|0.0 1.0 2.3", "0 1 2|0.1=1.0&0.2=2.0|0.3 1.3 2.3",
+              "0 1 2 3|0.1=1.0&1.1=2.0&2.1=3.0|0.3 3.3", "0 1 2|0.1=1.0&0.2=2.0&0.3<200|1.1 2.1 0.0"],
+    "zipf": ["0 1 2|0.1=1.0&1.1=2.0|0.2 1.2 2.2", "0 1 2|0.1=1.0&1.1=2.0&0.2<500|0.0 2.1"],
+}
+
+
+def _exec_db(kind, rows):
+    if kind == "pair":
+        return wl.gen_pair_db(rows, rows // 3, filt_domain=1000)
+    if kind == "chain":
+        return wl.gen_chain_db(rows)
+    return wl.gen_zipf_db(rows)
+
+
+def _exec_worker(rank, world, port, kind, rows, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import qce_b200  # noqa: F401
+    from qce_b200 import shardexec
+    from tests.numpy_shard_ops import NumpyShardOps
+    db = _exec_db(kind, rows)
+    comm = shardexec.Comm(dist, torch, torch.device("cpu"), rank, world)
+    ex = shardexec.ShardedExecutor(NumpyShardOps(db, rank, world), comm)
+    lines, refused = [], 0
+    for q in EXEC_QUERIES[kind]:
+        lines.append(shardexec.format_result(ex.run_query(q)))
+    for bad in ["0 1|0.1=1.1&0.2<20&1.2<20|0.0 1.0", "0|0.1=0.2|0.0", "0 0|0.1=1.1|0.0 1.0", "0 1 0|0.1=1.1&1.2=2.1&0.2=2.1|0.0"]:
+        try:
+            ex.run_query(bad)
+        except shardexec.UnsupportedQuery:
+            refused += 1
+    if rank == 0:
+        out.put((lines, refused, ex.stats.get("bytes_sent_off_rank", 0)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,kind,rows", [(2, "pair", 20011), (3, "pair", 9001), (2, "chain", 12000), (3, "chain", 20000),
+                                             (2, "zipf", 15000), (1, "chain", 5000)])
+def test_sharded_executor_matches_truth(world, kind, rows):
+    """Row-sharded columns, pushes into peer windows, bystander columns by slot, carried join
+    keys, projection by id push: checksums equal the relational truth (= the reference inside PDQ-T)."""
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 31500 + os.getpid() % 2000 + 7 * world + len(kind)
+    procs = [ctx.Process(target=_exec_worker, args=(r, world, port, kind, rows, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    lines, refused, sent = out.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    db = _exec_db(kind, rows)
+    for q, line in zip(EXEC_QUERIES[kind], lines):
+        assert line == wl.truth_query(orc.parse_query(q), db), q
+    assert refused == 4
+    assert (sent > 0) == (world > 1)
+    if kind == "pair":  # also the reference's own answer (oracle restatement), byte for byte
+        assert lines[0] == orc.run_batch(db, EXEC_QUERIES[kind][0] + "\n")
