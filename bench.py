@@ -212,11 +212,15 @@ def main():
     pk, pk_src = peaks()
 
     if world > 1:
-        from qce_b200 import sharded
+        from qce_b200 import sharded, shardexec
         rows = rows // 4096 * 4096  # equal, vector-aligned row windows on every rank
         sampler = ClockSampler(local_rank, period=float(os.environ.get('QCE_BENCH_CLOCK_PERIOD', '0.05')))
         sampler.start()
-        res = sharded.bench(eng, lib, dist, rank, world, rows, args.steps, args.warmup)
+        if os.environ.get("QCE_EXCHANGE", "push") == "nccl":
+            # earlier transport, kept for comparison: replicated columns, send buffer + NCCL all-to-all
+            res = sharded.bench(eng, lib, dist, rank, world, rows, args.steps, args.warmup)
+        else:
+            res = shardexec.bench(eng, lib, dist, torch, rank, world, rows, args.steps, args.warmup)
         res["clocks"] = sampler.stop()
         if rank == 0:
             res_line = res

@@ -246,8 +246,10 @@ int qce_tuples_from_u32(const qce_rowids *keys, uint32_t key_bits, qce_tuples **
 /* Views into this rank's own window (no copy; valid until the window is reused). */
 int qce_tuples_from_window(uint64_t word_offset, uint64_t n, uint32_t key_bits, uint32_t id_bound,
                            uint64_t key_lo, uint64_t key_hi, qce_tuples **out);
-int qce_rowids_from_window(uint64_t u32_offset, uint64_t n, uint32_t id_bound, int bucketed,
-                           qce_rowids **out);
+/* [id_min, id_bound) = range of the received ids (the owner's row window); bucketed != 0:
+ * they arrived grouped by L2-sized row regions, the checksum needs no bucketing pass. */
+int qce_rowids_from_window(uint64_t u32_offset, uint64_t n, uint32_t id_min, uint32_t id_bound,
+                           int bucketed, qce_rowids **out);
 /* out[i] = src[index[i]] (re-align a bystander row-id column with a join output whose
  * payloads are positions; SURVEY 8f-2, replaces join_payloads src/join.c:426-484 inside PDQ-T). */
 int qce_rowids_gather(const qce_rowids *src, const qce_rowids *index, qce_rowids **out);

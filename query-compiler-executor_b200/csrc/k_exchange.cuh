@@ -32,8 +32,9 @@
 
 #define QCE_MAX_RANKS 16
 #define QCE_PUSH_THREADS 512
-#define QCE_PUSH_ITEMS 8
-#define QCE_PUSH_TILE (QCE_PUSH_THREADS * QCE_PUSH_ITEMS)
+// 32 KB of shared-memory staging per tile: 4096 tuples, or 8192 row ids (a 256-bin id
+// scatter then leaves in runs of ~32 ids = 128 B, the NVLink write granularity that pays)
+template <typename KeyT> struct PushTile { static constexpr int ITEMS = sizeof(KeyT) == 8 ? 8 : 16; static constexpr int TILE = QCE_PUSH_THREADS * ITEMS; };
 
 struct PeerWindows {
     unsigned char *base[QCE_MAX_RANKS]; // receive window of every rank, mapped into this process
@@ -63,6 +64,11 @@ struct RowBins {
     u32 rows_per_rank, last_rank, width, bins_per_rank;
     __host__ __device__ __forceinline__ u32 operator()(u32 id) const
     {
+        if (bins_per_rank == 1) { // owner only: a few compares instead of an integer division
+            u32 r = 0;
+            for (u32 k = 1; k <= last_rank; k++) r += id >= k * rows_per_rank;
+            return r;
+        }
         const u32 r = min(id / rows_per_rank, last_rank);
         return r * bins_per_rank + min((id - r * rows_per_rank) / width, bins_per_rank - 1);
     }
@@ -80,17 +86,17 @@ __global__ void __launch_bounds__(QCE_PUSH_THREADS)
 k_push(const KeyT *__restrict__ in, u32 n, PushDigit<KeyT> digit, PushPlan plan, const __grid_constant__ PeerWindows peers, int digit_bits,
        u32 *__restrict__ slot_out)
 {
-    constexpr int THREADS = QCE_PUSH_THREADS, ITEMS = QCE_PUSH_ITEMS;
-    __shared__ KeyT skeys[QCE_PUSH_TILE];
+    constexpr int THREADS = QCE_PUSH_THREADS, ITEMS = PushTile<KeyT>::ITEMS, TILE = PushTile<KeyT>::TILE;
+    __shared__ KeyT skeys[TILE];
     __shared__ u32 cnt[256], excl[256];
     __shared__ unsigned long long goff[256]; // reserved start of the tile's run in the window, minus excl
     __shared__ unsigned long long sseg[256];
     __shared__ u32 srun[256];
     __shared__ u32 scratch[33];
     const int tid = threadIdx.x, lane = tid & 31;
-    const u32 begin = blockIdx.x * QCE_PUSH_TILE;
+    const u32 begin = blockIdx.x * TILE;
     if (begin >= n) return;
-    const u32 count = min((u32)QCE_PUSH_TILE, n - begin);
+    const u32 count = min((u32)TILE, n - begin);
     if (tid < 256) cnt[tid] = 0;
     __syncthreads();
 
@@ -102,7 +108,12 @@ k_push(const KeyT *__restrict__ in, u32 n, PushDigit<KeyT> digit, PushPlan plan,
         key[j] = (i < count) ? ld_stream_key<KeyT>(in + begin + i) : (KeyT)0;
     }
     if (FEW) {
+        // cnt[d * 16 + warp]: every warp counts its own elements per digit, so nothing is
+        // contended (one shared atomicAdd per warp-group on 2-16 addresses serialised the
+        // whole tile: 2.6x slower than the memory traffic).  The 256-entry scan below then
+        // yields, per (digit, warp), where that warp's elements start inside the tile.
         const u32 lt = lanemask_lt();
+        const u32 warp = tid >> 5;
 #pragma unroll
         for (int j = 0; j < ITEMS; j++) {
             const u32 i = tid + j * THREADS;
@@ -112,7 +123,11 @@ k_push(const KeyT *__restrict__ in, u32 n, PushDigit<KeyT> digit, PushPlan plan,
             const u32 peersm = warp_peers_dyn(d, digit_bits) & live;
             u32 b = 0;
             const int leader = __ffs(peersm) - 1;
-            if (valid && lane == leader) b = atomicAdd(&cnt[d], (u32)__popc(peersm));
+            if (valid && lane == leader) {
+                b = cnt[d * 16 + warp];
+                cnt[d * 16 + warp] = b + (u32)__popc(peersm);
+            }
+            __syncwarp();
             b = __shfl_sync(QCE_FULL_MASK, b, leader < 0 ? 0 : leader);
             slot[j] = (d << 16) | (b + (u32)__popc(peersm & lt));
         }
@@ -131,20 +146,30 @@ k_push(const KeyT *__restrict__ in, u32 n, PushDigit<KeyT> digit, PushPlan plan,
         const u32 c = (tid < 256) ? cnt[tid] : 0u;
         u32 tot;
         const u32 ex = block_scan_excl<u32, THREADS>(c, scratch, &tot);
-        if (tid < 256) {
-            excl[tid] = ex;
+        if (tid < 256) excl[tid] = ex;
+        if (FEW) {
+            __syncthreads();
+            if (tid < plan.ndigits) {
+                // digit tid: elements of all 16 warps
+                const u32 first = excl[tid * 16], end = (tid + 1 < 16) ? excl[(tid + 1) * 16] : tot;
+                const u32 cd = end - first;
+                unsigned long long r = 0;
+                if (cd) r = atomicAdd(&plan.cursor[tid], (unsigned long long)cd);
+                goff[tid] = r - first;
+            }
+        } else if (tid < 256) {
             unsigned long long r = 0;
             if (c) r = atomicAdd(&plan.cursor[tid], (unsigned long long)c);
             goff[tid] = r - ex;
-            if (tid < plan.ndigits) { sseg[tid] = plan.seg_start[tid]; srun[tid] = plan.run_base[tid]; }
         }
+        if (tid < plan.ndigits) { sseg[tid] = plan.seg_start[tid]; srun[tid] = plan.run_base[tid]; }
     }
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
         const u32 i = tid + j * THREADS;
         if (i < count) {
-            const u32 d = slot[j] >> 16, p = excl[d] + (slot[j] & 0xffffu);
+            const u32 d = slot[j] >> 16, p = excl[FEW ? d * 16 + (tid >> 5) : d] + (slot[j] & 0xffffu);
             skeys[p] = key[j];
             // where the element lands, relative to this rank's segment in the owner's window
             if (slot_out) slot_out[begin + i] = (d << 28) | (u32)(goff[d] + p - sseg[d]);
@@ -185,14 +210,46 @@ k_push_u32_by_slot(const u32 *__restrict__ vals, const u32 *__restrict__ slot, u
 // 256-bin histogram of row ids over equal-width bins (the counts every rank
 // all-gathers before k_push<u32>).
 __global__ void __launch_bounds__(512)
-k_hist_u32_div(const u32 *__restrict__ ids, u64 n, RowBins bins, u32 *__restrict__ ghist)
+k_hist_u32_div(const u32 *__restrict__ ids, u64 n, RowBins bins, u32 nbins, u32 *__restrict__ ghist)
 {
     __shared__ u32 sh[256];
     if (threadIdx.x < 256) sh[threadIdx.x] = 0;
     __syncthreads();
     const u64 stride = (u64)gridDim.x * 512;
-    for (u64 i = (u64)blockIdx.x * 512 + threadIdx.x; i < n; i += stride)
-        atomicAdd(&sh[bins(ld_stream_u32(ids + i))], 1u);
+    if (nbins <= 16) {
+        // few bins (one per owner rank): shared atomics on 2-16 addresses would serialise;
+        // count in registers, reduce per warp at the end
+        u32 c[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) c[k] = 0;
+        const u64 n4 = n & ~3ull; // 128-bit loads, two in flight per thread
+        for (u64 e = ((u64)blockIdx.x * 512 + threadIdx.x) * 4; e < n4; e += stride * 8) {
+            const uint4 a = ld_stream_u32x4(ids + e);
+            const bool two = e + stride * 4 < n4;
+            const uint4 b4 = two ? ld_stream_u32x4(ids + e + stride * 4) : make_uint4(0, 0, 0, 0);
+            const u32 v[8] = {a.x, a.y, a.z, a.w, b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                if (q >= 4 && !two) break;
+                const u32 b = bins(v[q]);
+#pragma unroll
+                for (int k = 0; k < 16; k++) c[k] += (b == (u32)k);
+            }
+        }
+        if (blockIdx.x == 0 && threadIdx.x < n - n4) {
+            const u32 b = bins(ids[n4 + threadIdx.x]);
+#pragma unroll
+            for (int k = 0; k < 16; k++) c[k] += (b == (u32)k);
+        }
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const u32 w = warp_sum_u32(c[k]);
+            if ((threadIdx.x & 31) == 0 && w) atomicAdd(&sh[k], w);
+        }
+    } else {
+        for (u64 i = (u64)blockIdx.x * 512 + threadIdx.x; i < n; i += stride)
+            atomicAdd(&sh[bins(ld_stream_u32(ids + i))], 1u);
+    }
     __syncthreads();
     if (threadIdx.x < 256 && sh[threadIdx.x]) atomicAdd(&ghist[threadIdx.x], sh[threadIdx.x]);
 }

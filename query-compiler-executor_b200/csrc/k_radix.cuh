@@ -138,7 +138,7 @@ k_radix_hist(const u64 *__restrict__ keys, u64 n, RadixShifts rs, u32 bins, u32 
 
 // One-digit histogram of 32-bit keys (row ids), for the bucketed checksum.
 __global__ void __launch_bounds__(512)
-k_hist_u32(const u32 *__restrict__ keys, u64 n, int shift, u32 *__restrict__ ghist)
+k_hist_u32(const u32 *__restrict__ keys, u64 n, u32 base, int shift, u32 *__restrict__ ghist)
 {
     __shared__ u32 sh[256];
     if (threadIdx.x < 256) sh[threadIdx.x] = 0;
@@ -147,12 +147,12 @@ k_hist_u32(const u32 *__restrict__ keys, u64 n, int shift, u32 *__restrict__ ghi
     const u64 n4 = n & ~3ull;
     for (u64 e = ((u64)blockIdx.x * 512 + threadIdx.x) * 4; e < n4; e += stride) {
         uint4 k = ld_stream_u32x4(keys + e);
-        atomicAdd(&sh[(k.x >> shift) & 255], 1u);
-        atomicAdd(&sh[(k.y >> shift) & 255], 1u);
-        atomicAdd(&sh[(k.z >> shift) & 255], 1u);
-        atomicAdd(&sh[(k.w >> shift) & 255], 1u);
+        atomicAdd(&sh[((k.x - base) >> shift) & 255], 1u);
+        atomicAdd(&sh[((k.y - base) >> shift) & 255], 1u);
+        atomicAdd(&sh[((k.z - base) >> shift) & 255], 1u);
+        atomicAdd(&sh[((k.w - base) >> shift) & 255], 1u);
     }
-    if (blockIdx.x == 0 && threadIdx.x < (n - n4)) atomicAdd(&sh[(keys[n4 + threadIdx.x] >> shift) & 255], 1u);
+    if (blockIdx.x == 0 && threadIdx.x < (n - n4)) atomicAdd(&sh[((keys[n4 + threadIdx.x] - base) >> shift) & 255], 1u);
     __syncthreads();
     if (threadIdx.x < 256 && sh[threadIdx.x]) atomicAdd(&ghist[threadIdx.x], sh[threadIdx.x]);
 }

@@ -34,6 +34,7 @@ struct qce_rowids {
     u64 n;
     u32 id_bound;  // exclusive upper bound of the ids (rows of the source relation), 0 = unknown
     bool bucketed = false; // already grouped by row region (received through qce_push_rowids)
+    u32 id_min = 0;        // inclusive lower bound of the ids (a row-sharded owner sees only its window)
 };
 struct qce_tuples {
     u64 *a;        // packed words (key << 32 | rowid), or keys when wide
@@ -772,6 +773,7 @@ bool bucketed_checksum_pays(const qce_rowids *ids, u64 col_rows)
     }
     if (mode == 1) return false;
     if (mode == 2) return ids->n >= 2;
+    if (ids->id_bound > ids->id_min) col_rows = std::min<u64>(col_rows, ids->id_bound - ids->id_min);
     return col_rows * sizeof(u64) > (256ull << 20) && ids->n >= (4ull << 20) && ids->n < (1ull << 30);
 }
 
@@ -780,7 +782,8 @@ int partition_ids_by_top_bits(const qce_rowids *ids, u32 **out)
     // unstable MSD partition of the 4-byte ids by their top 8 bits (the order inside
     // a bucket is irrelevant for a sum): histogram, prefix, one scatter pass
     const u64 n = ids->n;
-    const int bits = ids->id_bound ? bitlen(ids->id_bound - 1) : 32;
+    const u32 base = ids->id_bound > ids->id_min ? ids->id_min : 0u;
+    const int bits = ids->id_bound ? bitlen(ids->id_bound - 1 - base) : 32;
     const int shift = bits > 8 ? bits - 8 : 0;
     const u32 ntiles = (u32)ceil_div(n, QCE_MSD_TILE);
     u32 *ghist = nullptr, *cursor = nullptr, *lvl0 = nullptr, *dst = nullptr;
@@ -788,10 +791,10 @@ int partition_ids_by_top_bits(const qce_rowids *ids, u32 **out)
     const u32 h_lvl0[4] = {0u, ntiles, 0u, (u32)n};
     CK(cudaMemcpyAsync(lvl0, h_lvl0, sizeof h_lvl0, cudaMemcpyHostToDevice, g.stream));
     CK(cudaMemsetAsync(ghist, 0, QCE_RADIX_BINS * sizeof(u32), g.stream));
-    LAUNCH("hist_u32", k_hist_u32, grid_for(2048, n, 4), 512, 0, ids->d, n, shift, ghist);
+    LAUNCH("hist_u32", k_hist_u32, grid_for(2048, n, 4), 512, 0, ids->d, n, base, shift, ghist);
     LAUNCH("radix_bases", k_radix_bases, 1, 256, 0, ghist, cursor);
     LAUNCH("partition_u32", (k_msd_partition<512, 8, u32>), ntiles, 512, 0, (const u32 *)ids->d, dst, lvl0, lvl0 + 2,
-           lvl0 + 3, 1u, 0u, shift, 256u, cursor, (const u32 *)nullptr);
+           lvl0 + 3, 1u, base, shift, 256u, cursor, (const u32 *)nullptr);
     dfree(ghist); dfree(cursor); dfree(lvl0);
     *out = dst;
     return 0;
@@ -1701,7 +1704,7 @@ int qce_push_tuples(const qce_tuples *t, uint32_t key_bits, const uint64_t *spli
     dg.shift = 32 + bin_shift;
     dg.lut = dlut;
     PushPlan plan{d_seg, d_run, d_cur, nparts, 1u};
-    const u32 n = (u32)t->n, grid = (u32)ceil_div(n, QCE_PUSH_TILE);
+    const u32 n = (u32)t->n, grid = (u32)ceil_div(n, PushTile<u64>::TILE);
     const int dbits = bitlen(nparts - 1);
     u32 *so = slots_out ? (*slots_out)->d : nullptr;
     if (dst_run_index)
@@ -1746,7 +1749,8 @@ int qce_rowids_bin_histogram(const qce_rowids *ids, uint32_t rows_per_rank, uint
     u32 *gh = nullptr;
     if (dalloc(&gh, 256) != 0) return -1;
     CK(cudaMemsetAsync(gh, 0, 256 * sizeof(u32), g.stream));
-    if (ids->n) LAUNCH("hist_ids", k_hist_u32_div, grid_for(4096, ids->n, 4), 512, 0, ids->d, ids->n, rb, gh);
+    if (ids->n) LAUNCH("hist_ids", k_hist_u32_div, grid_for(4096, ids->n, 4), 512, 0, ids->d, ids->n, rb,
+                       bins_per_rank * nranks, gh);
     u32 tmp[256];
     CK(cudaMemcpyAsync(tmp, gh, sizeof tmp, cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
@@ -1773,9 +1777,13 @@ int qce_push_rowids(const qce_rowids *ids, uint32_t rows_per_rank, uint32_t bin_
     PushDigit<u32> dg;
     dg.bins = rb;
     PushPlan plan{d_seg, d_run, d_cur, nbins, bins_per_rank};
-    const u32 n = (u32)ids->n, grid = (u32)ceil_div(n, QCE_PUSH_TILE);
-    LAUNCH("push_rowids", (k_push<u32, false, false>), grid, QCE_PUSH_THREADS, 0, (const u32 *)ids->d, n, dg, plan, g.peers, 0,
-           (u32 *)nullptr);
+    const u32 n = (u32)ids->n, grid = (u32)ceil_div(n, PushTile<u32>::TILE);
+    if (nbins <= 16)
+        LAUNCH("push_rowids", (k_push<u32, true, false>), grid, QCE_PUSH_THREADS, 0, (const u32 *)ids->d, n, dg, plan, g.peers,
+               bitlen(nbins - 1), (u32 *)nullptr);
+    else
+        LAUNCH("push_rowids", (k_push<u32, false, false>), grid, QCE_PUSH_THREADS, 0, (const u32 *)ids->d, n, dg, plan, g.peers, 0,
+               (u32 *)nullptr);
     dfree(d_seg); dfree(d_cur); dfree(d_run);
     return 0;
 }
@@ -1846,7 +1854,8 @@ int qce_tuples_from_window(uint64_t word_offset, uint64_t n, uint32_t key_bits, 
     if (word_offset & 1) return fail("runs in the window start on 16-byte boundaries");
     return tuples_from_device(g.peers.base[g.xrank] + word_offset * 8, n, key_bits, id_bound, key_lo, key_hi, true, out);
 }
-int qce_rowids_from_window(uint64_t u32_offset, uint64_t n, uint32_t id_bound, int bucketed, qce_rowids **out)
+int qce_rowids_from_window(uint64_t u32_offset, uint64_t n, uint32_t id_min, uint32_t id_bound, int bucketed,
+                           qce_rowids **out)
 {
     NEED_INIT();
     if (!g.xwin) return fail("no exchange window (qce_xwin_create)");
@@ -1856,6 +1865,7 @@ int qce_rowids_from_window(uint64_t u32_offset, uint64_t n, uint32_t id_bound, i
     r->d = (u32 *)(g.peers.base[g.xrank] + u32_offset * 4); // not from the arena: freeing the handle leaves it alone
     r->n = n;
     r->id_bound = id_bound;
+    r->id_min = id_min;
     r->bucketed = bucketed != 0;
     *out = r;
     return 0;

@@ -83,7 +83,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "qce_column_window_u32": (i32, [u32, u32, u64, u64, P(vp)]), "qce_rowids_iota": (i32, [u64, u64, u32, P(vp)]),
         "qce_tuples_from_u32": (i32, [vp, u32, P(vp)]), "qce_column_gather_u32": (i32, [u32, u32, vp, P(vp)]),
         "qce_tuples_from_window": (i32, [u64, u64, u32, u32, u64, u64, P(vp)]),
-        "qce_rowids_from_window": (i32, [u64, u64, u32, i32, P(vp)]), "qce_rowids_gather": (i32, [vp, vp, P(vp)]),
+        "qce_rowids_from_window": (i32, [u64, u64, u32, u32, i32, P(vp)]), "qce_rowids_gather": (i32, [vp, vp, P(vp)]),
         "qce_adopt_column_window": (i32, [u32, u32, vp, u64, u64, u64, u64]),
         "qce_column_max_device": (i32, [vp, u64, P(u64)]),
     }
@@ -358,9 +358,9 @@ class Engine:
         self._ck(self.lib.qce_tuples_from_window(word_offset, n, key_bits, id_bound, key_lo, key_hi, C.byref(h)))
         return h.value
 
-    def rowids_from_window(self, u32_offset: int, n: int, id_bound: int = 0, bucketed: bool = False) -> int:
+    def rowids_from_window(self, u32_offset: int, n: int, id_bound: int = 0, bucketed: bool = False, id_min: int = 0) -> int:
         h = C.c_void_p()
-        self._ck(self.lib.qce_rowids_from_window(u32_offset, n, id_bound, 1 if bucketed else 0, C.byref(h)))
+        self._ck(self.lib.qce_rowids_from_window(u32_offset, n, id_min, id_bound, 1 if bucketed else 0, C.byref(h)))
         return h.value
 
     def rowids_gather(self, src: int, index: int) -> int:

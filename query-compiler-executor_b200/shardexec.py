@@ -121,6 +121,9 @@ class EngineOps:
     def key_bits(self, rel, col):
         return max(1, int(self.e.column_info(rel, col)[1]).bit_length())
 
+    def key_max(self, rel, col):
+        return int(self.e.column_info(rel, col)[1])
+
     def rows(self, rel, col=0):
         return int(self.e.column_info(rel, col)[0])
 
@@ -175,8 +178,8 @@ class EngineOps:
     def tuples_view(self, word_offset, n, key_bits, id_bound, key_range):
         return self.e.tuples_from_window(word_offset, n, key_bits, id_bound, key_range[0], key_range[1])
 
-    def col_view(self, u32_offset, n, id_bound=0, bucketed=False):
-        return self.e.rowids_from_window(u32_offset, n, id_bound, bucketed)
+    def col_view(self, u32_offset, n, id_bound=0, bucketed=False, id_min=0):
+        return self.e.rowids_from_window(u32_offset, n, id_bound, bucketed, id_min)
 
     def sort(self, t):
         self.e.sort_tuples(t)
@@ -242,7 +245,7 @@ class ShardedExecutor:
         self.stats: Dict[str, float] = {}
 
     # ---- one exchange of the two inputs of a join -----------------------------
-    def _exchange_pair(self, sides, key_bits: int):
+    def _exchange_pair(self, sides, key_bits: int, key_max: int):
         """sides = [(run, [u32 columns...]), (run, [...])].  Returns, per side, the
         received run (a view of this rank's window) and the received columns."""
         ops, world, me = self.ops, self.world, self.rank
@@ -288,7 +291,9 @@ class ShardedExecutor:
         ops.fence()
         self.comm.barrier()  # every peer's stores into this rank's window have completed
         lo = splitters[me - 1] if me > 0 else 0
-        hi = (splitters[me] - 1) if me < world - 1 else (1 << key_bits) - 1
+        # the last rank's range ends at the largest key that exists, not at 2^key_bits - 1: the
+        # local sort sizes its MSD buckets from this range (sparse buckets overflow the finish)
+        hi = (splitters[me] - 1) if me < world - 1 else key_max
         out = []
         for k, (_, cols) in enumerate(sides):
             n = int(recv[k, me])
@@ -318,8 +323,12 @@ class ShardedExecutor:
                     sums[(b, c)] = s
             return sums
         t0 = time.perf_counter()
-        bpr = max(1, 256 // world)
         geo, hists = {}, []
+        # One bin per owner rank: a tile's ids leave in a few long runs (NVLink wants >= 128-byte
+        # writes; a 256-bin scatter over the link measured 2.6x slower per id than the same
+        # scatter in local HBM).  The owner buckets what it received by L2-sized row regions
+        # itself (qce_checksum, window-relative digits) when its window is large enough to pay.
+        bpr = 1
         for b in by_binding:
             rows = ops.rows(relations[b])
             per = max(row_window(rows, 0, world)[1], 1)
@@ -355,7 +364,8 @@ class ShardedExecutor:
         self.comm.barrier()
         for b, cols in by_binding.items():
             off, n, rows = views[b]
-            v = ops.col_view(off, n, rows, True)
+            wb, wc = row_window(rows, me, world)
+            v = ops.col_view(off, n, wb + wc, bpr > 1, wb)
             for c, s in zip(cols, ops.checksum(v, relations[b], cols)):
                 sums[(b, c)] = s
             ops.free_ids(v)
@@ -463,7 +473,8 @@ class ShardedExecutor:
                     h = ops.narrow_window(relations[nb_], c, begin, count)
                     Rcols.append((("key", nb_, c), h))
                     temp.append(h)
-            (L2, Lv), (R2, Rv) = self._exchange_pair([(L, [h for _, h in Lcols]), (R, [h for _, h in Rcols])], key_bits)
+            key_max = max(ops.key_max(relations[eb], ec), ops.key_max(relations[nb_], nc))
+            (L2, Lv), (R2, Rv) = self._exchange_pair([(L, [h for _, h in Lcols]), (R, [h for _, h in Rcols])], key_bits, key_max)
             ops.free_tuples(L)
             ops.free_tuples(R)
             for h in temp:
@@ -507,3 +518,135 @@ def format_result(res: dict) -> str:
     """The line the reference prints for the same query (print_sums,
     /root/reference/src/utilities.c:212-223)."""
     return "".join("NULL " if res["pairs"] == 0 else f"{s} " for s in res["sums"]) + "\n"
+
+
+# ---------------------------------------------------------------------------- bench (N > 1)
+def bench(eng, host_lib, dist, torch, rank, world, rows, steps, warmup, verify=True):
+    """Weak scaling of config 2: every rank OWNS a `rows`-row window of two
+    relations of world*rows rows (row-sharded, generated on the device; nothing is
+    replicated).  value: windows resident in HBM.  e2e: every step first copies the
+    rank's six column windows from pinned host memory and re-derives their statistics."""
+    import ctypes as C
+    dev = torch.device("cuda", torch.cuda.current_device())
+    comm = Comm(dist, torch, dev, rank, world)
+    n = world * rows
+    begin, count = row_window(n, rank, world)
+    assert (begin, count) == (rank * rows, rows)
+    gen = torch.Generator(device=dev)
+    cols = {}
+    for r, seed in enumerate((1, 2)):
+        gen.manual_seed(1000 + 64 * seed + rank)
+        cols[(r, 0)] = torch.arange(begin, begin + rows, dtype=torch.int64, device=dev)
+        cols[(r, 1)] = torch.randint(0, n, (rows,), dtype=torch.int64, device=dev, generator=gen)
+        cols[(r, 2)] = torch.randint(0, 10 ** 6, (rows,), dtype=torch.int64, device=dev, generator=gen)
+    torch.cuda.synchronize()
+
+    def register():
+        for (r, c), t in cols.items():
+            mx = comm.allreduce_max(eng.column_max_device(t.data_ptr(), rows))
+            eng.adopt_column_window(r, c, t.data_ptr(), begin, rows, n, mx)
+
+    register()
+    open_windows(eng, comm, 24 * rows + (64 << 20))
+    ex = ShardedExecutor(EngineOps(eng), comm)
+    q = "0 1|0.1=1.1&0.2>500000|0.0 1.0 1.2"
+
+    def sync_all():
+        eng.sync()
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    res = ex.run_query(q)
+    want = format_result(res)
+    verified = None
+    if verify and n < (1 << 30):
+        # the unsharded host layer (parse -> arrange -> execute_filter/join -> print_sums) on rank 0
+        # over replicas of the same columns, once, untimed; the replicas are dropped afterwards
+        full = {}
+        for (r, c), t in cols.items():
+            f = torch.empty(n, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(f, t)
+            torch.cuda.synchronize()  # the engine reads f on its own stream (column statistics)
+            if rank == 0:
+                full[(r, c)] = f
+                eng.upload_column_device(2 + r, c, f.data_ptr(), n, adopt=True)
+            del f
+        torch.cuda.synchronize()
+        if rank == 0:
+            buf = C.create_string_buffer(4096)
+            failed = C.c_int(0)
+            host_lib.qce_host_run_batch(b"2 3|0.1=1.1&0.2>500000|0.0 1.0 1.2\n", buf, 4096, C.byref(failed))
+            verified = (buf.value.decode() == want) and failed.value == 0
+            eng.sync()
+        full.clear()
+        torch.cuda.empty_cache()
+    for _ in range(warmup):
+        ex.run_query(q)
+    sync_all()
+    times, ex_times = [], []
+    ncoll0 = comm.n_collectives
+    for _ in range(steps):
+        sync_all()
+        eng.timer_reset()
+        res = ex.run_query(q)
+        ms, launches = eng.timer_read()
+        torch.cuda.synchronize()
+        times.append(ms)
+        ex_times.append((ex.stats.get("exchange_s", 0.0) + ex.stats.get("project_exchange_s", 0.0)) * 1e3)
+        assert format_result(res) == want
+    ncoll = (comm.n_collectives - ncoll0) / steps - 1  # minus sync_all's barrier
+    t = torch.tensor([sum(times), sum(ex_times)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, ex_ms = float(t[0]), float(t[1])
+    ms_per_step = total_ms / steps
+    sent = torch.tensor([ex.stats["bytes_sent_off_rank"]], dtype=torch.float64, device=dev)
+    dist.all_reduce(sent, op=dist.ReduceOp.MAX)
+
+    # per-kernel times of one more pass (CUDA events around every launch; kept out of `value`)
+    eng.profile(True)
+    for _ in range(2):
+        ex.run_query(q)
+    prof = {k: v for k, v in eng.profile_read().items() if not k.startswith("gap_")}
+    eng.profile(False)
+    kernels = {k: round(v["ms"] / 2, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+    push_ms = sum(v for k, v in kernels.items() if k.startswith("push_"))
+
+    # ---- e2e: host windows in, checksums out, every step
+    pinned = {k: v.cpu().pin_memory() for k, v in cols.items()}
+    e2e_times = []
+    for i in range(min(warmup, 1) + steps):
+        sync_all()
+        eng.timer_reset()
+        for k, t in cols.items():
+            t.copy_(pinned[k], non_blocking=True)
+        torch.cuda.synchronize()
+        register()
+        res = ex.run_query(q)
+        ms, _ = eng.timer_read()
+        if i >= min(warmup, 1):
+            e2e_times.append(ms)
+        assert format_result(res) == want
+    te = torch.tensor([sum(e2e_times)], dtype=torch.float64, device=dev)
+    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te[0]) / steps
+    off_rank = float(sent[0])
+    return {
+        "value": 2.0 * n / (ms_per_step / 1e3), "ms_per_step": ms_per_step,
+        "config": {"workload": "C2 weak-scaled: 2-way equi-join + range filter, 2 x %d-row uint64 relations x 3 columns "
+                               "(%d rows per GPU per relation, ROW-SHARDED: each GPU holds only its window), query %s, "
+                               "sharded by key range over %d GPUs: histogram all-gather, partition+push kernel over "
+                               "NVLink peer windows (no all-to-all), row ids pushed to their owners for the checksums, "
+                               "uint64 all-reduce" % (n, rows, q, world),
+                   "rows_per_relation": n, "result": want.strip(), "verified_against_unsharded_engine": verified,
+                   "l2": "inputs larger than L2"},
+        "exchange": {"host_ms_per_step_incl_collectives": ex_ms / steps, "push_kernels_ms_per_step": push_ms,
+                     "max_bytes_pushed_off_rank_per_step": off_rank,
+                     "push_gbs_per_rank": off_rank / (push_ms / 1e3) / 1e9 if push_ms else None,
+                     "nvlink_peak_gbs_per_direction": 900.0, "small_collectives_per_step": ncoll},
+        "kernels_ms_per_step_rank0": kernels,
+        "gpu_launches": int(launches) * steps,
+        "e2e": {"value": 2.0 * n / (e2e_ms / 1e3), "unit": "rows/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": 6 * rows * 8, "d2h_bytes_per_step": 5 * 8,
+                "note": "per rank: its own row windows of the six columns from pinned host memory, column statistics "
+                        "recomputed, checksums back to the host"},
+    }

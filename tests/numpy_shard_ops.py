@@ -37,6 +37,9 @@ class NumpyShardOps:
     def key_bits(self, rel, col):
         return max(1, self.maxv[rel][col].bit_length())
 
+    def key_max(self, rel, col):
+        return self.maxv[rel][col]
+
     def rows(self, rel, col=0):
         return self.rows_of[rel]
 
@@ -130,7 +133,7 @@ class NumpyShardOps:
         assert n == 0 or ((t >> np.uint64(32)).min() >= key_range[0] and (t >> np.uint64(32)).max() <= key_range[1])
         return t
 
-    def col_view(self, u32_offset, n, id_bound=0, bucketed=False):
+    def col_view(self, u32_offset, n, id_bound=0, bucketed=False, id_min=0):
         return self.win[u32_offset * 4:(u32_offset + n) * 4].view(np.uint32).copy()
 
     # ---- local join

@@ -87,16 +87,17 @@ def test_push_tuples_loopback(xeng, n, world, rewrite):
             np.testing.assert_array_equal(k[np.argsort(pos)][(slots[idx] & U64(0x0FFFFFFF)).astype(np.int64)], keys[idx])
 
 
-@pytest.mark.parametrize("n", [0, 5, 4097, 300001])
+@pytest.mark.parametrize("n", [0, 5, 4097, 8193, 300001])
 @pytest.mark.parametrize("world", [1, 2, 3, 8])
-def test_push_rowids_loopback(xeng, n, world):
+@pytest.mark.parametrize("fine", [False, True])
+def test_push_rowids_loopback(xeng, n, world, fine):
     e = xeng
     e.xwin_loopback(world)
     per_bytes = WIN // world // 4096 * 4096
     rng = np.random.default_rng(7 * n + world)
     rows = 1_000_003
     rows_per_rank = -(-(-(-rows // world)) // 4096) * 4096
-    bpr = 256 // world
+    bpr = 256 // world if fine else 1  # one bin per owner (ballot-ranked kernel) or L2-sized regions
     width = -(-rows_per_rank // bpr)
     ids = rng.integers(0, rows, n, dtype=np.uint64)
     h = e.rowids_from_host(ids)
@@ -186,8 +187,9 @@ EXEC = {
 }
 
 
-@pytest.mark.parametrize("kind,rows", [("pair", 300_007), ("chain", 200_000), ("zipf", 150_000), ("chain", 2_000_000)])
-def test_sharded_executor_world1(kind, rows):
+@pytest.mark.parametrize("kind,rows,force_bucketing", [("pair", 300_007, False), ("chain", 200_000, False), ("zipf", 150_000, False),
+                                                       ("chain", 2_000_000, False), ("pair", 1_000_003, True)])
+def test_sharded_executor_world1(kind, rows, force_bucketing):
     """One rank: the same orchestration and kernels as N GPUs (windowed columns, push
     kernels, by-slot columns, id push, bucketed checksum) with every store local."""
     import subprocess, sys, os, json, tempfile
@@ -224,7 +226,10 @@ dist.destroy_process_group()
 ''' % (root, kind, rows, EXEC[kind])
     script = os.path.join(tempfile.mkdtemp(), "exec_child.py")
     open(script, "w").write(child)
-    p = subprocess.run([sys.executable, script], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    env = dict(os.environ)
+    if force_bucketing:  # the owner's window-relative bucketing pass before the checksum gathers
+        env["QCE_BUCKETED_CHECKSUM"] = "1"
+    p = subprocess.run([sys.executable, script], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600, env=env)
     lines = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
     assert p.returncode == 0 and lines, (p.stdout[-2000:], p.stderr[-3000:])
     assert json.loads(lines[-1][7:])["ok"], p.stdout[-2000:]
