@@ -221,6 +221,13 @@ int qce_xwin_destroy(void);
  * qce_push_u32_by_slot (bystander columns of the same entity, join.c:486-505). */
 int qce_push_tuples(const qce_tuples *t, uint32_t key_bits, const uint64_t *splitters, uint32_t nparts,
                     const uint64_t *dst_word_offset, const uint32_t *dst_run_index, qce_rowids **slots_out);
+/* Same with the run's bystander columns fused into the same kernel (requires dst_run_index):
+ * column c of input tuple i is stored at 4-byte element col_u32_offset[c * nparts + p] +
+ * (position of the tuple inside this rank's segment) of rank p's window; every column
+ * leaves in the same coalesced per-destination runs as the tuples.  ncols <= 6. */
+int qce_push_tuples_cols(const qce_tuples *t, uint32_t key_bits, const uint64_t *splitters, uint32_t nparts,
+                         const uint64_t *dst_word_offset, const uint32_t *dst_run_index, uint32_t ncols,
+                         const qce_rowids *const *cols, const uint64_t *col_u32_offset);
 /* vals[i] -> 4-byte element dst_u32_offset[p] + position of rank p's window, (p, position) = slots[i] */
 int qce_push_u32_by_slot(const qce_rowids *vals, const qce_rowids *slots, uint32_t nparts,
                          const uint64_t *dst_u32_offset);

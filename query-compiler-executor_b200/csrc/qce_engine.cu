@@ -1672,8 +1672,25 @@ static int push_scratch(u32 ndigits, const uint64_t *seg_start, const u32 *run_b
     return 0;
 }
 
+static int push_tuples_impl(const qce_tuples *t, uint32_t key_bits, const uint64_t *splitters, uint32_t nparts,
+                            const uint64_t *dst_word_offset, const uint32_t *dst_run_index, qce_rowids **slots_out,
+                            uint32_t ncols, const qce_rowids *const *cols, const uint64_t *col_u32_offset);
 int qce_push_tuples(const qce_tuples *t, uint32_t key_bits, const uint64_t *splitters, uint32_t nparts,
                     const uint64_t *dst_word_offset, const uint32_t *dst_run_index, qce_rowids **slots_out)
+{
+    return push_tuples_impl(t, key_bits, splitters, nparts, dst_word_offset, dst_run_index, slots_out, 0, nullptr, nullptr);
+}
+int qce_push_tuples_cols(const qce_tuples *t, uint32_t key_bits, const uint64_t *splitters, uint32_t nparts,
+                         const uint64_t *dst_word_offset, const uint32_t *dst_run_index, uint32_t ncols,
+                         const qce_rowids *const *cols, const uint64_t *col_u32_offset)
+{
+    if (ncols && (!cols || !col_u32_offset || !dst_run_index)) return fail("null argument");
+    if (ncols > QCE_PUSH_MAX_COLS) return fail("at most %d columns travel with one run", QCE_PUSH_MAX_COLS);
+    return push_tuples_impl(t, key_bits, splitters, nparts, dst_word_offset, dst_run_index, nullptr, ncols, cols, col_u32_offset);
+}
+static int push_tuples_impl(const qce_tuples *t, uint32_t key_bits, const uint64_t *splitters, uint32_t nparts,
+                            const uint64_t *dst_word_offset, const uint32_t *dst_run_index, qce_rowids **slots_out,
+                            uint32_t ncols, const qce_rowids *const *cols, const uint64_t *col_u32_offset)
 {
     NEED_INIT();
     if (!t || !dst_word_offset) return fail("null argument");
@@ -1707,10 +1724,18 @@ int qce_push_tuples(const qce_tuples *t, uint32_t key_bits, const uint64_t *spli
     const u32 n = (u32)t->n, grid = (u32)ceil_div(n, PushTile<u64>::TILE);
     const int dbits = bitlen(nparts - 1);
     u32 *so = slots_out ? (*slots_out)->d : nullptr;
+    PushCols pc;
+    memset(&pc, 0, sizeof pc);
+    pc.n = (int)ncols;
+    for (u32 c = 0; c < ncols; c++) {
+        if (!cols[c] || cols[c]->n != t->n) return fail("column %u travels with a run of different length", c);
+        pc.in[c] = cols[c]->d;
+        for (u32 r = 0; r < nparts; r++) pc.region[c][r] = col_u32_offset[(size_t)c * nparts + r];
+    }
     if (dst_run_index)
-        LAUNCH("push_tuples", (k_push<u64, true, true>), grid, QCE_PUSH_THREADS, 0, (const u64 *)t->a, n, dg, plan, g.peers, dbits, so);
+        LAUNCH("push_tuples", (k_push<u64, true, true>), grid, QCE_PUSH_THREADS, 0, (const u64 *)t->a, n, dg, plan, g.peers, dbits, so, pc);
     else
-        LAUNCH("push_tuples", (k_push<u64, true, false>), grid, QCE_PUSH_THREADS, 0, (const u64 *)t->a, n, dg, plan, g.peers, dbits, so);
+        LAUNCH("push_tuples", (k_push<u64, true, false>), grid, QCE_PUSH_THREADS, 0, (const u64 *)t->a, n, dg, plan, g.peers, dbits, so, pc);
     dfree(d_seg); dfree(d_cur); dfree(d_run); dfree(dlut);
     return 0;
 }
@@ -1734,6 +1759,7 @@ static int row_bins(uint32_t rows_per_rank, uint32_t bin_width, uint32_t bins_pe
     if (rows_per_rank == 0 || bin_width == 0 || bins_per_rank == 0 || nranks == 0 || (u64)bins_per_rank * nranks > 256)
         return fail("row bins: rows_per_rank, bin_width > 0 and bins_per_rank * nranks in 1..256");
     rb->rows_per_rank = rows_per_rank;
+    rb->inv_rows = 1.0f / (float)rows_per_rank;
     rb->last_rank = nranks - 1;
     rb->width = bin_width;
     rb->bins_per_rank = bins_per_rank;
@@ -1778,12 +1804,14 @@ int qce_push_rowids(const qce_rowids *ids, uint32_t rows_per_rank, uint32_t bin_
     dg.bins = rb;
     PushPlan plan{d_seg, d_run, d_cur, nbins, bins_per_rank};
     const u32 n = (u32)ids->n, grid = (u32)ceil_div(n, PushTile<u32>::TILE);
+    PushCols nocols;
+    memset(&nocols, 0, sizeof nocols);
     if (nbins <= 16)
         LAUNCH("push_rowids", (k_push<u32, true, false>), grid, QCE_PUSH_THREADS, 0, (const u32 *)ids->d, n, dg, plan, g.peers,
-               bitlen(nbins - 1), (u32 *)nullptr);
+               bitlen(nbins - 1), (u32 *)nullptr, nocols);
     else
         LAUNCH("push_rowids", (k_push<u32, false, false>), grid, QCE_PUSH_THREADS, 0, (const u32 *)ids->d, n, dg, plan, g.peers, 0,
-               (u32 *)nullptr);
+               (u32 *)nullptr, nocols);
     dfree(d_seg); dfree(d_cur); dfree(d_run);
     return 0;
 }

@@ -29,7 +29,7 @@ SYMBOLS = [
     "qce_tuples_from_host", "qce_tuples_to_host", "qce_tuples_free", "qce_partition_tuples",
     "qce_tuples_from_device_packed", "qce_tuples_adopt_device_packed", "qce_exchange_release", "qce_key_histogram",
     "qce_xwin_create", "qce_xwin_attach", "qce_xwin_loopback", "qce_xwin_info", "qce_xwin_destroy", "qce_push_tuples",
-    "qce_push_u32_by_slot", "qce_rowids_bin_histogram", "qce_push_rowids", "qce_tuples_from_window", "qce_rowids_from_window",
+    "qce_push_u32_by_slot", "qce_push_tuples_cols", "qce_rowids_bin_histogram", "qce_push_rowids", "qce_tuples_from_window", "qce_rowids_from_window",
     "qce_rowids_gather", "qce_adopt_column_window", "qce_column_max_device", "qce_column_window_u32", "qce_rowids_iota",
     "qce_tuples_from_u32", "qce_column_gather_u32",
 ]
@@ -78,6 +78,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "qce_xwin_info": (i32, [P(u64), P(vp)]), "qce_xwin_destroy": (i32, []),
         "qce_push_tuples": (i32, [vp, u32, vp, u32, vp, vp, P(vp)]),
         "qce_push_u32_by_slot": (i32, [vp, vp, u32, vp]),
+        "qce_push_tuples_cols": (i32, [vp, u32, vp, u32, vp, vp, u32, vp, vp]),
         "qce_rowids_bin_histogram": (i32, [vp, u32, u32, u32, u32, vp]),
         "qce_push_rowids": (i32, [vp, u32, u32, u32, u32, vp]),
         "qce_column_window_u32": (i32, [u32, u32, u64, u64, P(vp)]), "qce_rowids_iota": (i32, [u64, u64, u32, P(vp)]),
@@ -317,6 +318,16 @@ class Engine:
                                           ri.ctypes.data if ri is not None else None,
                                           C.byref(slots) if want_slots else None))
         return slots.value if want_slots else None
+
+    def push_tuples_cols(self, t: int, key_bits: int, splitters, nparts: int, dst_word_offset, dst_run_index,
+                         cols: Sequence[int], col_u32_offset) -> None:
+        sp = _u64(splitters if len(splitters) else [0])
+        off = _u64(dst_word_offset)
+        ri = np.ascontiguousarray(dst_run_index, dtype=np.uint32)
+        ca = (C.c_void_p * max(1, len(cols)))(*cols)
+        co = _u64(np.asarray(col_u32_offset).reshape(-1) if len(cols) else [0])
+        self._ck(self.lib.qce_push_tuples_cols(t, key_bits, sp.ctypes.data, nparts, off.ctypes.data, ri.ctypes.data,
+                                               len(cols), ca, co.ctypes.data))
 
     def push_u32_by_slot(self, vals: int, slots: int, nparts: int, dst_u32_offset) -> None:
         off = _u64(dst_u32_offset)

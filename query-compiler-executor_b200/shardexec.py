@@ -166,6 +166,9 @@ class EngineOps:
     def push_col(self, col, slots, nparts, dst_u32_offset):
         self.e.push_u32_by_slot(col, slots, nparts, dst_u32_offset)
 
+    def push_tuples_cols(self, t, key_bits, splitters, nparts, dst_word_offset, dst_run_index, cols, col_u32_offset):
+        self.e.push_tuples_cols(t, key_bits, splitters, nparts, dst_word_offset, dst_run_index, cols, col_u32_offset)
+
     def ids_hist(self, ids, per, width, bpr, world):
         return self.e.rowids_bin_histogram(ids, per, width, bpr, world)
 
@@ -279,14 +282,14 @@ class ShardedExecutor:
             raise MemoryError(f"exchange needs {int(top.max())} bytes of receive window, {cap} available")
         sent = 0
         for k, (run, cols) in enumerate(sides):
-            dst_words = run_off[k] // 8 + before[k, me]
-            rewrite = len(cols) > 0
-            slots = ops.push_tuples(run, key_bits, splitters, world, dst_words.astype(np.uint64),
-                                    before[k, me].astype(np.uint32) if rewrite else None, rewrite)
-            for j, col in enumerate(cols):
-                ops.push_col(col, slots, world, (col_off[k][j] // 4 + before[k, me]).astype(np.uint64))
-            if slots is not None:
-                ops.free_ids(slots)
+            dst_words = (run_off[k] // 8 + before[k, me]).astype(np.uint64)
+            if not cols:    # payloads are row ids and travel inside the tuples
+                ops.push_tuples(run, key_bits, splitters, world, dst_words, None, False)
+            else:           # payload := index in the receiver's run; the columns follow in the same kernel
+                for j0 in range(0, len(cols), 6):
+                    regions = np.stack([col_off[k][j] // 4 + before[k, me] for j in range(j0, min(j0 + 6, len(cols)))])
+                    ops.push_tuples_cols(run, key_bits, splitters, world, dst_words, before[k, me].astype(np.uint32),
+                                         cols[j0:j0 + 6], regions.astype(np.uint64))
             sent += int(C[k, me].sum() - C[k, me, me]) * (8 + 4 * len(cols))
         ops.fence()
         self.comm.barrier()  # every peer's stores into this rank's window have completed

@@ -100,6 +100,11 @@ class NumpyShardOps:
         self._deliver(parcels)
         return slots if want_slots else None
 
+    def push_tuples_cols(self, t, key_bits, splitters, nparts, dst_word_offset, dst_run_index, cols, col_u32_offset):
+        slots = self.push_tuples(t, key_bits, splitters, nparts, dst_word_offset, dst_run_index, True)
+        for c, col in enumerate(cols):
+            self.push_col(col, slots, nparts, np.asarray(col_u32_offset)[c])
+
     def push_col(self, col, slots, nparts, dst_u32_offset):
         parcels = []
         for d in range(nparts):

@@ -37,7 +37,7 @@ def _read_u32(e, byte_off, n):
 
 @pytest.mark.parametrize("n", [0, 1, 33, 4095, 4096, 4097, 100003, 1 << 20])
 @pytest.mark.parametrize("world", [1, 2, 3, 8])
-@pytest.mark.parametrize("rewrite", [False, True])
+@pytest.mark.parametrize("rewrite", [False, True, "fused"])
 def test_push_tuples_loopback(xeng, n, world, rewrite):
     e = xeng
     e.xwin_loopback(world)
@@ -55,10 +55,18 @@ def test_push_tuples_loopback(xeng, n, world, rewrite):
     counts = np.bincount(part, minlength=world)
     seg_words = np.array([64 + 2 * d for d in range(world)], dtype=U64)     # where "this rank's" segment starts
     run_index = np.array([1000 * (d + 1) for d in range(world)], dtype=np.uint32)
-    slots_h = e.push_tuples(t, key_bits, splitters, world, seg_words, run_index if rewrite else None, rewrite)
     col = rng.integers(0, 1 << 32, n, dtype=np.uint64)
     col_off = np.array([(per // 2) // 4 + 16 * d for d in range(world)], dtype=U64)
-    if rewrite:
+    fused = rewrite == "fused"
+    if fused:   # tuples and two bystander columns in ONE kernel; the second column is col ^ 5
+        ch, ch2 = e.rowids_from_host(col), e.rowids_from_host(col ^ U64(5))
+        col2_off = col_off + U64(per // 16)
+        e.push_tuples_cols(t, key_bits, splitters, world, seg_words, run_index, [ch, ch2], np.stack([col_off, col2_off]))
+        e.rowids_free(ch)
+        e.rowids_free(ch2)
+    else:
+        slots_h = e.push_tuples(t, key_bits, splitters, world, seg_words, run_index if rewrite else None, bool(rewrite))
+    if rewrite and not fused:
         ch = e.rowids_from_host(col)
         e.push_u32_by_slot(ch, slots_h, world, col_off)
         slots = e.rowids_to_host(slots_h)
@@ -82,6 +90,10 @@ def test_push_tuples_loopback(xeng, n, world, rewrite):
             pairs_got = sorted(zip(k.tolist(), got_col[pos].tolist()))
             pairs_exp = sorted(zip(keys[want].tolist(), col[want].tolist()))
             assert pairs_got == pairs_exp
+            if fused:
+                got2 = _read_u32(e, per * d + int(col2_off[d]) * 4, int(counts[d]))
+                np.testing.assert_array_equal(got2, got_col ^ U64(5))
+                continue
             # slots say where each input tuple went
             idx = np.nonzero(want)[0]
             np.testing.assert_array_equal(k[np.argsort(pos)][(slots[idx] & U64(0x0FFFFFFF)).astype(np.int64)], keys[idx])
