@@ -344,6 +344,9 @@ def main():
                 "share_of_kernel_time": dprof["ms"] / total_kernel_ms if total_kernel_ms else None,
                 "algorithmic_bytes": models[dom][1],
                 "kernels_ms_per_step": {k: round(v["ms"] / args.steps, 4) for k, v in prof.items()},
+                "stream_gaps_ms_per_step": {k[len("gap_before:"):]: round(v["ms"] / args.steps, 4)
+                                            for k, v in sorted(prof_all.items(), key=lambda kv: -kv[1]["ms"])
+                                            if k.startswith("gap_before") and v["ms"] / args.steps >= 0.01},
                 "kernels_frac_of_peak": {k: round(models[k][0] * args.steps / (prof[k]["ms"] / 1e3) / 1e9 / pk["hbm_gbs"], 3)
                                          for k in prof if k in models and prof[k]["ms"]},
                 "whole_query": {"algorithmic_gb_survey_8d": alg_query / 1e9, "lhs_rows": lhs, "pairs": pairs,

@@ -98,7 +98,7 @@ struct PushCols {
 // one shared atomicAdd per (warp, digit) group; otherwise one shared atomicAdd
 // per element (256 digits, little contention).
 template <typename KeyT, bool FEW, bool REWRITE>
-__global__ void __launch_bounds__(QCE_PUSH_THREADS)
+__global__ void __launch_bounds__(QCE_PUSH_THREADS, sizeof(KeyT) == 8 ? 3 : 2)
 k_push(const KeyT *__restrict__ in, u32 n, PushDigit<KeyT> digit, PushPlan plan, const __grid_constant__ PeerWindows peers, int digit_bits,
        u32 *__restrict__ slot_out, const __grid_constant__ PushCols cols)
 {
@@ -252,6 +252,7 @@ k_push_u32_by_slot(const u32 *__restrict__ vals, const u32 *__restrict__ slot, u
 
 // 256-bin histogram of row ids over equal-width bins (the counts every rank
 // all-gathers before k_push<u32>).
+template <int NB> // NB = 2, 4, 8, 16: register counters for nbins <= NB; 256: shared atomics
 __global__ void __launch_bounds__(512)
 k_hist_u32_div(const u32 *__restrict__ ids, u64 n, RowBins bins, u32 nbins, u32 *__restrict__ ghist)
 {
@@ -259,12 +260,12 @@ k_hist_u32_div(const u32 *__restrict__ ids, u64 n, RowBins bins, u32 nbins, u32 
     if (threadIdx.x < 256) sh[threadIdx.x] = 0;
     __syncthreads();
     const u64 stride = (u64)gridDim.x * 512;
-    if (nbins <= 16) {
+    if (NB <= 16) {
         // few bins (one per owner rank): shared atomics on 2-16 addresses would serialise;
         // count in registers, reduce per warp at the end
-        u32 c[16];
+        u32 c[NB <= 16 ? NB : 1];
 #pragma unroll
-        for (int k = 0; k < 16; k++) c[k] = 0;
+        for (int k = 0; k < (NB <= 16 ? NB : 1); k++) c[k] = 0;
         const u64 n4 = n & ~3ull; // 128-bit loads, two in flight per thread
         for (u64 e = ((u64)blockIdx.x * 512 + threadIdx.x) * 4; e < n4; e += stride * 8) {
             const uint4 a = ld_stream_u32x4(ids + e);
@@ -276,16 +277,16 @@ k_hist_u32_div(const u32 *__restrict__ ids, u64 n, RowBins bins, u32 nbins, u32 
                 if (q >= 4 && !two) break;
                 const u32 b = bins(v[q]);
 #pragma unroll
-                for (int k = 0; k < 16; k++) c[k] += (b == (u32)k);
+                for (int k = 0; k < (NB <= 16 ? NB : 1); k++) c[k] += (b == (u32)k);
             }
         }
         if (blockIdx.x == 0 && threadIdx.x < n - n4) {
             const u32 b = bins(ids[n4 + threadIdx.x]);
 #pragma unroll
-            for (int k = 0; k < 16; k++) c[k] += (b == (u32)k);
+            for (int k = 0; k < (NB <= 16 ? NB : 1); k++) c[k] += (b == (u32)k);
         }
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
+        for (int k = 0; k < (NB <= 16 ? NB : 1); k++) {
             const u32 w = warp_sum_u32(c[k]);
             if ((threadIdx.x & 31) == 0 && w) atomicAdd(&sh[k], w);
         }

@@ -27,7 +27,8 @@
 
 #define QCE_JTILE 2048     // R tuples per tile (256 threads x 8)
 #define QCE_JTHREADS 256
-#define QCE_JWIN 8192      // S window staged in shared memory (keys, 64 KB + skew, dynamic)
+#define QCE_JWIN 4096      // S window staged in shared memory (keys, 32 KB dynamic = the count table's size:
+                           // 64 KB capped the kernel at 3 CTAs/SM, 37 % occupancy, ncu profiles/ncu_summary_r1b.json)
 #define QCE_JCHUNK 4096    // output pairs per write CTA
 
 template <bool WIDE>
@@ -93,7 +94,7 @@ template <bool LT> __device__ __forceinline__ u32 bound_s(const u64 *skeys, u32 
 //    binary searches;
 //  * search path -- sparse keys: the S window (<= QCE_JWIN keys) is staged in shared
 //    memory and searched; beyond that, binary search in global memory.
-#define QCE_JTAB 8192
+#define QCE_JTAB 8190     // range + 2 table entries of 4 bytes fit the 32 KB of QCE_JSMEM_BYTES
 template <bool WR, bool WS>
 __global__ void __launch_bounds__(QCE_JTHREADS)
 k_join_bounds(TupleView R, u32 nR, TupleView S, const uint2 *__restrict__ win,

@@ -814,6 +814,7 @@ k_msd_count_sort(u64 *__restrict__ keys, const u32 *__restrict__ seg_off, const 
     constexpr int TILE = THREADS * ITEMS;
     constexpr int MAXB = 4096;
     constexpr int BPT = MAXB / THREADS; // counters per thread in the scan (consecutive)
+    static_assert(BPT % 4 == 0, "the counter scan works on uint4 groups");
     extern __shared__ __align__(16) unsigned char smem_raw[]; // TILE*8 + MAXB*4 + 33*4 bytes
     u64 *skeys = reinterpret_cast<u64 *>(smem_raw);
     u32 *cnt = reinterpret_cast<u32 *>(skeys + TILE);
@@ -823,7 +824,14 @@ k_msd_count_sort(u64 *__restrict__ keys, const u32 *__restrict__ seg_off, const 
     u64 *base = keys + seg_off[blockIdx.x];
     const int tid = threadIdx.x;
     const u32 nb = 1u << rbits, mask = nb - 1;
-    for (u32 i = tid; i < nb; i += THREADS) cnt[i] = 0;
+    // all MAXB counters are cleared and scanned with 128-bit shared-memory accesses (a scalar
+    // scan with `nb / THREADS` consecutive counters per thread is a 4- to 8-way bank conflict);
+    // the counters beyond nb stay zero
+    {
+        uint4 *c4 = reinterpret_cast<uint4 *>(cnt);
+#pragma unroll
+        for (int q = 0; q < BPT / 4; q++) c4[tid + q * THREADS] = make_uint4(0u, 0u, 0u, 0u);
+    }
     __syncthreads();
     u64 key[ITEMS];
     u32 slot[ITEMS];
@@ -838,23 +846,26 @@ k_msd_count_sort(u64 *__restrict__ keys, const u32 *__restrict__ seg_off, const 
         if (i < n) slot[j] = atomicAdd(&cnt[(u32)((key[j] - key_base) >> 32) & mask], 1u);
     }
     __syncthreads();
-    // exclusive scan of the counters in place (thread t owns nb/THREADS consecutive ones)
+    // exclusive scan of the counters in place (thread t owns BPT consecutive ones)
     {
-        const u32 per = (nb + THREADS - 1) / THREADS; // <= BPT
-        u32 c[BPT], sum = 0;
+        uint4 *c4 = reinterpret_cast<uint4 *>(cnt) + tid * (BPT / 4);
+        uint4 v[BPT / 4];
+        u32 sum = 0;
 #pragma unroll
-        for (int q = 0; q < BPT; q++) {
-            const u32 b = tid * per + q;
-            c[q] = (q < (int)per && b < nb) ? cnt[b] : 0u;
-            sum += c[q];
+        for (int q = 0; q < BPT / 4; q++) {
+            v[q] = c4[q];
+            sum += v[q].x + v[q].y + v[q].z + v[q].w;
         }
         u32 tot;
         u32 ex = block_scan_excl<u32, THREADS>(sum, scratch, &tot);
 #pragma unroll
-        for (int q = 0; q < BPT; q++) {
-            const u32 b = tid * per + q;
-            if (q < (int)per && b < nb) cnt[b] = ex;
-            ex += c[q];
+        for (int q = 0; q < BPT / 4; q++) {
+            uint4 o;
+            o.x = ex; ex += v[q].x;
+            o.y = ex; ex += v[q].y;
+            o.z = ex; ex += v[q].z;
+            o.w = ex; ex += v[q].w;
+            c4[q] = o;
         }
     }
     __syncthreads();

@@ -583,10 +583,14 @@ int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done)
         if (R > 0 && R <= 12) {
             const size_t sm8 = 256 * 8 * sizeof(u64) + 4096 * sizeof(u32) + 33 * sizeof(u32);
             const size_t sm16 = 256 * 16 * sizeof(u64) + 4096 * sizeof(u32) + 33 * sizeof(u32);
+            const size_t sm12 = 256 * 12 * sizeof(u64) + 4096 * sizeof(u32) + 33 * sizeof(u32);
+            static int mid_shape = -1; // QCE_COUNT_SORT_MID=0 disables the 3072-tuple shape
+            if (mid_shape < 0) { const char *e = getenv("QCE_COUNT_SORT_MID"); mid_shape = e ? atoi(e) : 1; }
             static bool attr_set = false;
             if (!attr_set) {
                 CK(cudaFuncSetAttribute(k_msd_count_sort<256, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm8));
                 CK(cudaFuncSetAttribute(k_msd_count_sort<256, 16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16));
+                CK(cudaFuncSetAttribute(k_msd_count_sort<256, 12, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm12));
                 CK(cudaFuncSetAttribute(k_msd_count_sort<512, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16));
                 CK(cudaFuncSetAttribute(k_msd_count_sort<512, 8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16));
                 CK(cudaFuncSetAttribute(k_msd_count_sort<512, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16));
@@ -594,6 +598,8 @@ int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done)
             }
             if (max_sub <= 256 * 8)
                 LAUNCH("msd_count_sort", (k_msd_count_sort<256, 8, 4>), nsub, 256, sm8, *keys, suboff, histB, base, R);
+            else if (mid_shape && max_sub <= 256 * 12) // sparse key ranges leave sub-buckets of 2-3 K tuples
+                LAUNCH("msd_count_sort", (k_msd_count_sort<256, 12, 4>), nsub, 256, sm12, *keys, suboff, histB, base, R);
             else if (shape == 1)
                 LAUNCH("msd_count_sort", (k_msd_count_sort<512, 8, 2>), nsub, 512, sm16, *keys, suboff, histB, base, R);
             else if (shape == 2)
@@ -1775,8 +1781,15 @@ int qce_rowids_bin_histogram(const qce_rowids *ids, uint32_t rows_per_rank, uint
     u32 *gh = nullptr;
     if (dalloc(&gh, 256) != 0) return -1;
     CK(cudaMemsetAsync(gh, 0, 256 * sizeof(u32), g.stream));
-    if (ids->n) LAUNCH("hist_ids", k_hist_u32_div, grid_for(4096, ids->n, 4), 512, 0, ids->d, ids->n, rb,
-                       bins_per_rank * nranks, gh);
+    const u32 nbins = bins_per_rank * nranks;
+    const int hgrid = grid_for(4096, ids->n, 4);
+    if (ids->n) {
+        if (nbins <= 2) LAUNCH("hist_ids", k_hist_u32_div<2>, hgrid, 512, 0, ids->d, ids->n, rb, nbins, gh);
+        else if (nbins <= 4) LAUNCH("hist_ids", k_hist_u32_div<4>, hgrid, 512, 0, ids->d, ids->n, rb, nbins, gh);
+        else if (nbins <= 8) LAUNCH("hist_ids", k_hist_u32_div<8>, hgrid, 512, 0, ids->d, ids->n, rb, nbins, gh);
+        else if (nbins <= 16) LAUNCH("hist_ids", k_hist_u32_div<16>, hgrid, 512, 0, ids->d, ids->n, rb, nbins, gh);
+        else LAUNCH("hist_ids", k_hist_u32_div<256>, hgrid, 512, 0, ids->d, ids->n, rb, nbins, gh);
+    }
     u32 tmp[256];
     CK(cudaMemcpyAsync(tmp, gh, sizeof tmp, cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
