@@ -43,28 +43,45 @@ struct RadixShifts {
 
 // ---- tuple build ---------------------------------------------------------------
 // Packed, from a base column: out[i] = col[i] << 32 | i   (src/join.c:131-134)
+// HIST: also count the top 8 key bits (key >> hist_shift) into ghist[256] -- level A of the
+// MSD sort and the exchange's splitter histogram, taken while the keys stream through
+// anyway instead of in a pass of its own (8 B/tuple saved).
+template <bool HIST>
 __global__ void __launch_bounds__(256)
-k_build_packed_base(const u64 *__restrict__ col, u64 n, u64 *__restrict__ out, u64 id_base)
+k_build_packed_base(const u64 *__restrict__ col, u64 n, u64 *__restrict__ out, u64 id_base, int hist_shift,
+                    u32 *__restrict__ ghist)
 {
     // id_base: first row id of the window when a rank builds only its row range
+    __shared__ u32 sh[HIST ? 256 : 1];
+    if (HIST) { sh[threadIdx.x] = 0; __syncthreads(); }
     const u64 stride = (u64)gridDim.x * 512;
     for (u64 e = ((u64)blockIdx.x * 256 + threadIdx.x) * 2; e < n; e += stride) {
         if (e + 1 < n) {
             u64 a, b;
             ld_stream_u64x2(col + e, a, b);
             st_stream_u64x2(out + e, (a << 32) | (e + id_base), (b << 32) | (e + 1 + id_base));
+            if (HIST) { atomicAdd(&sh[(u32)(a >> hist_shift) & 255u], 1u); atomicAdd(&sh[(u32)(b >> hist_shift) & 255u], 1u); }
         } else {
-            out[e] = (col[e] << 32) | (e + id_base);
+            const u64 a = col[e];
+            out[e] = (a << 32) | (e + id_base);
+            if (HIST) atomicAdd(&sh[(u32)(a >> hist_shift) & 255u], 1u);
         }
+    }
+    if (HIST) {
+        __syncthreads();
+        if (sh[threadIdx.x]) atomicAdd(&ghist[threadIdx.x], sh[threadIdx.x]);
     }
 }
 // Packed, through a row-id column: out[i] = col[ids[i]] << 32 | ids[i]
 // (src/join.c:107-112).  The gather is sector-bound unless ids are clustered
 // (filter outputs are ascending).
+template <bool HIST>
 __global__ void __launch_bounds__(256)
 k_build_packed_ids(const u64 *__restrict__ col, const u32 *__restrict__ ids, u64 n,
-                   u64 *__restrict__ out)
+                   u64 *__restrict__ out, int hist_shift, u32 *__restrict__ ghist)
 {
+    __shared__ u32 sh[HIST ? 256 : 1];
+    if (HIST) { sh[threadIdx.x] = 0; __syncthreads(); }
     const u64 stride = (u64)gridDim.x * 256 * 4;
     for (u64 i0 = (u64)blockIdx.x * 256 * 4 + threadIdx.x; i0 < n; i0 += stride) {
         u32 id[4];
@@ -75,7 +92,14 @@ k_build_packed_ids(const u64 *__restrict__ col, const u32 *__restrict__ ids, u64
         for (int k = 0; k < 4; k++) v[k] = (i0 + k * 256 < n) ? __ldg(col + id[k]) : 0;
 #pragma unroll
         for (int k = 0; k < 4; k++)
-            if (i0 + k * 256 < n) out[i0 + k * 256] = (v[k] << 32) | id[k];
+            if (i0 + k * 256 < n) {
+                out[i0 + k * 256] = (v[k] << 32) | id[k];
+                if (HIST) atomicAdd(&sh[(u32)(v[k] >> hist_shift) & 255u], 1u);
+            }
+    }
+    if (HIST) {
+        __syncthreads();
+        if (sh[threadIdx.x]) atomicAdd(&ghist[threadIdx.x], sh[threadIdx.x]);
     }
 }
 // Wide (keys may exceed 32 bits): SoA keys[] / ids[].

@@ -46,8 +46,8 @@ struct qce_tuples {
     u64 key_max;   // range after an exchange); they size the MSD buckets
     u32 id_bound;
     bool sorted;
-    u32 *hist256;     // device, cached by qce_key_histogram for qce_partition_tuples
-    int hist_key_bits;
+    u32 *hist256 = nullptr; // device: 256-bin histogram of the top 8 of hist_key_bits key bits (taken by the build
+    int hist_key_bits = 0;  // kernels, or by qce_key_histogram); valid while the run is unsorted and unmodified
     std::vector<unsigned int> hist_host; // the same 256 counts on the host
 };
 
@@ -509,7 +509,8 @@ RadixShifts shifts_for(int base_shift, int bits, int digit_bits = QCE_RADIX_BITS
 // For large packed runs.  *done = false means "not applicable or skewed": the
 // caller sorts with the LSD passes instead (the run is left untouched).
 constexpr u32 MSD_LOCAL_CAP = 256 * 16; // tuples the largest k_msd_local_sort shape can hold
-int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done)
+int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done, const u32 *hist_top8 = nullptr,
+             int hist_key_bits = 0)
 {
     *done = false;
     static int enabled = -1;
@@ -547,8 +548,11 @@ int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done)
     CK(cudaMemsetAsync(histA, 0, nbA * sizeof(u32), g.stream));
     CK(cudaMemsetAsync(histB, 0, nsub * sizeof(u32), g.stream));
     CK(cudaMemsetAsync(g.d_scalars + 10, 0, sizeof(u64), g.stream));
-    LAUNCH("msd_hist", k_msd_hist, ntiles0, QCE_MSD_THREADS, 0, *keys, lvl0, lvl0 + 2, lvl0 + 3, 1u, base, shiftA, nbA,
-           histA);
+    if (hist_top8 && key_min == 0 && hist_key_bits == key_bits) // level A was counted while the run was built
+        CK(cudaMemcpyAsync(histA, hist_top8, nbA * sizeof(u32), cudaMemcpyDeviceToDevice, g.stream));
+    else
+        LAUNCH("msd_hist", k_msd_hist, ntiles0, QCE_MSD_THREADS, 0, *keys, lvl0, lvl0 + 2, lvl0 + 3, 1u, base, shiftA, nbA,
+               histA);
     LAUNCH("radix_bases", k_radix_bases, 1, (int)nbA, 0, histA, offA);
     CK(cudaMemcpyAsync(curA, offA, nbA * sizeof(u32), cudaMemcpyDeviceToDevice, g.stream));
     static int shape = -1; // QCE_MSD_SHAPE: 0 = 256 threads x 16 tuples, 1 = 512 x 8
@@ -631,12 +635,13 @@ int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done)
 }
 
 // Sort a packed run on its `key_bits` key bits.
-int sort_packed(u64 **a, u64 n, int key_bits, u64 key_min, u64 key_max)
+int sort_packed(u64 **a, u64 n, int key_bits, u64 key_min, u64 key_max, const u32 *hist_top8 = nullptr,
+                int hist_key_bits = 0)
 {
     bool done = false;
     if (key_max == 0 || key_max >= (1ull << key_bits)) key_max = (1ull << key_bits) - 1;
     if (key_min > key_max) key_min = 0;
-    if (msd_sort(a, n, key_min, key_max, &done) != 0) return -1;
+    if (msd_sort(a, n, key_min, key_max, &done, hist_top8, hist_key_bits) != 0) return -1;
     if (done) return 0;
     const int db = digit_bits_for(key_bits, true);
     RadixShifts rs = shifts_for(32, key_bits, db);
@@ -1120,6 +1125,12 @@ int qce_filter_refine(qce_rowids *ids, uint32_t rel, uint32_t col, char op, uint
 }
 
 // ---------------------------------------------------------------- tuples
+static bool fused_build_hist()
+{
+    static int on = -1; // QCE_FUSED_BUILD_HIST=0: histogram in passes of their own (for comparison)
+    if (on < 0) { const char *e = getenv("QCE_FUSED_BUILD_HIST"); on = e ? atoi(e) : 1; }
+    return on != 0;
+}
 static int build_tuples(const Column *cl, const qce_rowids *ids, qce_tuples **out, u64 begin = 0,
                         u64 count = ~0ull)
 {
@@ -1142,10 +1153,24 @@ static int build_tuples(const Column *cl, const qce_rowids *ids, qce_tuples **ou
         if (t->wide)
             LAUNCH("build_tuples", k_build_wide, grid_for(256, n), 256, 0, ids ? cl->d : cl->d + begin,
                    ids ? ids->d : nullptr, n, t->a, t->ids, (u32)begin);
-        else if (ids)
-            LAUNCH("build_tuples", k_build_packed_ids, grid_for(1024, n), 256, 0, cl->d, ids->d, n, t->a);
-        else
-            LAUNCH("build_tuples", k_build_packed_base, grid_for(512, n), 256, 0, cl->d + begin, n, t->a, begin);
+        else {
+            // large packed runs: the top-8-bit key histogram rides along (MSD level A / exchange splitters)
+            const bool hist = fused_build_hist() && n >= (1ull << 20) && t->key_bits >= 9;
+            const int hshift = t->key_bits - 8;
+            if (hist) {
+                if (dalloc(&t->hist256, QCE_RADIX_BINS) != 0) { delete t; return -1; }
+                CK(cudaMemsetAsync(t->hist256, 0, QCE_RADIX_BINS * sizeof(u32), g.stream));
+                t->hist_key_bits = t->key_bits;
+            }
+            if (ids && hist)
+                LAUNCH("build_tuples", k_build_packed_ids<true>, grid_for(1024, n), 256, 0, cl->d, ids->d, n, t->a, hshift, t->hist256);
+            else if (ids)
+                LAUNCH("build_tuples", k_build_packed_ids<false>, grid_for(1024, n), 256, 0, cl->d, ids->d, n, t->a, 0, (u32 *)nullptr);
+            else if (hist)
+                LAUNCH("build_tuples", k_build_packed_base<true>, grid_for(512, n), 256, 0, cl->d + begin, n, t->a, begin, hshift, t->hist256);
+            else
+                LAUNCH("build_tuples", k_build_packed_base<false>, grid_for(512, n), 256, 0, cl->d + begin, n, t->a, begin, 0, (u32 *)nullptr);
+        }
     }
     *out = t;
     return 0;
@@ -1184,7 +1209,10 @@ int qce_sort_tuples(qce_tuples *t)
         RadixShifts rs = shifts_for(0, t->key_bits, 8);
         rc = radix_sort(&t->a, &t->ids, t->n, rs);
     } else {
-        rc = sort_packed(&t->a, t->n, t->key_bits, t->key_min, t->key_max);
+        // the cached histogram counts key >> (hist_key_bits - 8); level A of the MSD sort counts
+        // key >> (bitlen(key_max) - 8): the same digit when the statistics are the column's own
+        rc = sort_packed(&t->a, t->n, t->key_bits, t->key_min, t->key_max, t->hist256,
+                         bitlen(t->key_max) == t->hist_key_bits ? t->hist_key_bits : -1);
     }
     if (rc == 0) t->sorted = true;
     return rc;
@@ -1465,14 +1493,17 @@ int qce_key_histogram(const qce_tuples *t, uint32_t key_bits, uint64_t *hist)
     if (!t || !hist) return fail("null argument");
     if (t->wide) return fail("the sharded exchange supports packed (key < 2^32) runs only");
     qce_tuples *mt = const_cast<qce_tuples *>(t); // the device histogram is cached on the run
+    const bool have = mt->hist256 && mt->hist_key_bits == (int)key_bits && key_bits >= 9 && !t->sorted; // from the build kernel
     if (!mt->hist256 && dalloc(&mt->hist256, QCE_RADIX_BINS) != 0) return -1;
     u32 *gh = mt->hist256;
-    CK(cudaMemsetAsync(gh, 0, QCE_RADIX_BINS * sizeof(u32), g.stream));
-    RadixShifts rs;
-    rs.npass = 1;
-    for (int i = 0; i < QCE_MAX_PASSES; i++) rs.shift[i] = 0;
-    rs.shift[0] = 32 + (key_bits > 8 ? (int)key_bits - 8 : 0);
-    if (t->n) LAUNCH("radix_hist", k_radix_hist, grid_for(1024, t->n, 4), 512, 0, t->a, t->n, rs, 256u, gh);
+    if (!have) {
+        CK(cudaMemsetAsync(gh, 0, QCE_RADIX_BINS * sizeof(u32), g.stream));
+        RadixShifts rs;
+        rs.npass = 1;
+        for (int i = 0; i < QCE_MAX_PASSES; i++) rs.shift[i] = 0;
+        rs.shift[0] = 32 + (key_bits > 8 ? (int)key_bits - 8 : 0);
+        if (t->n) LAUNCH("radix_hist", k_radix_hist, grid_for(1024, t->n, 4), 512, 0, t->a, t->n, rs, 256u, gh);
+    }
     std::vector<u32> tmp(QCE_RADIX_BINS);
     CK(cudaMemcpyAsync(tmp.data(), gh, QCE_RADIX_BINS * sizeof(u32), cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
