@@ -11,13 +11,15 @@ columns (c0 = i, c1 = uniform[0, rows), c2 = uniform[0, 1e6)), query
   value   rows/s with the base columns already resident in HBM
   e2e     same, but every step first copies the six referenced columns from
           pinned host memory to the device and reads the checksums back
-  roofline  dominant kernel (one-sweep radix pass), live CUDA-event times
+  roofline  dominant kernel (the MSD partition pass of the sort on these inputs), live CUDA-event times
   cpu_baseline  the reference's own binary (oracle/_ref/queries) on a bounded
           scaled twin of the workload, on this box's host cores
 
 `--impl reference` times that CPU binary as the reference arm.
 N>1 (torchrun): the join is sharded by key range across ranks,
-weak scaling -- every rank scans/builds its own 2 x 100M-row slice.
+weak scaling -- every rank owns a 2 x 100M-row window (row-sharded columns) and
+the exchange is a partition kernel that stores into the peers' windows over
+NVLink (query-compiler-executor_b200/shardexec.py).
 """
 import argparse
 import ctypes as C
