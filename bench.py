@@ -222,7 +222,12 @@ def main():
             # earlier transport, kept for comparison: replicated columns, send buffer + NCCL all-to-all
             res = sharded.bench(eng, lib, dist, rank, world, rows, args.steps, args.warmup)
         else:
-            res = shardexec.bench(eng, lib, dist, torch, rank, world, rows, args.steps, args.warmup)
+            try:
+                res = shardexec.bench(eng, lib, dist, torch, rank, world, rows, args.steps, args.warmup)
+            except shardexec.PeerWindowsUnavailable as e:
+                # no P2P / CUDA IPC between these GPUs: every rank lands here together
+                res = sharded.bench(eng, lib, dist, rank, world, rows, args.steps, args.warmup)
+                res["config"]["transport_note"] = "peer windows unavailable (%s): NCCL all-to-all transport" % (e,)
         res["clocks"] = sampler.stop()
         if rank == 0:
             res_line = res

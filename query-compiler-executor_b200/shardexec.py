@@ -212,14 +212,29 @@ class EngineOps:
         return self.e.xwin_info()[0]
 
 
+class PeerWindowsUnavailable(RuntimeError):
+    """Some rank could not create or map the receive windows (no P2P / CUDA IPC between
+    the GPUs of this box): raised on EVERY rank, so callers can switch transport together."""
+
+
 def open_windows(engine, comm: Comm, nbytes: int) -> None:
     """Create this rank's receive window and map every peer's (CUDA IPC handles
     all-gathered once).  world == 1: the window is only ever addressed locally."""
-    handle = engine.xwin_create(nbytes)
+    err = ""
+    try:
+        handle = engine.xwin_create(nbytes)
+    except Exception as e:  # noqa: BLE001 -- the outcome is agreed on collectively below
+        handle, err = bytes(64), repr(e)
     if comm.world > 1:
         handles = comm.all_gather_bytes(handle)
-        engine.xwin_attach(comm.world, comm.rank, b"".join(handles))
-    comm.barrier()
+        if not err:
+            try:
+                engine.xwin_attach(comm.world, comm.rank, b"".join(handles))
+            except Exception as e:  # noqa: BLE001
+                err = repr(e)
+    if comm.allreduce_max(1 if err else 0):
+        engine.xwin_destroy()
+        raise PeerWindowsUnavailable(err or "a peer rank could not map the windows")
 
 
 def load_sharded_columns(engine, torch, comm: Comm, db: Sequence[Sequence[np.ndarray]], keep: list) -> None:
@@ -257,26 +272,25 @@ class ShardedExecutor:
         H = self.comm.all_gather_u64(hists).reshape(world, len(sides), 256)
         splitters = choose_splitters(H.sum(axis=(0, 1)), key_bits, world)
         shift = max(key_bits - 8, 0)
-        part_of_bin = np.searchsorted(np.array(splitters, dtype=np.uint64),
-                                      np.arange(256, dtype=np.uint64) << np.uint64(shift), side="right") \
-            if world > 1 else np.zeros(256, dtype=np.int64)
-        # C[k][s][d]: tuples of side k that rank s sends to rank d
-        C = np.zeros((len(sides), world, world), dtype=np.int64)
-        for d in range(world):
-            C[:, :, d] = H[:, :, part_of_bin == d].sum(axis=2).T.astype(np.int64)
+        # the bins of destination d are the contiguous range [bnd[d], bnd[d+1]) (splitters ascend),
+        # so C[k][s][d] (tuples of side k that rank s sends to rank d) is a difference of prefix sums
+        bnd = np.minimum(np.array([0] + [sp >> shift for sp in splitters] + [256], dtype=np.int64), 256)
+        Hc = np.zeros((world, len(sides), 257), dtype=np.int64)
+        np.cumsum(H, axis=2, out=Hc[:, :, 1:])
+        C = (Hc[:, :, bnd[1:]] - Hc[:, :, bnd[:-1]]).transpose(1, 0, 2)
         recv = C.sum(axis=1)                        # [k][d]
         before = np.cumsum(C, axis=1) - C           # [k][s][d]: tuples of earlier ranks in d's segment order
         # window layout of every destination (bytes): per side the run, then its columns
-        run_off = np.zeros((len(sides), world), dtype=np.int64)
-        col_off = [np.zeros((len(cols), world), dtype=np.int64) for _, cols in sides]
+        run_off, col_off = [], []
         top = np.zeros(world, dtype=np.int64)
         for k, (_, cols) in enumerate(sides):
-            run_off[k] = top
-            top = top + 8 * recv[k]
-            top = (top + 15) // 16 * 16
+            run_off.append(top)
+            top = (top + 8 * recv[k] + 15) // 16 * 16
+            offs = []
             for j in range(len(cols)):
-                col_off[k][j] = top
+                offs.append(top)
                 top = (top + 4 * recv[k] + 15) // 16 * 16
+            col_off.append(offs)
         cap = ops.window_bytes()
         if int(top.max()) > cap:
             raise MemoryError(f"exchange needs {int(top.max())} bytes of receive window, {cap} available")
@@ -300,8 +314,8 @@ class ShardedExecutor:
         out = []
         for k, (_, cols) in enumerate(sides):
             n = int(recv[k, me])
-            run = ops.tuples_view(int(run_off[k, me]) // 8, n, key_bits, 0, (lo, max(lo, hi)))
-            views = [ops.col_view(int(col_off[k][j, me]) // 4, n) for j in range(len(cols))]
+            run = ops.tuples_view(int(run_off[k][me]) // 8, n, key_bits, 0, (lo, max(lo, hi)))
+            views = [ops.col_view(int(col_off[k][j][me]) // 4, n) for j in range(len(cols))]
             out.append((run, views))
         self.stats["exchange_s"] = self.stats.get("exchange_s", 0.0) + time.perf_counter() - t0
         self.stats["bytes_sent_off_rank"] = self.stats.get("bytes_sent_off_rank", 0) + sent
@@ -343,26 +357,24 @@ class ShardedExecutor:
         top = np.zeros(world, dtype=np.int64)
         views = {}
         sent = 0
+        owner = np.arange(nb) // bpr
+        first_bin = owner * bpr
         for k, b in enumerate(by_binding):
             per, width, rows = geo[b]
             Hk = H[:, k, :]                                    # [src][bin]
             bin_tot = Hk.sum(axis=0)                           # [bin]
-            owner = np.arange(nb) // bpr
-            # bin-major inside each owner: offset of (bin, src) relative to the owner's region
-            bin_start = np.zeros(nb, dtype=np.int64)
-            for d in range(world):
-                sel = owner == d
-                bin_start[sel] = np.cumsum(bin_tot[sel]) - bin_tot[sel]
-            src_before = (np.cumsum(Hk, axis=0) - Hk)[me]      # ids of earlier ranks in the same bin
-            region = top.copy()                                 # bytes, per owner
-            total = np.array([bin_tot[owner == d].sum() for d in range(world)], dtype=np.int64)
+            cs = np.cumsum(bin_tot) - bin_tot                  # bins are owner-major: exclusive prefix over all bins
+            bin_start = cs - cs[first_bin]                     # ... relative to the owner's first bin (bin-major inside an owner)
+            total = np.add.reduceat(bin_tot, np.arange(0, nb, bpr))  # ids per owner
+            src_before = Hk[:me].sum(axis=0)                   # ids of earlier ranks in the same bin
+            region = top                                        # bytes, per owner
             top = (top + 4 * total + 15) // 16 * 16
             if int(top.max()) > ops.window_bytes():
                 raise MemoryError("projection needs more receive window than is available")
             offs = region[owner] // 4 + bin_start + src_before
             ops.push_ids(ent[b], per, width, bpr, world, offs.astype(np.uint64))
             views[b] = (int(region[me]) // 4, int(total[me]), rows)
-            sent += 4 * int(Hk[me].sum() - Hk[me][owner == me].sum())
+            sent += 4 * int(Hk[me].sum() - Hk[me, me * bpr:(me + 1) * bpr].sum())
         ops.fence()
         self.comm.barrier()
         for b, cols in by_binding.items():
