@@ -230,6 +230,23 @@ def main():
                 res["config"]["transport_note"] = "peer windows unavailable (%s): NCCL all-to-all transport" % (e,)
         res["clocks"] = sampler.stop()
         if rank == 0:
+            # roofline of the dominant HBM kernel on rank 0 (the MSD partition of the received runs:
+            # 8 B read + 8 B written per tuple per level) and the link roofline of the push kernels
+            k = res.get("kernels_ms_per_step_rank0", {})
+            r0 = res.get("rank0", {})
+            if k.get("msd_partition") and r0.get("local_join_input_tuples"):
+                levels = max(1, r0.get("msd_partition_launches_per_step", 4) // 2)
+                alg = 16.0 * r0["local_join_input_tuples"] * levels
+                ach = alg / (k["msd_partition"] / 1e3) / 1e9
+                res["roofline"] = {"bound": "hbm", "kernel": "msd_partition (rank 0)", "achieved": ach, "peak": pk["hbm_gbs"],
+                                   "peak_source": pk_src, "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
+                                   "algorithmic_bytes": "16 B per received tuple per level, %d levels" % levels}
+            ex_ = res.get("exchange", {})
+            if ex_.get("push_gbs_per_rank"):
+                res["nvlink"] = {"bound": "nvlink", "kernel": "push_tuples + push_rowids", "achieved": ex_["push_gbs_per_rank"],
+                                 "peak": 900.0, "peak_source": "NVLink 5 nominal per direction per GPU", "unit": "GB/s",
+                                 "frac": ex_["push_gbs_per_rank"] / 900.0,
+                                 "note": "off-rank bytes / time of the whole push kernels (their local share included in the time)"}
             res_line = res
             res_line.update({"metric": METRIC, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
                              "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

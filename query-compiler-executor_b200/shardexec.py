@@ -625,6 +625,7 @@ def bench(eng, host_lib, dist, torch, rank, world, rows, steps, warmup, verify=T
     eng.profile(False)
     kernels = {k: round(v["ms"] / 2, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
     push_ms = sum(v for k, v in kernels.items() if k.startswith("push_"))
+    local_tuples = int(ex.stats.get("local_join_input", 0))  # tuples this rank received and sorted
 
     # ---- e2e: host windows in, checksums out, every step
     pinned = {k: v.cpu().pin_memory() for k, v in cols.items()}
@@ -659,6 +660,7 @@ def bench(eng, host_lib, dist, torch, rank, world, rows, steps, warmup, verify=T
                      "push_gbs_per_rank": off_rank / (push_ms / 1e3) / 1e9 if push_ms else None,
                      "nvlink_peak_gbs_per_direction": 900.0, "small_collectives_per_step": ncoll},
         "kernels_ms_per_step_rank0": kernels,
+        "rank0": {"local_join_input_tuples": local_tuples, "msd_partition_launches_per_step": prof.get("msd_partition", {}).get("launches", 0) // 2},
         "gpu_launches": int(launches) * steps,
         "e2e": {"value": 2.0 * n / (e2e_ms / 1e3), "unit": "rows/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": 6 * rows * 8, "d2h_bytes_per_step": 5 * 8,

@@ -168,7 +168,9 @@ def _exec_worker(rank, world, port, kind, rows, out):
 
 
 @pytest.mark.parametrize("world,kind,rows", [(2, "pair", 20011), (3, "pair", 9001), (2, "chain", 12000), (3, "chain", 20000),
-                                             (2, "zipf", 15000), (1, "chain", 5000)])
+                                             (2, "zipf", 15000), (1, "chain", 5000),
+                                             (3, "chain", 3000),    # fewer rows than one 4096-row window: ranks 1, 2 own nothing
+                                             (3, "zipf", 9000)])
 def test_sharded_executor_matches_truth(world, kind, rows):
     """Row-sharded columns, pushes into peer windows, bystander columns by slot, carried join
     keys, projection by id push: checksums equal the relational truth (= the reference inside PDQ-T)."""
