@@ -634,8 +634,10 @@ k_msd_hist(const u64 *__restrict__ keys, const u32 *__restrict__ tile_start, con
 
 // One unstable partition pass.  cursor[bucket * bins + digit] starts at the
 // global output offset of that (bucket, digit) range and is advanced by the tiles.
-template <int THREADS, int ITEMS, typename KeyT = u64>
-__global__ void __launch_bounds__(THREADS)
+// MIN_CTAS = 4 caps the kernel at 32 registers (100 % occupancy with 512 threads); VEC loads
+// two adjacent tuples with one 128-bit load where the tile starts on a 16-byte boundary.
+template <int THREADS, int ITEMS, typename KeyT = u64, int MIN_CTAS = (THREADS == 512 ? 3 : 1), bool VEC = false>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS)
 k_msd_partition(const KeyT *__restrict__ in, KeyT *__restrict__ out, const u32 *__restrict__ tile_start,
                 const u32 *__restrict__ bucket_off, const u32 *__restrict__ bucket_size, u32 nbuckets, KeyT base,
                 int shift, u32 bins, u32 *__restrict__ cursor, const u32 *__restrict__ lut)
@@ -659,14 +661,32 @@ k_msd_partition(const KeyT *__restrict__ in, KeyT *__restrict__ out, const u32 *
 
     KeyT key[ITEMS];
     u32 slot[ITEMS]; // digit << 16 | slot among the tile's keys with that digit
+    // element index of item j: strided by THREADS, or (VEC) adjacent pairs strided by 2 * THREADS
+    const bool vec = VEC && sizeof(KeyT) == 8 && ((begin & 1u) == 0);
+#define MSD_ITEM_INDEX(j) (vec ? (u32)(2 * tid + ((j) & 1) + ((j) >> 1) * 2 * THREADS) : (u32)(tid + (j) * THREADS))
+    if (vec) {
 #pragma unroll
-    for (int j = 0; j < ITEMS; j++) {
-        const u32 i = tid + j * THREADS;
-        if (i < count) key[j] = ld_stream_key<KeyT>(in + begin + i);
+        for (int j = 0; j < ITEMS; j += 2) {
+            const u32 i = MSD_ITEM_INDEX(j);
+            if (i + 1 < count) {
+                u64 a, b;
+                ld_stream_u64x2(reinterpret_cast<const u64 *>(in) + begin + i, a, b);
+                key[j] = (KeyT)a;
+                key[j + 1] = (KeyT)b;
+            } else if (i < count) {
+                key[j] = ld_stream_key<KeyT>(in + begin + i);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) {
+            const u32 i = tid + j * THREADS;
+            if (i < count) key[j] = ld_stream_key<KeyT>(in + begin + i);
+        }
     }
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
-        const u32 i = tid + j * THREADS;
+        const u32 i = MSD_ITEM_INDEX(j);
         if (i < count) {
             u32 d = (u32)((key[j] - base) >> shift) & mask;
             // exchange partition: the digit is a histogram bin, its destination rank comes from a table
@@ -688,9 +708,10 @@ k_msd_partition(const KeyT *__restrict__ in, KeyT *__restrict__ out, const u32 *
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
-        const u32 i = tid + j * THREADS;
+        const u32 i = MSD_ITEM_INDEX(j);
         if (i < count) skeys[excl[slot[j] >> 16] + (slot[j] & 0xffffu)] = key[j];
     }
+#undef MSD_ITEM_INDEX
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {

@@ -560,7 +560,21 @@ int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done, const u32 
         const char *e = getenv("QCE_MSD_SHAPE");
         shape = e ? atoi(e) : 2;
     }
-    if (shape >= 1)
+    static int variant = -1; // QCE_MSD_VARIANT: 0 = 40 regs, 1 = 32 regs (4 CTAs/SM), 2 = 40 regs + 128-bit loads, 3 = both
+    if (variant < 0) {
+        const char *e = getenv("QCE_MSD_VARIANT");
+        variant = e ? atoi(e) : 0;
+    }
+    if (shape >= 1 && variant == 1)
+        LAUNCH("msd_partition", (k_msd_partition<512, 8, u64, 4, false>), ntiles0, 512, 0, *keys, alt, lvl0, lvl0 + 2, lvl0 + 3, 1u,
+               base, shiftA, nbA, curA, (const u32 *)nullptr);
+    else if (shape >= 1 && variant == 2)
+        LAUNCH("msd_partition", (k_msd_partition<512, 8, u64, 3, true>), ntiles0, 512, 0, *keys, alt, lvl0, lvl0 + 2, lvl0 + 3, 1u,
+               base, shiftA, nbA, curA, (const u32 *)nullptr);
+    else if (shape >= 1 && variant == 3)
+        LAUNCH("msd_partition", (k_msd_partition<512, 8, u64, 4, true>), ntiles0, 512, 0, *keys, alt, lvl0, lvl0 + 2, lvl0 + 3, 1u,
+               base, shiftA, nbA, curA, (const u32 *)nullptr);
+    else if (shape >= 1)
         LAUNCH("msd_partition", (k_msd_partition<512, 8>), ntiles0, 512, 0, *keys, alt, lvl0, lvl0 + 2, lvl0 + 3, 1u,
                base, shiftA, nbA, curA, (const u32 *)nullptr);
     else
@@ -578,7 +592,16 @@ int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done, const u32 
     const u32 max_sub = (u32)(g.h_scalars[10] & 0xffffffffu);
     if (max_sub <= MSD_LOCAL_CAP) {
         CK(cudaMemcpyAsync(curB, suboff, nsub * sizeof(u32), cudaMemcpyDeviceToDevice, g.stream));
-        if (shape >= 1)
+        if (shape >= 1 && variant == 1)
+            LAUNCH("msd_partition", (k_msd_partition<512, 8, u64, 4, false>), ntiles1, 512, 0, alt, *keys, tstart1, offA, histA, nbA,
+                   base, shiftB, nbB, curB, (const u32 *)nullptr);
+        else if (shape >= 1 && variant == 2)
+            LAUNCH("msd_partition", (k_msd_partition<512, 8, u64, 3, true>), ntiles1, 512, 0, alt, *keys, tstart1, offA, histA, nbA,
+                   base, shiftB, nbB, curB, (const u32 *)nullptr);
+        else if (shape >= 1 && variant == 3)
+            LAUNCH("msd_partition", (k_msd_partition<512, 8, u64, 4, true>), ntiles1, 512, 0, alt, *keys, tstart1, offA, histA, nbA,
+                   base, shiftB, nbB, curB, (const u32 *)nullptr);
+        else if (shape >= 1)
             LAUNCH("msd_partition", (k_msd_partition<512, 8>), ntiles1, 512, 0, alt, *keys, tstart1, offA, histA, nbA,
                    base, shiftB, nbB, curB, (const u32 *)nullptr);
         else
