@@ -191,3 +191,45 @@ def test_sharded_executor_matches_truth(world, kind, rows):
     assert (sent > 0) == (world > 1)
     if kind == "pair":  # also the reference's own answer (oracle restatement), byte for byte
         assert lines[0] == orc.run_batch(db, EXEC_QUERIES[kind][0] + "\n")
+
+
+# ---------------------------------------------------------------- query-level replicas (config 5)
+def _replica_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import qce_b200  # noqa: F401
+    from qce_b200 import batch_replicas
+    from tests.helpers import load_db, load_json
+    db = load_db("ops_db.npz")
+    text = "".join(r["query"] + "\nF\n" for r in load_json("ops.json") if r["class"] == "PDQ-T")
+    queries = batch_replicas.split_queries(text)
+    calls = []
+
+    def run_one(q):
+        calls.append(q)
+        return orc.run_batch(db, q + "\n")
+    res = batch_replicas.run_batch_replicated(run_one, queries, dist, rank, world)
+    if rank == 0:
+        out.put((res, len(queries), len(calls)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [1, 3])
+def test_replicated_batch_keeps_input_order(world):
+    """Whole queries dealt round-robin over ranks; rank 0 emits every query's block (count
+    lines + result line) in input order = the reference's recorded stdout."""
+    from tests.helpers import load_json
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 33500 + os.getpid() % 2000 + world
+    procs = [ctx.Process(target=_replica_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res, nq, ncalls = out.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    recs = [r for r in load_json("ops.json") if r["class"] == "PDQ-T"]
+    assert res == "".join(r["stdout"] for r in recs)
+    assert nq == len(recs) and ncalls == -(-nq // world)
