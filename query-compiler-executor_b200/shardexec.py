@@ -401,6 +401,25 @@ class ShardedExecutor:
         for (b1, c1), (b2, c2) in chain:
             if relations[b1] == relations[b2] and c1 == c2:
                 raise UnsupportedQuery("same relation and column on both sides: the reference skips this join (8c-v)")
+        # the whole plan is checked before anything runs: a refusal never leaves device state behind
+        for (b, _), _ in self_joins:
+            if b not in fbind:
+                raise UnsupportedQuery("self-join predicate on a binding without a prior filter (reference exits, 8c-iii)")
+        joined, todo = set(fbind), list(chain)
+        while todo:
+            nxt = next((j for j in todo if not joined or (j[0][0] in joined) != (j[1][0] in joined)), None)
+            if nxt is None:
+                raise UnsupportedQuery("join between two bindings that are both (or neither) in the intermediate result")
+            todo.remove(nxt)
+            for b, c in nxt:
+                if ops.key_bits(relations[b], c) > 32:
+                    raise UnsupportedQuery("join keys >= 2^32: the exchange carries packed runs only")
+                joined.add(b)
+        if not joined:
+            raise UnsupportedQuery("query without predicates")
+        for b, _ in selects:
+            if b not in joined:
+                raise UnsupportedQuery(f"projected binding {b} takes part in no predicate")
 
         ent: Dict[int, int] = {}          # binding -> row-id column (aligned, this rank's slice)
         carried: Dict[Tuple[int, int], int] = {}  # (binding, column) -> 4-byte key column, aligned with ent

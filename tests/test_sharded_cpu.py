@@ -154,15 +154,18 @@ def _exec_worker(rank, world, port, kind, rows, out):
     comm = shardexec.Comm(dist, torch, torch.device("cpu"), rank, world)
     ex = shardexec.ShardedExecutor(NumpyShardOps(db, rank, world), comm)
     lines, refused = [], 0
+    sent = 0
     for q in EXEC_QUERIES[kind]:
         lines.append(shardexec.format_result(ex.run_query(q)))
+        sent += ex.stats.get("bytes_sent_off_rank", 0)
     for bad in ["0 1|0.1=1.1&0.2<20&1.2<20|0.0 1.0", "0|0.1=0.2|0.0", "0 0|0.1=1.1|0.0 1.0", "0 1 0|0.1=1.1&1.2=2.1&0.2=2.1|0.0"]:
         try:
             ex.run_query(bad)
         except shardexec.UnsupportedQuery:
             refused += 1
+            assert ex.stats == {}  # refused while planning: nothing ran, nothing is left on the device
     if rank == 0:
-        out.put((lines, refused, ex.stats.get("bytes_sent_off_rank", 0)))
+        out.put((lines, refused, sent))
     dist.barrier()
     dist.destroy_process_group()
 
