@@ -268,6 +268,24 @@ int qce_adopt_column_window(uint32_t rel, uint32_t col, const void *dev, uint64_
                             uint64_t row_count, uint64_t rows_global, uint64_t max_value_global);
 int qce_column_max_device(const void *dev, uint64_t n, uint64_t *max_value);
 
+/* Exchange bookkeeping, identical on every rank (pure host arithmetic, no device needed):
+ * from the all-gathered histograms (hists[world][nsides][256]) derive the world-1 splitters,
+ * per (side, destination) the tuples the destination receives (recv), the tuples earlier
+ * ranks put before this rank's segment (before = dst_run_index), the byte offset of the
+ * side's run in the destination's window (run_off) and of each of its ncols[side] columns
+ * (col_off[column][dst], columns numbered side-major), the window bytes the largest receiver
+ * needs, and the tuples this rank sends off-rank per side. */
+int qce_exchange_plan(const uint64_t *hists, uint32_t world, uint32_t rank, uint32_t nsides,
+                      const uint32_t *ncols, uint32_t key_bits, uint64_t *splitters, uint64_t *recv,
+                      uint64_t *before, uint64_t *run_off, uint64_t *col_off, uint64_t *window_bytes,
+                      uint64_t *sent_tuples);
+/* The same for qce_push_rowids: hists[world][nbind][bins_per_rank * world] -> per binding the
+ * 4-byte element offset of this rank's ids of every bin in the owner's window, and the view
+ * (offset, count) of the ids this rank receives. */
+int qce_rowid_push_plan(const uint64_t *hists, uint32_t world, uint32_t rank, uint32_t nbind,
+                        uint32_t bins_per_rank, uint64_t *bin_u32_offset, uint64_t *view_u32_offset,
+                        uint64_t *view_count, uint64_t *window_bytes, uint64_t *sent_ids);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1976,4 +1976,108 @@ int qce_rowids_gather(const qce_rowids *src, const qce_rowids *index, qce_rowids
     return 0;
 }
 
+// ---- exchange bookkeeping (pure host arithmetic: usable without a device) ------------
+// Every rank runs this on the same all-gathered histograms and therefore derives the same
+// splitters, count matrix and window layout; nothing about a transfer is communicated.
+int qce_exchange_plan(const uint64_t *hists, uint32_t world, uint32_t rank, uint32_t nsides, const uint32_t *ncols,
+                      uint32_t key_bits, uint64_t *splitters, uint64_t *recv, uint64_t *before, uint64_t *run_off,
+                      uint64_t *col_off, uint64_t *window_bytes, uint64_t *sent_tuples)
+{
+    if (!hists || !ncols || !splitters || !recv || !before || !run_off || !col_off || !window_bytes || !sent_tuples)
+        return fail("null argument");
+    if (world < 1 || world > QCE_MAX_RANKS || rank >= world || nsides < 1 || nsides > 8) return fail("bad exchange shape");
+    if (key_bits == 0 || key_bits > 32) return fail("packed runs carry keys of 1..32 bits");
+    const int shift = key_bits > 8 ? (int)key_bits - 8 : 0;
+    // global histogram -> splitters on bin boundaries that balance tuples per rank
+    u64 cum[256], total = 0;
+    for (u32 b = 0; b < 256; b++) {
+        u64 v = 0;
+        for (u32 s = 0; s < world; s++)
+            for (u32 k = 0; k < nsides; k++) v += hists[((size_t)s * nsides + k) * 256 + b];
+        total += v;
+        cum[b] = total;
+    }
+    u32 bnd[QCE_MAX_RANKS + 1];
+    bnd[0] = 0;
+    u32 prev = 0;
+    for (u32 k = 1; k < world; k++) {
+        // first bin whose cumulative count reaches total * k / world, plus one = first bin of the next part
+        u32 i = 0;
+        while (i < 256 && (unsigned __int128)cum[i] * world < (unsigned __int128)total * k) i++;
+        u32 b = i + 1;
+        if (b < prev) b = prev;
+        if (b > 256) b = 256;
+        splitters[k - 1] = (u64)b << shift;
+        prev = b;
+        bnd[k] = b;
+    }
+    bnd[world] = 256;
+    // C[k][s][d] = tuples of side k that rank s sends to rank d; recv, this rank's segment starts
+    std::vector<u64> top(world, 0);
+    size_t col_at = 0;
+    for (u32 k = 0; k < nsides; k++) {
+        sent_tuples[k] = 0;
+        for (u32 d = 0; d < world; d++) {
+            u64 r = 0, bef = 0;
+            for (u32 s = 0; s < world; s++) {
+                u64 c = 0;
+                const uint64_t *h = hists + ((size_t)s * nsides + k) * 256;
+                for (u32 b = bnd[d]; b < bnd[d + 1]; b++) c += h[b];
+                if (s < rank) bef += c;
+                if (s == rank && d != rank) sent_tuples[k] += c;
+                r += c;
+            }
+            recv[(size_t)k * world + d] = r;
+            before[(size_t)k * world + d] = bef;
+        }
+        // window layout of every destination (bytes): the run, then its columns, 16-byte aligned
+        for (u32 d = 0; d < world; d++) {
+            run_off[(size_t)k * world + d] = top[d];
+            top[d] = (top[d] + 8 * recv[(size_t)k * world + d] + 15) / 16 * 16;
+        }
+        for (u32 j = 0; j < ncols[k]; j++, col_at++)
+            for (u32 d = 0; d < world; d++) {
+                col_off[col_at * world + d] = top[d];
+                top[d] = (top[d] + 4 * recv[(size_t)k * world + d] + 15) / 16 * 16;
+            }
+    }
+    *window_bytes = *std::max_element(top.begin(), top.end());
+    return 0;
+}
+
+// Row ids routed to the ranks that own the rows: per binding, where this rank's ids of every
+// bin go in the owner's window (bin-major inside an owner, earlier ranks first inside a bin).
+int qce_rowid_push_plan(const uint64_t *hists, uint32_t world, uint32_t rank, uint32_t nbind, uint32_t bins_per_rank,
+                        uint64_t *bin_u32_offset, uint64_t *view_u32_offset, uint64_t *view_count, uint64_t *window_bytes,
+                        uint64_t *sent_ids)
+{
+    if (!hists || !bin_u32_offset || !view_u32_offset || !view_count || !window_bytes || !sent_ids) return fail("null argument");
+    if (world < 1 || world > QCE_MAX_RANKS || rank >= world || bins_per_rank < 1 || (u64)bins_per_rank * world > 256)
+        return fail("bad row-bin shape");
+    const u32 nb = bins_per_rank * world;
+    std::vector<u64> top(world, 0);
+    for (u32 k = 0; k < nbind; k++) {
+        sent_ids[k] = 0;
+        for (u32 d = 0; d < world; d++) {
+            u64 at = 0; // ids before the current bin inside owner d's region
+            for (u32 j = 0; j < bins_per_rank; j++) {
+                const u32 b = d * bins_per_rank + j;
+                u64 tot = 0, bef = 0;
+                for (u32 s = 0; s < world; s++) {
+                    const u64 c = hists[((size_t)s * nbind + k) * nb + b];
+                    if (s < rank) bef += c;
+                    if (s == rank && d != rank) sent_ids[k] += c;
+                    tot += c;
+                }
+                bin_u32_offset[(size_t)k * nb + b] = top[d] / 4 + at + bef;
+                at += tot;
+            }
+            if (d == rank) { view_u32_offset[k] = top[d] / 4; view_count[k] = at; }
+            top[d] = (top[d] + 4 * at + 15) / 16 * 16;
+        }
+    }
+    *window_bytes = *std::max_element(top.begin(), top.end());
+    return 0;
+}
+
 } // extern "C"

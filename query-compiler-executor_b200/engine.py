@@ -31,7 +31,7 @@ SYMBOLS = [
     "qce_xwin_create", "qce_xwin_attach", "qce_xwin_loopback", "qce_xwin_info", "qce_xwin_destroy", "qce_push_tuples",
     "qce_push_u32_by_slot", "qce_push_tuples_cols", "qce_rowids_bin_histogram", "qce_push_rowids", "qce_tuples_from_window", "qce_rowids_from_window",
     "qce_rowids_gather", "qce_adopt_column_window", "qce_column_max_device", "qce_column_window_u32", "qce_rowids_iota",
-    "qce_tuples_from_u32", "qce_column_gather_u32",
+    "qce_tuples_from_u32", "qce_column_gather_u32", "qce_exchange_plan", "qce_rowid_push_plan",
 ]
 
 
@@ -87,6 +87,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "qce_rowids_from_window": (i32, [u64, u64, u32, u32, i32, P(vp)]), "qce_rowids_gather": (i32, [vp, vp, P(vp)]),
         "qce_adopt_column_window": (i32, [u32, u32, vp, u64, u64, u64, u64]),
         "qce_column_max_device": (i32, [vp, u64, P(u64)]),
+        "qce_exchange_plan": (i32, [vp, u32, u32, u32, vp, u32, vp, vp, vp, vp, vp, P(u64), vp]),
+        "qce_rowid_push_plan": (i32, [vp, u32, u32, u32, u32, vp, vp, vp, P(u64), vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -97,6 +99,36 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
 
 def _u64(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+def exchange_plan(lib, hists: np.ndarray, world: int, rank: int, ncols: Sequence[int], key_bits: int):
+    """qce_exchange_plan (host arithmetic only: works without a device)."""
+    h = np.ascontiguousarray(hists, dtype=np.uint64)
+    nsides = len(ncols)
+    nc = np.ascontiguousarray(ncols, dtype=np.uint32)
+    splitters = np.zeros(max(world - 1, 1), dtype=np.uint64)
+    recv, before, run_off = (np.zeros((nsides, world), dtype=np.uint64) for _ in range(3))
+    col_off = np.zeros((max(int(nc.sum()), 1), world), dtype=np.uint64)
+    sent = np.zeros(nsides, dtype=np.uint64)
+    need = C.c_uint64()
+    if lib.qce_exchange_plan(h.ctypes.data, world, rank, nsides, nc.ctypes.data, key_bits, splitters.ctypes.data,
+                             recv.ctypes.data, before.ctypes.data, run_off.ctypes.data, col_off.ctypes.data,
+                             C.byref(need), sent.ctypes.data) != 0:
+        raise EngineError(lib.qce_last_error().decode())
+    return [int(x) for x in splitters[:world - 1]], recv, before, run_off, col_off, need.value, sent
+
+
+def rowid_push_plan(lib, hists: np.ndarray, world: int, rank: int, nbind: int, bins_per_rank: int):
+    """qce_rowid_push_plan (host arithmetic only)."""
+    h = np.ascontiguousarray(hists, dtype=np.uint64)
+    nb = bins_per_rank * world
+    offs = np.zeros((nbind, nb), dtype=np.uint64)
+    view_off, view_cnt, sent = (np.zeros(nbind, dtype=np.uint64) for _ in range(3))
+    need = C.c_uint64()
+    if lib.qce_rowid_push_plan(h.ctypes.data, world, rank, nbind, bins_per_rank, offs.ctypes.data, view_off.ctypes.data,
+                               view_cnt.ctypes.data, C.byref(need), sent.ctypes.data) != 0:
+        raise EngineError(lib.qce_last_error().decode())
+    return offs, view_off, view_cnt, need.value, sent
 
 
 class Engine:

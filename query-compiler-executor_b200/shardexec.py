@@ -40,7 +40,19 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from .sharded import choose_splitters, row_window
+from .engine import exchange_plan, load_library, rowid_push_plan
+from .sharded import row_window
+
+_LIB = None
+
+
+def _lib():
+    """libqce_b200.so: the exchange bookkeeping is host arithmetic inside the C-ABI library
+    (qce_exchange_plan / qce_rowid_push_plan); it needs the library, not a device."""
+    global _LIB
+    if _LIB is None:
+        _LIB = load_library()
+    return _LIB
 
 
 class UnsupportedQuery(NotImplementedError):
@@ -270,41 +282,27 @@ class ShardedExecutor:
         t0 = time.perf_counter()
         hists = np.concatenate([ops.histogram(run, key_bits) for run, _ in sides])
         H = self.comm.all_gather_u64(hists).reshape(world, len(sides), 256)
-        splitters = choose_splitters(H.sum(axis=(0, 1)), key_bits, world)
-        shift = max(key_bits - 8, 0)
-        # the bins of destination d are the contiguous range [bnd[d], bnd[d+1]) (splitters ascend),
-        # so C[k][s][d] (tuples of side k that rank s sends to rank d) is a difference of prefix sums
-        bnd = np.minimum(np.array([0] + [sp >> shift for sp in splitters] + [256], dtype=np.int64), 256)
-        Hc = np.zeros((world, len(sides), 257), dtype=np.int64)
-        np.cumsum(H, axis=2, out=Hc[:, :, 1:])
-        C = (Hc[:, :, bnd[1:]] - Hc[:, :, bnd[:-1]]).transpose(1, 0, 2)
-        recv = C.sum(axis=1)                        # [k][d]
-        before = np.cumsum(C, axis=1) - C           # [k][s][d]: tuples of earlier ranks in d's segment order
-        # window layout of every destination (bytes): per side the run, then its columns
-        run_off, col_off = [], []
-        top = np.zeros(world, dtype=np.int64)
-        for k, (_, cols) in enumerate(sides):
-            run_off.append(top)
-            top = (top + 8 * recv[k] + 15) // 16 * 16
-            offs = []
-            for j in range(len(cols)):
-                offs.append(top)
-                top = (top + 4 * recv[k] + 15) // 16 * 16
-            col_off.append(offs)
+        # splitters, count matrix and window layout: the same arithmetic on every rank (C-ABI)
+        ncols = [len(cols) for _, cols in sides]
+        splitters, recv, before, run_off, col_flat, need, sent_tuples = exchange_plan(_lib(), H, world, me, ncols, key_bits)
+        col_off, at = [], 0
+        for n in ncols:
+            col_off.append([col_flat[at + j] for j in range(n)])
+            at += n
         cap = ops.window_bytes()
-        if int(top.max()) > cap:
-            raise MemoryError(f"exchange needs {int(top.max())} bytes of receive window, {cap} available")
+        if need > cap:
+            raise MemoryError(f"exchange needs {need} bytes of receive window, {cap} available")
         sent = 0
         for k, (run, cols) in enumerate(sides):
-            dst_words = (run_off[k] // 8 + before[k, me]).astype(np.uint64)
+            dst_words = run_off[k] // np.uint64(8) + before[k]
             if not cols:    # payloads are row ids and travel inside the tuples
                 ops.push_tuples(run, key_bits, splitters, world, dst_words, None, False)
             else:           # payload := index in the receiver's run; the columns follow in the same kernel
                 for j0 in range(0, len(cols), 6):
-                    regions = np.stack([col_off[k][j] // 4 + before[k, me] for j in range(j0, min(j0 + 6, len(cols)))])
-                    ops.push_tuples_cols(run, key_bits, splitters, world, dst_words, before[k, me].astype(np.uint32),
+                    regions = np.stack([col_off[k][j] // np.uint64(4) + before[k] for j in range(j0, min(j0 + 6, len(cols)))])
+                    ops.push_tuples_cols(run, key_bits, splitters, world, dst_words, before[k].astype(np.uint32),
                                          cols[j0:j0 + 6], regions.astype(np.uint64))
-            sent += int(C[k, me].sum() - C[k, me, me]) * (8 + 4 * len(cols))
+            sent += int(sent_tuples[k]) * (8 + 4 * len(cols))
         ops.fence()
         self.comm.barrier()  # every peer's stores into this rank's window have completed
         lo = splitters[me - 1] if me > 0 else 0
@@ -313,7 +311,7 @@ class ShardedExecutor:
         hi = (splitters[me] - 1) if me < world - 1 else key_max
         out = []
         for k, (_, cols) in enumerate(sides):
-            n = int(recv[k, me])
+            n = int(recv[k][me])
             run = ops.tuples_view(int(run_off[k][me]) // 8, n, key_bits, 0, (lo, max(lo, hi)))
             views = [ops.col_view(int(col_off[k][j][me]) // 4, n) for j in range(len(cols))]
             out.append((run, views))
@@ -353,28 +351,17 @@ class ShardedExecutor:
             geo[b] = (per, width, rows)
             hists.append(ops.ids_hist(ent[b], per, width, bpr, world))
         nb = bpr * world
-        H = self.comm.all_gather_u64(np.concatenate(hists)).reshape(world, len(by_binding), nb).astype(np.int64)
-        top = np.zeros(world, dtype=np.int64)
+        H = self.comm.all_gather_u64(np.concatenate(hists)).reshape(world, len(by_binding), nb)
+        offs, view_off, view_cnt, need, sent_ids = rowid_push_plan(_lib(), H, world, me, len(by_binding), bpr)
+        if need > ops.window_bytes():
+            raise MemoryError("projection needs more receive window than is available")
         views = {}
         sent = 0
-        owner = np.arange(nb) // bpr
-        first_bin = owner * bpr
         for k, b in enumerate(by_binding):
             per, width, rows = geo[b]
-            Hk = H[:, k, :]                                    # [src][bin]
-            bin_tot = Hk.sum(axis=0)                           # [bin]
-            cs = np.cumsum(bin_tot) - bin_tot                  # bins are owner-major: exclusive prefix over all bins
-            bin_start = cs - cs[first_bin]                     # ... relative to the owner's first bin (bin-major inside an owner)
-            total = np.add.reduceat(bin_tot, np.arange(0, nb, bpr))  # ids per owner
-            src_before = Hk[:me].sum(axis=0)                   # ids of earlier ranks in the same bin
-            region = top                                        # bytes, per owner
-            top = (top + 4 * total + 15) // 16 * 16
-            if int(top.max()) > ops.window_bytes():
-                raise MemoryError("projection needs more receive window than is available")
-            offs = region[owner] // 4 + bin_start + src_before
-            ops.push_ids(ent[b], per, width, bpr, world, offs.astype(np.uint64))
-            views[b] = (int(region[me]) // 4, int(total[me]), rows)
-            sent += 4 * int(Hk[me].sum() - Hk[me, me * bpr:(me + 1) * bpr].sum())
+            ops.push_ids(ent[b], per, width, bpr, world, offs[k])
+            views[b] = (int(view_off[k]), int(view_cnt[k]), rows)
+            sent += 4 * int(sent_ids[k])
         ops.fence()
         self.comm.barrier()
         for b, cols in by_binding.items():
