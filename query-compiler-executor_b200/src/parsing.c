@@ -64,7 +64,8 @@ static void parse_relation_list(const char *text, query *q)
     }
 }
 
-static void parse_predicate_list(const char *text, query *q)
+/* returns the number of well-formed predicates (== q->predicates_size for a valid section) */
+static size_t parse_predicate_list(const char *text, query *q)
 {
     size_t slots = count_char(text, '&') + 1;
     q->predicates = CALLOC(slots, sizeof(predicate), predicate);
@@ -102,6 +103,16 @@ static void parse_predicate_list(const char *text, query *q)
         if (*tok_end != '&') break;
         p = tok_end + 1;
     }
+    return i;
+}
+
+static void free_query_lists(query *q)
+{
+    for (size_t j = 0; j < q->predicates_size; j++) FREE(q->predicates[j].second);
+    FREE(q->predicates);
+    FREE(q->relations);
+    FREE(q->selects);
+    memset(q, 0, sizeof *q);
 }
 
 static void parse_select_list(const char *text, query *q)
@@ -143,8 +154,25 @@ int parse_query_line(const char *line, query *q)
     if (n == 0) return -1;
     memset(q, 0, sizeof *q);
     parse_relation_list(rels, q);
-    parse_predicate_list(preds, q);
+    const size_t parsed = parse_predicate_list(preds, q);
     parse_select_list(sels, q);
+    /* Hardening: the reference sizes its arrays by separator counts and then executes
+     * whatever sscanf left in them (src/parsing.c:32-39, :92-99).  A predicate section with an
+     * unparsable element, or a binding index outside the relation list, is refused here with a
+     * diagnostic instead of reaching the operators with a NULL operand / an out-of-range index. */
+    int ok = parsed == q->predicates_size;
+    for (size_t j = 0; ok && j < q->predicates_size; j++) {
+        const predicate *pr = &q->predicates[j];
+        if (pr->first.relation >= q->relations_size) ok = 0;
+        if (pr->type == 0 && ((const relation_column *)pr->second)->relation >= q->relations_size) ok = 0;
+    }
+    for (size_t j = 0; ok && j < q->select_size; j++)
+        if (q->selects[j].relation >= q->relations_size) ok = 0;
+    if (!ok) {
+        fprintf(stderr, "[ERROR] malformed query line skipped: %.*s\n", (int)strcspn(line, "\n"), line);
+        free_query_lists(q);
+        return -1;
+    }
     return 0;
 }
 

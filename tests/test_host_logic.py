@@ -41,6 +41,23 @@ def test_host_parser_sections():
     assert meta[1] == "#rels=1 sels=1 r0 s0.0"
 
 
+def test_malformed_lines_are_skipped_not_executed():
+    """Parser hardening: an unparsable predicate element or a binding index outside the
+    relation list is refused with a diagnostic; the well-formed lines around it are unaffected.
+    (The reference sizes its arrays by separator counts and executes whatever sscanf left there.)"""
+    lines = ["0 1|0.1=1.1|0.0\n",
+             "9999999999|9999999999|9999999999\n",        # no predicate at all in the predicate section
+             "0 1|0.1=1.1&0.2|0.0\n",                    # second element has no operator
+             "0 1|0.1=2.1|0.0\n",                        # binding 2 of a 2-relation query
+             "0 1|0.1=1.1|2.0\n",                        # select on binding 2
+             "0 1|0.1=1.1&&0.2<5|0.0\n",                 # empty element
+             "0|0.2<5|0.0\n"]
+    p = subprocess.run([HOST_PROBE], input="".join(lines).encode(), stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True)
+    rows = p.stdout.decode().splitlines()
+    assert rows[0::2] == ["0.1=1.1", "0.2<5"]
+    assert p.stderr.decode().count("malformed query line skipped") == 5
+
+
 def test_library_exports_every_declared_symbol():
     import qce_b200
     header = open(os.path.join(ROOT, "include", "qce_b200.h")).read()
