@@ -40,7 +40,11 @@ static int load_relation_file(const char *path, uint32_t rel_index, metadata *ou
 
     out->tuples = map[0];
     out->columns = map[1];
-    check((uint64_t)sb.st_size >= (2 + out->tuples * out->columns) * sizeof(uint64_t), "relation file truncated");
+    /* the header is untrusted: no wrap-around in rows x columns, row ids are 32-bit on the device */
+    uint64_t cells = 0;
+    check(out->tuples < (1ull << 32) && out->columns <= 65536 && !__builtin_mul_overflow(out->tuples, out->columns, &cells),
+          "implausible relation header (%lu rows x %lu columns)", (unsigned long)out->tuples, (unsigned long)out->columns);
+    check(cells <= ((uint64_t)sb.st_size - 2 * sizeof(uint64_t)) / sizeof(uint64_t), "relation file truncated");
     out->data = MALLOC(relation *, out->columns ? out->columns : 1);
     check_mem(out->data);
     for (uint64_t c = 0; c < out->columns; c++) {
