@@ -870,10 +870,12 @@ int qce_init(int device)
     return 0;
 }
 
+int qce_xwin_destroy(void);
 void qce_shutdown(void)
 {
     if (!g.inited) return;
     qce_drop_relations();
+    qce_xwin_destroy(); // unmaps the peers' windows and frees this rank's
     cudaStreamSynchronize(g.stream);
     g_arena.release_all();
     cudaFree(g.d_scalars);
