@@ -37,8 +37,9 @@ typedef struct qce_tuples qce_tuples; /* device (key,rowid) run, maybe sorted   
 
 /* ---- engine lifetime ---------------------------------------------------- */
 
-/* Bind the calling process to CUDA device `device` (one process per GPU) and
- * create the stream / memory pool.  Idempotent.  No reference counterpart. */
+/* Bind the calling process to CUDA device `device` (one process per GPU; -1: LOCAL_RANK or
+ * the rank inside the node, modulo the visible devices) and create the main context.
+ * Idempotent; every entry point does it on first use.  No reference counterpart. */
 int qce_init(int device);
 void qce_shutdown(void);
 /* Last error text of the calling thread ("" when none). */
@@ -59,14 +60,73 @@ int qce_mempool_stats(uint64_t *reserved_bytes, uint64_t *used_bytes);
 int qce_profile_enable(int on);
 const char *qce_profile_json(void);
 
+/* ---- engine contexts ------------------------------------
+ * The reference runs one query at a time on one thread (execute_queries,
+ * src/utilities.c:289-300).  A context is a stream with its own scratch and HBM
+ * arena; the host layer's batch scheduler binds one per worker thread so that
+ * independent small queries overlap on the device.  Calls made by a thread that
+ * never bound a context use the main one.  A bound context is `solo`: it runs
+ * whole queries on this rank alone (never the sharded operators). */
+void *qce_ctx_create(void);
+int qce_ctx_bind(void *ctx); /* NULL: back to the main context */
+void qce_ctx_destroy(void *ctx);
+int qce_ctx_solo(int on);    /* the calling thread's context */
+/* One batch = one execute_queries call: sorted runs of whole base columns are kept
+ * between its queries (the same rel.col is sorted again and again, 8f-3) and dropped
+ * at its end. */
+int qce_batch_begin(void);
+int qce_batch_end(void);
+int qce_batch_cache_stats(uint64_t *hits, uint64_t *misses);
+
+/* ---- ranks of the node --------------------------------------
+ * One process per GPU, SPMD: every rank runs the same host operator layer over its
+ * share of the data.  Small host vectors (histograms, counts, checksums) are agreed
+ * through a shared-memory segment; tuples and row ids move GPU to GPU over NVLink,
+ * stored by the pushing kernels into the peers' CUDA-IPC-mapped windows.  With more
+ * than one rank every operator below works on distributed objects: a handle is this
+ * rank's share, counts are global, results are identical on every rank.
+ * qce_comm_fork: the calling process becomes rank 0 and forks ranks 1..world-1; must
+ * run before the process touches CUDA (the host layer does it in execute_queries when
+ * QCE_GPUS=n).  Returns the rank, or -1.  qce_comm_attach: independently started
+ * processes (torchrun) meet in /dev/shm/<name>; `token` tells a stale segment apart. */
+int qce_comm_fork(uint32_t world);
+int qce_comm_attach(const char *name, uint32_t rank, uint32_t world, uint64_t token);
+uint32_t qce_comm_rank(void);
+uint32_t qce_comm_world(void);
+int qce_comm_is_child(void);
+int qce_comm_barrier(void);
+int qce_comm_allreduce_sum_u64(uint64_t *v, uint32_t n);
+int qce_comm_allreduce_max_u64(uint64_t *v, uint32_t n);
+/* blobs to rank 0: *out (malloc'ed, rank 0 only; may be NULL) = the ranks' blobs back to back,
+ * lens[r] (every rank) = rank r's length */
+int qce_comm_gatherv(const void *mine, uint64_t bytes, char **out, uint64_t *lens);
+void qce_comm_abort(void);
+/* fork mode: a child exits here with `status`; rank 0 waits for the children and returns
+ * how many of them failed */
+int qce_comm_finish(int status);
+
 /* ---- base relations ------------------------------------------------------
  * Replaces fill_data()/read_relations(), src/utilities.c:105-162: the column
  * is uploaded as-is (SoA uint64), the row id stays implicit (= index); the
  * reference's AoS tuple{key,payload=i} copy is never materialised.
  * Also records max(column) so the sort knows its significant bits. */
 int qce_upload_column(uint32_t rel, uint32_t col, const uint64_t *host, uint64_t n);
-/* Same, source already in device memory (device-to-device copy). */
+/* With several ranks the column is placed by size: up to qce_set_replicate_bytes (default
+ * 2 GB) every rank holds all rows, larger columns are ROW-SHARDED -- rank r keeps rows
+ * [r * rpr, (r+1) * rpr), rpr = ceil(n / world) rounded up to 4096 (qce_row_share) -- and
+ * the peers' windows are mapped so that a gather of a foreign row is an NVLink load.
+ * Collective: every rank makes the same call. `host` pointers of pageable memory (the
+ * mapped relation file) are staged through pinned chunks by a small thread pool. */
 int qce_upload_column_device(uint32_t rel, uint32_t col, const void *dev, uint64_t n);
+/* The caller holds only rows [row_begin, row_begin + row_count): at least its share. */
+int qce_upload_column_window(uint32_t rel, uint32_t col, const uint64_t *host, uint64_t row_begin,
+                             uint64_t row_count, uint64_t rows_global);
+int qce_upload_column_window_device(uint32_t rel, uint32_t col, const void *dev, uint64_t row_begin,
+                                    uint64_t row_count, uint64_t rows_global);
+int qce_row_share(uint64_t rows_global, uint32_t rank, uint32_t world, uint64_t *row_begin, uint64_t *row_count);
+int qce_set_replicate_bytes(uint64_t bytes);
+int qce_column_would_be_whole(uint64_t rows);
+int qce_column_is_whole(uint32_t rel, uint32_t col); /* 1 whole / 0 row-sharded / -1 unknown */
 /* Adopt a device buffer without copying (caller keeps ownership, must outlive use). */
 int qce_adopt_column_device(uint32_t rel, uint32_t col, const void *dev, uint64_t n);
 int qce_column_info(uint32_t rel, uint32_t col, uint64_t *n, uint64_t *max_value);
@@ -155,7 +215,8 @@ int qce_checksum(const qce_rowids *ids, uint32_t rel, const uint32_t *cols, uint
                  uint64_t *sums);
 
 /* ---- handles -------------------------------------------------------------*/
-uint64_t qce_rowids_count(const qce_rowids *ids);
+uint64_t qce_rowids_count(const qce_rowids *ids);       /* over all ranks */
+uint64_t qce_rowids_count_local(const qce_rowids *ids); /* this rank's share */
 int qce_rowids_from_host(const uint64_t *host, uint64_t n, qce_rowids **out);
 int qce_rowids_to_host(const qce_rowids *ids, uint64_t *host);
 int qce_rowids_clone(const qce_rowids *ids, qce_rowids **out);
@@ -211,6 +272,8 @@ int qce_xwin_attach(uint32_t world, uint32_t rank, const unsigned char *handles 
 int qce_xwin_loopback(uint32_t world);
 int qce_xwin_info(uint64_t *bytes, void **local_base);
 int qce_xwin_destroy(void);
+/* first half of a collective re-creation: unmap the peers' windows (then barrier, then destroy) */
+int qce_xwin_unmap_peers(void);
 /* Scatter a packed run by key range (same splitter rules as qce_partition_tuples) into
  * the destination windows: the tuples for rank p are stored from 8-byte word offset
  * dst_word_offset[p] of p's window on (order inside unspecified).  Asynchronous on the

@@ -30,7 +30,6 @@
 #pragma once
 #include "k_radix.cuh"
 
-#define QCE_MAX_RANKS 16
 #define QCE_PUSH_THREADS 512
 // 32 KB of shared-memory staging per tile: 4096 tuples, or 8192 row ids (a 256-bin id
 // scatter then leaves in runs of ~32 ids = 128 B, the NVLink write granularity that pays)
@@ -327,8 +326,8 @@ k_pack_u32_index(const u32 *__restrict__ keys, u64 n, u64 *__restrict__ out)
 }
 // Carried key column through a row-id column: out[i] = (u32)col[ids[i]].
 __global__ void __launch_bounds__(256)
-k_gather_u64_narrow(const u64 *__restrict__ col, const u32 *__restrict__ ids, u64 n, u32 *__restrict__ out)
+k_gather_u64_narrow(const __grid_constant__ ColRef col, const u32 *__restrict__ ids, u64 n, u32 *__restrict__ out)
 {
     const u64 stride = (u64)gridDim.x * 256;
-    for (u64 i = (u64)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) out[i] = (u32)__ldg(col + ld_stream_u32(ids + i));
+    for (u64 i = (u64)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) out[i] = (u32)col(ld_stream_u32(ids + i));
 }

@@ -82,7 +82,7 @@ k_filter_mask_base(const u64 *__restrict__ col, u64 n, u64 c, u32 *__restrict__ 
 // Mask layout NATURAL: word w holds elements 32w .. 32w+31.
 template <int OP>
 __global__ void __launch_bounds__(QCE_FTHREADS)
-k_refine_mask(const u32 *__restrict__ ids, u64 n, const u64 *__restrict__ col, u64 c,
+k_refine_mask(const u32 *__restrict__ ids, u64 n, const __grid_constant__ ColRef col, u64 c,
               u32 *__restrict__ mask, u32 *__restrict__ tile_count)
 {
     __shared__ u32 wcnt[QCE_FTHREADS / 32];
@@ -98,7 +98,7 @@ k_refine_mask(const u32 *__restrict__ ids, u64 n, const u64 *__restrict__ col, u
     }
     u64 v[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) v[k] = (id[k] != 0xffffffffu) ? __ldg(col + id[k]) : 0;
+    for (int k = 0; k < 16; k++) v[k] = (id[k] != 0xffffffffu) ? col(id[k]) : 0;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         bool p = (id[k] != 0xffffffffu) && qce_pred<OP>(v[k], c);
@@ -119,8 +119,8 @@ k_refine_mask(const u32 *__restrict__ ids, u64 n, const u64 *__restrict__ col, u
 // ---- pass 1, positional key equality (scan_join, src/join.c:407-412) ---------
 // idsR / idsS may be NULL: the side is then a base column (row id = position).
 __global__ void __launch_bounds__(QCE_FTHREADS)
-k_scanjoin_mask(const u32 *__restrict__ idsR, const u64 *__restrict__ colR,
-                const u32 *__restrict__ idsS, const u64 *__restrict__ colS, u64 n,
+k_scanjoin_mask(const u32 *__restrict__ idsR, const __grid_constant__ ColRef colR,
+                const u32 *__restrict__ idsS, const __grid_constant__ ColRef colS, u64 n,
                 u32 *__restrict__ mask, u32 *__restrict__ tile_count)
 {
     __shared__ u32 wcnt[QCE_FTHREADS / 32];
@@ -133,9 +133,9 @@ k_scanjoin_mask(const u32 *__restrict__ idsR, const u64 *__restrict__ colR,
         u64 i = base + k * 256 + tid;
         bool p = false;
         if (i < n) {
-            u64 r = idsR ? (u64)idsR[i] : i;
-            u64 s = idsS ? (u64)idsS[i] : i;
-            p = __ldg(colR + r) == __ldg(colS + s);
+            u32 r = idsR ? idsR[i] : (u32)i;
+            u32 s = idsS ? idsS[i] : (u32)i;
+            p = colR(r) == colS(s);
         }
         u32 b = __ballot_sync(QCE_FULL_MASK, p);
         if (lane == 0) words[k * 8 + warp] = b;

@@ -77,7 +77,7 @@ k_build_packed_base(const u64 *__restrict__ col, u64 n, u64 *__restrict__ out, u
 // (filter outputs are ascending).
 template <bool HIST>
 __global__ void __launch_bounds__(256)
-k_build_packed_ids(const u64 *__restrict__ col, const u32 *__restrict__ ids, u64 n,
+k_build_packed_ids(const __grid_constant__ ColRef col, const u32 *__restrict__ ids, u64 n,
                    u64 *__restrict__ out, int hist_shift, u32 *__restrict__ ghist)
 {
     __shared__ u32 sh[HIST ? 256 : 1];
@@ -89,7 +89,7 @@ k_build_packed_ids(const u64 *__restrict__ col, const u32 *__restrict__ ids, u64
 #pragma unroll
         for (int k = 0; k < 4; k++) id[k] = (i0 + k * 256 < n) ? ids[i0 + k * 256] : 0;
 #pragma unroll
-        for (int k = 0; k < 4; k++) v[k] = (i0 + k * 256 < n) ? __ldg(col + id[k]) : 0;
+        for (int k = 0; k < 4; k++) v[k] = (i0 + k * 256 < n) ? col(id[k]) : 0;
 #pragma unroll
         for (int k = 0; k < 4; k++)
             if (i0 + k * 256 < n) {
@@ -104,13 +104,13 @@ k_build_packed_ids(const u64 *__restrict__ col, const u32 *__restrict__ ids, u64
 }
 // Wide (keys may exceed 32 bits): SoA keys[] / ids[].
 __global__ void __launch_bounds__(256)
-k_build_wide(const u64 *__restrict__ col, const u32 *__restrict__ ids, u64 n,
+k_build_wide(const __grid_constant__ ColRef col, const u32 *__restrict__ ids, u64 n,
              u64 *__restrict__ keys, u32 *__restrict__ out_ids, u32 id_base)
 {
     const u64 stride = (u64)gridDim.x * 256;
     for (u64 i = (u64)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
         u32 id = ids ? ids[i] : (u32)i + id_base;
-        keys[i] = __ldg(col + (ids ? (u64)id : i));
+        keys[i] = col(id);
         out_ids[i] = id;
     }
 }

@@ -152,6 +152,32 @@ __device__ __forceinline__ T block_scan_excl(T v, T *scratch, T *total)
     return r;
 }
 
+// ---------------------------------------------------------------- base columns
+// A base column as the gathering kernels see it.  Whole column in this GPU's HBM
+// (one GPU, or a replicated column): rpr == 0, value = d[id].  Row-sharded over
+// the ranks of the node: rank r holds rows [r * rpr, (r+1) * rpr),
+// vb[r] = (r's window pointer, mapped through CUDA IPC) - r * rpr, so the value is
+// vb[owner(id)][id] -- an NVLink load when the owner is a peer.
+#define QCE_MAX_RANKS 16
+struct ColRef {
+    const u64 *d;
+    u32 rpr, last;   // rows per rank, last rank
+    float inv;       // 1 / rpr, rounded down
+    const u64 *vb[QCE_MAX_RANKS];
+    __device__ __forceinline__ u32 owner(u32 id) const
+    {
+        u32 r = min(__float2uint_rz(__uint2float_rz(id) * inv), last);
+        r -= (id < r * rpr);
+        r += (r < last) & (id >= (r + 1) * rpr);
+        return r;
+    }
+    __device__ __forceinline__ u64 operator()(u32 id) const
+    {
+        if (rpr == 0) return __ldg(d + id);
+        return __ldg(vb[owner(id)] + id);
+    }
+};
+
 // ---------------------------------------------------------------- tuple runs
 // A run of (key,rowid) tuples.  Packed: one uint64 = key << 32 | rowid (every
 // key < 2^32).  Wide: separate uint64 keys[] and uint32 ids[] arrays (SoA).

@@ -10,12 +10,16 @@
 // There is deliberately no CPU path: if the CUDA runtime reports no usable
 // device every entry point returns -1 and qce_last_error() says why.
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <map>
+#include <mutex>
 #include <set>
 #include <string>
 #include <vector>
@@ -25,16 +29,30 @@
 #include "k_join.cuh"
 #include "k_radix.cuh"
 #include "k_exchange.cuh"
+#include "qce_comm.cuh"
 
 #define QCE_ABI_VERSION 1
 
 // ------------------------------------------------------------------ handles
+// How the elements of a column / run are spread over the ranks of the node.
+// The global order is always "rank 0's elements, then rank 1's, ...": a filter output
+// (ascending row ids, each rank its own row window) and a join output (key order, each rank
+// its key range) both keep the order the reference's serial loops produce.
+struct Dist {
+    enum Kind : int { LOCAL = 0, ROWS, KEYS, ANY };
+    int kind = LOCAL;        // LOCAL: one rank holds everything (world 1 / a solo context)
+    u32 rel = 0, col = 0;    // ROWS: ids are rows of this rank's window of `rel`; KEYS: sorted by (rel, col)
+    int key_bits = 0;        // KEYS: the exchange's key width (splitters sit on its 256-bin boundaries)
+    std::vector<uint64_t> split;  // KEYS: world-1 ascending splitters, rank r holds keys in [split[r-1], split[r])
+};
 struct qce_rowids {
-    u32 *d;        // device row ids
+    u32 *d;        // device row ids (this rank's share)
     u64 n;
     u32 id_bound;  // exclusive upper bound of the ids (rows of the source relation), 0 = unknown
     bool bucketed = false; // already grouped by row region (received through qce_push_rowids)
     u32 id_min = 0;        // inclusive lower bound of the ids (a row-sharded owner sees only its window)
+    u64 n_others = 0;      // elements held by the other ranks (0 on one GPU): count = n + n_others
+    Dist dist;
 };
 struct qce_tuples {
     u64 *a;        // packed words (key << 32 | rowid), or keys when wide
@@ -49,6 +67,13 @@ struct qce_tuples {
     u32 *hist256 = nullptr; // device: 256-bin histogram of the top 8 of hist_key_bits key bits (taken by the build
     int hist_key_bits = 0;  // kernels, or by qce_key_histogram); valid while the run is unsorted and unmodified
     std::vector<unsigned int> hist_host; // the same 256 counts on the host
+    u64 n_others = 0;         // tuples held by the other ranks
+    Dist dist;
+    bool sort_pending = false; // sharded: qce_sort_tuples is deferred to the join, which first moves
+                               // every tuple to the rank that owns its key range
+    bool borrowed = false;     // `a` belongs to the batch's sorted-run cache
+    u32 src_rel = 0, src_col = 0; // the base column a whole-column run was built from
+    bool whole_base = false;
 };
 
 namespace {
@@ -60,35 +85,67 @@ struct Column {
     bool owned = false;
     bool windowed = false;
     u64 win_begin = 0, win_count = 0;
+    // sharded over the ranks of the node: every rank's window mapped through CUDA IPC
+    bool peer_mapped = false;
+    u32 rpr = 0;                       // rows per rank
+    const u64 *vb[QCE_MAX_RANKS] = {}; // virtual bases: row id r of rank q's window lives at vb[q][r]
+    void *alloc = nullptr;             // the cudaMalloc behind d (reused by a re-upload of the same shape)
+    u64 alloc_bytes = 0;
+    std::vector<void *> opened;        // the peers' mappings (cudaIpcCloseMemHandle on drop)
 };
+ColRef ref_of(const Column *c)
+{
+    ColRef r;
+    memset(&r, 0, sizeof r);
+    r.d = c->d;
+    if (c->peer_mapped) {
+        r.rpr = c->rpr;
+        r.inv = 1.0f / (float)c->rpr;
+        // rounded down: the owner estimate may only err low (corrected upwards in ColRef::owner)
+        r.inv = nextafterf(r.inv, 0.0f);
+        for (int q = 0; q < QCE_MAX_RANKS; q++) r.vb[q] = c->vb[q];
+    }
+    return r;
+}
 
 struct ProfRec {
     const char *tag;
     cudaEvent_t e0, e1;
 };
 
-struct Engine {
+// Per host thread that drives the engine: its own stream, scalar scratch, timers and HBM arena.
+// The main context serves the classic one-thread host loop; the batch scheduler
+// (src/utilities.c: execute_queries) creates more with qce_ctx_create and binds one per worker
+// thread, so independent small queries overlap on the device.
+class Arena;
+struct Ctx;
+struct Global {
     bool inited = false;
     int device = -1;
     int sms = 148;
-    cudaStream_t stream = nullptr;
-    std::map<u64, Column> cols;
-    u64 *d_scalars = nullptr; // 16 u64 of device scratch for totals
-    u64 *h_scalars = nullptr; // pinned mirror
-    cudaEvent_t t0 = nullptr, t1 = nullptr;
-    u64 launches = 0;
-    bool profile = false;
-    std::vector<ProfRec> prof;
-    std::vector<cudaEvent_t> ev_pool; // recycled profiling events
-    std::string prof_json;
+    std::map<u64, Column> cols;  // read-mostly: written by uploads (main thread, before a batch runs)
     // peer-memory exchange: this rank's receive window + the peers' windows mapped through CUDA IPC
     unsigned char *xwin = nullptr;
     u64 xwin_bytes = 0;
     u32 xworld = 0, xrank = 0;
     PeerWindows peers;
     std::vector<void *> xopened;
+    u32 world = 1, rank = 0;     // ranks of the node (qce_comm.cuh); 1 / 0 on a single GPU
+    u64 replicate_bytes = 2ull << 30; // columns up to this size are held whole by every rank
+    std::mutex mu;               // guards cols / run cache when worker contexts are live
+    // sorted base runs of the running batch, keyed by (relation, column): the same column is
+    // sorted again and again across the ~1000 queries of a batch
+    struct CachedRun {
+        u64 *a; u64 n; int key_bits; u64 key_min, key_max; u32 id_bound;
+        cudaEvent_t ready;      // recorded on the producer's stream after the sort
+        class Arena *owner;
+    };
+    std::map<u64, CachedRun> run_cache;
+    bool cache_on = false;
+    u64 cache_bytes = 0, cache_budget = 0, cache_hits = 0, cache_misses = 0;
+    std::vector<Ctx *> workers;
 };
-Engine g;
+Global G;
 thread_local char g_err[512] = "";
 
 int fail(const char *fmt, ...)
@@ -103,12 +160,14 @@ int fail(const char *fmt, ...)
 #define CK(call)                                                                              \
     do {                                                                                      \
         cudaError_t e_ = (call);                                                              \
-        if (e_ != cudaSuccess)                                                                \
+        if (e_ != cudaSuccess) {                                                              \
+            (void)cudaGetLastError(); /* a non-sticky failure must not poison the next launch check */ \
             return fail("%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+        }                                                                                     \
     } while (0)
 #define NEED_INIT()                                                                 \
     do {                                                                            \
-        if (!g.inited && qce_init(-1) != 0) return -1;                              \
+        if (!G.inited && qce_init(-1) != 0) return -1;                              \
     } while (0)
 
 inline int bitlen(u64 v)
@@ -119,6 +178,15 @@ inline int bitlen(u64 v)
 }
 inline u64 ceil_div(u64 a, u64 b) { return (a + b - 1) / b; }
 inline u64 col_key(u32 rel, u32 col) { return ((u64)rel << 32) | col; }
+void row_share(u64 n, u32 rank, u32 world, u64 *begin, u64 *count, u64 *per_out = nullptr)
+{
+    u64 per = ceil_div(n ? n : 1, world);
+    per = ceil_div(per, 4096) * 4096;
+    const u64 b = std::min<u64>((u64)rank * per, n);
+    *begin = b;
+    *count = std::min<u64>(per, n - b);
+    if (per_out) *per_out = per;
+}
 
 // ---- HBM arena ----------------------------------------------------------------
 // Temporaries (tuple runs, ping-pong buffers, masks, look-back words, join
@@ -132,7 +200,7 @@ inline u64 col_key(u32 rel, u32 col) { return ((u64)rel << 32) | col; }
 class Arena {
   public:
     static constexpr u64 kAlign = 512;
-    static constexpr u64 kMinSlab = 1ull << 30;
+    u64 min_slab = 1ull << 30; // worker contexts (small queries) grow in smaller steps
 
     int alloc(void **out, u64 bytes)
     {
@@ -192,7 +260,7 @@ class Arena {
     int grow(u64 need)
     {
         // at least as much again as is already reserved, so the slab count stays small
-        u64 bytes = std::max<u64>(std::max<u64>(need, kMinSlab), reserved_);
+        u64 bytes = std::max<u64>(std::max<u64>(need, min_slab), reserved_);
         void *p = nullptr;
         cudaError_t e = cudaMalloc(&p, bytes);
         if (e != cudaSuccess && bytes > need) {
@@ -221,48 +289,64 @@ class Arena {
     std::map<u64, u64> live_;               // handed out: addr -> size
     u64 reserved_ = 0, used_ = 0;
 };
-Arena g_arena;
+
+struct Ctx {
+    cudaStream_t stream = nullptr;
+    u64 *d_scalars = nullptr; // 16 u64 of device scratch for totals
+    u64 *h_scalars = nullptr; // pinned mirror
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    u64 launches = 0;
+    bool profile = false;
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> ev_pool; // recycled profiling events
+    std::string prof_json;
+    Arena arena;
+    bool solo = false; // a worker context: whole queries on this rank alone, never the sharded path
+};
+Ctx g_main;
+thread_local Ctx *tl_ctx = nullptr;
+inline Ctx &cx() { return tl_ctx ? *tl_ctx : g_main; }
 
 template <typename T> int dalloc(T **p, u64 count)
 {
     *p = nullptr;
-    return g_arena.alloc((void **)p, (count ? count : 1) * sizeof(T));
+    return cx().arena.alloc((void **)p, (count ? count : 1) * sizeof(T));
 }
-template <typename T> void dfree(T *p) { g_arena.free((void *)p); }
+template <typename T> void dfree(T *p) { cx().arena.free((void *)p); }
 
 void prof_begin(const char *tag)
 {
-    if (!g.profile) return;
+    if (!cx().profile) return;
     ProfRec r;
     r.tag = tag;
     cudaEvent_t *ev[2] = {&r.e0, &r.e1};
     for (auto e : ev) {
-        if (!g.ev_pool.empty()) { *e = g.ev_pool.back(); g.ev_pool.pop_back(); }
+        if (!cx().ev_pool.empty()) { *e = cx().ev_pool.back(); cx().ev_pool.pop_back(); }
         else cudaEventCreate(e);
     }
-    cudaEventRecord(r.e0, g.stream);
-    g.prof.push_back(r);
+    cudaEventRecord(r.e0, cx().stream);
+    cx().prof.push_back(r);
 }
 void prof_end()
 {
-    if (!g.profile) return;
-    cudaEventRecord(g.prof.back().e1, g.stream);
+    if (!cx().profile) return;
+    cudaEventRecord(cx().prof.back().e1, cx().stream);
 }
 
 #define LAUNCH(tag, kern, grid, block, smem, ...)                         \
     do {                                                                  \
         prof_begin(tag);                                                  \
-        (kern)<<<(grid), (block), (smem), g.stream>>>(__VA_ARGS__);       \
+        (kern)<<<(grid), (block), (smem), cx().stream>>>(__VA_ARGS__);       \
         prof_end();                                                       \
-        g.launches++;                                                     \
+        cx().launches++;                                                     \
         CK(cudaGetLastError());                                           \
     } while (0)
 
 // read `k` device scalars (d_scalars[0..k)) back; the one sync point of an op
 int read_scalars(int k)
 {
-    CK(cudaMemcpyAsync(g.h_scalars, g.d_scalars, k * sizeof(u64), cudaMemcpyDeviceToHost, g.stream));
-    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaMemcpyAsync(cx().h_scalars, cx().d_scalars, k * sizeof(u64), cudaMemcpyDeviceToHost, cx().stream));
+    CK(cudaStreamSynchronize(cx().stream));
     return 0;
 }
 
@@ -270,8 +354,9 @@ int read_scalars(int k)
 bool window_resident(const struct Column *cl, u64 begin, u64 count);
 int get_column(u32 rel, u32 col, const Column **out)
 {
-    auto it = g.cols.find(col_key(rel, col));
-    if (it == g.cols.end()) return fail("relation %u column %u was never uploaded", rel, col);
+    std::lock_guard<std::mutex> lk(G.mu); // map nodes are stable: the pointer outlives the lock
+    auto it = G.cols.find(col_key(rel, col));
+    if (it == G.cols.end()) return fail("relation %u column %u was never uploaded", rel, col);
     *out = &it->second;
     return 0;
 }
@@ -305,7 +390,7 @@ int new_rowids(u64 n, u32 id_bound, qce_rowids **out)
 int grid_for(u64 items_per_block, u64 n, int waves = 8)
 {
     u64 blocks = ceil_div(n ? n : 1, items_per_block);
-    u64 cap = (u64)g.sms * waves;
+    u64 cap = (u64)G.sms * waves;
     return (int)(blocks < cap ? blocks : cap);
 }
 
@@ -317,11 +402,11 @@ int compact_from_mask(int layout, int mode, const u32 *mask, const u32 *tile_cou
     u32 *tile_off = nullptr;
     if (dalloc(&tile_off, ntiles) != 0) return -1;
     if (ntiles <= 512)
-        LAUNCH("scan_tiles", (k_scan_excl_warp<u32, u32>), 1, 32, 0, tile_count, tile_off, ntiles, g.d_scalars);
+        LAUNCH("scan_tiles", (k_scan_excl_warp<u32, u32>), 1, 32, 0, tile_count, tile_off, ntiles, cx().d_scalars);
     else
-        LAUNCH("scan_tiles", (k_scan_excl<u32, u32>), 1, 1024, 0, tile_count, tile_off, ntiles, g.d_scalars);
+        LAUNCH("scan_tiles", (k_scan_excl<u32, u32>), 1, 1024, 0, tile_count, tile_off, ntiles, cx().d_scalars);
     if (read_scalars(1) != 0) return -1;
-    const u64 m = g.h_scalars[0];
+    const u64 m = cx().h_scalars[0];
     if (new_rowids(m, id_bound0, out0) != 0) return -1;
     if (out1 && new_rowids(m, id_bound1, out1) != 0) return -1;
     u32 *o0 = (*out0)->d, *o1 = out1 ? (*out1)->d : nullptr;
@@ -441,9 +526,9 @@ int radix_sort(u64 **keys, u32 **vals, u64 n, const RadixShifts &rs, int digit_b
     if (dalloc(&gbase, (u64)rs.npass * bins) != 0) return -1;
     if (dalloc(&status, (u64)rs.npass * ntiles * bins) != 0) return -1;
     if (dalloc(&counters, (u64)rs.npass) != 0) return -1;
-    CK(cudaMemsetAsync(ghist, 0, (u64)rs.npass * bins * sizeof(u32), g.stream));
-    CK(cudaMemsetAsync(status, 0, (u64)rs.npass * ntiles * bins * sizeof(u32), g.stream));
-    CK(cudaMemsetAsync(counters, 0, (u64)rs.npass * sizeof(u32), g.stream));
+    CK(cudaMemsetAsync(ghist, 0, (u64)rs.npass * bins * sizeof(u32), cx().stream));
+    CK(cudaMemsetAsync(status, 0, (u64)rs.npass * ntiles * bins * sizeof(u32), cx().stream));
+    CK(cudaMemsetAsync(counters, 0, (u64)rs.npass * sizeof(u32), cx().stream));
     LAUNCH("radix_hist", k_radix_hist, grid_for(1024, n, 4), 512, 0, *keys, n, rs, bins, ghist);
     LAUNCH("radix_bases", k_radix_bases, rs.npass, bins, 0, ghist, gbase);
 
@@ -544,17 +629,17 @@ int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done, const u32 
         return -1;
     // level 0: one bucket = the whole run.  lvl0 = {tile_start[0], tile_start[1], bucket_off, bucket_size}
     const u32 h_lvl0[4] = {0u, ntiles0, 0u, (u32)n};
-    CK(cudaMemcpyAsync(lvl0, h_lvl0, sizeof h_lvl0, cudaMemcpyHostToDevice, g.stream));
-    CK(cudaMemsetAsync(histA, 0, nbA * sizeof(u32), g.stream));
-    CK(cudaMemsetAsync(histB, 0, nsub * sizeof(u32), g.stream));
-    CK(cudaMemsetAsync(g.d_scalars + 10, 0, sizeof(u64), g.stream));
+    CK(cudaMemcpyAsync(lvl0, h_lvl0, sizeof h_lvl0, cudaMemcpyHostToDevice, cx().stream));
+    CK(cudaMemsetAsync(histA, 0, nbA * sizeof(u32), cx().stream));
+    CK(cudaMemsetAsync(histB, 0, nsub * sizeof(u32), cx().stream));
+    CK(cudaMemsetAsync(cx().d_scalars + 10, 0, sizeof(u64), cx().stream));
     if (hist_top8 && key_min == 0 && hist_key_bits == key_bits) // level A was counted while the run was built
-        CK(cudaMemcpyAsync(histA, hist_top8, nbA * sizeof(u32), cudaMemcpyDeviceToDevice, g.stream));
+        CK(cudaMemcpyAsync(histA, hist_top8, nbA * sizeof(u32), cudaMemcpyDeviceToDevice, cx().stream));
     else
         LAUNCH("msd_hist", k_msd_hist, ntiles0, QCE_MSD_THREADS, 0, *keys, lvl0, lvl0 + 2, lvl0 + 3, 1u, base, shiftA, nbA,
                histA);
     LAUNCH("radix_bases", k_radix_bases, 1, (int)nbA, 0, histA, offA);
-    CK(cudaMemcpyAsync(curA, offA, nbA * sizeof(u32), cudaMemcpyDeviceToDevice, g.stream));
+    CK(cudaMemcpyAsync(curA, offA, nbA * sizeof(u32), cudaMemcpyDeviceToDevice, cx().stream));
     static int shape = -1; // QCE_MSD_SHAPE: 0 = 256 threads x 16 tuples, 1 = 512 x 8
     if (shape < 0) {
         const char *e = getenv("QCE_MSD_SHAPE");
@@ -585,13 +670,13 @@ int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done, const u32 
     LAUNCH("msd_tiles", k_msd_tile_starts, 1, 256, 0, histA, nbA, tstart1);
     LAUNCH("msd_hist", k_msd_hist, ntiles1, QCE_MSD_THREADS, 0, alt, tstart1, offA, histA, nbA, base, shiftB, nbB,
            histB);
-    LAUNCH("scan_tiles", (k_scan_excl<u32, u32>), 1, 1024, 0, histB, suboff, (u64)nsub, g.d_scalars + 11);
-    LAUNCH("msd_max", k_max_u32, grid_for(256, nsub, 1), 256, 0, histB, nsub, (u32 *)(g.d_scalars + 10));
-    CK(cudaMemcpyAsync(g.h_scalars + 10, g.d_scalars + 10, sizeof(u64), cudaMemcpyDeviceToHost, g.stream));
-    CK(cudaStreamSynchronize(g.stream));
-    const u32 max_sub = (u32)(g.h_scalars[10] & 0xffffffffu);
+    LAUNCH("scan_tiles", (k_scan_excl<u32, u32>), 1, 1024, 0, histB, suboff, (u64)nsub, cx().d_scalars + 11);
+    LAUNCH("msd_max", k_max_u32, grid_for(256, nsub, 1), 256, 0, histB, nsub, (u32 *)(cx().d_scalars + 10));
+    CK(cudaMemcpyAsync(cx().h_scalars + 10, cx().d_scalars + 10, sizeof(u64), cudaMemcpyDeviceToHost, cx().stream));
+    CK(cudaStreamSynchronize(cx().stream));
+    const u32 max_sub = (u32)(cx().h_scalars[10] & 0xffffffffu);
     if (max_sub <= MSD_LOCAL_CAP) {
-        CK(cudaMemcpyAsync(curB, suboff, nsub * sizeof(u32), cudaMemcpyDeviceToDevice, g.stream));
+        CK(cudaMemcpyAsync(curB, suboff, nsub * sizeof(u32), cudaMemcpyDeviceToDevice, cx().stream));
         if (shape >= 1 && variant == 1)
             LAUNCH("msd_partition", (k_msd_partition<512, 8, u64, 4, false>), ntiles1, 512, 0, alt, *keys, tstart1, offA, histA, nbA,
                    base, shiftB, nbB, curB, (const u32 *)nullptr);
@@ -715,16 +800,16 @@ int merge_join_t(const qce_tuples *R, const qce_tuples *S, bool want_r, bool wan
                lb, cnt, tile_total, tile_chunks);
     }
     if (ntiles <= 512) {
-        LAUNCH("scan_tiles", (k_scan_excl_warp<u64, u64>), 1, 32, 0, tile_total, tile_off, (u64)ntiles, g.d_scalars);
+        LAUNCH("scan_tiles", (k_scan_excl_warp<u64, u64>), 1, 32, 0, tile_total, tile_off, (u64)ntiles, cx().d_scalars);
         LAUNCH("scan_tiles", (k_scan_excl_warp<u32, u32>), 1, 32, 0, tile_chunks, chunk_off, (u64)ntiles,
-               g.d_scalars + 1);
+               cx().d_scalars + 1);
     } else {
-        LAUNCH("scan_tiles", (k_scan_excl<u64, u64>), 1, 1024, 0, tile_total, tile_off, (u64)ntiles, g.d_scalars);
+        LAUNCH("scan_tiles", (k_scan_excl<u64, u64>), 1, 1024, 0, tile_total, tile_off, (u64)ntiles, cx().d_scalars);
         LAUNCH("scan_tiles", (k_scan_excl<u32, u32>), 1, 1024, 0, tile_chunks, chunk_off, (u64)ntiles,
-               g.d_scalars + 1);
+               cx().d_scalars + 1);
     }
     if (read_scalars(2) != 0) return -1;
-    const u64 m = g.h_scalars[0], nchunks = g.h_scalars[1];
+    const u64 m = cx().h_scalars[0], nchunks = cx().h_scalars[1];
     if (m >= (1ull << 32)) return fail("join output of %llu pairs exceeds the 2^32 row-id column limit", (unsigned long long)m);
     qce_rowids *oR = nullptr, *oS = nullptr;
     if (want_r && new_rowids(m, R->id_bound, &oR) != 0) return -1;
@@ -823,8 +908,8 @@ int partition_ids_by_top_bits(const qce_rowids *ids, u32 **out)
     u32 *ghist = nullptr, *cursor = nullptr, *lvl0 = nullptr, *dst = nullptr;
     if (dalloc(&dst, n) || dalloc(&ghist, QCE_RADIX_BINS) || dalloc(&cursor, QCE_RADIX_BINS) || dalloc(&lvl0, 4)) return -1;
     const u32 h_lvl0[4] = {0u, ntiles, 0u, (u32)n};
-    CK(cudaMemcpyAsync(lvl0, h_lvl0, sizeof h_lvl0, cudaMemcpyHostToDevice, g.stream));
-    CK(cudaMemsetAsync(ghist, 0, QCE_RADIX_BINS * sizeof(u32), g.stream));
+    CK(cudaMemcpyAsync(lvl0, h_lvl0, sizeof h_lvl0, cudaMemcpyHostToDevice, cx().stream));
+    CK(cudaMemsetAsync(ghist, 0, QCE_RADIX_BINS * sizeof(u32), cx().stream));
     LAUNCH("hist_u32", k_hist_u32, grid_for(2048, n, 4), 512, 0, ids->d, n, base, shift, ghist);
     LAUNCH("radix_bases", k_radix_bases, 1, 256, 0, ghist, cursor);
     LAUNCH("partition_u32", (k_msd_partition<512, 8, u32>), ntiles, 512, 0, (const u32 *)ids->d, dst, lvl0, lvl0 + 2,
@@ -834,7 +919,30 @@ int partition_ids_by_top_bits(const qce_rowids *ids, u32 **out)
     return 0;
 }
 
+int scan_join_impl(const Column *cr, const qce_rowids *idsR, const Column *cs, const qce_rowids *idsS,
+                          qce_rowids **outR, qce_rowids **outS)
+{
+    const u64 nr = idsR ? idsR->n : cr->n, ns = idsS ? idsS->n : cs->n;
+    const u64 n = nr < ns ? nr : ns;
+    if (n == 0) {
+        if (new_rowids(0, (u32)cr->n, outR) != 0) return -1;
+        return new_rowids(0, (u32)cs->n, outS);
+    }
+    const u64 ntiles = ceil_div(n, QCE_FTILE);
+    u32 *mask = nullptr, *tile_count = nullptr;
+    if (dalloc(&mask, ntiles * QCE_FWORDS) || dalloc(&tile_count, ntiles)) return -1;
+    LAUNCH("scan_join", k_scanjoin_mask, (int)ntiles, QCE_FTHREADS, 0, idsR ? idsR->d : nullptr, ref_of(cr),
+           idsS ? idsS->d : nullptr, ref_of(cs), n, mask, tile_count);
+    int rc = compact_from_mask(QCE_LAYOUT_NATURAL, QCE_EMIT_SRC2, mask, tile_count, ntiles,
+                               idsR ? idsR->d : nullptr, idsS ? idsS->d : nullptr, (u32)cr->n, (u32)cs->n, outR, outS);
+    dfree(mask);
+    dfree(tile_count);
+    return rc;
+}
+
 } // namespace
+
+#include "qce_shard.cuh"
 
 // =============================================================== C-ABI
 extern "C" {
@@ -842,81 +950,149 @@ extern "C" {
 int qce_abi_version(void) { return QCE_ABI_VERSION; }
 const char *qce_last_error(void) { return g_err; }
 
+static int ctx_open(Ctx *c)
+{
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaMalloc((void **)&c->d_scalars, 16 * sizeof(u64)));
+    CK(cudaMallocHost((void **)&c->h_scalars, 16 * sizeof(u64)));
+    CK(cudaEventCreate(&c->t0));
+    CK(cudaEventCreate(&c->t1));
+    return 0;
+}
+static void ctx_close(Ctx *c)
+{
+    if (!c->stream) return;
+    cudaStreamSynchronize(c->stream);
+    c->arena.release_all();
+    for (auto &r : c->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
+    c->prof.clear();
+    c->ev_pool.clear();
+    cudaFree(c->d_scalars);
+    cudaFreeHost(c->h_scalars);
+    cudaEventDestroy(c->t0);
+    cudaEventDestroy(c->t1);
+    cudaStreamDestroy(c->stream);
+    c->stream = nullptr;
+}
+
 int qce_init(int device)
 {
-    if (g.inited) return 0;
+    if (G.inited) return 0;
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0)
         return fail("no CUDA device available (%s); this engine has no CPU path",
                     e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
     if (device < 0) {
+        // one process per GPU: the rank inside the node picks the device (several ranks may
+        // share one when there are fewer devices than ranks, e.g. the single-GPU test box)
         const char *lr = getenv("LOCAL_RANK");
-        device = lr ? atoi(lr) % count : 0;
+        const bool forked = qcecomm::st().forked_child || !qcecomm::st().children.empty();
+        device = (lr && !forked) ? atoi(lr) % count : (int)(qcecomm::st().rank % (u32)count);
     }
     if (device >= count) return fail("device %d out of range (%d visible)", device, count);
     CK(cudaSetDevice(device));
-    g.device = device;
+    G.device = device;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
-    g.sms = prop.multiProcessorCount;
-    CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
-    CK(cudaMalloc((void **)&g.d_scalars, 16 * sizeof(u64)));
-    CK(cudaMallocHost((void **)&g.h_scalars, 16 * sizeof(u64)));
-    CK(cudaEventCreate(&g.t0));
-    CK(cudaEventCreate(&g.t1));
-    g.inited = true;
+    G.sms = prop.multiProcessorCount;
+    if (ctx_open(&g_main) != 0) return -1;
+    G.inited = true;
     g_err[0] = 0;
     return 0;
 }
 
 int qce_xwin_destroy(void);
+int qce_xwin_unmap_peers(void);
+namespace stager { static void release(); }
 void qce_shutdown(void)
 {
-    if (!g.inited) return;
+    if (!G.inited) return;
+    for (Ctx *w : G.workers) { ctx_close(w); delete w; }
+    G.workers.clear();
+    tl_ctx = nullptr;
     qce_drop_relations();
     qce_xwin_destroy(); // unmaps the peers' windows and frees this rank's
-    cudaStreamSynchronize(g.stream);
-    g_arena.release_all();
-    cudaFree(g.d_scalars);
-    cudaFreeHost(g.h_scalars);
-    cudaEventDestroy(g.t0);
-    cudaEventDestroy(g.t1);
-    cudaStreamDestroy(g.stream);
-    g = Engine();
+    stager::release();
+    ctx_close(&g_main);
+    G.inited = false;
+}
+
+// ---- worker contexts (the batch scheduler's streams) -----------------
+// A context is a stream with its own scalar scratch and arena.  qce_ctx_bind(handle)
+// makes it the calling thread's context (NULL = back to the main one); handles are
+// created and destroyed by the main thread while no worker is running.
+void *qce_ctx_create(void)
+{
+    if (!G.inited && qce_init(-1) != 0) return nullptr;
+    Ctx *c = new Ctx();
+    c->arena.min_slab = 64ull << 20;
+    c->solo = true;
+    if (ctx_open(c) != 0) { delete c; return nullptr; }
+    std::lock_guard<std::mutex> lk(G.mu);
+    G.workers.push_back(c);
+    return c;
+}
+int qce_ctx_bind(void *handle)
+{
+    if (!G.inited && qce_init(-1) != 0) return -1;
+    CK(cudaSetDevice(G.device)); // a fresh host thread starts on device 0
+    tl_ctx = (Ctx *)handle;
+    return 0;
+}
+/* The calling thread's context runs whole queries on this rank alone (1) or takes part in the
+ * ranks' sharded operators (0, the main context's default). */
+int qce_ctx_solo(int on)
+{
+    if (!G.inited && qce_init(-1) != 0) return -1;
+    cx().solo = on != 0;
+    return 0;
+}
+void qce_ctx_destroy(void *handle)
+{
+    Ctx *c = (Ctx *)handle;
+    if (!c) return;
+    if (tl_ctx == c) tl_ctx = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(G.mu);
+        G.workers.erase(std::remove(G.workers.begin(), G.workers.end(), c), G.workers.end());
+    }
+    ctx_close(c);
+    delete c;
 }
 
 int qce_sync(void)
 {
     NEED_INIT();
-    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaStreamSynchronize(cx().stream));
     return 0;
 }
 
 int qce_timer_reset(void)
 {
     NEED_INIT();
-    g.launches = 0;
-    CK(cudaEventRecord(g.t0, g.stream));
+    cx().launches = 0;
+    CK(cudaEventRecord(cx().t0, cx().stream));
     return 0;
 }
 int qce_timer_read(double *ms, uint64_t *kernel_launches)
 {
     NEED_INIT();
-    CK(cudaEventRecord(g.t1, g.stream));
-    CK(cudaEventSynchronize(g.t1));
+    CK(cudaEventRecord(cx().t1, cx().stream));
+    CK(cudaEventSynchronize(cx().t1));
     float f = 0;
-    CK(cudaEventElapsedTime(&f, g.t0, g.t1));
+    CK(cudaEventElapsedTime(&f, cx().t0, cx().t1));
     if (ms) *ms = f;
-    if (kernel_launches) *kernel_launches = g.launches;
+    if (kernel_launches) *kernel_launches = cx().launches;
     return 0;
 }
 
 int qce_mempool_stats(uint64_t *reserved_bytes, uint64_t *used_bytes)
 {
     NEED_INIT();
-    if (reserved_bytes) *reserved_bytes = g_arena.reserved();
-    if (used_bytes) *used_bytes = g_arena.used();
+    if (reserved_bytes) *reserved_bytes = cx().arena.reserved();
+    if (used_bytes) *used_bytes = cx().arena.used();
     return 0;
 }
 
@@ -924,21 +1100,21 @@ int qce_mempool_stats(uint64_t *reserved_bytes, uint64_t *used_bytes)
 int qce_profile_enable(int on)
 {
     NEED_INIT();
-    CK(cudaStreamSynchronize(g.stream));
-    for (auto &r : g.prof) { g.ev_pool.push_back(r.e0); g.ev_pool.push_back(r.e1); }
-    g.prof.clear();
-    g.profile = on != 0;
+    CK(cudaStreamSynchronize(cx().stream));
+    for (auto &r : cx().prof) { cx().ev_pool.push_back(r.e0); cx().ev_pool.push_back(r.e1); }
+    cx().prof.clear();
+    cx().profile = on != 0;
     return 0;
 }
 // JSON object {"tag": {"launches": n, "ms": total}, ...} of everything recorded
 // since qce_profile_enable(1); the pointer stays valid until the next call.
 const char *qce_profile_json(void)
 {
-    if (!g.inited) return "{}";
-    cudaStreamSynchronize(g.stream);
+    if (!G.inited) return "{}";
+    cudaStreamSynchronize(cx().stream);
     std::map<std::string, std::pair<u64, double>> agg;
-    for (size_t k = 0; k < g.prof.size(); k++) {
-        auto &r = g.prof[k];
+    for (size_t k = 0; k < cx().prof.size(); k++) {
+        auto &r = cx().prof[k];
         float f = 0;
         if (cudaEventElapsedTime(&f, r.e0, r.e1) == cudaSuccess) {
             auto &a = agg[r.tag];
@@ -947,80 +1123,382 @@ const char *qce_profile_json(void)
         }
         // stream time between the end of the previous kernel and the start of
         // this one: memsets, copies and host round trips
-        if (k > 0 && cudaEventElapsedTime(&f, g.prof[k - 1].e1, r.e0) == cudaSuccess) {
+        if (k > 0 && cudaEventElapsedTime(&f, cx().prof[k - 1].e1, r.e0) == cudaSuccess) {
             auto &a = agg[std::string("gap_before:") + r.tag];
             a.first++;
             a.second += f;
         }
     }
-    g.prof_json = "{";
+    cx().prof_json = "{";
     bool first = true;
     for (auto &kv : agg) {
         char buf[256];
         snprintf(buf, sizeof buf, "%s\"%s\": {\"launches\": %llu, \"ms\": %.6f}", first ? "" : ", ",
                  kv.first.c_str(), (unsigned long long)kv.second.first, kv.second.second);
-        g.prof_json += buf;
+        cx().prof_json += buf;
         first = false;
     }
-    g.prof_json += "}";
-    return g.prof_json.c_str();
+    cx().prof_json += "}";
+    return cx().prof_json.c_str();
+}
+
+// ---------------------------------------------------------------- ranks of the node
+// See qce_comm.cuh.  world == 1 until one of these is called.
+int qce_comm_fork(uint32_t world)
+{
+    if (G.inited) return fail("qce_comm_fork must run before the process touches CUDA");
+    if (qcecomm::fork_ranks(world) != 0) return fail("%s", qcecomm::st().err);
+    G.world = qcecomm::st().world;
+    G.rank = qcecomm::st().rank;
+    return (int)G.rank;
+}
+int qce_comm_attach(const char *name, uint32_t rank, uint32_t world, uint64_t token)
+{
+    if (!name) return fail("null argument");
+    if (qcecomm::attach_named(name, rank, world, token) != 0) return fail("%s", qcecomm::st().err);
+    G.world = world;
+    G.rank = rank;
+    return 0;
+}
+uint32_t qce_comm_rank(void) { return G.rank; }
+uint32_t qce_comm_world(void) { return G.world; }
+int qce_comm_is_child(void) { return qcecomm::st().forked_child ? 1 : 0; }
+int qce_comm_barrier(void)
+{
+    if (qcecomm::barrier() != 0) return fail("%s", qcecomm::st().err);
+    return 0;
+}
+int qce_comm_allreduce_sum_u64(uint64_t *v, uint32_t n)
+{
+    if (qcecomm::allreduce_sum(v, n) != 0) return fail("%s", qcecomm::st().err);
+    return 0;
+}
+int qce_comm_allreduce_max_u64(uint64_t *v, uint32_t n)
+{
+    if (qcecomm::allreduce_max(v, n) != 0) return fail("%s", qcecomm::st().err);
+    return 0;
+}
+// Variable-length blobs to rank 0: *out (malloc'ed, rank 0 only) = the ranks' blobs one after
+// another, lens[r] = rank r's length (every rank receives the lengths).
+int qce_comm_gatherv(const void *mine, uint64_t bytes, char **out, uint64_t *lens)
+{
+    std::vector<std::string> all;
+    if (qcecomm::gatherv_root(mine, bytes, &all) != 0) return fail("%s", qcecomm::st().err);
+    u64 total = 0;
+    for (u32 r = 0; r < G.world; r++) total += all[r].size();
+    if (lens) {
+        std::vector<uint64_t> l(G.world, 0);
+        uint64_t me = bytes;
+        if (qcecomm::allgather(&me, sizeof me, l.data()) != 0) return fail("%s", qcecomm::st().err);
+        for (u32 r = 0; r < G.world; r++) lens[r] = l[r];
+    }
+    if (out) {
+        *out = nullptr;
+        if (G.rank == 0) {
+            *out = (char *)malloc(total ? total : 1);
+            u64 at = 0;
+            for (u32 r = 0; r < G.world; r++) { memcpy(*out + at, all[r].data(), all[r].size()); at += all[r].size(); }
+        }
+    }
+    return 0;
+}
+void qce_comm_abort(void) { qcecomm::abort_all(); }
+// fork mode: rank 0 collects its children (returns how many failed); a child never returns
+int qce_comm_finish(int status)
+{
+    if (qcecomm::st().forked_child) {
+        fflush(stderr);
+        _exit(status);
+    }
+    const int bad = qcecomm::join_children();
+    qcecomm::detach();
+    G.world = 1;
+    G.rank = 0;
+    return bad;
 }
 
 // ---------------------------------------------------------------- relations
-// A column uploaded again with the same row count (a refreshed batch of the
-// same relation) reuses its HBM buffer instead of cudaFree + cudaMalloc.
-static u64 *reusable_buffer(u32 rel, u32 col, u64 n)
+// Placement of a base column over the ranks of the node (world > 1):
+//   whole    every rank holds all rows (columns up to G.replicate_bytes): every gather is local,
+//            whole queries over such relations can run on one rank alone (replica queries);
+//   window   rank r holds rows [r * rpr, (r+1) * rpr) only, rpr = ceil(n / world) rounded up to
+//            4096; the peers' windows are mapped through CUDA IPC, so a gather of a foreign row
+//            is an NVLink load (ColRef) and nothing is replicated.
+static void release_column(Column &c)
 {
-    auto it = g.cols.find(col_key(rel, col));
-    if (it != g.cols.end() && it->second.owned && it->second.n == n) return (u64 *)it->second.d;
-    return nullptr;
+    for (void *p : c.opened) cudaIpcCloseMemHandle(p);
+    c.opened.clear();
+    if (c.owned && c.alloc) cudaFree(c.alloc);
+    c.alloc = nullptr;
+    c.owned = false;
+}
+// the buffer of (rel, col): the previous upload's when the shape is unchanged (a refreshed
+// batch of the same relation), else a fresh cudaMalloc.  *reused tells the caller whether the
+// peers' IPC mappings of a window are still valid.
+static int column_buffer(u32 rel, u32 col, u64 bytes, Column *c, bool *reused)
+{
+    *reused = false;
+    {
+        std::lock_guard<std::mutex> lk(G.mu);
+        auto it = G.cols.find(col_key(rel, col));
+        if (it != G.cols.end()) {
+            if (it->second.owned && it->second.alloc && it->second.alloc_bytes == bytes) {
+                *c = it->second;
+                *reused = true;
+                return 0;
+            }
+            release_column(it->second);
+            G.cols.erase(it);
+        }
+    }
+    *c = Column();
+    CK(cudaMalloc(&c->alloc, bytes ? bytes : 16));
+    c->alloc_bytes = bytes;
+    c->owned = true;
+    return 0;
+}
+static int column_max(const u64 *d, u64 n, u64 *maxv)
+{
+    CK(cudaMemsetAsync(cx().d_scalars + 8, 0, sizeof(u64), cx().stream));
+    if (n > 0) LAUNCH("column_stats", k_column_stats, grid_for(512, n, 4), 256, 0, d, n, cx().d_scalars + 8);
+    CK(cudaMemcpyAsync(cx().h_scalars + 8, cx().d_scalars + 8, sizeof(u64), cudaMemcpyDeviceToHost, cx().stream));
+    CK(cudaStreamSynchronize(cx().stream));
+    *maxv = cx().h_scalars[8];
+    return 0;
+}
+static void install_column(u32 rel, u32 col, const Column &c)
+{
+    std::lock_guard<std::mutex> lk(G.mu);
+    G.cols[col_key(rel, col)] = c;
 }
 
-static int register_column(u32 rel, u32 col, const u64 *d, u64 n, bool owned)
+// ---- host -> device copies --------------------------------------------------------
+// A relation file is mmap'ed pageable memory: a plain cudaMemcpy goes through the driver's
+// single bounce buffer (~11 GB/s measured on the B200 box).  Large copies are staged by a
+// small pool of threads through pinned chunks instead (8 threads x 2 x 8 MB: 40-45 GB/s
+// measured, tools/probes/ipc_probe.cu); pinned sources and small copies go straight down.
+namespace stager {
+constexpr size_t kChunk = 8u << 20;
+constexpr int kThreads = 8;
+struct Pool {
+    char *pin = nullptr;
+    cudaStream_t st[kThreads];
+    cudaEvent_t ev[kThreads * 2];
+    bool ok = false;
+};
+static Pool g_pool;
+static std::mutex g_pool_mu;
+static int ensure()
 {
-    CK(cudaMemsetAsync(g.d_scalars + 8, 0, sizeof(u64), g.stream));
-    if (n > 0) LAUNCH("column_stats", k_column_stats, grid_for(512, n, 4), 256, 0, d, n, g.d_scalars + 8);
-    CK(cudaMemcpyAsync(g.h_scalars + 8, g.d_scalars + 8, sizeof(u64), cudaMemcpyDeviceToHost, g.stream));
-    CK(cudaStreamSynchronize(g.stream));
-    Column c;
-    c.d = d;
-    c.n = n;
-    c.maxv = g.h_scalars[8];
-    c.owned = owned;
-    auto it = g.cols.find(col_key(rel, col));
-    if (it != g.cols.end() && it->second.owned && it->second.d != d) cudaFree((void *)it->second.d);
-    g.cols[col_key(rel, col)] = c;
+    if (g_pool.ok) return 0;
+    CK(cudaMallocHost((void **)&g_pool.pin, kChunk * kThreads * 2));
+    for (auto &x : g_pool.st) CK(cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking));
+    for (auto &x : g_pool.ev) CK(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
+    g_pool.ok = true;
+    return 0;
+}
+static void release()
+{
+    if (!g_pool.ok) return;
+    for (auto &x : g_pool.st) cudaStreamDestroy(x);
+    for (auto &x : g_pool.ev) cudaEventDestroy(x);
+    cudaFreeHost(g_pool.pin);
+    g_pool = Pool();
+}
+static int copy(void *dst, const void *src, size_t bytes)
+{
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (ensure() != 0) return -1;
+    const size_t nch = (bytes + kChunk - 1) / kChunk;
+    std::atomic<size_t> next{0};
+    std::atomic<int> bad{0};
+    const int device = G.device;
+    std::vector<std::thread> th;
+    const int nthr = (int)std::min<size_t>(kThreads, nch);
+    for (int t = 0; t < nthr; t++)
+        th.emplace_back([&, t] {
+            cudaSetDevice(device);
+            int flip = 0;
+            size_t c;
+            while ((c = next.fetch_add(1)) < nch) {
+                const int b = t * 2 + flip;
+                flip ^= 1;
+                const size_t off = c * kChunk, len = std::min(kChunk, bytes - off);
+                if (cudaEventSynchronize(g_pool.ev[b]) != cudaSuccess) bad = 1;
+                memcpy(g_pool.pin + (size_t)b * kChunk, (const char *)src + off, len);
+                if (cudaMemcpyAsync((char *)dst + off, g_pool.pin + (size_t)b * kChunk, len, cudaMemcpyHostToDevice,
+                                    g_pool.st[t]) != cudaSuccess)
+                    bad = 1;
+                cudaEventRecord(g_pool.ev[b], g_pool.st[t]);
+            }
+            if (cudaStreamSynchronize(g_pool.st[t]) != cudaSuccess) bad = 1;
+        });
+    for (auto &x : th) x.join();
+    if (bad) {
+        (void)cudaGetLastError();
+        return fail("staged host-to-device copy failed");
+    }
+    return 0;
+}
+} // namespace stager
+
+static int h2d(void *dst, const void *src, u64 bytes)
+{
+    if (bytes == 0) return 0;
+    static int mode = -1; // QCE_STAGED_UPLOAD=0: always the plain copy (for comparison)
+    if (mode < 0) { const char *e = getenv("QCE_STAGED_UPLOAD"); mode = e ? atoi(e) : 1; }
+    bool pageable = false;
+    if (mode && bytes >= (32ull << 20)) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, src) != cudaSuccess) { (void)cudaGetLastError(); pageable = true; }
+        else pageable = at.type == cudaMemoryTypeUnregistered;
+    }
+    if (pageable) return stager::copy(dst, src, bytes);
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, cx().stream));
     return 0;
 }
 
-// A threaded pinned-staging pipeline (4 host threads, 2 x 16 MB pinned buffers and a stream
-// each) was measured here: 0.9-1.0 s for 4.8 GB of page-cache-resident relation files
-// against 0.45-0.55 s for the plain copy below (the driver's own bounce path already reaches
-// 9-10 GB/s; per-column pinned allocations and thread set-up cost more than the overlap gains).
+// map every rank's window of a row-sharded column (collective)
+static int share_window(Column *c, u64 per, bool reused)
+{
+    c->rpr = (u32)per;
+    c->peer_mapped = true;
+    if (!reused) {
+        cudaIpcMemHandle_t mine, all[QCE_MAX_RANKS];
+        CK(cudaIpcGetMemHandle(&mine, c->alloc));
+        if (qcecomm::allgather(&mine, sizeof mine, all) != 0) return fail("%s", qcecomm::st().err);
+        for (u32 q = 0; q < G.world; q++) {
+            if (q == G.rank) { c->vb[q] = (const u64 *)c->alloc - (u64)q * per; continue; }
+            void *p = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&p, all[q], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                (void)cudaGetLastError();
+                qcecomm::abort_all();
+                return fail("cannot map rank %u's column window (%s): no peer access between these GPUs", q, cudaGetErrorString(e));
+            }
+            c->opened.push_back(p);
+            c->vb[q] = (const u64 *)p - (u64)q * per;
+        }
+    }
+    uint64_t m = c->maxv;
+    if (qcecomm::allreduce_max(&m, 1) != 0) return fail("%s", qcecomm::st().err);
+    c->maxv = m;
+    return 0;
+}
+
+// QCE_REPLICATE_BYTES: read once, before the first placement decision (which the host layer
+// takes before the engine is initialised: it forks the ranks first)
+static void placement_env()
+{
+    static bool done = false;
+    if (done) return;
+    done = true;
+    if (const char *rb = getenv("QCE_REPLICATE_BYTES")) G.replicate_bytes = strtoull(rb, nullptr, 10);
+}
+enum { SRC_HOST = 0, SRC_DEVICE = 1 };
+// `src` holds rows [src_begin, src_begin + src_count) of the relation (the whole column when
+// src_count == rows_global)
+static int upload_impl(u32 rel, u32 col, const void *src, int src_kind, u64 src_begin, u64 src_count, u64 rows_global)
+{
+    if (rows_global >= (1ull << 32)) return fail("relation %u has %llu rows; device row ids are 32-bit", rel, (unsigned long long)rows_global);
+    placement_env();
+    const bool have_all = src_begin == 0 && src_count == rows_global;
+    const bool whole = G.world == 1 || (have_all && rows_global * sizeof(u64) <= G.replicate_bytes);
+    u64 begin = 0, count = rows_global, per = rows_global;
+    if (!whole) row_share(rows_global, G.rank, G.world, &begin, &count, &per);
+    if (!whole && !(src_begin <= begin && begin + count <= src_begin + src_count))
+        return fail("rank %u needs rows [%llu, +%llu) of relation %u; the caller supplied [%llu, +%llu)", G.rank,
+                    (unsigned long long)begin, (unsigned long long)count, rel, (unsigned long long)src_begin, (unsigned long long)src_count);
+    Column c;
+    bool reused = false;
+    if (column_buffer(rel, col, (whole ? rows_global : per) * sizeof(u64), &c, &reused) != 0) return -1;
+    const char *from = (const char *)src + (begin - src_begin) * sizeof(u64);
+    if (count) {
+        if (src_kind == SRC_HOST) { if (h2d(c.alloc, from, count * sizeof(u64)) != 0) return -1; }
+        else CK(cudaMemcpyAsync(c.alloc, from, count * sizeof(u64), cudaMemcpyDeviceToDevice, cx().stream));
+    }
+    c.d = (const u64 *)c.alloc - begin; // virtual base: row id r lives at d[r]
+    c.n = rows_global;
+    c.windowed = !whole;
+    c.win_begin = begin;
+    c.win_count = count;
+    if (column_max((const u64 *)c.alloc, count, &c.maxv) != 0) return -1;
+    if (!whole && share_window(&c, per, reused) != 0) return -1;
+    install_column(rel, col, c);
+    return 0;
+}
+
 int qce_upload_column(uint32_t rel, uint32_t col, const uint64_t *host, uint64_t n)
 {
     NEED_INIT();
-    if (n >= (1ull << 32)) return fail("relation %u has %llu rows; device row ids are 32-bit", rel, (unsigned long long)n);
-    u64 *d = reusable_buffer(rel, col, n);
-    if (!d) CK(cudaMalloc((void **)&d, (n ? n : 1) * sizeof(u64)));
-    if (n) CK(cudaMemcpyAsync(d, host, n * sizeof(u64), cudaMemcpyHostToDevice, g.stream));
-    return register_column(rel, col, d, n, true);
+    return upload_impl(rel, col, host, SRC_HOST, 0, n, n);
 }
 int qce_upload_column_device(uint32_t rel, uint32_t col, const void *dev, uint64_t n)
 {
     NEED_INIT();
-    if (n >= (1ull << 32)) return fail("relation %u has %llu rows; device row ids are 32-bit", rel, (unsigned long long)n);
-    u64 *d = reusable_buffer(rel, col, n);
-    if (!d) CK(cudaMalloc((void **)&d, (n ? n : 1) * sizeof(u64)));
-    if (n) CK(cudaMemcpyAsync(d, dev, n * sizeof(u64), cudaMemcpyDeviceToDevice, g.stream));
-    return register_column(rel, col, d, n, true);
+    return upload_impl(rel, col, dev, SRC_DEVICE, 0, n, n);
+}
+/* The caller holds only rows [row_begin, row_begin + row_count) -- its rank's share of a
+ * row-sharded relation (qce_row_share) -- in host or device memory. */
+int qce_upload_column_window(uint32_t rel, uint32_t col, const uint64_t *host, uint64_t row_begin, uint64_t row_count,
+                             uint64_t rows_global)
+{
+    NEED_INIT();
+    return upload_impl(rel, col, host, SRC_HOST, row_begin, row_count, rows_global);
+}
+int qce_upload_column_window_device(uint32_t rel, uint32_t col, const void *dev, uint64_t row_begin, uint64_t row_count,
+                                    uint64_t rows_global)
+{
+    NEED_INIT();
+    return upload_impl(rel, col, dev, SRC_DEVICE, row_begin, row_count, rows_global);
+}
+int qce_row_share(uint64_t rows_global, uint32_t rank, uint32_t world, uint64_t *row_begin, uint64_t *row_count)
+{
+    if (!row_begin || !row_count || world == 0 || rank >= world) return fail("bad argument");
+    u64 b, c;
+    row_share(rows_global, rank, world, &b, &c);
+    *row_begin = b;
+    *row_count = c;
+    return 0;
+}
+int qce_column_would_be_whole(uint64_t rows)
+{
+    placement_env();
+    return (G.world == 1 || rows * sizeof(u64) <= G.replicate_bytes) ? 1 : 0;
+}
+int qce_set_replicate_bytes(uint64_t bytes)
+{
+    placement_env();
+    G.replicate_bytes = bytes;
+    return 0;
+}
+/* 1: every rank holds the whole column (a query over such columns only can run on one rank
+ * alone); 0: row-sharded. */
+int qce_column_is_whole(uint32_t rel, uint32_t col)
+{
+    const Column *c;
+    if (get_column(rel, col, &c) != 0) return -1;
+    return c->windowed ? 0 : 1;
 }
 int qce_adopt_column_device(uint32_t rel, uint32_t col, const void *dev, uint64_t n)
 {
     NEED_INIT();
     if (n >= (1ull << 32)) return fail("relation %u has %llu rows; device row ids are 32-bit", rel, (unsigned long long)n);
     if (((uintptr_t)dev & 15) != 0) return fail("adopted column must be 16-byte aligned");
-    return register_column(rel, col, (const u64 *)dev, n, false);
+    if (G.world > 1) return fail("adopted buffers cannot be shared between ranks: upload the column instead");
+    Column c;
+    bool reused;
+    {
+        std::lock_guard<std::mutex> lk(G.mu);
+        auto it = G.cols.find(col_key(rel, col));
+        if (it != G.cols.end()) { release_column(it->second); G.cols.erase(it); }
+    }
+    (void)reused;
+    c.d = (const u64 *)dev;
+    c.n = n;
+    if (column_max(c.d, n, &c.maxv) != 0) return -1;
+    install_column(rel, col, c);
+    return 0;
 }
 int qce_adopt_column_window(uint32_t rel, uint32_t col, const void *dev, uint64_t row_begin, uint64_t row_count,
                             uint64_t rows_global, uint64_t max_value_global)
@@ -1033,24 +1511,24 @@ int qce_adopt_column_window(uint32_t rel, uint32_t col, const void *dev, uint64_
     c.d = (const u64 *)dev - row_begin; // virtual base: row id r of the window lives at c.d[r]
     c.n = rows_global;
     c.maxv = max_value_global;
-    c.owned = false;
     c.windowed = true;
     c.win_begin = row_begin;
     c.win_count = row_count;
-    auto it = g.cols.find(col_key(rel, col));
-    if (it != g.cols.end() && it->second.owned) cudaFree((void *)it->second.d);
-    g.cols[col_key(rel, col)] = c;
+    {
+        std::lock_guard<std::mutex> lk(G.mu);
+        auto it = G.cols.find(col_key(rel, col));
+        if (it != G.cols.end()) { release_column(it->second); G.cols.erase(it); }
+    }
+    install_column(rel, col, c);
     return 0;
 }
 int qce_column_max_device(const void *dev, uint64_t n, uint64_t *max_value)
 {
     NEED_INIT();
     if (!max_value) return fail("null argument");
-    CK(cudaMemsetAsync(g.d_scalars + 8, 0, sizeof(u64), g.stream));
-    if (n > 0) LAUNCH("column_stats", k_column_stats, grid_for(512, n, 4), 256, 0, (const u64 *)dev, n, g.d_scalars + 8);
-    CK(cudaMemcpyAsync(g.h_scalars + 8, g.d_scalars + 8, sizeof(u64), cudaMemcpyDeviceToHost, g.stream));
-    CK(cudaStreamSynchronize(g.stream));
-    *max_value = g.h_scalars[8];
+    u64 m = 0;
+    if (column_max((const u64 *)dev, n, &m) != 0) return -1;
+    *max_value = m;
     return 0;
 }
 int qce_column_info(uint32_t rel, uint32_t col, uint64_t *n, uint64_t *max_value)
@@ -1064,11 +1542,20 @@ int qce_column_info(uint32_t rel, uint32_t col, uint64_t *n, uint64_t *max_value
 }
 int qce_drop_relations(void)
 {
-    if (!g.inited) return 0;
-    cudaStreamSynchronize(g.stream);
-    for (auto &kv : g.cols)
-        if (kv.second.owned) cudaFree((void *)kv.second.d);
-    g.cols.clear();
+    if (!G.inited) return 0;
+    cudaDeviceSynchronize(); // every context's stream
+    std::lock_guard<std::mutex> lk(G.mu);
+    // with several ranks this is a collective: nobody frees a window a peer still maps
+    bool mapped = false;
+    for (auto &kv : G.cols) {
+        Column &c = kv.second;
+        mapped = mapped || c.peer_mapped;
+        for (void *p : c.opened) cudaIpcCloseMemHandle(p);
+        c.opened.clear();
+    }
+    if (G.world > 1 && mapped && qcecomm::st().h && qcecomm::barrier() != 0) return fail("%s", qcecomm::st().err);
+    for (auto &kv : G.cols) release_column(kv.second);
+    G.cols.clear();
     return 0;
 }
 
@@ -1108,6 +1595,7 @@ static int filter_scan_window(uint32_t rel, uint32_t col, char op, uint64_t c, u
 int qce_filter_scan(uint32_t rel, uint32_t col, char op, uint64_t c, qce_rowids **out)
 {
     NEED_INIT();
+    if (sharded()) return sh_filter_scan(rel, col, op, c, out);
     return filter_scan_window(rel, col, op, c, 0, 0, true, out);
 }
 int qce_filter_scan_range(uint32_t rel, uint32_t col, char op, uint64_t c, uint64_t row_begin, uint64_t row_count,
@@ -1123,6 +1611,7 @@ int qce_filter_refine(qce_rowids *ids, uint32_t rel, uint32_t col, char op, uint
     const Column *cl;
     int code;
     if (!ids) return fail("null row-id column");
+    if (sharded()) return sh_filter_refine(ids, rel, col, op, c, survivors);
     if (get_column(rel, col, &cl) != 0 || op_code(op, &code) != 0) return -1;
     const u64 n = ids->n;
     if (n == 0) { if (survivors) *survivors = 0; return 0; }
@@ -1130,11 +1619,11 @@ int qce_filter_refine(qce_rowids *ids, uint32_t rel, uint32_t col, char op, uint
     u32 *mask = nullptr, *tile_count = nullptr;
     if (dalloc(&mask, ntiles * QCE_FWORDS) || dalloc(&tile_count, ntiles)) return -1;
     if (code == QCE_OP_EQ)
-        LAUNCH("filter_refine", (k_refine_mask<QCE_OP_EQ>), (int)ntiles, QCE_FTHREADS, 0, ids->d, n, cl->d, c, mask, tile_count);
+        LAUNCH("filter_refine", (k_refine_mask<QCE_OP_EQ>), (int)ntiles, QCE_FTHREADS, 0, ids->d, n, ref_of(cl), c, mask, tile_count);
     else if (code == QCE_OP_GT)
-        LAUNCH("filter_refine", (k_refine_mask<QCE_OP_GT>), (int)ntiles, QCE_FTHREADS, 0, ids->d, n, cl->d, c, mask, tile_count);
+        LAUNCH("filter_refine", (k_refine_mask<QCE_OP_GT>), (int)ntiles, QCE_FTHREADS, 0, ids->d, n, ref_of(cl), c, mask, tile_count);
     else
-        LAUNCH("filter_refine", (k_refine_mask<QCE_OP_LT>), (int)ntiles, QCE_FTHREADS, 0, ids->d, n, cl->d, c, mask, tile_count);
+        LAUNCH("filter_refine", (k_refine_mask<QCE_OP_LT>), (int)ntiles, QCE_FTHREADS, 0, ids->d, n, ref_of(cl), c, mask, tile_count);
     qce_rowids *kept = nullptr;
     int rc = compact_from_mask(QCE_LAYOUT_NATURAL, QCE_EMIT_SRC, mask, tile_count, ntiles, ids->d, nullptr,
                                ids->id_bound, 0, &kept, nullptr);
@@ -1176,7 +1665,7 @@ static int build_tuples(const Column *cl, const qce_rowids *ids, qce_tuples **ou
     if (t->wide && dalloc(&t->ids, n) != 0) { delete t; return -1; }
     if (n > 0) {
         if (t->wide)
-            LAUNCH("build_tuples", k_build_wide, grid_for(256, n), 256, 0, ids ? cl->d : cl->d + begin,
+            LAUNCH("build_tuples", k_build_wide, grid_for(256, n), 256, 0, ref_of(cl),
                    ids ? ids->d : nullptr, n, t->a, t->ids, (u32)begin);
         else {
             // large packed runs: the top-8-bit key histogram rides along (MSD level A / exchange splitters)
@@ -1184,13 +1673,13 @@ static int build_tuples(const Column *cl, const qce_rowids *ids, qce_tuples **ou
             const int hshift = t->key_bits - 8;
             if (hist) {
                 if (dalloc(&t->hist256, QCE_RADIX_BINS) != 0) { delete t; return -1; }
-                CK(cudaMemsetAsync(t->hist256, 0, QCE_RADIX_BINS * sizeof(u32), g.stream));
+                CK(cudaMemsetAsync(t->hist256, 0, QCE_RADIX_BINS * sizeof(u32), cx().stream));
                 t->hist_key_bits = t->key_bits;
             }
             if (ids && hist)
-                LAUNCH("build_tuples", k_build_packed_ids<true>, grid_for(1024, n), 256, 0, cl->d, ids->d, n, t->a, hshift, t->hist256);
+                LAUNCH("build_tuples", k_build_packed_ids<true>, grid_for(1024, n), 256, 0, ref_of(cl), ids->d, n, t->a, hshift, t->hist256);
             else if (ids)
-                LAUNCH("build_tuples", k_build_packed_ids<false>, grid_for(1024, n), 256, 0, cl->d, ids->d, n, t->a, 0, (u32 *)nullptr);
+                LAUNCH("build_tuples", k_build_packed_ids<false>, grid_for(1024, n), 256, 0, ref_of(cl), ids->d, n, t->a, 0, (u32 *)nullptr);
             else if (hist)
                 LAUNCH("build_tuples", k_build_packed_base<true>, grid_for(512, n), 256, 0, cl->d + begin, n, t->a, begin, hshift, t->hist256);
             else
@@ -1204,8 +1693,30 @@ int qce_build_tuples_base(uint32_t rel, uint32_t col, qce_tuples **out)
 {
     NEED_INIT();
     const Column *cl;
+    if (sharded()) return sh_build_base(rel, col, out);
     if (get_column(rel, col, &cl) != 0) return -1;
-    return build_tuples(cl, nullptr, out);
+    if (G.cache_on) {
+        std::unique_lock<std::mutex> lk(G.mu);
+        auto it = G.run_cache.find(col_key(rel, col));
+        if (it != G.run_cache.end()) {
+            const Global::CachedRun c = it->second;
+            G.cache_hits++;
+            lk.unlock();
+            qce_tuples *t = new qce_tuples();
+            t->a = c.a; t->ids = nullptr; t->n = c.n; t->wide = false; t->key_bits = c.key_bits;
+            t->key_min = c.key_min; t->key_max = c.key_max; t->id_bound = c.id_bound;
+            t->sorted = true; t->borrowed = true; t->src_rel = rel; t->src_col = col; t->whole_base = true;
+            CK(cudaStreamWaitEvent(cx().stream, c.ready, 0)); // sorted on another context's stream
+            *out = t;
+            return 0;
+        }
+        G.cache_misses++;
+    }
+    if (build_tuples(cl, nullptr, out) != 0) return -1;
+    (*out)->src_rel = rel;
+    (*out)->src_col = col;
+    (*out)->whole_base = true;
+    return 0;
 }
 int qce_build_tuples_base_range(uint32_t rel, uint32_t col, uint64_t row_begin, uint64_t row_count, qce_tuples **out)
 {
@@ -1214,21 +1725,33 @@ int qce_build_tuples_base_range(uint32_t rel, uint32_t col, uint64_t row_begin, 
     if (get_column(rel, col, &cl) != 0) return -1;
     if (row_begin > cl->n || row_count > cl->n - row_begin) return fail("row window outside relation %u", rel);
     if (row_begin & 1) return fail("row window must start on an even row (128-bit loads)");
-    return build_tuples(cl, nullptr, out, row_begin, row_count);
+    if (build_tuples(cl, nullptr, out, row_begin, row_count) != 0) return -1;
+    (*out)->src_rel = rel;
+    (*out)->src_col = col;
+    return 0;
 }
 int qce_build_tuples_rowids(uint32_t rel, uint32_t col, const qce_rowids *ids, qce_tuples **out)
 {
     NEED_INIT();
     const Column *cl;
     if (!ids) return fail("null row-id column");
+    if (sharded()) return sh_build_rowids(rel, col, ids, out);
     if (get_column(rel, col, &cl) != 0) return -1;
-    return build_tuples(cl, ids, out);
+    if (build_tuples(cl, ids, out) != 0) return -1;
+    (*out)->src_rel = rel;
+    (*out)->src_col = col;
+    return 0;
 }
 
 int qce_sort_tuples(qce_tuples *t)
 {
     NEED_INIT();
     if (!t) return fail("null tuple run");
+    if (sharded()) { // deferred: the join first moves every tuple to the rank that owns its key range
+        t->sort_pending = true;
+        return 0;
+    }
+    if (t->borrowed && t->sorted) return 0; // a cached sorted base run
     int rc;
     if (t->wide) {
         RadixShifts rs = shifts_for(0, t->key_bits, 8);
@@ -1240,23 +1763,76 @@ int qce_sort_tuples(qce_tuples *t)
                          bitlen(t->key_max) == t->hist_key_bits ? t->hist_key_bits : -1);
     }
     if (rc == 0) t->sorted = true;
+    if (rc == 0 && G.cache_on && t->whole_base && !t->wide && !t->borrowed && t->n >= 1024) {
+        // hand the run to the batch's cache; this handle (and later ones) borrow it
+        std::lock_guard<std::mutex> lk(G.mu);
+        const u64 bytes = t->n * sizeof(u64);
+        if (!G.run_cache.count(col_key(t->src_rel, t->src_col)) && G.cache_bytes + bytes <= G.cache_budget) {
+            Global::CachedRun c{t->a, t->n, t->key_bits, t->key_min, t->key_max, t->id_bound, nullptr, &cx().arena};
+            if (cudaEventCreateWithFlags(&c.ready, cudaEventDisableTiming) == cudaSuccess) {
+                cudaEventRecord(c.ready, cx().stream);
+                G.run_cache[col_key(t->src_rel, t->src_col)] = c;
+                G.cache_bytes += bytes;
+                t->borrowed = true;
+            } else (void)cudaGetLastError();
+        }
+    }
     return rc;
+}
+
+/* A batch = one execute_queries call: sorted base runs are kept between its queries and
+ * dropped at its end (nothing survives into the next batch). */
+int qce_batch_begin(void)
+{
+    NEED_INIT();
+    static int on = -1; // QCE_RUN_CACHE=0 disables
+    if (on < 0) { const char *e = getenv("QCE_RUN_CACHE"); on = e ? atoi(e) : 1; }
+    if (!on) return 0;
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    std::lock_guard<std::mutex> lk(G.mu);
+    G.cache_on = true;
+    G.cache_budget = total_b / 4;
+    return 0;
+}
+int qce_batch_end(void)
+{
+    if (!G.inited) return 0;
+    std::lock_guard<std::mutex> lk(G.mu);
+    G.cache_on = false;
+    if (!G.run_cache.empty()) {
+        cudaDeviceSynchronize(); // every context's stream: nobody reads the runs any more
+        for (auto &kv : G.run_cache) {
+            kv.second.owner->free(kv.second.a);
+            cudaEventDestroy(kv.second.ready);
+        }
+        G.run_cache.clear();
+    }
+    G.cache_bytes = 0;
+    return 0;
+}
+int qce_batch_cache_stats(uint64_t *hits, uint64_t *misses)
+{
+    if (hits) *hits = G.cache_hits;
+    if (misses) *misses = G.cache_misses;
+    return 0;
 }
 
 int qce_tuples_is_sorted(const qce_tuples *t, int *sorted)
 {
     NEED_INIT();
     if (!t || !sorted) return fail("null argument");
+    if (sharded()) return sh_is_sorted(t, sorted);
     if (t->n < 2) { *sorted = 1; return 0; }
-    u32 *flag = (u32 *)(g.d_scalars + 9);
-    CK(cudaMemsetAsync(flag, 0, sizeof(u64), g.stream));
+    u32 *flag = (u32 *)(cx().d_scalars + 9);
+    CK(cudaMemsetAsync(flag, 0, sizeof(u64), cx().stream));
     if (t->wide)
         LAUNCH("is_sorted", (k_is_unsorted<true>), grid_for(256, t->n), 256, 0, view_of(t), t->n, flag);
     else
         LAUNCH("is_sorted", (k_is_unsorted<false>), grid_for(256, t->n), 256, 0, view_of(t), t->n, flag);
-    CK(cudaMemcpyAsync(g.h_scalars + 9, g.d_scalars + 9, sizeof(u64), cudaMemcpyDeviceToHost, g.stream));
-    CK(cudaStreamSynchronize(g.stream));
-    *sorted = (g.h_scalars[9] & 0xffffffffu) ? 0 : 1;
+    CK(cudaMemcpyAsync(cx().h_scalars + 9, cx().d_scalars + 9, sizeof(u64), cudaMemcpyDeviceToHost, cx().stream));
+    CK(cudaStreamSynchronize(cx().stream));
+    *sorted = (cx().h_scalars[9] & 0xffffffffu) ? 0 : 1;
     return 0;
 }
 
@@ -1266,6 +1842,7 @@ int qce_merge_join(const qce_tuples *R, const qce_tuples *S, qce_rowids **outR, 
 {
     NEED_INIT();
     if (!R || !S || !outR || !outS) return fail("null argument");
+    if (sharded()) return sh_merge_join(R, S, outR, outS, distinctR, distinctS, false);
     if (merge_join_any(R, S, true, true, outR, outS) != 0) return -1;
     if (distinctR || distinctS) {
         qce_rowids *dr = nullptr, *ds = nullptr;
@@ -1280,6 +1857,7 @@ int qce_merge_join_walk(const qce_tuples *R, const qce_tuples *S, qce_rowids **o
 {
     NEED_INIT();
     if (!R || !S || !outR || !outS) return fail("null argument");
+    if (sharded()) return sh_merge_join(R, S, outR, outS, nullptr, nullptr, true);
     return merge_join_any(R, S, true, true, outR, outS, true);
 }
 
@@ -1289,36 +1867,18 @@ int qce_distinct_pairs(const qce_rowids *pairsR, const qce_rowids *pairsS, qce_r
     NEED_INIT();
     if (!pairsR || !pairsS || !distinctR || !distinctS) return fail("null argument");
     if (pairsR->n != pairsS->n) return fail("pair columns differ in length");
+    if (sharded()) return sh_distinct_pairs(pairsR, pairsS, distinctR, distinctS);
     return distinct_pairs(pairsR, pairsS, distinctR, distinctS);
 }
 
-static int scan_join_impl(const Column *cr, const qce_rowids *idsR, const Column *cs, const qce_rowids *idsS,
-                          qce_rowids **outR, qce_rowids **outS)
-{
-    const u64 nr = idsR ? idsR->n : cr->n, ns = idsS ? idsS->n : cs->n;
-    const u64 n = nr < ns ? nr : ns;
-    if (n == 0) {
-        if (new_rowids(0, (u32)cr->n, outR) != 0) return -1;
-        return new_rowids(0, (u32)cs->n, outS);
-    }
-    const u64 ntiles = ceil_div(n, QCE_FTILE);
-    u32 *mask = nullptr, *tile_count = nullptr;
-    if (dalloc(&mask, ntiles * QCE_FWORDS) || dalloc(&tile_count, ntiles)) return -1;
-    LAUNCH("scan_join", k_scanjoin_mask, (int)ntiles, QCE_FTHREADS, 0, idsR ? idsR->d : nullptr, cr->d,
-           idsS ? idsS->d : nullptr, cs->d, n, mask, tile_count);
-    int rc = compact_from_mask(QCE_LAYOUT_NATURAL, QCE_EMIT_SRC2, mask, tile_count, ntiles,
-                               idsR ? idsR->d : nullptr, idsS ? idsS->d : nullptr, (u32)cr->n, (u32)cs->n, outR, outS);
-    dfree(mask);
-    dfree(tile_count);
-    return rc;
-}
 int qce_scan_join(uint32_t relR, uint32_t colR, const qce_rowids *idsR, uint32_t relS, uint32_t colS,
                   const qce_rowids *idsS, qce_rowids **outR, qce_rowids **outS)
 {
     NEED_INIT();
     const Column *cr, *cs;
     if (!idsR || !idsS || !outR || !outS) return fail("null argument");
-    if (get_column(relR, colR, &cr) != 0 || get_column(relS, colS, &cs) != 0) return -1;
+    if (get_column(relR, colR, &cr) != 0 || get_column(relS, colS, &cs) != 0) { if (sharded()) qcecomm::abort_all(); return -1; }
+    if (sharded()) return sh_scan_join(cr, idsR, cs, idsS, outR, outS);
     return scan_join_impl(cr, idsR, cs, idsS, outR, outS);
 }
 int qce_scan_join_base(uint32_t relR, uint32_t colR, uint32_t relS, uint32_t colS, qce_rowids **outR,
@@ -1327,7 +1887,8 @@ int qce_scan_join_base(uint32_t relR, uint32_t colR, uint32_t relS, uint32_t col
     NEED_INIT();
     const Column *cr, *cs;
     if (!outR || !outS) return fail("null argument");
-    if (get_column(relR, colR, &cr) != 0 || get_column(relS, colS, &cs) != 0) return -1;
+    if (get_column(relR, colR, &cr) != 0 || get_column(relS, colS, &cs) != 0) { if (sharded()) qcecomm::abort_all(); return -1; }
+    if (sharded()) return sh_scan_join_base(cr, cs, outR, outS);
     return scan_join_impl(cr, nullptr, cs, nullptr, outR, outS);
 }
 
@@ -1335,6 +1896,7 @@ int qce_rejoin(const qce_rowids *driver, const qce_rowids *last, const qce_rowid
 {
     NEED_INIT();
     if (!driver || !last || !edit || !out) return fail("null argument");
+    if (sharded()) return sh_rejoin(driver, last, edit, out);
     if (edit->n < last->n)
         return fail("bystander column has %llu row ids but its entity's joined column has %llu "
                     "(the reference reads past the array here, src/join.c:433)",
@@ -1361,6 +1923,7 @@ int qce_checksum(const qce_rowids *ids, uint32_t rel, const uint32_t *cols, uint
     if (!ids || !cols || !sums) return fail("null argument");
     if (ncols == 0) return 0;
     if (ncols > 8) return fail("at most 8 columns per checksum call");
+    if (sharded()) return sh_checksum(ids, rel, cols, ncols, sums);
     ChecksumCols cc;
     u64 col_rows = 0;
     for (u32 k = 0; k < 8; k++) cc.col[k] = nullptr;
@@ -1370,7 +1933,7 @@ int qce_checksum(const qce_rowids *ids, uint32_t rel, const uint32_t *cols, uint
         cc.col[k] = cl->d;
         col_rows = cl->n;
     }
-    CK(cudaMemsetAsync(g.d_scalars, 0, 8 * sizeof(u64), g.stream));
+    CK(cudaMemsetAsync(cx().d_scalars, 0, 8 * sizeof(u64), cx().stream));
     if (ids->n > 0) {
         // A large row-id column in arbitrary order makes every gather a DRAM miss
         // that moves ~77 B for 8 useful bytes (ncu, profiles/).  The sum does not
@@ -1385,24 +1948,26 @@ int qce_checksum(const qce_rowids *ids, uint32_t rel, const uint32_t *cols, uint
         }
         const int grid = grid_for(1024, ids->n);
         switch (ncols) {
-        case 1: LAUNCH("checksum", (k_checksum<1>), grid, 256, 0, src, ids->n, cc, g.d_scalars); break;
-        case 2: LAUNCH("checksum", (k_checksum<2>), grid, 256, 0, src, ids->n, cc, g.d_scalars); break;
-        case 3: LAUNCH("checksum", (k_checksum<3>), grid, 256, 0, src, ids->n, cc, g.d_scalars); break;
-        case 4: LAUNCH("checksum", (k_checksum<4>), grid, 256, 0, src, ids->n, cc, g.d_scalars); break;
-        case 5: LAUNCH("checksum", (k_checksum<5>), grid, 256, 0, src, ids->n, cc, g.d_scalars); break;
-        case 6: LAUNCH("checksum", (k_checksum<6>), grid, 256, 0, src, ids->n, cc, g.d_scalars); break;
-        case 7: LAUNCH("checksum", (k_checksum<7>), grid, 256, 0, src, ids->n, cc, g.d_scalars); break;
-        default: LAUNCH("checksum", (k_checksum<8>), grid, 256, 0, src, ids->n, cc, g.d_scalars); break;
+        case 1: LAUNCH("checksum", (k_checksum<1>), grid, 256, 0, src, ids->n, cc, cx().d_scalars); break;
+        case 2: LAUNCH("checksum", (k_checksum<2>), grid, 256, 0, src, ids->n, cc, cx().d_scalars); break;
+        case 3: LAUNCH("checksum", (k_checksum<3>), grid, 256, 0, src, ids->n, cc, cx().d_scalars); break;
+        case 4: LAUNCH("checksum", (k_checksum<4>), grid, 256, 0, src, ids->n, cc, cx().d_scalars); break;
+        case 5: LAUNCH("checksum", (k_checksum<5>), grid, 256, 0, src, ids->n, cc, cx().d_scalars); break;
+        case 6: LAUNCH("checksum", (k_checksum<6>), grid, 256, 0, src, ids->n, cc, cx().d_scalars); break;
+        case 7: LAUNCH("checksum", (k_checksum<7>), grid, 256, 0, src, ids->n, cc, cx().d_scalars); break;
+        default: LAUNCH("checksum", (k_checksum<8>), grid, 256, 0, src, ids->n, cc, cx().d_scalars); break;
         }
         dfree(bucketed);
     }
     if (read_scalars((int)ncols) != 0) return -1;
-    for (u32 k = 0; k < ncols; k++) sums[k] = g.h_scalars[k];
+    for (u32 k = 0; k < ncols; k++) sums[k] = cx().h_scalars[k];
     return 0;
 }
 
 // ---------------------------------------------------------------- handles
-uint64_t qce_rowids_count(const qce_rowids *ids) { return ids ? ids->n : 0; }
+uint64_t qce_rowids_count(const qce_rowids *ids) { return ids ? ids->n + ids->n_others : 0; }
+/* this rank's share only (== qce_rowids_count on one GPU) */
+uint64_t qce_rowids_count_local(const qce_rowids *ids) { return ids ? ids->n : 0; }
 
 int qce_rowids_from_host(const uint64_t *host, uint64_t n, qce_rowids **out)
 {
@@ -1415,8 +1980,8 @@ int qce_rowids_from_host(const uint64_t *host, uint64_t n, qce_rowids **out)
         if (tmp[i] > mx) mx = tmp[i];
     }
     if (new_rowids(n, n ? (mx == 0xffffffffu ? 0 : mx + 1) : 0, out) != 0) return -1;
-    if (n) CK(cudaMemcpyAsync((*out)->d, tmp.data(), n * sizeof(u32), cudaMemcpyHostToDevice, g.stream));
-    CK(cudaStreamSynchronize(g.stream));
+    if (n) CK(cudaMemcpyAsync((*out)->d, tmp.data(), n * sizeof(u32), cudaMemcpyHostToDevice, cx().stream));
+    CK(cudaStreamSynchronize(cx().stream));
     return 0;
 }
 int qce_rowids_to_host(const qce_rowids *ids, uint64_t *host)
@@ -1424,8 +1989,8 @@ int qce_rowids_to_host(const qce_rowids *ids, uint64_t *host)
     NEED_INIT();
     if (!ids) return fail("null row-id column");
     std::vector<u32> tmp(ids->n ? ids->n : 1);
-    if (ids->n) CK(cudaMemcpyAsync(tmp.data(), ids->d, ids->n * sizeof(u32), cudaMemcpyDeviceToHost, g.stream));
-    CK(cudaStreamSynchronize(g.stream));
+    if (ids->n) CK(cudaMemcpyAsync(tmp.data(), ids->d, ids->n * sizeof(u32), cudaMemcpyDeviceToHost, cx().stream));
+    CK(cudaStreamSynchronize(cx().stream));
     for (u64 i = 0; i < ids->n; i++) host[i] = tmp[i];
     return 0;
 }
@@ -1434,17 +1999,19 @@ int qce_rowids_clone(const qce_rowids *ids, qce_rowids **out)
     NEED_INIT();
     if (!ids) return fail("null row-id column");
     if (new_rowids(ids->n, ids->id_bound, out) != 0) return -1;
-    if (ids->n) CK(cudaMemcpyAsync((*out)->d, ids->d, ids->n * sizeof(u32), cudaMemcpyDeviceToDevice, g.stream));
+    if (ids->n) CK(cudaMemcpyAsync((*out)->d, ids->d, ids->n * sizeof(u32), cudaMemcpyDeviceToDevice, cx().stream));
+    (*out)->n_others = ids->n_others;
+    (*out)->dist = ids->dist;
     return 0;
 }
 void qce_rowids_free(qce_rowids *ids)
 {
     if (!ids) return;
-    if (g.inited) dfree(ids->d);
+    if (G.inited) dfree(ids->d);
     delete ids;
 }
 
-uint64_t qce_tuples_count(const qce_tuples *t) { return t ? t->n : 0; }
+uint64_t qce_tuples_count(const qce_tuples *t) { return t ? t->n + t->n_others : 0; }
 
 int qce_tuples_from_host(const uint64_t *keys, const uint64_t *rowids, uint64_t n, qce_tuples **out)
 {
@@ -1470,15 +2037,15 @@ int qce_tuples_from_host(const uint64_t *keys, const uint64_t *rowids, uint64_t 
         std::vector<u32> tmp(n ? n : 1);
         for (u64 i = 0; i < n; i++) tmp[i] = (u32)rowids[i];
         if (n) {
-            CK(cudaMemcpyAsync(t->a, keys, n * sizeof(u64), cudaMemcpyHostToDevice, g.stream));
-            CK(cudaMemcpyAsync(t->ids, tmp.data(), n * sizeof(u32), cudaMemcpyHostToDevice, g.stream));
+            CK(cudaMemcpyAsync(t->a, keys, n * sizeof(u64), cudaMemcpyHostToDevice, cx().stream));
+            CK(cudaMemcpyAsync(t->ids, tmp.data(), n * sizeof(u32), cudaMemcpyHostToDevice, cx().stream));
         }
-        CK(cudaStreamSynchronize(g.stream));
+        CK(cudaStreamSynchronize(cx().stream));
     } else {
         std::vector<u64> tmp(n ? n : 1);
         for (u64 i = 0; i < n; i++) tmp[i] = (keys[i] << 32) | rowids[i];
-        if (n) CK(cudaMemcpyAsync(t->a, tmp.data(), n * sizeof(u64), cudaMemcpyHostToDevice, g.stream));
-        CK(cudaStreamSynchronize(g.stream));
+        if (n) CK(cudaMemcpyAsync(t->a, tmp.data(), n * sizeof(u64), cudaMemcpyHostToDevice, cx().stream));
+        CK(cudaStreamSynchronize(cx().stream));
     }
     *out = t;
     return 0;
@@ -1491,15 +2058,15 @@ int qce_tuples_to_host(const qce_tuples *t, uint64_t *keys, uint64_t *rowids)
     if (t->wide) {
         std::vector<u32> tmp(n ? n : 1);
         if (n) {
-            CK(cudaMemcpyAsync(keys, t->a, n * sizeof(u64), cudaMemcpyDeviceToHost, g.stream));
-            CK(cudaMemcpyAsync(tmp.data(), t->ids, n * sizeof(u32), cudaMemcpyDeviceToHost, g.stream));
+            CK(cudaMemcpyAsync(keys, t->a, n * sizeof(u64), cudaMemcpyDeviceToHost, cx().stream));
+            CK(cudaMemcpyAsync(tmp.data(), t->ids, n * sizeof(u32), cudaMemcpyDeviceToHost, cx().stream));
         }
-        CK(cudaStreamSynchronize(g.stream));
+        CK(cudaStreamSynchronize(cx().stream));
         for (u64 i = 0; i < n; i++) rowids[i] = tmp[i];
     } else {
         std::vector<u64> tmp(n ? n : 1);
-        if (n) CK(cudaMemcpyAsync(tmp.data(), t->a, n * sizeof(u64), cudaMemcpyDeviceToHost, g.stream));
-        CK(cudaStreamSynchronize(g.stream));
+        if (n) CK(cudaMemcpyAsync(tmp.data(), t->a, n * sizeof(u64), cudaMemcpyDeviceToHost, cx().stream));
+        CK(cudaStreamSynchronize(cx().stream));
         for (u64 i = 0; i < n; i++) { keys[i] = tmp[i] >> 32; rowids[i] = tmp[i] & 0xffffffffu; }
     }
     return 0;
@@ -1507,7 +2074,7 @@ int qce_tuples_to_host(const qce_tuples *t, uint64_t *keys, uint64_t *rowids)
 void qce_tuples_free(qce_tuples *t)
 {
     if (!t) return;
-    if (g.inited) { dfree(t->a); dfree(t->ids); dfree(t->hist256); }
+    if (G.inited) { if (!t->borrowed) dfree(t->a); dfree(t->ids); dfree(t->hist256); }
     delete t;
 }
 
@@ -1522,7 +2089,7 @@ int qce_key_histogram(const qce_tuples *t, uint32_t key_bits, uint64_t *hist)
     if (!mt->hist256 && dalloc(&mt->hist256, QCE_RADIX_BINS) != 0) return -1;
     u32 *gh = mt->hist256;
     if (!have) {
-        CK(cudaMemsetAsync(gh, 0, QCE_RADIX_BINS * sizeof(u32), g.stream));
+        CK(cudaMemsetAsync(gh, 0, QCE_RADIX_BINS * sizeof(u32), cx().stream));
         RadixShifts rs;
         rs.npass = 1;
         for (int i = 0; i < QCE_MAX_PASSES; i++) rs.shift[i] = 0;
@@ -1530,8 +2097,8 @@ int qce_key_histogram(const qce_tuples *t, uint32_t key_bits, uint64_t *hist)
         if (t->n) LAUNCH("radix_hist", k_radix_hist, grid_for(1024, t->n, 4), 512, 0, t->a, t->n, rs, 256u, gh);
     }
     std::vector<u32> tmp(QCE_RADIX_BINS);
-    CK(cudaMemcpyAsync(tmp.data(), gh, QCE_RADIX_BINS * sizeof(u32), cudaMemcpyDeviceToHost, g.stream));
-    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaMemcpyAsync(tmp.data(), gh, QCE_RADIX_BINS * sizeof(u32), cudaMemcpyDeviceToHost, cx().stream));
+    CK(cudaStreamSynchronize(cx().stream));
     for (int i = 0; i < QCE_RADIX_BINS; i++) hist[i] = tmp[i];
     mt->hist_key_bits = (int)key_bits;
     mt->hist_host.assign(tmp.begin(), tmp.end());
@@ -1576,14 +2143,14 @@ int qce_partition_tuples(const qce_tuples *t, uint32_t key_bits, const uint64_t 
         for (u32 p = 1; p < 256; p++) offs[p] = offs[p - 1] + parts[p - 1];
         const u32 ntiles = (u32)ceil_div(n, QCE_MSD_TILE);
         const u32 h_lvl0[4] = {0u, ntiles, 0u, (u32)n};
-        CK(cudaMemcpyAsync(lvl0, h_lvl0, sizeof h_lvl0, cudaMemcpyHostToDevice, g.stream));
-        CK(cudaMemcpyAsync(dlut, lut, sizeof lut, cudaMemcpyHostToDevice, g.stream));
-        CK(cudaMemcpyAsync(cursor, offs.data(), QCE_RADIX_BINS * sizeof(u32), cudaMemcpyHostToDevice, g.stream));
+        CK(cudaMemcpyAsync(lvl0, h_lvl0, sizeof h_lvl0, cudaMemcpyHostToDevice, cx().stream));
+        CK(cudaMemcpyAsync(dlut, lut, sizeof lut, cudaMemcpyHostToDevice, cx().stream));
+        CK(cudaMemcpyAsync(cursor, offs.data(), QCE_RADIX_BINS * sizeof(u32), cudaMemcpyHostToDevice, cx().stream));
         // the unstable MSD partition kernel with the destination table as digit: no ranking
         // ballots, no look-back (the order inside a destination does not matter, it is sorted next)
         LAUNCH("exchange_partition", (k_msd_partition<512, 8>), ntiles, 512, 0, (const u64 *)t->a, out, lvl0, lvl0 + 2,
                lvl0 + 3, 1u, 0ull, ds.shift, 256u, cursor, (const u32 *)dlut);
-        CK(cudaStreamSynchronize(g.stream)); // the caller hands *sendbuf to another stream
+        CK(cudaStreamSynchronize(cx().stream)); // the caller hands *sendbuf to another stream
     }
     for (u32 p = 0; p < nparts; p++) counts[p] = parts[p];
     dfree(dlut); dfree(lvl0); dfree(cursor);
@@ -1634,7 +2201,7 @@ static int tuples_from_device(const void *dev_words, uint64_t n, uint32_t key_bi
         if (dalloc(&t->a, n) != 0) { delete t; return -1; }
         // the caller's buffer may live on another stream (torch): order by a full device sync
         CK(cudaDeviceSynchronize());
-        if (n) CK(cudaMemcpyAsync(t->a, dev_words, n * sizeof(u64), cudaMemcpyDeviceToDevice, g.stream));
+        if (n) CK(cudaMemcpyAsync(t->a, dev_words, n * sizeof(u64), cudaMemcpyDeviceToDevice, cx().stream));
     }
     *out = t;
     return 0;
@@ -1648,17 +2215,17 @@ static int tuples_from_device(const void *dev_words, uint64_t n, uint32_t key_bi
 int qce_xwin_create(uint64_t bytes, unsigned char *ipc_handle_out)
 {
     NEED_INIT();
-    if (g.xwin) return fail("exchange window already exists");
+    if (G.xwin) return fail("exchange window already exists");
     if (bytes == 0) return fail("empty exchange window");
     bytes = (bytes + 4095) / 4096 * 4096;
     void *p = nullptr;
     CK(cudaMalloc(&p, bytes));
-    g.xwin = (unsigned char *)p;
-    g.xwin_bytes = bytes;
-    g.xworld = 1;
-    g.xrank = 0;
-    for (int r = 0; r < QCE_MAX_RANKS; r++) g.peers.base[r] = nullptr;
-    g.peers.base[0] = g.xwin;
+    G.xwin = (unsigned char *)p;
+    G.xwin_bytes = bytes;
+    G.xworld = 1;
+    G.xrank = 0;
+    for (int r = 0; r < QCE_MAX_RANKS; r++) G.peers.base[r] = nullptr;
+    G.peers.base[0] = G.xwin;
     if (ipc_handle_out) {
         cudaIpcMemHandle_t h;
         CK(cudaIpcGetMemHandle(&h, p));
@@ -1670,21 +2237,21 @@ int qce_xwin_create(uint64_t bytes, unsigned char *ipc_handle_out)
 int qce_xwin_attach(uint32_t world, uint32_t rank, const unsigned char *handles)
 {
     NEED_INIT();
-    if (!g.xwin) return fail("create the exchange window first");
+    if (!G.xwin) return fail("create the exchange window first");
     if (world < 1 || world > QCE_MAX_RANKS || rank >= world) return fail("world size must be 1..%d", QCE_MAX_RANKS);
     if (world > 1 && !handles) return fail("null argument");
-    for (int r = 0; r < QCE_MAX_RANKS; r++) g.peers.base[r] = nullptr;
+    for (int r = 0; r < QCE_MAX_RANKS; r++) G.peers.base[r] = nullptr;
     for (u32 r = 0; r < world; r++) {
-        if (r == rank) { g.peers.base[r] = g.xwin; continue; }
+        if (r == rank) { G.peers.base[r] = G.xwin; continue; }
         cudaIpcMemHandle_t h;
         memcpy(&h, handles + 64 * (size_t)r, sizeof h);
         void *p = nullptr;
         CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-        g.xopened.push_back(p);
-        g.peers.base[r] = (unsigned char *)p;
+        G.xopened.push_back(p);
+        G.peers.base[r] = (unsigned char *)p;
     }
-    g.xworld = world;
-    g.xrank = rank;
+    G.xworld = world;
+    G.xrank = rank;
     return 0;
 }
 // Single-process testing: present this rank's window as `world` ranks, rank r
@@ -1692,31 +2259,43 @@ int qce_xwin_attach(uint32_t world, uint32_t rank, const unsigned char *handles)
 int qce_xwin_loopback(uint32_t world)
 {
     NEED_INIT();
-    if (!g.xwin) return fail("create the exchange window first");
+    if (!G.xwin) return fail("create the exchange window first");
     if (world < 1 || world > QCE_MAX_RANKS) return fail("world size must be 1..%d", QCE_MAX_RANKS);
-    const u64 per = g.xwin_bytes / world / 4096 * 4096;
-    for (int r = 0; r < QCE_MAX_RANKS; r++) g.peers.base[r] = (u32)r < world ? g.xwin + per * r : nullptr;
-    g.xworld = world;
-    g.xrank = 0;
+    const u64 per = G.xwin_bytes / world / 4096 * 4096;
+    for (int r = 0; r < QCE_MAX_RANKS; r++) G.peers.base[r] = (u32)r < world ? G.xwin + per * r : nullptr;
+    G.xworld = world;
+    G.xrank = 0;
     return 0;
 }
 int qce_xwin_info(uint64_t *bytes, void **local_base)
 {
     NEED_INIT();
-    if (bytes) *bytes = g.xwin_bytes;
-    if (local_base) *local_base = g.xwin;
+    if (bytes) *bytes = G.xwin_bytes;
+    if (local_base) *local_base = G.xwin;
     return 0;
+}
+static void xwin_close_peers()
+{
+    for (void *p : G.xopened) cudaIpcCloseMemHandle(p);
+    G.xopened.clear();
 }
 int qce_xwin_destroy(void)
 {
-    if (!g.inited) return 0;
-    cudaStreamSynchronize(g.stream);
-    for (void *p : g.xopened) cudaIpcCloseMemHandle(p);
-    g.xopened.clear();
-    if (g.xwin) cudaFree(g.xwin);
-    g.xwin = nullptr;
-    g.xwin_bytes = 0;
-    g.xworld = 0;
+    if (!G.inited) return 0;
+    cudaStreamSynchronize(cx().stream);
+    xwin_close_peers();
+    if (G.xwin) cudaFree(G.xwin);
+    G.xwin = nullptr;
+    G.xwin_bytes = 0;
+    G.xworld = 0;
+    return 0;
+}
+/* the ranks' half of a collective re-creation: nobody frees a window a peer still maps */
+int qce_xwin_unmap_peers(void)
+{
+    if (!G.inited) return 0;
+    CK(cudaStreamSynchronize(cx().stream));
+    xwin_close_peers();
     return 0;
 }
 
@@ -1728,9 +2307,9 @@ static int push_scratch(u32 ndigits, const uint64_t *seg_start, const u32 *run_b
     std::vector<unsigned long long> seg(256, 0);
     std::vector<u32> run(256, 0);
     for (u32 d = 0; d < ndigits; d++) { seg[d] = seg_start[d]; run[d] = run_base ? run_base[d] : 0u; }
-    CK(cudaMemcpyAsync(*d_seg, seg.data(), 256 * sizeof(unsigned long long), cudaMemcpyHostToDevice, g.stream));
-    CK(cudaMemcpyAsync(*d_cur, seg.data(), 256 * sizeof(unsigned long long), cudaMemcpyHostToDevice, g.stream));
-    CK(cudaMemcpyAsync(*d_run, run.data(), 256 * sizeof(u32), cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(*d_seg, seg.data(), 256 * sizeof(unsigned long long), cudaMemcpyHostToDevice, cx().stream));
+    CK(cudaMemcpyAsync(*d_cur, seg.data(), 256 * sizeof(unsigned long long), cudaMemcpyHostToDevice, cx().stream));
+    CK(cudaMemcpyAsync(*d_run, run.data(), 256 * sizeof(u32), cudaMemcpyHostToDevice, cx().stream));
     return 0;
 }
 
@@ -1756,9 +2335,9 @@ static int push_tuples_impl(const qce_tuples *t, uint32_t key_bits, const uint64
 {
     NEED_INIT();
     if (!t || !dst_word_offset) return fail("null argument");
-    if (!g.xwin) return fail("no exchange window (qce_xwin_create)");
+    if (!G.xwin) return fail("no exchange window (qce_xwin_create)");
     if (t->wide) return fail("the sharded exchange supports packed (key < 2^32) runs only");
-    if (nparts != g.xworld) return fail("nparts (%u) differs from the attached world size (%u)", nparts, g.xworld);
+    if (nparts != G.xworld) return fail("nparts (%u) differs from the attached world size (%u)", nparts, G.xworld);
     if (key_bits == 0 || key_bits > 32) return fail("packed runs carry keys of 1..32 bits");
     if (t->n >= (1ull << 28)) return fail("push of %llu tuples exceeds the 2^28 per-run limit", (unsigned long long)t->n);
     if (nparts > 1 && !splitters) return fail("null argument");
@@ -1778,7 +2357,7 @@ static int push_tuples_impl(const qce_tuples *t, uint32_t key_bits, const uint64
     unsigned long long *d_seg = nullptr, *d_cur = nullptr;
     u32 *d_run = nullptr, *dlut = nullptr;
     if (push_scratch(nparts, dst_word_offset, dst_run_index, &d_seg, &d_run, &d_cur) != 0 || dalloc(&dlut, 64)) return -1;
-    CK(cudaMemcpyAsync(dlut, lut, sizeof lut, cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(dlut, lut, sizeof lut, cudaMemcpyHostToDevice, cx().stream));
     PushDigit<u64> dg;
     dg.shift = 32 + bin_shift;
     dg.lut = dlut;
@@ -1795,9 +2374,9 @@ static int push_tuples_impl(const qce_tuples *t, uint32_t key_bits, const uint64
         for (u32 r = 0; r < nparts; r++) pc.region[c][r] = col_u32_offset[(size_t)c * nparts + r];
     }
     if (dst_run_index)
-        LAUNCH("push_tuples", (k_push<u64, true, true>), grid, QCE_PUSH_THREADS, 0, (const u64 *)t->a, n, dg, plan, g.peers, dbits, so, pc);
+        LAUNCH("push_tuples", (k_push<u64, true, true>), grid, QCE_PUSH_THREADS, 0, (const u64 *)t->a, n, dg, plan, G.peers, dbits, so, pc);
     else
-        LAUNCH("push_tuples", (k_push<u64, true, false>), grid, QCE_PUSH_THREADS, 0, (const u64 *)t->a, n, dg, plan, g.peers, dbits, so, pc);
+        LAUNCH("push_tuples", (k_push<u64, true, false>), grid, QCE_PUSH_THREADS, 0, (const u64 *)t->a, n, dg, plan, G.peers, dbits, so, pc);
     dfree(d_seg); dfree(d_cur); dfree(d_run); dfree(dlut);
     return 0;
 }
@@ -1806,13 +2385,13 @@ int qce_push_u32_by_slot(const qce_rowids *vals, const qce_rowids *slots, uint32
 {
     NEED_INIT();
     if (!vals || !slots || !dst_u32_offset) return fail("null argument");
-    if (!g.xwin) return fail("no exchange window (qce_xwin_create)");
+    if (!G.xwin) return fail("no exchange window (qce_xwin_create)");
     if (vals->n != slots->n) return fail("column (%llu) and slot (%llu) lengths differ", (unsigned long long)vals->n, (unsigned long long)slots->n);
-    if (nparts != g.xworld) return fail("nparts (%u) differs from the attached world size (%u)", nparts, g.xworld);
+    if (nparts != G.xworld) return fail("nparts (%u) differs from the attached world size (%u)", nparts, G.xworld);
     if (vals->n == 0) return 0;
     SlotRegions reg;
     for (u32 r = 0; r < QCE_MAX_RANKS; r++) reg.region[r] = r < nparts ? dst_u32_offset[r] : 0;
-    LAUNCH("push_by_slot", k_push_u32_by_slot, grid_for(2048, vals->n), 256, 0, vals->d, slots->d, vals->n, reg, g.peers);
+    LAUNCH("push_by_slot", k_push_u32_by_slot, grid_for(2048, vals->n), 256, 0, vals->d, slots->d, vals->n, reg, G.peers);
     return 0;
 }
 
@@ -1836,7 +2415,7 @@ int qce_rowids_bin_histogram(const qce_rowids *ids, uint32_t rows_per_rank, uint
     if (row_bins(rows_per_rank, bin_width, bins_per_rank, nranks, &rb) != 0) return -1;
     u32 *gh = nullptr;
     if (dalloc(&gh, 256) != 0) return -1;
-    CK(cudaMemsetAsync(gh, 0, 256 * sizeof(u32), g.stream));
+    CK(cudaMemsetAsync(gh, 0, 256 * sizeof(u32), cx().stream));
     const u32 nbins = bins_per_rank * nranks;
     const int hgrid = grid_for(4096, ids->n, 4);
     if (ids->n) {
@@ -1847,8 +2426,8 @@ int qce_rowids_bin_histogram(const qce_rowids *ids, uint32_t rows_per_rank, uint
         else LAUNCH("hist_ids", k_hist_u32_div<256>, hgrid, 512, 0, ids->d, ids->n, rb, nbins, gh);
     }
     u32 tmp[256];
-    CK(cudaMemcpyAsync(tmp, gh, sizeof tmp, cudaMemcpyDeviceToHost, g.stream));
-    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaMemcpyAsync(tmp, gh, sizeof tmp, cudaMemcpyDeviceToHost, cx().stream));
+    CK(cudaStreamSynchronize(cx().stream));
     for (u32 b = 0; b < bins_per_rank * nranks; b++) hist[b] = tmp[b];
     dfree(gh);
     return 0;
@@ -1859,10 +2438,10 @@ int qce_push_rowids(const qce_rowids *ids, uint32_t rows_per_rank, uint32_t bin_
 {
     NEED_INIT();
     if (!ids || !bin_u32_offset) return fail("null argument");
-    if (!g.xwin) return fail("no exchange window (qce_xwin_create)");
+    if (!G.xwin) return fail("no exchange window (qce_xwin_create)");
     RowBins rb;
     if (row_bins(rows_per_rank, bin_width, bins_per_rank, nranks, &rb) != 0) return -1;
-    if (nranks != g.xworld) return fail("nranks (%u) differs from the attached world size (%u)", nranks, g.xworld);
+    if (nranks != G.xworld) return fail("nranks (%u) differs from the attached world size (%u)", nranks, G.xworld);
     if (ids->n >= (1ull << 32)) return fail("row-id column too long");
     if (ids->n == 0) return 0;
     const u32 nbins = bins_per_rank * nranks;
@@ -1876,10 +2455,10 @@ int qce_push_rowids(const qce_rowids *ids, uint32_t rows_per_rank, uint32_t bin_
     PushCols nocols;
     memset(&nocols, 0, sizeof nocols);
     if (nbins <= 16)
-        LAUNCH("push_rowids", (k_push<u32, true, false>), grid, QCE_PUSH_THREADS, 0, (const u32 *)ids->d, n, dg, plan, g.peers,
+        LAUNCH("push_rowids", (k_push<u32, true, false>), grid, QCE_PUSH_THREADS, 0, (const u32 *)ids->d, n, dg, plan, G.peers,
                bitlen(nbins - 1), (u32 *)nullptr, nocols);
     else
-        LAUNCH("push_rowids", (k_push<u32, false, false>), grid, QCE_PUSH_THREADS, 0, (const u32 *)ids->d, n, dg, plan, g.peers, 0,
+        LAUNCH("push_rowids", (k_push<u32, false, false>), grid, QCE_PUSH_THREADS, 0, (const u32 *)ids->d, n, dg, plan, G.peers, 0,
                (u32 *)nullptr, nocols);
     dfree(d_seg); dfree(d_cur); dfree(d_run);
     return 0;
@@ -1907,7 +2486,7 @@ int qce_column_gather_u32(uint32_t rel, uint32_t col, const qce_rowids *ids, qce
     if (get_column(rel, col, &cl) != 0) return -1;
     if (cl->maxv >> 32) return fail("column %u.%u holds values >= 2^32: cannot be carried as 4-byte keys", rel, col);
     if (new_rowids(ids->n, 0, out) != 0) return -1;
-    if (ids->n) LAUNCH("gather_col", k_gather_u64_narrow, grid_for(2048, ids->n), 256, 0, cl->d, ids->d, ids->n, (*out)->d);
+    if (ids->n) LAUNCH("gather_col", k_gather_u64_narrow, grid_for(2048, ids->n), 256, 0, ref_of(cl), ids->d, ids->n, (*out)->d);
     return 0;
 }
 int qce_rowids_iota(uint64_t begin, uint64_t count, uint32_t id_bound, qce_rowids **out)
@@ -1946,20 +2525,20 @@ int qce_tuples_from_window(uint64_t word_offset, uint64_t n, uint32_t key_bits, 
                            uint64_t key_hi, qce_tuples **out)
 {
     NEED_INIT();
-    if (!g.xwin) return fail("no exchange window (qce_xwin_create)");
-    if ((word_offset + n) * 8 > g.xwin_bytes) return fail("run [%llu, +%llu) words exceeds the exchange window", (unsigned long long)word_offset, (unsigned long long)n);
+    if (!G.xwin) return fail("no exchange window (qce_xwin_create)");
+    if ((word_offset + n) * 8 > G.xwin_bytes) return fail("run [%llu, +%llu) words exceeds the exchange window", (unsigned long long)word_offset, (unsigned long long)n);
     if (word_offset & 1) return fail("runs in the window start on 16-byte boundaries");
-    return tuples_from_device(g.peers.base[g.xrank] + word_offset * 8, n, key_bits, id_bound, key_lo, key_hi, true, out);
+    return tuples_from_device(G.peers.base[G.xrank] + word_offset * 8, n, key_bits, id_bound, key_lo, key_hi, true, out);
 }
 int qce_rowids_from_window(uint64_t u32_offset, uint64_t n, uint32_t id_min, uint32_t id_bound, int bucketed,
                            qce_rowids **out)
 {
     NEED_INIT();
-    if (!g.xwin) return fail("no exchange window (qce_xwin_create)");
+    if (!G.xwin) return fail("no exchange window (qce_xwin_create)");
     if (!out) return fail("null argument");
-    if ((u32_offset + n) * 4 > g.xwin_bytes) return fail("row-id column exceeds the exchange window");
+    if ((u32_offset + n) * 4 > G.xwin_bytes) return fail("row-id column exceeds the exchange window");
     qce_rowids *r = new qce_rowids();
-    r->d = (u32 *)(g.peers.base[g.xrank] + u32_offset * 4); // not from the arena: freeing the handle leaves it alone
+    r->d = (u32 *)(G.peers.base[G.xrank] + u32_offset * 4); // not from the arena: freeing the handle leaves it alone
     r->n = n;
     r->id_bound = id_bound;
     r->id_min = id_min;
@@ -1985,6 +2564,52 @@ int qce_exchange_plan(const uint64_t *hists, uint32_t world, uint32_t rank, uint
                       uint32_t key_bits, uint64_t *splitters, uint64_t *recv, uint64_t *before, uint64_t *run_off,
                       uint64_t *col_off, uint64_t *window_bytes, uint64_t *sent_tuples)
 {
+    return exchange_plan_impl(hists, world, rank, nsides, ncols, key_bits, nullptr, splitters, recv, before, run_off, col_off,
+                              window_bytes, sent_tuples);
+}
+
+// Row ids routed to the ranks that own the rows: per binding, where this rank's ids of every
+// bin go in the owner's window (bin-major inside an owner, earlier ranks first inside a bin).
+int qce_rowid_push_plan(const uint64_t *hists, uint32_t world, uint32_t rank, uint32_t nbind, uint32_t bins_per_rank,
+                        uint64_t *bin_u32_offset, uint64_t *view_u32_offset, uint64_t *view_count, uint64_t *window_bytes,
+                        uint64_t *sent_ids)
+{
+    if (!hists || !bin_u32_offset || !view_u32_offset || !view_count || !window_bytes || !sent_ids) return fail("null argument");
+    if (world < 1 || world > QCE_MAX_RANKS || rank >= world || bins_per_rank < 1 || (u64)bins_per_rank * world > 256)
+        return fail("bad row-bin shape");
+    const u32 nb = bins_per_rank * world;
+    std::vector<u64> top(world, 0);
+    for (u32 k = 0; k < nbind; k++) {
+        sent_ids[k] = 0;
+        for (u32 d = 0; d < world; d++) {
+            u64 at = 0; // ids before the current bin inside owner d's region
+            for (u32 j = 0; j < bins_per_rank; j++) {
+                const u32 b = d * bins_per_rank + j;
+                u64 tot = 0, bef = 0;
+                for (u32 s = 0; s < world; s++) {
+                    const u64 c = hists[((size_t)s * nbind + k) * nb + b];
+                    if (s < rank) bef += c;
+                    if (s == rank && d != rank) sent_ids[k] += c;
+                    tot += c;
+                }
+                bin_u32_offset[(size_t)k * nb + b] = top[d] / 4 + at + bef;
+                at += tot;
+            }
+            if (d == rank) { view_u32_offset[k] = top[d] / 4; view_count[k] = at; }
+            top[d] = (top[d] + 4 * at + 15) / 16 * 16;
+        }
+    }
+    *window_bytes = *std::max_element(top.begin(), top.end());
+    return 0;
+}
+
+} // extern "C"
+
+namespace {
+int exchange_plan_impl(const uint64_t *hists, uint32_t world, uint32_t rank, uint32_t nsides, const uint32_t *ncols,
+                      uint32_t key_bits, const uint64_t *fixed_splitters, uint64_t *splitters, uint64_t *recv, uint64_t *before, uint64_t *run_off,
+                      uint64_t *col_off, uint64_t *window_bytes, uint64_t *sent_tuples)
+{
     if (!hists || !ncols || !splitters || !recv || !before || !run_off || !col_off || !window_bytes || !sent_tuples)
         return fail("null argument");
     if (world < 1 || world > QCE_MAX_RANKS || rank >= world || nsides < 1 || nsides > 8) return fail("bad exchange shape");
@@ -2007,6 +2632,10 @@ int qce_exchange_plan(const uint64_t *hists, uint32_t world, uint32_t rank, uint
         u32 i = 0;
         while (i < 256 && (unsigned __int128)cum[i] * world < (unsigned __int128)total * k) i++;
         u32 b = i + 1;
+        if (fixed_splitters) { // a run already in place dictates the cut (must sit on a bin boundary)
+            if (fixed_splitters[k - 1] & ((1ull << shift) - 1)) return fail("fixed splitter off the histogram bins");
+            b = (u32)std::min<u64>(256, fixed_splitters[k - 1] >> shift);
+        }
         if (b < prev) b = prev;
         if (b > 256) b = 256;
         splitters[k - 1] = (u64)b << shift;
@@ -2047,39 +2676,4 @@ int qce_exchange_plan(const uint64_t *hists, uint32_t world, uint32_t rank, uint
     return 0;
 }
 
-// Row ids routed to the ranks that own the rows: per binding, where this rank's ids of every
-// bin go in the owner's window (bin-major inside an owner, earlier ranks first inside a bin).
-int qce_rowid_push_plan(const uint64_t *hists, uint32_t world, uint32_t rank, uint32_t nbind, uint32_t bins_per_rank,
-                        uint64_t *bin_u32_offset, uint64_t *view_u32_offset, uint64_t *view_count, uint64_t *window_bytes,
-                        uint64_t *sent_ids)
-{
-    if (!hists || !bin_u32_offset || !view_u32_offset || !view_count || !window_bytes || !sent_ids) return fail("null argument");
-    if (world < 1 || world > QCE_MAX_RANKS || rank >= world || bins_per_rank < 1 || (u64)bins_per_rank * world > 256)
-        return fail("bad row-bin shape");
-    const u32 nb = bins_per_rank * world;
-    std::vector<u64> top(world, 0);
-    for (u32 k = 0; k < nbind; k++) {
-        sent_ids[k] = 0;
-        for (u32 d = 0; d < world; d++) {
-            u64 at = 0; // ids before the current bin inside owner d's region
-            for (u32 j = 0; j < bins_per_rank; j++) {
-                const u32 b = d * bins_per_rank + j;
-                u64 tot = 0, bef = 0;
-                for (u32 s = 0; s < world; s++) {
-                    const u64 c = hists[((size_t)s * nbind + k) * nb + b];
-                    if (s < rank) bef += c;
-                    if (s == rank && d != rank) sent_ids[k] += c;
-                    tot += c;
-                }
-                bin_u32_offset[(size_t)k * nb + b] = top[d] / 4 + at + bef;
-                at += tot;
-            }
-            if (d == rank) { view_u32_offset[k] = top[d] / 4; view_count[k] = at; }
-            top[d] = (top[d] + 4 * at + 15) / 16 * 16;
-        }
-    }
-    *window_bytes = *std::max_element(top.begin(), top.end());
-    return 0;
-}
-
-} // extern "C"
+} // namespace

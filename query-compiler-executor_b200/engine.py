@@ -32,6 +32,11 @@ SYMBOLS = [
     "qce_push_u32_by_slot", "qce_push_tuples_cols", "qce_rowids_bin_histogram", "qce_push_rowids", "qce_tuples_from_window", "qce_rowids_from_window",
     "qce_rowids_gather", "qce_adopt_column_window", "qce_column_max_device", "qce_column_window_u32", "qce_rowids_iota",
     "qce_tuples_from_u32", "qce_column_gather_u32", "qce_exchange_plan", "qce_rowid_push_plan",
+    "qce_ctx_create", "qce_ctx_bind", "qce_ctx_destroy", "qce_ctx_solo", "qce_batch_begin", "qce_batch_end",
+    "qce_batch_cache_stats", "qce_comm_fork", "qce_comm_attach", "qce_comm_rank", "qce_comm_world", "qce_comm_is_child",
+    "qce_comm_barrier", "qce_comm_allreduce_sum_u64", "qce_comm_allreduce_max_u64", "qce_comm_gatherv", "qce_comm_abort",
+    "qce_comm_finish", "qce_upload_column_window", "qce_upload_column_window_device", "qce_row_share",
+    "qce_set_replicate_bytes", "qce_column_would_be_whole", "qce_column_is_whole", "qce_rowids_count_local", "qce_xwin_unmap_peers",
 ]
 
 
@@ -89,6 +94,17 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "qce_column_max_device": (i32, [vp, u64, P(u64)]),
         "qce_exchange_plan": (i32, [vp, u32, u32, u32, vp, u32, vp, vp, vp, vp, vp, P(u64), vp]),
         "qce_rowid_push_plan": (i32, [vp, u32, u32, u32, u32, vp, vp, vp, P(u64), vp]),
+        "qce_ctx_create": (vp, []), "qce_ctx_bind": (i32, [vp]), "qce_ctx_destroy": (None, [vp]), "qce_ctx_solo": (i32, [i32]),
+        "qce_batch_begin": (i32, []), "qce_batch_end": (i32, []), "qce_batch_cache_stats": (i32, [P(u64), P(u64)]),
+        "qce_comm_fork": (i32, [u32]), "qce_comm_attach": (i32, [C.c_char_p, u32, u32, u64]),
+        "qce_comm_rank": (u32, []), "qce_comm_world": (u32, []), "qce_comm_is_child": (i32, []), "qce_comm_barrier": (i32, []),
+        "qce_comm_allreduce_sum_u64": (i32, [vp, u32]), "qce_comm_allreduce_max_u64": (i32, [vp, u32]),
+        "qce_comm_gatherv": (i32, [vp, u64, P(vp), vp]), "qce_comm_abort": (None, []), "qce_comm_finish": (i32, [i32]),
+        "qce_upload_column_window": (i32, [u32, u32, vp, u64, u64, u64]),
+        "qce_upload_column_window_device": (i32, [u32, u32, vp, u64, u64, u64]),
+        "qce_row_share": (i32, [u64, u32, u32, P(u64), P(u64)]), "qce_set_replicate_bytes": (i32, [u64]),
+        "qce_column_would_be_whole": (i32, [u64]), "qce_column_is_whole": (i32, [u32, u32]),
+        "qce_rowids_count_local": (u64, [vp]), "qce_xwin_unmap_peers": (i32, []),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

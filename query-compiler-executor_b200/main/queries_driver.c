@@ -30,11 +30,8 @@ static double now_s(void)
 int main(void)
 {
     const int timing = getenv("QCE_TIMING") != NULL;
-    if (qce_init(-1) != 0) {
-        log_err("%s", qce_last_error());
-        return EXIT_FAILURE;
-    }
-
+    /* CUDA is touched lazily, by the first column load inside execute_queries: with QCE_GPUS=n
+     * the host layer forks one process per GPU before that (schedule.c) */
     DArray *relations = DArray_create(sizeof(metadata), 10);
     double t0 = now_s();
     check(read_relations(relations) != -1, "Something went wrong in reading the relations");

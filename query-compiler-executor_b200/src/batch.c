@@ -8,6 +8,7 @@
 
 #include "parsing.h"
 #include "pred_arrange.h"
+#include "schedule.h"
 #include "structs.h"
 #include "utilities.h"
 
@@ -35,11 +36,9 @@ long qce_host_run_batch(const char *text, char *out, size_t cap, int *failed)
     size_t len = 0;
     FILE *mem = open_memstream(&buf, &len);
     int bad = 0;
-    for (size_t i = 0; i < DArray_count(queries); i++) {
-        query *q = (query *)DArray_get(queries, i);
-        arrange_predicates(q);
-        if (execute_query_to(q, NULL, mem) != 0) bad++;
-    }
+    /* the same scheduler as execute_queries (schedule.c); a reference exit(EXIT_FAILURE) site
+     * ends the output after that query's partial line and counts as a failure */
+    if (qce_run_queries(queries, NULL, mem, &bad) == QCE_RUN_FATAL) bad++;
     fclose(mem);
     free_queries(queries);
     if (failed) *failed = bad;

@@ -10,7 +10,7 @@
 
 #include "../../include/qce_b200.h"
 
-static FILE *g_query_out = NULL;
+static __thread FILE *g_query_out = NULL; /* one query per host thread (schedule.c) */
 
 void qce_set_query_stdout(FILE *out) { g_query_out = out; }
 FILE *qce_query_stdout(void) { return g_query_out ? g_query_out : stdout; }

@@ -29,6 +29,7 @@
 #include "join.h"
 
 #include "../../include/qce_b200.h"
+#include "schedule.h"
 
 /* one operand of the predicate, resolved against the entity list */
 typedef struct join_side {
@@ -245,7 +246,7 @@ static int replace_and_rejoin(join_result *res, DArray *entities, exists_info wh
 static void fatal_inconsistent(void)
 {
     log_err("Something went really wrong");
-    exit(EXIT_FAILURE); /* src/join.c:563,601,610,620 */
+    qce_fatal(); /* src/join.c:563,601,610,620: exit(EXIT_FAILURE), after the earlier queries' stdout */
 }
 
 /* update_mid_results, src/join.c:507-628. */

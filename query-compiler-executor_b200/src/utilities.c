@@ -24,13 +24,28 @@
 #include "filter.h"
 #include "join.h"
 #include "pred_arrange.h"
+#include "schedule.h"
 
 /* ------------------------------------------------------------------ loader */
+/* Relation files stay mapped; a column goes to HBM when a batch first references it
+ * (the reference copies every column of every relation, src/utilities.c:105-121).
+ * Nothing here touches CUDA, so the host layer may still fork one process per GPU
+ * (QCE_GPUS, schedule.c) after the relations have been read. */
+typedef struct rel_file {
+    uint64_t *map;
+    size_t bytes;
+    uint64_t rows, cols;
+    unsigned char *uploaded; /* per column */
+} rel_file;
+static rel_file *g_files = NULL;
+static size_t g_nfiles = 0, g_files_cap = 0;
+
 static int load_relation_file(const char *path, uint32_t rel_index, metadata *out)
 {
     int rc = -1;
     uint64_t *map = MAP_FAILED;
     struct stat sb;
+    out->data = NULL;
     int fd = open(path, O_RDONLY);
     check(fd != -1, "open failed");
     check(fstat(fd, &sb) != -1, "fstat failed");
@@ -51,11 +66,28 @@ static int load_relation_file(const char *path, uint32_t rel_index, metadata *ou
         relation *col = MALLOC(relation, 1);
         check_mem(col);
         col->num_tuples = out->tuples;
-        col->tuples = NULL; /* resident in HBM; the driver's FREE(tuples) is NULL-safe */
+        col->tuples = NULL; /* resident in HBM once referenced; the driver's FREE(tuples) is NULL-safe */
         out->data[c] = col;
-        check(qce_upload_column(rel_index, (uint32_t)c, map + 2 + c * out->tuples, out->tuples) == 0,
-              "column upload failed: %s", qce_last_error());
     }
+    if (rel_index >= g_files_cap) {
+        size_t cap = g_files_cap ? g_files_cap * 2 : 16;
+        while (cap <= rel_index) cap *= 2;
+        rel_file *grown = (rel_file *)realloc(g_files, cap * sizeof(rel_file));
+        check_mem(grown);
+        memset(grown + g_files_cap, 0, (cap - g_files_cap) * sizeof(rel_file));
+        g_files = grown;
+        g_files_cap = cap;
+    }
+    rel_file *f = &g_files[rel_index];
+    if (f->map) { munmap(f->map, f->bytes); free(f->uploaded); }
+    f->map = map;
+    f->bytes = (size_t)sb.st_size;
+    f->rows = out->tuples;
+    f->cols = out->columns;
+    f->uploaded = (unsigned char *)calloc(out->columns ? out->columns : 1, 1);
+    check_mem(f->uploaded);
+    if (rel_index + 1 > g_nfiles) g_nfiles = rel_index + 1;
+    map = MAP_FAILED; /* kept */
     rc = 0;
 
 error:
@@ -85,6 +117,26 @@ int read_relations_from(FILE *in, DArray *metadata_arr)
 }
 
 int read_relations(DArray *metadata_arr) { return read_relations_from(stdin, metadata_arr); }
+
+/* relation files known to the loader (0 when the relations were uploaded by an embedder) */
+size_t qce_host_file_count(void) { return g_nfiles; }
+uint64_t qce_host_file_rows(uint32_t rel) { return rel < g_nfiles ? g_files[rel].rows : 0; }
+/* 1: (rel, col) exists in a mapped file and is not in HBM yet */
+int qce_host_column_pending(uint32_t rel, uint32_t col)
+{
+    return rel < g_nfiles && g_files[rel].map && col < g_files[rel].cols && !g_files[rel].uploaded[col];
+}
+int qce_host_upload_column(uint32_t rel, uint32_t col)
+{
+    if (!qce_host_column_pending(rel, col)) return 0;
+    rel_file *f = &g_files[rel];
+    if (qce_upload_column(rel, col, f->map + 2 + (uint64_t)col * f->rows, f->rows) != 0) {
+        log_err("column upload failed: %s", qce_last_error());
+        return -1;
+    }
+    f->uploaded[col] = 1;
+    return 0;
+}
 
 /* ------------------------------------------------------------------ lookups */
 exists_info relation_exists(DArray *mid_results_array, uint64_t relation, uint64_t predicate_id)
@@ -176,8 +228,7 @@ static int print_sums(DArray *entities, const query *q, FILE *out)
     if (limit < ns_all) {
         log_err("Something went really wrong...");
         fflush(out);
-        if (out != stdout) { /* batch mode: hand the partial line to the caller's stream owner */ }
-        exit(EXIT_FAILURE); /* src/utilities.c:204-207 */
+        qce_fatal(); /* src/utilities.c:204-207: exit(EXIT_FAILURE) once the earlier queries' lines are out */
     }
     fputc('\n', out);
     return 0;
@@ -223,10 +274,9 @@ error:
 
 void execute_queries(DArray *q_list, DArray *metadata_arr)
 {
-    for (size_t i = 0; i < DArray_count(q_list); i++) {
-        query *q = (query *)DArray_get(q_list, i);
-        arrange_predicates(q);
-        execute_query_to(q, metadata_arr, stdout); /* a failed query prints nothing, as in the reference */
-    }
+    /* the batch scheduler (schedule.c): lazy column loads, one process per GPU when QCE_GPUS > 1,
+     * small queries overlapped on several streams, stdout in query order */
+    const int status = qce_run_queries(q_list, metadata_arr, stdout, NULL);
     fflush(stdout);
+    if (status == QCE_RUN_FATAL) exit(EXIT_FAILURE); /* src/utilities.c:204-207, src/join.c:563-620 */
 }

@@ -33,7 +33,7 @@ static struct {
     uint64_t *d;
     uint64_t n;
 } g_col[MAX_REL][MAX_COL];
-static char g_err[256];
+static __thread char g_err[256];
 
 static int fail(const char *fmt, ...)
 {
@@ -80,6 +80,41 @@ static int cmp(uint64_t v, char op, uint64_t c, int *ok)
     case '<': *ok = v < c; return 0;
     }
     return fail("Wrong operator '%c'", op);
+}
+
+/* ---- contexts, batches, ranks: one thread-safe "device", one rank ---------------------------
+ * The mock keeps no per-context state: handles are plain malloc blocks and the column table
+ * is only written by uploads, so the scheduler's worker threads may call it concurrently. */
+void *qce_ctx_create(void) { return xalloc(1, 8); }
+int qce_ctx_bind(void *ctx) { (void)ctx; return 0; }
+void qce_ctx_destroy(void *ctx) { free(ctx); }
+int qce_ctx_solo(int on) { (void)on; return 0; }
+int qce_batch_begin(void) { return 0; }
+int qce_batch_end(void) { return 0; }
+int qce_comm_fork(uint32_t world) { (void)world; return fail("the mock engine is a single rank"); }
+uint32_t qce_comm_rank(void) { return 0; }
+uint32_t qce_comm_world(void) { return 1; }
+int qce_comm_is_child(void) { return 0; }
+int qce_comm_finish(int status) { (void)status; return 0; }
+int qce_comm_gatherv(const void *mine, uint64_t bytes, char **out, uint64_t *lens)
+{
+    if (lens) lens[0] = bytes;
+    if (out) { *out = xalloc(bytes ? bytes : 1, 1); memcpy(*out, mine, bytes); }
+    return 0;
+}
+int qce_column_would_be_whole(uint64_t rows) { (void)rows; return 1; }
+int qce_column_is_whole(uint32_t rel, uint32_t col)
+{
+    return (rel < MAX_REL && col < MAX_COL && g_col[rel][col].d != NULL) ? 1 : -1;
+}
+int qce_column_info(uint32_t rel, uint32_t col, uint64_t *n, uint64_t *max_value)
+{
+    const uint64_t *d;
+    uint64_t rows;
+    if (column(rel, col, &d, &rows) != 0) return -1;
+    if (n) *n = rows;
+    if (max_value) { *max_value = 0; for (uint64_t i = 0; i < rows; i++) if (d[i] > *max_value) *max_value = d[i]; }
+    return 0;
 }
 
 int qce_init(int device) { (void)device; return 0; }

@@ -29,7 +29,11 @@ def load_json(name):
     return json.load(open(os.path.join(GOLDEN, name)))
 
 
-def run_queries_bin(binary, paths, query_text, timeout=300):
+def run_queries_bin(binary, paths, query_text, timeout=300, env=None):
     text = "".join(p + "\n" for p in paths) + "Done\n" + query_text
-    p = subprocess.run([binary], input=text.encode(), stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=timeout)
+    full_env = dict(os.environ)
+    if env:
+        full_env.update({k: str(v) for k, v in env.items()})
+    p = subprocess.run([binary], input=text.encode(), stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=timeout,
+                       env=full_env)
     return p.stdout.decode(), p.stderr.decode(), p.returncode

@@ -26,7 +26,7 @@ def _build(name, flags):
     newest = max(os.path.getmtime(s) for s in SOURCES)
     if not os.path.exists(exe) or os.path.getmtime(exe) < newest:
         subprocess.run(["gcc", "-g", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(PKG, "src"),
-                        "-o", exe] + flags + SOURCES, check=True, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+                        "-o", exe] + flags + SOURCES + ["-lpthread"], check=True, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     return exe
 
 
