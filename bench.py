@@ -462,6 +462,8 @@ def config_c2(rig, rows, steps, warmup, args, local_rank):
                 "unit": "rows/s", "note": "the reference arm's workload (config-2 scaled twin) through the same product path"}
 
     # ---- (b) full size
+    if world > 1:
+        rows = rows // 4096 * 4096  # equal, vector-aligned row windows on every rank (qce_row_share)
     n = world * rows
     gen_s = time.time()
     host_cols = {}
@@ -679,6 +681,8 @@ def main():
 
     if args.config in ("all", "c2"):
         line = config_c2(rig, args.rows, args.steps, args.warmup, args, local_rank)
+        if world > 1:
+            rig.ck(rig.lib.qce_set_replicate_bytes(2 << 30))  # config 2 forces row-sharding; the others place by size
         others = {}
         if args.config == "all":
             drop()

@@ -725,6 +725,158 @@ k_msd_partition(const KeyT *__restrict__ in, KeyT *__restrict__ out, const u32 *
     }
 }
 
+// ---- the same pass, Blackwell-native data movement --------------------------------------
+// Persistent CTAs; the tiles stream into shared memory through the bulk-copy engine
+// (cp.async.bulk, 1-D TMA: SASS UBLKCP) and complete on an mbarrier (SYNCS), two tiles in
+// flight per CTA: while tile k is ranked, staged and written, tile k+1 is already landing.
+// The landing buffer doubles as the staging buffer (once a tile's keys are in registers its
+// buffer is free), so a CTA needs 2 x 32 KB and three of them share an SM.  The plain kernel
+// above issues its loads at tile start and hides their latency only by CTA co-residency: its
+// four phases serialise behind the load (issue 51 %, DRAM 51 %, barrier +
+// short-scoreboard stalls).
+struct MsdTileDesc { u32 bucket, begin, count, pad; };
+__global__ void __launch_bounds__(256)
+k_msd_tile_desc(const u32 *__restrict__ tile_start, const u32 *__restrict__ bucket_off, const u32 *__restrict__ bucket_size,
+                u32 nbuckets, u32 ntiles_cap, MsdTileDesc *__restrict__ desc)
+{
+    const u32 t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= ntiles_cap) return;
+    MsdTileDesc d{0u, 0u, 0u, 0u};
+    u32 b = 0, beg = 0, c = 0;
+    if (msd_locate_tile(t, tile_start, bucket_off, bucket_size, nbuckets, b, beg, c)) { d.bucket = b; d.begin = beg; d.count = c; }
+    desc[t] = d;
+}
+
+__device__ __forceinline__ u32 smem_addr(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "WAIT_LOOP:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra WAIT_DONE;\n"
+                 "bra WAIT_LOOP;\n"
+                 "WAIT_DONE:\n"
+                 "}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy; dst, src and bytes are multiples of 16
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, u32 bytes, u64 *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+constexpr int QCE_MSDB_THREADS = 512, QCE_MSDB_ITEMS = 8;
+constexpr int QCE_MSDB_SLOTS = QCE_MSD_TILE + 2;                 // a misaligned tile start costs up to 2 extra words
+constexpr size_t QCE_MSDB_SMEM = 2 * QCE_MSDB_SLOTS * sizeof(u64); // dynamic shared memory of the kernel
+__global__ void __launch_bounds__(QCE_MSDB_THREADS, 3)
+k_msd_partition_bulk(const u64 *__restrict__ in, u64 *__restrict__ out, const MsdTileDesc *__restrict__ desc, u32 ntiles,
+                     u64 base, int shift, u32 bins, u32 *__restrict__ cursor)
+{
+    constexpr int THREADS = QCE_MSDB_THREADS, ITEMS = QCE_MSDB_ITEMS;
+    extern __shared__ __align__(128) unsigned char msdb_smem[];
+    u64 *const buf0 = reinterpret_cast<u64 *>(msdb_smem);
+#define MSDB_BUF(b) (buf0 + (b) * QCE_MSDB_SLOTS)
+    __shared__ __align__(8) u64 bar[2];
+    __shared__ u32 cnt[256], excl[256], goff[256];
+    __shared__ u32 scratch[33];
+    __shared__ MsdTileDesc sdesc[2];
+    const int tid = threadIdx.x;
+    const u32 mask = bins - 1;
+
+    // thread 0 is the producer: describe + fetch tile t into buffer b
+    auto fetch = [&](u32 t, int b) {
+        MsdTileDesc d = desc[t];
+        sdesc[b] = d;
+        if (d.count == 0) return;
+        const u32 first = d.begin & ~1u, last = (d.begin + d.count + 1u) & ~1u; // 16-byte aligned superset
+        const u32 bytes = (last - first) * (u32)sizeof(u64);
+        mbar_expect_tx(&bar[b], bytes);
+        bulk_g2s(MSDB_BUF(b), in + first, bytes, &bar[b]);
+    };
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 256) cnt[tid] = 0;
+    __syncthreads();
+    const u32 t0 = blockIdx.x, stride = gridDim.x;
+    if (tid == 0) {
+        if (t0 < ntiles) fetch(t0, 0);
+        if (t0 + stride < ntiles) fetch(t0 + stride, 1);
+    }
+    __syncthreads();
+
+    u32 it = 0;
+    for (u32 t = t0; t < ntiles; t += stride, it++) {
+        const int b = it & 1;
+        const MsdTileDesc d = sdesc[b];
+        const u32 count = d.count;
+        u64 key[ITEMS];
+        u32 slot[ITEMS];
+        if (count) {
+            mbar_wait(&bar[b], (it >> 1) & 1);
+            const u64 *src = MSDB_BUF(b) + (d.begin & 1u);
+#pragma unroll
+            for (int j = 0; j < ITEMS; j++) {
+                const u32 i = tid + j * THREADS;
+                if (i < count) {
+                    key[j] = src[i];
+                    const u32 dg = (u32)((key[j] - base) >> shift) & mask;
+                    slot[j] = (dg << 16) | atomicAdd(&cnt[dg], 1u);
+                }
+            }
+        }
+        __syncthreads(); // every key of the tile is in registers: the buffer is free for staging
+        {
+            const u32 c = tid < 256 ? cnt[tid] : 0u;
+            u32 tot;
+            const u32 ex = block_scan_excl<u32, THREADS>(c, scratch, &tot);
+            if (tid < 256) {
+                excl[tid] = ex;
+                goff[tid] = (c ? atomicAdd(&cursor[d.bucket * bins + tid], c) : 0u) - ex;
+                cnt[tid] = 0; // for the next tile
+            }
+        }
+        __syncthreads();
+        u64 *stage = MSDB_BUF(b);
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) {
+            const u32 i = tid + j * THREADS;
+            if (i < count) stage[excl[slot[j] >> 16] + (slot[j] & 0xffffu)] = key[j];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) {
+            const u32 p = tid + j * THREADS;
+            if (p < count) {
+                const u64 k = stage[p];
+                out[goff[(u32)((k - base) >> shift) & mask] + p] = k;
+            }
+        }
+        __syncthreads(); // staging reads done: the buffer may take the tile after next
+        if (tid == 0 && t + 2 * stride < ntiles) {
+            fence_proxy_async(); // generic-proxy writes to the buffer before the async-proxy copy into it
+            fetch(t + 2 * stride, b);
+        }
+    }
+#undef MSDB_BUF
+}
+
 // Largest segment length (to decide whether every sub-bucket fits the finish kernel).
 __global__ void __launch_bounds__(256) k_max_u32(const u32 *__restrict__ v, u32 n, u32 *__restrict__ out)
 {

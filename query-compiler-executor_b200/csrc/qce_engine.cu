@@ -87,7 +87,7 @@ struct Column {
     u64 win_begin = 0, win_count = 0;
     // sharded over the ranks of the node: every rank's window mapped through CUDA IPC
     bool peer_mapped = false;
-    u32 rpr = 0;                       // rows per rank
+    u32 rpr = 0, last_rank = 0;        // rows per rank; world - 1
     const u64 *vb[QCE_MAX_RANKS] = {}; // virtual bases: row id r of rank q's window lives at vb[q][r]
     void *alloc = nullptr;             // the cudaMalloc behind d (reused by a re-upload of the same shape)
     u64 alloc_bytes = 0;
@@ -100,6 +100,7 @@ ColRef ref_of(const Column *c)
     r.d = c->d;
     if (c->peer_mapped) {
         r.rpr = c->rpr;
+        r.last = c->last_rank;
         r.inv = 1.0f / (float)c->rpr;
         // rounded down: the owner estimate may only err low (corrected upwards in ColRef::owner)
         r.inv = nextafterf(r.inv, 0.0f);
@@ -271,6 +272,7 @@ class Arena {
         if (e != cudaSuccess)
             return fail("out of device memory: %llu bytes requested, %llu reserved (%s)", (unsigned long long)need,
                         (unsigned long long)reserved_, cudaGetErrorString(e));
+        if (getenv("QCE_TRACE")) fprintf(stderr, "[qce] arena %p grows by %.1f MB (need %.1f MB, reserved %.1f MB)\n", (void *)this, bytes / 1e6, need / 1e6, reserved_ / 1e6);
         slabs_.push_back({(u64)p, bytes});
         slab_starts_.insert((u64)p);
         reserved_ += bytes;
@@ -650,6 +652,21 @@ int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done, const u32 
         const char *e = getenv("QCE_MSD_VARIANT");
         variant = e ? atoi(e) : 0;
     }
+    static int bulk = -1; // QCE_MSD_BULK=0: the plain-load partition kernel (for comparison)
+    if (bulk < 0) {
+        const char *e = getenv("QCE_MSD_BULK");
+        bulk = e ? atoi(e) : 1;
+        if (bulk) CK(cudaFuncSetAttribute(k_msd_partition_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QCE_MSDB_SMEM));
+    }
+    MsdTileDesc *tdesc = nullptr;
+    const u32 ntiles_cap = ntiles0 + nbA;
+    const int bulk_grid = G.sms * 3;
+    if (bulk) {
+        if (dalloc(&tdesc, ntiles_cap) != 0) return -1;
+        LAUNCH("msd_tiles", k_msd_tile_desc, (int)ceil_div(ntiles0, 256), 256, 0, lvl0, lvl0 + 2, lvl0 + 3, 1u, ntiles0, tdesc);
+        LAUNCH("msd_partition", k_msd_partition_bulk, (int)std::min<u32>(ntiles0, (u32)bulk_grid), QCE_MSDB_THREADS, QCE_MSDB_SMEM, *keys, alt,
+               tdesc, ntiles0, base, shiftA, nbA, curA);
+    } else
     if (shape >= 1 && variant == 1)
         LAUNCH("msd_partition", (k_msd_partition<512, 8, u64, 4, false>), ntiles0, 512, 0, *keys, alt, lvl0, lvl0 + 2, lvl0 + 3, 1u,
                base, shiftA, nbA, curA, (const u32 *)nullptr);
@@ -677,6 +694,11 @@ int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done, const u32 
     const u32 max_sub = (u32)(cx().h_scalars[10] & 0xffffffffu);
     if (max_sub <= MSD_LOCAL_CAP) {
         CK(cudaMemcpyAsync(curB, suboff, nsub * sizeof(u32), cudaMemcpyDeviceToDevice, cx().stream));
+        if (bulk) {
+            LAUNCH("msd_tiles", k_msd_tile_desc, (int)ceil_div(ntiles1, 256), 256, 0, tstart1, offA, histA, nbA, ntiles1, tdesc);
+            LAUNCH("msd_partition", k_msd_partition_bulk, (int)std::min<u32>(ntiles1, (u32)bulk_grid), QCE_MSDB_THREADS, QCE_MSDB_SMEM, alt,
+                   *keys, tdesc, ntiles1, base, shiftB, nbB, curB);
+        } else
         if (shape >= 1 && variant == 1)
             LAUNCH("msd_partition", (k_msd_partition<512, 8, u64, 4, false>), ntiles1, 512, 0, alt, *keys, tstart1, offA, histA, nbA,
                    base, shiftB, nbB, curB, (const u32 *)nullptr);
@@ -738,7 +760,7 @@ int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done, const u32 
         *done = true;
     }
     dfree(alt); dfree(lvl0); dfree(histA); dfree(offA); dfree(curA); dfree(tstart1); dfree(histB); dfree(suboff);
-    dfree(curB);
+    dfree(curB); dfree(tdesc);
     return 0;
 }
 
@@ -1073,6 +1095,10 @@ int qce_timer_reset(void)
 {
     NEED_INIT();
     cx().launches = 0;
+    {
+        std::lock_guard<std::mutex> lk(G.mu); // the worker contexts are idle between batches
+        for (Ctx *w : G.workers) w->launches = 0;
+    }
     CK(cudaEventRecord(cx().t0, cx().stream));
     return 0;
 }
@@ -1084,7 +1110,13 @@ int qce_timer_read(double *ms, uint64_t *kernel_launches)
     float f = 0;
     CK(cudaEventElapsedTime(&f, cx().t0, cx().t1));
     if (ms) *ms = f;
-    if (kernel_launches) *kernel_launches = cx().launches;
+    if (kernel_launches) {
+        u64 n = cx().launches;
+        std::lock_guard<std::mutex> lk(G.mu);
+        for (Ctx *w : G.workers)
+            if (w != &cx()) n += w->launches;
+        *kernel_launches = n;
+    }
     return 0;
 }
 
@@ -1362,6 +1394,7 @@ static int h2d(void *dst, const void *src, u64 bytes)
 static int share_window(Column *c, u64 per, bool reused)
 {
     c->rpr = (u32)per;
+    c->last_rank = G.world - 1;
     c->peer_mapped = true;
     if (!reused) {
         cudaIpcMemHandle_t mine, all[QCE_MAX_RANKS];
@@ -1570,7 +1603,7 @@ static int filter_scan_window(uint32_t rel, uint32_t col, char op, uint64_t c, u
     if (begin > cl->n || count > cl->n - begin) return fail("row window [%llu, +%llu) outside relation %u (%llu rows)",
                                                            (unsigned long long)begin, (unsigned long long)count, rel,
                                                            (unsigned long long)cl->n);
-    if (begin & 1) return fail("row window must start on an even row (128-bit loads)");
+    if ((begin & 1) && count) return fail("row window must start on an even row (128-bit loads)");
     if (!window_resident(cl, begin, count)) return fail("rows [%llu, +%llu) of relation %u are not resident on this rank",
                                                         (unsigned long long)begin, (unsigned long long)count, rel);
     const u64 n = count;
@@ -1724,7 +1757,7 @@ int qce_build_tuples_base_range(uint32_t rel, uint32_t col, uint64_t row_begin, 
     const Column *cl;
     if (get_column(rel, col, &cl) != 0) return -1;
     if (row_begin > cl->n || row_count > cl->n - row_begin) return fail("row window outside relation %u", rel);
-    if (row_begin & 1) return fail("row window must start on an even row (128-bit loads)");
+    if ((row_begin & 1) && row_count) return fail("row window must start on an even row (128-bit loads)");
     if (build_tuples(cl, nullptr, out, row_begin, row_count) != 0) return -1;
     (*out)->src_rel = rel;
     (*out)->src_col = col;
@@ -1788,8 +1821,11 @@ int qce_batch_begin(void)
     static int on = -1; // QCE_RUN_CACHE=0 disables
     if (on < 0) { const char *e = getenv("QCE_RUN_CACHE"); on = e ? atoi(e) : 1; }
     if (!on) return 0;
-    size_t free_b = 0, total_b = 0;
-    CK(cudaMemGetInfo(&free_b, &total_b));
+    static size_t total_b = 0; // cudaMemGetInfo costs milliseconds: once
+    if (total_b == 0) {
+        size_t free_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+    }
     std::lock_guard<std::mutex> lk(G.mu);
     G.cache_on = true;
     G.cache_budget = total_b / 4;
@@ -1946,7 +1982,19 @@ int qce_checksum(const qce_rowids *ids, uint32_t rel, const uint32_t *cols, uint
             if (partition_ids_by_top_bits(ids, &bucketed) != 0) return -1;
             src = bucketed;
         }
-        const int grid = grid_for(1024, ids->n);
+        static int waves = -1, per_col = -1; // QCE_CHECKSUM_WAVES / QCE_CHECKSUM_PER_COL: experiment switches
+        if (waves < 0) { const char *e = getenv("QCE_CHECKSUM_WAVES"); waves = e ? atoi(e) : 8; if (waves < 1) waves = 1; }
+        if (per_col < 0) { const char *e = getenv("QCE_CHECKSUM_PER_COL"); per_col = e ? atoi(e) : 0; }
+        const int grid = grid_for(1024, ids->n, waves);
+        if (per_col && ncols > 1) {
+            // one pass over the (bucketed) ids per column: half the working set in L2 at any time
+            for (u32 k = 0; k < ncols; k++) {
+                ChecksumCols one;
+                for (u32 j = 0; j < 8; j++) one.col[j] = nullptr;
+                one.col[0] = cc.col[k];
+                LAUNCH("checksum", (k_checksum<1>), grid, 256, 0, src, ids->n, one, cx().d_scalars + k);
+            }
+        } else
         switch (ncols) {
         case 1: LAUNCH("checksum", (k_checksum<1>), grid, 256, 0, src, ids->n, cc, cx().d_scalars); break;
         case 2: LAUNCH("checksum", (k_checksum<2>), grid, 256, 0, src, ids->n, cc, cx().d_scalars); break;

@@ -7,6 +7,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "../../include/qce_b200.h"
 #include "dbg.h"
@@ -248,8 +249,17 @@ static uint64_t rows_of(uint32_t rel)
     return n;
 }
 
+static double now_ms(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec;
+}
+
 int qce_run_queries(DArray *q_list, DArray *metadata_arr, FILE *out, int *failed)
 {
+    const int trace = getenv("QCE_TRACE") != NULL;
+    const double t_enter = now_ms();
     const size_t n = DArray_count(q_list);
     int status = QCE_RUN_OK, bad = 0;
     batch b;
@@ -307,6 +317,17 @@ int qce_run_queries(DArray *q_list, DArray *metadata_arr, FILE *out, int *failed
         else if (!j->whole) j->owner = -1;
     }
     if (world > 1 && load) {
+        /* a query over replicated relations may still be too large for one rank's fair share of the
+         * batch (a lone 100M-row join, an outlier among small queries): it runs sharded like the
+         * queries over row-sharded relations -- every rank takes its row share of the whole columns */
+        uint64_t total = 0;
+        for (size_t i = 0; i < n; i++)
+            if (b.jobs[i].whole) total += b.jobs[i].cost;
+        for (size_t i = 0; i < n; i++)
+            if (b.jobs[i].whole && b.jobs[i].heavy && b.jobs[i].cost > total / (uint64_t)world) {
+                b.jobs[i].whole = 0;
+                b.jobs[i].owner = -1;
+            }
         /* replicas: longest queries first, each to the least loaded rank (the same on every rank) */
         char *assigned = (char *)calloc(n ? n : 1, 1);
         for (;;) {
@@ -340,7 +361,9 @@ int qce_run_queries(DArray *q_list, DArray *metadata_arr, FILE *out, int *failed
     if (streams > MAX_STREAMS) streams = MAX_STREAMS;
     if (b.nlight < 2) streams = 0; /* nothing to overlap */
     if ((size_t)streams > b.nlight) streams = (long)b.nlight;
+    const double t_plan = now_ms();
     qce_batch_begin();
+    const double t_begin = now_ms();
     for (long s = 0; s < streams; s++) {
         if (!g_stream_ctx[s]) g_stream_ctx[s] = qce_ctx_create();
         if (!g_stream_ctx[s]) break;
@@ -361,7 +384,11 @@ int qce_run_queries(DArray *q_list, DArray *metadata_arr, FILE *out, int *failed
     if (world > 1) qce_ctx_solo(0);
     for (int w = 0; w < nworkers; w++) pthread_join(workers[w], NULL);
     if (have_loader) pthread_join(loader, NULL);
+    const double t_ran = now_ms();
     qce_batch_end();
+    if (trace)
+        fprintf(stderr, "[qce] batch of %zu: plan %.3f ms, batch_begin %.3f, run %.3f, batch_end %.3f (rank %d, %d streams)\n", n,
+                t_plan - t_enter, t_begin - t_plan, t_ran - t_begin, now_ms() - t_ran, rank, nworkers);
 
     /* the queries the other ranks ran alone */
     if (world > 1) {
