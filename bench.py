@@ -235,6 +235,14 @@ class Rig:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t[0])
 
+    def verdict_of_rank0(self, ok):
+        """rank 0 holds the whole batch's stdout: its verdict is everybody's"""
+        if self.world == 1:
+            return bool(ok)
+        t = self.torch.tensor([1 if ok else 0], dtype=self.torch.int64, device="cuda")
+        self.dist.broadcast(t, 0)
+        return bool(int(t[0]))
+
     def sum_over_ranks(self, vals):
         """uint64 sums mod 2^64 over the ranks"""
         if self.world == 1:
@@ -342,7 +350,7 @@ def config_c3(rig, rows_per_gpu, steps, warmup, sampler=None):
         b, n = rig.share(w.rows(0)) if rig.world > 1 else (0, w.rows(0))
         pairs, sums = bk.c3_check(rig.torch, w, b, n)
         tot = rig.sum_over_ranks([pairs] + sums)
-        return got == bk.format_line(tot[0], tot[1:])
+        return rig.verdict_of_rank0(got == bk.format_line(tot[0], tot[1:]))
     res = run_generated(rig, "c3", w, twin, check, 10, steps, warmup, sampler=sampler)
     res["scaling"] = "weak (%d rows per relation per GPU; BASELINE config 3 = 500M rows per relation over 8 GPUs)" % rows_per_gpu
     return res
@@ -357,7 +365,7 @@ def config_c4(rig, rows_per_gpu, steps, warmup, sampler=None):
         b, n = rig.share(w.rows(0)) if rig.world > 1 else (0, w.rows(0))
         pairs, sums = bk.c4_check(rig.torch, w, b, n)
         tot = rig.sum_over_ranks([pairs] + sums)
-        return got == bk.format_line(tot[0], tot[1:])
+        return rig.verdict_of_rank0(got == bk.format_line(tot[0], tot[1:]))
     res = run_generated(rig, "c4", w, twin, check, 20, steps, warmup, sampler=sampler)
     res["scaling"] = "weak (%d rows per relation per GPU)" % rows_per_gpu
     return res
@@ -370,31 +378,28 @@ def config_c5(rig, scale, nqueries, steps, warmup, check_queries=48, sampler=Non
 
     def check(got):
         # a spread of the batch (every len/check_queries-th query, always including those over the largest
-        # relations) against the index-map checker; the stdout lines of a query are located by replaying
-        # the batch's line structure (filter-only queries print a count line first)
+        # relations) against the index-map checker.  Every rank evaluates its row share of every picked
+        # query (the same collectives on every rank); rank 0, which holds the whole batch's stdout, locates
+        # each query's lines by replaying the batch's line structure (filter-only queries print a count line).
+        by_size = sorted(range(len(w.queries)), key=lambda k: -sum(w.rows(r) for r in w.plans[k][0]))
+        pick = sorted(set(by_size[:check_queries // 4] + list(range(0, len(w.queries), max(1, len(w.queries) // check_queries)))))
+        wants = {}
+        for k in pick:
+            r0 = w.plans[k][0][0]
+            per = -(-w.rows(r0) // rig.world)
+            b = min(rig.rank * per, w.rows(r0))
+            n = min(per, w.rows(r0) - b)
+            first, pairs, sums = bk.c5_check_query(rig.torch, w, k, b, n)
+            tot = rig.sum_over_ranks([pairs, first or 0] + sums)
+            wants[k] = ("%d\n" % tot[1] if first is not None else "") + bk.format_line(tot[0], tot[2:])
         lines = got.splitlines(keepends=True)
         at, where = 0, []
         for k in range(len(w.queries)):
             n = 2 if not w.plans[k][1] else 1
             where.append((at, n))
             at += n
-        if at != len(lines):
-            return False
-        by_size = sorted(range(len(w.queries)), key=lambda k: -sum(w.rows(r) for r in w.plans[k][0]))
-        pick = sorted(set(by_size[:check_queries // 4] + list(range(0, len(w.queries), max(1, len(w.queries) // check_queries)))))
-        ok = True
-        for k in pick:
-            r0 = w.plans[k][0][0]
-            b, n = (rig.rank * (-(-w.rows(r0) // rig.world)), 0)
-            per = -(-w.rows(r0) // rig.world)
-            b = min(rig.rank * per, w.rows(r0))
-            n = min(per, w.rows(r0) - b)
-            first, pairs, sums = bk.c5_check_query(rig.torch, w, k, b, n)
-            tot = rig.sum_over_ranks([pairs, first or 0] + sums)
-            want = ("%d\n" % tot[1] if first is not None else "") + bk.format_line(tot[0], tot[2:])
-            a, cnt = where[k]
-            ok = ok and "".join(lines[a:a + cnt]) == want
-        return ok
+        ok = at == len(lines) and all("".join(lines[where[k][0]:where[k][0] + where[k][1]]) == wants[k] for k in pick)
+        return rig.verdict_of_rank0(ok)
     res = run_generated(rig, "c5", w, twin, check, 30, steps, warmup, twin_first=100, sampler=sampler)
     res["scaling"] = "strong (the same batch on every N)"
     res["relation_rows"] = bk.c5_sizes(scale)
@@ -691,11 +696,18 @@ def main():
                              ("c5", lambda: config_c5(rig, args.c5_scale or 0.125, args.c5_queries, 2, 1))):
                 try:
                     others[name] = fn()
+                    drop()
                 except Exception as e:  # a side config never takes the headline down
                     others[name] = {"error": repr(e)[:400]}
                     if world > 1:
-                        raise
-                drop()
+                        # the ranks are out of step after a failure: keep the headline, skip the rest, and do
+                        # not wait for peers that may be gone
+                        rig.lib.qce_comm_abort()
+                        line["configs"] = others
+                        if rank == 0:
+                            print(json.dumps(line), flush=True)
+                        os._exit(0 if rank == 0 else 1)
+                    drop()
             line["configs"] = others
     else:
         sampler = ClockSampler(local_rank, period=float(os.environ.get("QCE_BENCH_CLOCK_PERIOD", "0.05")))

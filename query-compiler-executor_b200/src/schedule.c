@@ -133,8 +133,12 @@ static void mark_col(batch *b, size_t i, int state)
 }
 
 /* ------------------------------------------------------------------ one query */
+static int g_trace_jobs = -1;
 static void run_job(batch *b, qjob *j)
 {
+    if (g_trace_jobs < 0) g_trace_jobs = getenv("QCE_TRACE_JOBS") != NULL;
+    if (g_trace_jobs) fprintf(stderr, "[qce] rank %u thread %lx: query %ld starts (cost %lu, heavy %d, owner %d)\n", qce_comm_rank(),
+                              (unsigned long)pthread_self(), (long)(j - b->jobs), (unsigned long)j->cost, j->heavy, j->owner);
     for_each_col(j->q, wait_cb, b);
     FILE *mem = open_memstream(&j->text, &j->len);
     if (mem == NULL) { j->failed = 1; return; }
@@ -148,6 +152,7 @@ static void run_job(batch *b, qjob *j)
     tl_fatal_jmp = NULL;
     fclose(mem);
     j->ran = 1;
+    if (g_trace_jobs) fprintf(stderr, "[qce] rank %u thread %lx: query %ld done\n", qce_comm_rank(), (unsigned long)pthread_self(), (long)(j - b->jobs));
 }
 
 /* ------------------------------------------------------------------ threads */
