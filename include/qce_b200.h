@@ -320,6 +320,17 @@ int qce_tuples_from_window(uint64_t word_offset, uint64_t n, uint32_t key_bits, 
  * they arrived grouped by L2-sized row regions, the checksum needs no bucketing pass. */
 int qce_rowids_from_window(uint64_t u32_offset, uint64_t n, uint32_t id_min, uint32_t id_bound,
                            int bucketed, qce_rowids **out);
+/* Bystander re-join elision, used by the host layer's join operator when it can show
+ * that the reference's join_payloads (src/join.c:426-484) yields the same multisets:
+ * qce_build_tuples_positions: (key = col[ids[i]], payload = i) instead of payload = ids[i];
+ * qce_merge_join_stats: qce_merge_join + min / max matches per outer tuple (uniform multiplicity
+ * test); qce_rowids_gather re-aligns every column of the entity with the positions the merge
+ * returned.  qce_elision_supported: 1 on a single rank (or a solo context), 0 when the join's
+ * inputs are exchanged between ranks (QCE_ELIDE=0 forces 0). */
+int qce_build_tuples_positions(uint32_t rel, uint32_t col, const qce_rowids *ids, qce_tuples **out);
+int qce_merge_join_stats(const qce_tuples *R, const qce_tuples *S, qce_rowids **outR, qce_rowids **outS,
+                         uint32_t *min_matches, uint32_t *max_matches);
+int qce_elision_supported(void);
 /* out[i] = src[index[i]] (re-align a bystander row-id column with a join output whose
  * payloads are positions; SURVEY 8f-2, replaces join_payloads src/join.c:426-484 inside PDQ-T). */
 int qce_rowids_gather(const qce_rowids *src, const qce_rowids *index, qce_rowids **out);

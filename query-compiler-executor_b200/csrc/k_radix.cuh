@@ -75,7 +75,9 @@ k_build_packed_base(const u64 *__restrict__ col, u64 n, u64 *__restrict__ out, u
 // Packed, through a row-id column: out[i] = col[ids[i]] << 32 | ids[i]
 // (src/join.c:107-112).  The gather is sector-bound unless ids are clustered
 // (filter outputs are ascending).
-template <bool HIST>
+// POS: the payload is the element's POSITION in the row-id column instead of the row id, so
+// that the columns aligned with it can be gathered after the merge.
+template <bool HIST, bool POS = false>
 __global__ void __launch_bounds__(256)
 k_build_packed_ids(const __grid_constant__ ColRef col, const u32 *__restrict__ ids, u64 n,
                    u64 *__restrict__ out, int hist_shift, u32 *__restrict__ ghist)
@@ -93,7 +95,7 @@ k_build_packed_ids(const __grid_constant__ ColRef col, const u32 *__restrict__ i
 #pragma unroll
         for (int k = 0; k < 4; k++)
             if (i0 + k * 256 < n) {
-                out[i0 + k * 256] = (v[k] << 32) | id[k];
+                out[i0 + k * 256] = (v[k] << 32) | (POS ? (u64)(i0 + k * 256) : (u64)id[k]);
                 if (HIST) atomicAdd(&sh[(u32)(v[k] >> hist_shift) & 255u], 1u);
             }
     }
@@ -878,6 +880,18 @@ k_msd_partition_bulk(const u64 *__restrict__ in, u64 *__restrict__ out, const Ms
 }
 
 // Largest segment length (to decide whether every sub-bucket fits the finish kernel).
+// min and max of the per-tuple match counts of a merge (uniform multiplicity test, 8f-2)
+__global__ void __launch_bounds__(256) k_minmax_u32(const u32 *__restrict__ v, u32 n, u32 *__restrict__ out_min, u32 *__restrict__ out_max)
+{
+    u32 lo = 0xffffffffu, hi = 0;
+    for (u32 i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) { const u32 x = v[i]; lo = min(lo, x); hi = max(hi, x); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(QCE_FULL_MASK, lo, o));
+        hi = max(hi, __shfl_xor_sync(QCE_FULL_MASK, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(out_min, lo); atomicMax(out_max, hi); }
+}
 __global__ void __launch_bounds__(256) k_max_u32(const u32 *__restrict__ v, u32 n, u32 *__restrict__ out)
 {
     u32 m = 0;

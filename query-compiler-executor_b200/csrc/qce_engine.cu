@@ -787,6 +787,8 @@ TupleView view_of(const qce_tuples *t)
 }
 
 // ---- merge join driver -------------------------------------------------------
+thread_local u32 *tl_join_stats = nullptr; // when set: {min, max} match count per outer tuple of the next merge
+
 template <bool WR, bool WS>
 int merge_join_t(const qce_tuples *R, const qce_tuples *S, bool want_r, bool want_s, qce_rowids **outR,
                  qce_rowids **outS, bool walk)
@@ -830,8 +832,17 @@ int merge_join_t(const qce_tuples *R, const qce_tuples *S, bool want_r, bool wan
         LAUNCH("scan_tiles", (k_scan_excl<u32, u32>), 1, 1024, 0, tile_chunks, chunk_off, (u64)ntiles,
                cx().d_scalars + 1);
     }
-    if (read_scalars(2) != 0) return -1;
+    if (tl_join_stats) {
+        const u32 init[4] = {0xffffffffu, 0u, 0u, 0u}; // d_scalars[2] = {min, max}
+        CK(cudaMemcpyAsync(cx().d_scalars + 2, init, sizeof init, cudaMemcpyHostToDevice, cx().stream));
+        LAUNCH("join_stats", k_minmax_u32, grid_for(1024, nR, 4), 256, 0, cnt, nR, (u32 *)(cx().d_scalars + 2), (u32 *)(cx().d_scalars + 2) + 1);
+    }
+    if (read_scalars(3) != 0) return -1;
     const u64 m = cx().h_scalars[0], nchunks = cx().h_scalars[1];
+    if (tl_join_stats) {
+        tl_join_stats[0] = (u32)(cx().h_scalars[2] & 0xffffffffu);
+        tl_join_stats[1] = (u32)(cx().h_scalars[2] >> 32);
+    }
     if (m >= (1ull << 32)) return fail("join output of %llu pairs exceeds the 2^32 row-id column limit", (unsigned long long)m);
     qce_rowids *oR = nullptr, *oS = nullptr;
     if (want_r && new_rowids(m, R->id_bound, &oR) != 0) return -1;
@@ -1679,7 +1690,7 @@ static bool fused_build_hist()
     return on != 0;
 }
 static int build_tuples(const Column *cl, const qce_rowids *ids, qce_tuples **out, u64 begin = 0,
-                        u64 count = ~0ull)
+                        u64 count = ~0ull, bool positions = false)
 {
     if (count == ~0ull) count = cl->n - begin;
     if (!ids && !window_resident(cl, begin, count)) return fail("rows [%llu, +%llu) are not resident on this rank",
@@ -1709,7 +1720,11 @@ static int build_tuples(const Column *cl, const qce_rowids *ids, qce_tuples **ou
                 CK(cudaMemsetAsync(t->hist256, 0, QCE_RADIX_BINS * sizeof(u32), cx().stream));
                 t->hist_key_bits = t->key_bits;
             }
-            if (ids && hist)
+            if (ids && positions && hist)
+                LAUNCH("build_tuples", (k_build_packed_ids<true, true>), grid_for(1024, n), 256, 0, ref_of(cl), ids->d, n, t->a, hshift, t->hist256);
+            else if (ids && positions)
+                LAUNCH("build_tuples", (k_build_packed_ids<false, true>), grid_for(1024, n), 256, 0, ref_of(cl), ids->d, n, t->a, 0, (u32 *)nullptr);
+            else if (ids && hist)
                 LAUNCH("build_tuples", k_build_packed_ids<true>, grid_for(1024, n), 256, 0, ref_of(cl), ids->d, n, t->a, hshift, t->hist256);
             else if (ids)
                 LAUNCH("build_tuples", k_build_packed_ids<false>, grid_for(1024, n), 256, 0, ref_of(cl), ids->d, n, t->a, 0, (u32 *)nullptr);
@@ -1774,6 +1789,50 @@ int qce_build_tuples_rowids(uint32_t rel, uint32_t col, const qce_rowids *ids, q
     (*out)->src_rel = rel;
     (*out)->src_col = col;
     return 0;
+}
+
+/* Bystander re-join elision (replaces join_payloads, src/join.c:426-484, inside the
+ * parity-defined query class): (key = col[ids[i]], payload = i) -- the POSITION in the row-id column,
+ * so that after the merge every column aligned with `ids` is re-aligned with one gather
+ * (qce_rowids_gather) instead of a distinct-pair pass, two sorts and a merge per column.
+ * Packed keys (< 2^32) on one rank only; -1 otherwise (the caller replays join_payloads). */
+int qce_build_tuples_positions(uint32_t rel, uint32_t col, const qce_rowids *ids, qce_tuples **out)
+{
+    NEED_INIT();
+    const Column *cl;
+    if (!ids) return fail("null row-id column");
+    if (sharded()) return fail("position-carrying runs are not exchanged between ranks");
+    if (get_column(rel, col, &cl) != 0) return -1;
+    if (bitlen(cl->maxv) > 32) return fail("position-carrying runs need keys below 2^32");
+    if (build_tuples(cl, ids, out, 0, ~0ull, true) != 0) return -1;
+    (*out)->src_rel = rel;
+    (*out)->src_col = col;
+    (*out)->id_bound = (u32)ids->n;
+    return 0;
+}
+int qce_elision_supported(void)
+{
+    if (!G.inited && qce_init(-1) != 0) return 0;
+    static int on = -1; // QCE_ELIDE=0: always replay join_payloads
+    if (on < 0) { const char *e = getenv("QCE_ELIDE"); on = e ? atoi(e) : 1; }
+    return on && !sharded();
+}
+/* qce_merge_join that also reports the smallest and largest number of matches of an outer (R)
+ * tuple: min == max means uniform multiplicity, under which join_payloads' positional pairing
+ * cannot change a re-joined column's multiset. */
+int qce_merge_join_stats(const qce_tuples *R, const qce_tuples *S, qce_rowids **outR, qce_rowids **outS,
+                         uint32_t *min_matches, uint32_t *max_matches)
+{
+    NEED_INIT();
+    if (!R || !S || !outR || !outS || !min_matches || !max_matches) return fail("null argument");
+    if (sharded()) return fail("merge statistics are per rank");
+    u32 st[2] = {0, 0};
+    if (R->n && S->n) tl_join_stats = st;
+    const int rc = merge_join_any(R, S, true, true, outR, outS);
+    tl_join_stats = nullptr;
+    *min_matches = st[0];
+    *max_matches = st[1];
+    return rc;
 }
 
 int qce_sort_tuples(qce_tuples *t)
@@ -2387,7 +2446,9 @@ static int push_tuples_impl(const qce_tuples *t, uint32_t key_bits, const uint64
     if (t->wide) return fail("the sharded exchange supports packed (key < 2^32) runs only");
     if (nparts != G.xworld) return fail("nparts (%u) differs from the attached world size (%u)", nparts, G.xworld);
     if (key_bits == 0 || key_bits > 32) return fail("packed runs carry keys of 1..32 bits");
-    if (t->n >= (1ull << 28)) return fail("push of %llu tuples exceeds the 2^28 per-run limit", (unsigned long long)t->n);
+    // slots carry (destination << 28 | position): 2^28 tuples per run; a plain push only needs 32-bit tile offsets
+    if (t->n >= ((slots_out || dst_run_index) ? (1ull << 28) : (1ull << 32) - 4096))
+        return fail("push of %llu tuples exceeds the per-run limit", (unsigned long long)t->n);
     if (nparts > 1 && !splitters) return fail("null argument");
     const int bin_shift = key_bits > 8 ? (int)key_bits - 8 : 0;
     unsigned char lut[256];

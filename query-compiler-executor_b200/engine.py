@@ -36,7 +36,8 @@ SYMBOLS = [
     "qce_batch_cache_stats", "qce_comm_fork", "qce_comm_attach", "qce_comm_rank", "qce_comm_world", "qce_comm_is_child",
     "qce_comm_barrier", "qce_comm_allreduce_sum_u64", "qce_comm_allreduce_max_u64", "qce_comm_gatherv", "qce_comm_abort",
     "qce_comm_finish", "qce_upload_column_window", "qce_upload_column_window_device", "qce_row_share",
-    "qce_set_replicate_bytes", "qce_column_would_be_whole", "qce_column_is_whole", "qce_rowids_count_local", "qce_xwin_unmap_peers",
+    "qce_set_replicate_bytes", "qce_column_would_be_whole", "qce_column_is_whole", "qce_rowids_count_local", "qce_xwin_unmap_peers", "qce_build_tuples_positions", "qce_merge_join_stats",
+    "qce_elision_supported",
 ]
 
 
@@ -105,6 +106,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "qce_row_share": (i32, [u64, u32, u32, P(u64), P(u64)]), "qce_set_replicate_bytes": (i32, [u64]),
         "qce_column_would_be_whole": (i32, [u64]), "qce_column_is_whole": (i32, [u32, u32]),
         "qce_rowids_count_local": (u64, [vp]), "qce_xwin_unmap_peers": (i32, []),
+        "qce_build_tuples_positions": (i32, [u32, u32, vp, P(vp)]),
+        "qce_merge_join_stats": (i32, [vp, vp, P(vp), P(vp), P(u32), P(u32)]), "qce_elision_supported": (i32, []),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -9,6 +9,7 @@
 #include "filter.h"
 
 #include "../../include/qce_b200.h"
+#include "join.h"
 
 static __thread FILE *g_query_out = NULL; /* one query per host thread (schedule.c) */
 
@@ -41,6 +42,12 @@ int execute_filter(predicate *pred, uint32_t *relations, DArray *metadata_arr, D
         DArray *entity = *(DArray **)DArray_get(mid_results_array, where.mid_result);
         mid_result *entry = (mid_result *)DArray_get(entity, where.index);
         uint64_t survivors = 0;
+        if (qce_join_elide_active() && DArray_count(entity) > 1) {
+            /* a refine narrows ONE column of the entity (src/filter.c:3-35): its siblings keep their length,
+             * and what the reference does with such an entity afterwards depends on their order */
+            qce_join_elide_raise();
+            return -1;
+        }
         check(qce_filter_refine(entry->payloads, rel, col, pred->operator, constant, &survivors) == 0,
               "Execution of filter failed! %s", qce_last_error());
         fprintf(qce_query_stdout(), "%d\n", (int)survivors);

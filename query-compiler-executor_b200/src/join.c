@@ -31,6 +31,51 @@
 #include "../../include/qce_b200.h"
 #include "schedule.h"
 
+/* ---- bystander re-join elision ------------------------------------------------
+ * join_payloads (src/join.c:426-484) re-aligns every other column of an entity after a join with
+ * a distinct-pair pass, two sorts and a merge PER COLUMN.  Inside the parity-defined query class
+ * the multiset it produces is {B[i] x matches(U[i])} -- exactly what gathering B through the
+ * POSITIONS of the joined column's tuples gives (qce_build_tuples_positions + qce_rowids_gather).
+ * The two differ only in the ORDER of the re-joined column (the reference's is by row id of U,
+ * the gathered one stays aligned with U'), which the reference itself never relies on inside the
+ * class: it matters only when a later operator pairs columns of that entity positionally, and
+ * then the reference's own result is pairing-dependent unless every tuple has the same number of
+ * matches.  So a query runs in elided mode while, per join with bystanders,
+ *   - the other side is a base relation (distinct row ids: matches == distinct partners),
+ *   - the entity has not been re-joined before, OR every outer tuple has the same match count
+ *     (min == max, qce_merge_join_stats) -- then any pairing yields the same multiset,
+ * and no positional operator (scan_join, a JOIN_SORT_* that trusts an order, a refine) touches an
+ * entity that has been re-joined.  Anything else raises `unsafe`: the scheduler discards the
+ * attempt and replays the query faithfully (schedule.c), so nothing is ever answered differently. */
+#define MAX_TRACKED_ENTITIES 16
+static __thread int tl_elide = 0, tl_unsafe = 0;
+static __thread DArray *tl_rejoined[MAX_TRACKED_ENTITIES];
+static __thread int tl_nrejoined = 0;
+
+void qce_join_elide_begin(int on)
+{
+    tl_elide = on;
+    tl_unsafe = 0;
+    tl_nrejoined = 0;
+}
+int qce_join_elide_unsafe(void) { return tl_unsafe; }
+int qce_join_elide_active(void) { return tl_elide && !tl_unsafe; }
+void qce_join_elide_raise(void) { tl_unsafe = 1; }
+
+static int entity_rejoined(const DArray *entity)
+{
+    for (int i = 0; i < tl_nrejoined; i++)
+        if (tl_rejoined[i] == entity) return 1;
+    return 0;
+}
+static void mark_rejoined(DArray *entity)
+{
+    if (entity_rejoined(entity)) return;
+    if (tl_nrejoined == MAX_TRACKED_ENTITIES) { tl_unsafe = 1; return; }
+    tl_rejoined[tl_nrejoined++] = entity;
+}
+int qce_entity_was_rejoined(const DArray *entity) { return entity_rejoined(entity); }
+
 /* one operand of the predicate, resolved against the entity list */
 typedef struct join_side {
     uint32_t rel;       /* relation id */
@@ -229,6 +274,12 @@ static int replace_and_rejoin(join_result *res, DArray *entities, exists_info wh
     for (size_t i = 0; i < DArray_count(entity); i++) {
         mid_result *bystander = (mid_result *)DArray_get(entity, i);
         if (bystander->relation == plan->lhs.rel || bystander->relation == plan->rhs.rel) continue;
+        if (qce_join_elide_active() && entity_rejoined(entity)) {
+            /* a faithful replay on top of an elided one would pair columns the reference has in another order */
+            qce_join_elide_raise();
+            return -1;
+        }
+        mark_rejoined(entity);
         if (need_distinct(res) != 0) return -1;
         struct qce_rowids *rejoined = NULL;
         if (qce_rejoin(res->non_duplicates[side], joined->payloads, bystander->payloads, &rejoined) != 0) {
@@ -300,6 +351,123 @@ static int install_results(join_result *res, DArray *entities, const join_plan *
     return 0;
 }
 
+/* ---- the elided join (see the top of this file) ----------------------------------------------- */
+static DArray *entity_of(DArray *entities, const mid_result *m)
+{
+    for (size_t e = 0; e < DArray_count(entities); e++) {
+        DArray *entity = *(DArray **)DArray_get(entities, e);
+        for (size_t j = 0; j < DArray_count(entity); j++)
+            if ((const mid_result *)DArray_get(entity, j) == m) return entity;
+    }
+    return NULL;
+}
+static int has_bystanders(DArray *entity, const join_plan *plan)
+{
+    for (size_t i = 0; i < DArray_count(entity); i++) {
+        const mid_result *m = (const mid_result *)DArray_get(entity, i);
+        if (m->relation != plan->lhs.rel && m->relation != plan->rhs.rel) return 1;
+    }
+    return 0;
+}
+
+/* 1: the join ran in elided mode and its results are installed; 0: not applicable, take the
+ * faithful path; QCE_JOIN_UNSAFE: elided mode can no longer vouch for the reference's result. */
+static int elided_join(const join_plan *plan, DArray *entities)
+{
+    const join_side *sides[2] = {&plan->lhs, &plan->rhs};
+    DArray *ent[2] = {NULL, NULL};
+    int bys[2] = {0, 0};
+    for (int s = 0; s < 2; s++)
+        if (sides[s]->source) {
+            ent[s] = entity_of(entities, sides[s]->source);
+            bys[s] = ent[s] ? has_bystanders(ent[s], plan) : 0;
+        }
+    const int rej0 = ent[0] && entity_rejoined(ent[0]), rej1 = ent[1] && entity_rejoined(ent[1]);
+
+    if (plan->kind == SCAN_JOIN) /* positional: the order inside a re-joined entity differs from the reference's */
+        return (rej0 || rej1) ? QCE_JOIN_UNSAFE : 0;
+    if (!bys[0] && !bys[1]) {
+        /* no column is re-joined; but a JOIN_SORT_* trusts the order of a column the reference has re-ordered */
+        if (plan->kind == JOIN_SORT_RHS && rej0) return QCE_JOIN_UNSAFE;
+        if (plan->kind == JOIN_SORT_LHS && rej1) return QCE_JOIN_UNSAFE;
+        return 0;
+    }
+    /* exactly one side comes from an entity with bystanders; the other one is a base relation */
+    const int s = bys[0] ? 0 : 1, o = 1 - s;
+    if (bys[o] || sides[o]->source != NULL) return QCE_JOIN_UNSAFE;
+    const int rejoined = s == 0 ? rej0 : rej1;
+    if (rejoined && (s != 0 || plan->kind != CLASSIC_JOIN)) return QCE_JOIN_UNSAFE; /* the match counts are per outer tuple */
+    if (plan->kind == JOIN_SORT_RHS && s != 0) return QCE_JOIN_UNSAFE;
+    if (plan->kind == JOIN_SORT_LHS && s != 1) return QCE_JOIN_UNSAFE;
+
+    qce_tuples *t[2] = {NULL, NULL};
+    struct qce_rowids *out[2] = {NULL, NULL}, *fresh_ids = NULL;
+    int rc = -1;
+    if (qce_build_tuples_positions(sides[s]->rel, sides[s]->col, sides[s]->source->payloads, &t[s]) != 0)
+        return 0; /* keys >= 2^32: the faithful path handles them */
+    if (qce_build_tuples_base(sides[o]->rel, sides[o]->col, &t[o]) != 0) {
+        log_err("Couldn't allocate relations: %s", qce_last_error());
+        goto done;
+    }
+    if (plan->kind == CLASSIC_JOIN) {
+        if (qce_sort_tuples(t[0]) != 0 || qce_sort_tuples(t[1]) != 0) { log_err("sort failed: %s", qce_last_error()); goto done; }
+    } else {
+        /* the entity side is trusted to be in key order (src/join.c:197-204): only vouched for when it is */
+        int sorted = 0;
+        if (qce_tuples_count(t[s]) && qce_tuples_count(t[o])) {
+            if (qce_tuples_is_sorted(t[s], &sorted) != 0) { log_err("%s", qce_last_error()); goto done; }
+            if (!sorted) { rc = QCE_JOIN_UNSAFE; goto done; }
+        }
+        if (qce_sort_tuples(t[o]) != 0) { log_err("sort failed: %s", qce_last_error()); goto done; }
+    }
+    uint32_t lo = 0, hi = 0;
+    if (qce_merge_join_stats(t[0], t[1], &out[0], &out[1], &lo, &hi) != 0) { log_err("merge join failed: %s", qce_last_error()); goto done; }
+    if (rejoined && lo != hi && qce_tuples_count(t[0]) && qce_tuples_count(t[1])) { rc = QCE_JOIN_UNSAFE; goto done; }
+
+    /* out[s] holds POSITIONS in the entity: every column of the entity follows them */
+    for (size_t i = 0; i < DArray_count(ent[s]); i++) {
+        mid_result *m = (mid_result *)DArray_get(ent[s], i);
+        const int joined = m == sides[s]->source;
+        if (!joined && (m->relation == plan->lhs.rel || m->relation == plan->rhs.rel)) continue; /* src/join.c:495: by relation id */
+        if (qce_rowids_count(m->payloads) < qce_rowids_count(sides[s]->source->payloads)) { rc = QCE_JOIN_UNSAFE; goto done; }
+    }
+    for (size_t i = 0; i < DArray_count(ent[s]); i++) {
+        mid_result *m = (mid_result *)DArray_get(ent[s], i);
+        const int joined = m == sides[s]->source;
+        if (!joined && (m->relation == plan->lhs.rel || m->relation == plan->rhs.rel)) continue;
+        struct qce_rowids *g = NULL;
+        if (qce_rowids_gather(m->payloads, out[s], &g) != 0) { log_err("gather failed: %s", qce_last_error()); goto done; }
+        if (joined) { fresh_ids = g; continue; } /* installed last: it still indexes nothing else */
+        qce_rowids_free(m->payloads);
+        m->payloads = g;
+    }
+    {
+        mid_result *joined = sides[s]->source;
+        qce_rowids_free(joined->payloads);
+        joined->payloads = fresh_ids;
+        joined->last_column_sorted = (int32_t)sides[s]->col;
+        fresh_ids = NULL;
+        mid_result other;
+        other.relation = sides[o]->rel;
+        other.predicate_id = sides[o]->binding;
+        other.last_column_sorted = (int32_t)sides[o]->col;
+        other.payloads = out[o];
+        out[o] = NULL;
+        DArray *last = *(DArray **)DArray_last(entities);
+        DArray_push(last, &other);
+    }
+    mark_rejoined(ent[s]);
+    rc = 1;
+
+done:
+    qce_tuples_free(t[0]);
+    qce_tuples_free(t[1]);
+    qce_rowids_free(out[0]);
+    qce_rowids_free(out[1]);
+    qce_rowids_free(fresh_ids);
+    return rc;
+}
+
 int execute_join(predicate *pred, uint32_t *relations, DArray *metadata_arr, DArray *mid_results_array)
 {
     (void)metadata_arr;
@@ -309,6 +477,11 @@ int execute_join(predicate *pred, uint32_t *relations, DArray *metadata_arr, DAr
     if (plan_join(pred, relations, mid_results_array, &plan) != 0) return -1;
     if (plan.kind == DO_NOTHING) return 0;
     debug("join kind %d", plan.kind);
+    if (qce_join_elide_active()) {
+        const int r = elided_join(&plan, mid_results_array);
+        if (r == QCE_JOIN_UNSAFE) { qce_join_elide_raise(); return QCE_JOIN_UNSAFE; }
+        if (r != 0) return r == 1 ? 0 : -1;
+    }
 
     if (run_join(&plan, &res) != 0) goto error;
     if (install_results(&res, mid_results_array, &plan) != 0) goto error_installed;

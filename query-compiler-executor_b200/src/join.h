@@ -25,6 +25,16 @@ typedef struct result {
     struct qce_rowids *non_duplicates[2];
 } join_result;
 
+/* Bystander re-join elision (join.c): the scheduler runs a query in elided mode
+ * first when its shape allows it and replays it faithfully when the join operator reports that
+ * elided mode can no longer vouch for the reference's result. */
+#define QCE_JOIN_UNSAFE (-2)
+void qce_join_elide_begin(int on);
+int qce_join_elide_unsafe(void);
+int qce_join_elide_active(void);
+void qce_join_elide_raise(void);
+int qce_entity_was_rejoined(const DArray *entity);
+
 /* Applies `a.x = b.y` to the query's entity list.  Returns 0, or -1 on error
  * (including a merge that would run over unsorted input, which the reference
  * executes with undefined results). */

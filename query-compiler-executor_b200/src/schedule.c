@@ -11,6 +11,7 @@
 
 #include "../../include/qce_b200.h"
 #include "dbg.h"
+#include "join.h"
 #include "pred_arrange.h"
 #include "structs.h"
 #include "utilities.h"
@@ -133,6 +134,27 @@ static void mark_col(batch *b, size_t i, int state)
 }
 
 /* ------------------------------------------------------------------ one query */
+/* Shape test for elided mode (the parity-defined class): distinct relation ids, filters
+ * on at most one binding, and at least two join predicates (otherwise no bystander ever exists). */
+static int elidable(const query *q)
+{
+    size_t joins = 0;
+    long fbind = -1;
+    for (size_t i = 0; i < q->relations_size; i++)
+        for (size_t k = i + 1; k < q->relations_size; k++)
+            if (q->relations[i] == q->relations[k]) return 0;
+    for (size_t i = 0; i < q->predicates_size; i++) {
+        const predicate *p = &q->predicates[i];
+        if (p->type == 1) {
+            if (fbind >= 0 && (long)p->first.relation != fbind) return 0;
+            fbind = (long)p->first.relation;
+        } else {
+            joins++;
+        }
+    }
+    return joins >= 2;
+}
+
 static int g_trace_jobs = -1;
 static void run_job(batch *b, qjob *j)
 {
@@ -140,17 +162,32 @@ static void run_job(batch *b, qjob *j)
     if (g_trace_jobs) fprintf(stderr, "[qce] rank %u thread %lx: query %ld starts (cost %lu, heavy %d, owner %d)\n", qce_comm_rank(),
                               (unsigned long)pthread_self(), (long)(j - b->jobs), (unsigned long)j->cost, j->heavy, j->owner);
     for_each_col(j->q, wait_cb, b);
-    FILE *mem = open_memstream(&j->text, &j->len);
-    if (mem == NULL) { j->failed = 1; return; }
-    jmp_buf jb;
-    tl_fatal_jmp = &jb;
-    if (setjmp(jb) == 0) {
-        if (execute_query_to(j->q, b->meta, mem) != 0) j->failed = 1;
-    } else {
-        j->fatal = 1; /* the reference exits here; what the query printed so far stays */
+    /* first with the bystander re-joins elided (join.c) when the query's shape allows it; withdrawn
+     * attempts are replayed faithfully, their output discarded */
+    for (int attempt = elidable(j->q) && qce_elision_supported() ? 0 : 1; attempt < 2; attempt++) {
+        free(j->text);
+        j->text = NULL;
+        j->len = 0;
+        j->failed = j->fatal = 0;
+        FILE *mem = open_memstream(&j->text, &j->len);
+        if (mem == NULL) { j->failed = 1; return; }
+        jmp_buf jb;
+        volatile int withdrawn = 0;
+        tl_fatal_jmp = &jb;
+        qce_join_elide_begin(attempt == 0);
+        if (setjmp(jb) == 0) {
+            if (execute_query_to(j->q, b->meta, mem) != 0) j->failed = 1;
+            withdrawn = qce_join_elide_unsafe();
+        } else {
+            j->fatal = 1; /* the reference exits here; what the query printed so far stays */
+            withdrawn = attempt == 0; /* its partial output must be the faithful path's */
+        }
+        tl_fatal_jmp = NULL;
+        qce_join_elide_begin(0);
+        fclose(mem);
+        if (!withdrawn) break;
+        if (g_trace_jobs) fprintf(stderr, "[qce] query %ld: elided attempt withdrawn, replaying\n", (long)(j - b->jobs));
     }
-    tl_fatal_jmp = NULL;
-    fclose(mem);
     j->ran = 1;
     if (g_trace_jobs) fprintf(stderr, "[qce] rank %u thread %lx: query %ld done\n", qce_comm_rank(), (unsigned long)pthread_self(), (long)(j - b->jobs));
 }

@@ -257,10 +257,13 @@ int execute_query_to(query *q, DArray *metadata_arr, FILE *out)
 
     for (size_t i = 0; i < q->predicates_size; i++) {
         predicate *p = &q->predicates[i];
+        const int r = p->type == 1 ? execute_filter(p, q->relations, metadata_arr, entities)
+                                   : execute_join(p, q->relations, metadata_arr, entities);
+        if (qce_join_elide_unsafe()) goto error; /* elided attempt withdrawn: the scheduler replays the query */
         if (p->type == 1) {
-            check(execute_filter(p, q->relations, metadata_arr, entities) != -1, "Filter failed!");
+            check(r != -1, "Filter failed!");
         } else {
-            check(execute_join(p, q->relations, metadata_arr, entities) != -1, "Join failed!");
+            check(r != -1, "Join failed!");
         }
     }
     check(print_sums(entities, q, out ? out : stdout) == 0, "Projection failed!");

@@ -273,6 +273,45 @@ static void walk(const qce_tuples *R, const qce_tuples *S, qce_rowids **outR, qc
     if (outR) *outR = r; else qce_rowids_free(r);
     if (outS) *outS = s; else qce_rowids_free(s);
 }
+/* ---- bystander re-join elision: positions through the merge, then gathers */
+int qce_elision_supported(void) { return getenv("QCE_ELIDE") ? atoi(getenv("QCE_ELIDE")) : 1; }
+int qce_build_tuples_positions(uint32_t rel, uint32_t col, const qce_rowids *ids, qce_tuples **out)
+{
+    if (qce_build_tuples_rowids(rel, col, ids, out) != 0) return -1;
+    for (uint64_t i = 0; i < (*out)->n; i++) {
+        if ((*out)->k[i] >> 32) { qce_tuples_free(*out); return fail("position-carrying runs need keys below 2^32"); }
+        (*out)->p[i] = i;
+    }
+    return 0;
+}
+int qce_merge_join_stats(const qce_tuples *R, const qce_tuples *S, qce_rowids **outR, qce_rowids **outS,
+                         uint32_t *min_matches, uint32_t *max_matches)
+{
+    if (!R || !S || !outR || !outS || !min_matches || !max_matches) return fail("null argument");
+    walk(R, S, outR, outS);
+    uint32_t lo = 0xffffffffu, hi = 0;
+    for (uint64_t i = 0; i < R->n; i++) {
+        uint32_t c = 0;
+        for (uint64_t j = 0; j < S->n; j++) c += S->k[j] == R->k[i]; /* tiny inputs only */
+        if (c < lo) lo = c;
+        if (c > hi) hi = c;
+    }
+    *min_matches = R->n && S->n ? lo : 0;
+    *max_matches = R->n && S->n ? hi : 0;
+    return 0;
+}
+int qce_rowids_gather(const qce_rowids *src, const qce_rowids *index, qce_rowids **out)
+{
+    if (!src || !index || !out) return fail("null argument");
+    qce_rowids *g = new_ids(index->n);
+    for (uint64_t i = 0; i < index->n; i++) {
+        if (index->d[i] >= src->n) { qce_rowids_free(g); return fail("gather index out of range"); }
+        g->d[i] = src->d[index->d[i]];
+    }
+    *out = g;
+    return 0;
+}
+
 int qce_distinct_pairs(const qce_rowids *pairsR, const qce_rowids *pairsS, qce_rowids **distinctR, qce_rowids **distinctS)
 {
     if (!pairsR || !pairsS || !distinctR || !distinctS) return fail("null argument");

@@ -7,7 +7,7 @@ import pytest
 
 import qce_b200
 from qce_b200 import engine as eng_mod
-from qce_b200.sharded import choose_splitters
+from tests.helpers import choose_splitters
 
 
 def _numpy_plan(H, world, rank, ncols, key_bits):

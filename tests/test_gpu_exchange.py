@@ -1,7 +1,7 @@
 """GPU parity of the peer-memory exchange primitives (k_exchange.cuh) on ONE GPU:
 the local window is presented as `world` ranks (qce_xwin_loopback), so every
 store of the push kernels lands where a multi-GPU run would put it, and the
-sharded executor at world size 1 (same code path as N GPUs, all stores local)
+sharded operators themselves are exercised by tests/test_gpu_ranks.py (real ranks, same kernels)
 against the relational truth / the oracle."""
 import numpy as np
 import pytest
@@ -48,9 +48,8 @@ def test_push_tuples_loopback(xeng, n, world, rewrite):
     ids = rng.permutation(n).astype(U64)
     t = e.tuples_from_host(keys, ids)
     hist = e.key_histogram(t, key_bits)
-    import qce_b200
-    from qce_b200 import sharded
-    splitters = sharded.choose_splitters(hist, key_bits, world)
+    from tests.helpers import choose_splitters
+    splitters = choose_splitters(hist, key_bits, world)
     part = np.searchsorted(np.array(splitters, dtype=U64), keys, side="right") if world > 1 else np.zeros(n, dtype=np.int64)
     counts = np.bincount(part, minlength=world)
     seg_words = np.array([64 + 2 * d for d in range(world)], dtype=U64)     # where "this rank's" segment starts
@@ -191,57 +190,19 @@ def test_windowed_column_refuses_non_resident_rows(engine):
 
 
 # ---------------------------------------------------------------- executor, world size 1
-EXEC = {
-    "pair": ["0 1|0.1=1.1&0.2>500|0.0 1.0 1.2", "0 1|0.1=1.1|0.0 1.2", "0|0.2<100&0.1>3000|0.2", "0 1|0.1=1.1&0.2>999999|0.0 1.0"],
-    "chain": ["0 1 2 3|0.1=0.2&0.1=1.0&1.1=2.0&2.1=3.0&0.3<900|0.3 1.3 2.3 3.3", "0 1 2|0.1=1.0&0.2=2.0&0.3<200|1.1 2.1 0.0",
-              "0 1 2 3|0.1=1.0&1.1=2.0&2.1=3.0|0.3 3.3"],
-    "zipf": ["0 1 2|0.1=1.0&1.1=2.0|0.2 1.2 2.2"],
-}
 
 
-@pytest.mark.parametrize("kind,rows,force_bucketing", [("pair", 300_007, False), ("chain", 200_000, False), ("zipf", 150_000, False),
-                                                       ("chain", 2_000_000, False), ("pair", 1_000_003, True)])
-def test_sharded_executor_world1(kind, rows, force_bucketing):
-    """One rank: the same orchestration and kernels as N GPUs (windowed columns, push
-    kernels, by-slot columns, id push, bucketed checksum) with every store local."""
-    import subprocess, sys, os, json, tempfile
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    child = r'''
-import os, sys, json
-sys.path.insert(0, %r)
-import numpy as np, torch, torch.distributed as dist
-import qce_b200
-from qce_b200 import shardexec
-from oracle import workload as wl, qce_oracle as orc
-os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT="29655", RANK="0", WORLD_SIZE="1")
-torch.cuda.set_device(0)
-dist.init_process_group("nccl", device_id=torch.device("cuda", 0))
-eng = qce_b200.Engine(0)
-kind, rows = %r, %d
-db = {"pair": lambda: wl.gen_pair_db(rows, rows // 3, filt_domain=1000), "chain": lambda: wl.gen_chain_db(rows),
-      "zipf": lambda: wl.gen_zipf_db(rows)}[kind]()
-comm = shardexec.Comm(dist, torch, torch.device("cuda", 0), 0, 1)
-keep = []
-shardexec.load_sharded_columns(eng, torch, comm, db, keep)
-shardexec.open_windows(eng, comm, 1 << 30)
-ex = shardexec.ShardedExecutor(shardexec.EngineOps(eng), comm)
-ok = True
-for q in %r:
-    got = shardexec.format_result(ex.run_query(q))
-    got2 = shardexec.format_result(ex.run_query(q))
-    want = wl.truth_query(orc.parse_query(q), db)
-    if got != want or got2 != want:
-        ok = False
-        print("MISMATCH", q, got, want)
-print("RESULT " + json.dumps({"ok": ok}))
-dist.destroy_process_group()
-''' % (root, kind, rows, EXEC[kind])
-    script = os.path.join(tempfile.mkdtemp(), "exec_child.py")
-    open(script, "w").write(child)
-    env = dict(os.environ)
-    if force_bucketing:  # the owner's window-relative bucketing pass before the checksum gathers
-        env["QCE_BUCKETED_CHECKSUM"] = "1"
-    p = subprocess.run([sys.executable, script], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600, env=env)
-    lines = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
-    assert p.returncode == 0 and lines, (p.stdout[-2000:], p.stderr[-3000:])
-    assert json.loads(lines[-1][7:])["ok"], p.stdout[-2000:]
+def test_failed_ipc_attach_does_not_poison_the_next_launch(xeng):
+    """A non-sticky CUDA failure (an IPC handle that cannot be opened) must not leave its error code in
+    the runtime's last-error slot: the next kernel launch checks cudaGetLastError() and would report
+    the stale failure as its own (CK() now clears it)."""
+    import qce_b200
+    e = xeng
+    with pytest.raises(qce_b200.EngineError):
+        e.xwin_attach(2, 0, bytes(128))  # rank 1's "handle" is garbage
+    e.xwin_loopback(1)
+    col = np.arange(50_000, dtype=U64)
+    e.upload_column(61, 0, col)
+    ids = e.filter_scan(61, 0, "<", 1000)   # launches kernels right after the failed call
+    assert e.rowids_count(ids) == 1000
+    e.rowids_free(ids)

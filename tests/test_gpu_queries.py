@@ -187,3 +187,33 @@ def test_three_join_queries_agree_with_oracle_beyond_pdq(binaries, seed):
         assert rc == 0 and out == want, (q, out, want, err[-300:])
         checked += 1
     assert checked >= 40 and refused <= checked // 4
+
+
+@pytest.mark.parametrize("kind", ["chain", "zipf", "small"])
+def test_elided_rejoins_equal_the_faithful_replay(binaries, kind):
+    """bystander columns re-aligned by the positions carried through the merge (default)
+    against the faithful join_payloads replay (QCE_ELIDE=0) and the oracle -- same stdout, byte for byte."""
+    if kind == "chain":
+        db = wl.gen_chain_db(300_000, nrel=4, seed=5)
+        text = ("0 1 2 3|0.1=0.2&0.1=1.0&1.1=2.0&2.1=3.0&0.3<900|0.3 1.3 2.3 3.3\n"
+                "0 1 2|0.1=1.0&1.1=2.0&0.3<500|0.0 1.3 2.3\n0 1 2 3|0.1=1.0&1.1=2.0&2.1=3.0|0.3 3.3\n")
+    elif kind == "zipf":
+        db = wl.gen_zipf_db(400_000, seed=6)
+        text = "0 1 2|0.1=1.0&1.1=2.0|0.0 1.2 2.1\n0 1 2|0.1=1.0&1.1=2.0&0.2<300|0.2 1.2 2.2\n"
+    else:
+        db = wl.gen_small_db(seed=21, scale=0.05)
+        lines = []
+        for q in wl.gen_queries(db, 80, seed=77, max_joins=3):
+            try:
+                orc.run_batch(db, q + "\n")
+            except orc.ReferenceAbort:
+                continue
+            lines.append(q + "\n")
+        text = "".join(lines)
+    paths = _paths(db)
+    a, ea, rca = run_queries_bin(binaries[0], paths, text)
+    b, eb, rcb = run_queries_bin(binaries[0], paths, text, env={"QCE_ELIDE": 0})
+    assert rca == 0 and rcb == 0, (ea[-800:], eb[-800:])
+    assert a == b
+    if kind != "small":
+        assert a == orc.run_batch(db, text)
