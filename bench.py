@@ -6,7 +6,10 @@ Metric (BASELINE.json): join input rows/s (and queries/s for the batch config).
   python bench.py [--gpus N --steps K --warmup W]     headline = config 2 (BASELINE.json configs[1]):
       single 2-way equi-join + range filter over 2 x 100M-row relations of 3 uint64 columns, query
       `0 1|0.1=1.1&0.2>500000|0.0 1.0 1.2`.  The same line carries, under "configs",
-      short driver-visible runs of configs 3, 4 and 5 (chain join, Zipf join, 1000-query batch).
+      short driver-visible runs of configs 3, 4 and 5 at their BASELINE sizes: the 4-way chain at
+      62.5M rows per relation per GPU (500M over 8 GPUs), the Zipf(1.2) 3-way join at 100M rows per
+      relation per GPU, and the 1000-query batch over 14 relations of 10^6..10^9 rows (one cold run +
+      one timed step: a step is ~10 s on one GPU).
   python bench.py --config c3|c4|c5 ...                that config alone, at full size, as the line's workload
   python bench.py --impl reference ...                 the reference's own CPU binary (oracle/_ref/queries)
                                                        on the config-2 scaled twin
@@ -311,6 +314,12 @@ def run_generated(rig, name, w, twin, check, rel_offset, steps, warmup, twin_fir
     twin_s = time.time() - t0
     t0 = time.time()
     placement = {}
+    if rig.world > 1:
+        # replicate what fits (smallest relations first, 45 % of HBM), row-shard the rest: the engine's planner
+        rows = np.array([w.rows(r) for (r, c) in w.referenced()], dtype=np.uint64)
+        cap = C.c_uint64()
+        rig.ck(rig.lib.qce_placement_cap(rows.ctypes.data, len(rows), C.byref(cap)))
+        rig.ck(rig.lib.qce_set_replicate_bytes(cap.value))
     for (r, c) in w.referenced():
         rows = w.rows(r)
         rig.upload_fn(rel_offset + r, c, rows, lambda b, n, r=r, c=c: w.column_t(torch, r, c, b, n))
@@ -686,14 +695,12 @@ def main():
 
     if args.config in ("all", "c2"):
         line = config_c2(rig, args.rows, args.steps, args.warmup, args, local_rank)
-        if world > 1:
-            rig.ck(rig.lib.qce_set_replicate_bytes(2 << 30))  # config 2 forces row-sharding; the others place by size
         others = {}
         if args.config == "all":
             drop()
             for name, fn in (("c3", lambda: config_c3(rig, args.c3_rows, short, 2)),
                              ("c4", lambda: config_c4(rig, args.rows, short, 2)),
-                             ("c5", lambda: config_c5(rig, args.c5_scale or 0.125, args.c5_queries, 2, 1))):
+                             ("c5", lambda: config_c5(rig, args.c5_scale or 1.0, args.c5_queries, 1, 0))):
                 try:
                     others[name] = fn()
                     drop()

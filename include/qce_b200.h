@@ -125,6 +125,9 @@ int qce_upload_column_window_device(uint32_t rel, uint32_t col, const void *dev,
                                     uint64_t row_count, uint64_t rows_global);
 int qce_row_share(uint64_t rows_global, uint32_t rank, uint32_t world, uint64_t *row_begin, uint64_t *row_count);
 int qce_set_replicate_bytes(uint64_t bytes);
+/* Plan a batch: the largest column size that still fits replicated when the batch's columns (rows of
+ * each) are taken smallest first into QCE_REPLICATE_FRACTION (0.45) of the device memory. */
+int qce_placement_cap(const uint64_t *col_rows, uint32_t ncols, uint64_t *cap_bytes);
 int qce_column_would_be_whole(uint64_t rows);
 int qce_column_is_whole(uint32_t rel, uint32_t col); /* 1 whole / 0 row-sharded / -1 unknown */
 /* Adopt a device buffer without copying (caller keeps ownership, must outlive use). */
@@ -325,9 +328,11 @@ int qce_rowids_from_window(uint64_t u32_offset, uint64_t n, uint32_t id_min, uin
  * qce_build_tuples_positions: (key = col[ids[i]], payload = i) instead of payload = ids[i];
  * qce_merge_join_stats: qce_merge_join + min / max matches per outer tuple (uniform multiplicity
  * test); qce_rowids_gather re-aligns every column of the entity with the positions the merge
- * returned.  qce_elision_supported: 1 on a single rank (or a solo context), 0 when the join's
- * inputs are exchanged between ranks (QCE_ELIDE=0 forces 0). */
+ * returned.  qce_elision_supported: 1 unless QCE_ELIDE=0. */
 int qce_build_tuples_positions(uint32_t rel, uint32_t col, const qce_rowids *ids, qce_tuples **out);
+/* the row-id columns aligned with the run's positions (<= 6): with several ranks they travel with the
+ * tuples when the join exchanges the run, and qce_rowids_gather reads the received copies */
+int qce_tuples_attach(qce_tuples *t, uint32_t ncols, const qce_rowids *const *cols);
 int qce_merge_join_stats(const qce_tuples *R, const qce_tuples *S, qce_rowids **outR, qce_rowids **outS,
                          uint32_t *min_matches, uint32_t *max_matches);
 int qce_elision_supported(void);

@@ -53,6 +53,7 @@ struct qce_rowids {
     u32 id_min = 0;        // inclusive lower bound of the ids (a row-sharded owner sees only its window)
     u64 n_others = 0;      // elements held by the other ranks (0 on one GPU): count = n + n_others
     Dist dist;
+    u64 attach_gen = 0;    // positions into the columns that travelled with the exchange of that generation
 };
 struct qce_tuples {
     u64 *a;        // packed words (key << 32 | rowid), or keys when wide
@@ -74,6 +75,10 @@ struct qce_tuples {
     bool borrowed = false;     // `a` belongs to the batch's sorted-run cache
     u32 src_rel = 0, src_col = 0; // the base column a whole-column run was built from
     bool whole_base = false;
+    // elided re-joins: the payloads are positions, and these row-id columns are
+    // aligned with them -- when the run is exchanged between ranks they travel with the tuples
+    bool positions = false;
+    std::vector<const qce_rowids *> attached;
 };
 
 namespace {
@@ -133,6 +138,7 @@ struct Global {
     std::vector<void *> xopened;
     u32 world = 1, rank = 0;     // ranks of the node (qce_comm.cuh); 1 / 0 on a single GPU
     u64 replicate_bytes = 2ull << 30; // columns up to this size are held whole by every rank
+    bool replicate_forced = false;    // QCE_REPLICATE_BYTES was given: the batch planner leaves it alone
     std::mutex mu;               // guards cols / run cache when worker contexts are live
     // sorted base runs of the running batch, keyed by (relation, column): the same column is
     // sorted again and again across the ~1000 queries of a batch
@@ -304,6 +310,9 @@ struct Ctx {
     std::string prof_json;
     Arena arena;
     bool solo = false; // a worker context: whole queries on this rank alone, never the sharded path
+    // columns that travelled with the last exchange: caller's handle -> view of the received copy
+    u64 attach_gen = 0;
+    std::vector<std::pair<const qce_rowids *, qce_rowids *>> recv_cols;
 };
 Ctx g_main;
 thread_local Ctx *tl_ctx = nullptr;
@@ -870,6 +879,7 @@ int merge_join_any(const qce_tuples *R, const qce_tuples *S, bool want_r, bool w
 {
     if (R->n >= (1ull << 32) || S->n >= (1ull << 32)) return fail("join input exceeds 2^32 tuples");
     if (R->n == 0 || S->n == 0) {
+        if (tl_join_stats && R->n) tl_join_stats[0] = 0; // outer tuples without a single match
         if (outR) *outR = nullptr;
         if (outS) *outS = nullptr;
         if (want_r && new_rowids(0, R->id_bound, outR) != 0) return -1;
@@ -1437,7 +1447,10 @@ static void placement_env()
     static bool done = false;
     if (done) return;
     done = true;
-    if (const char *rb = getenv("QCE_REPLICATE_BYTES")) G.replicate_bytes = strtoull(rb, nullptr, 10);
+    if (const char *rb = getenv("QCE_REPLICATE_BYTES")) {
+        G.replicate_bytes = strtoull(rb, nullptr, 10);
+        G.replicate_forced = true;
+    }
 }
 enum { SRC_HOST = 0, SRC_DEVICE = 1 };
 // `src` holds rows [src_begin, src_begin + src_count) of the relation (the whole column when
@@ -1509,6 +1522,46 @@ int qce_column_would_be_whole(uint64_t rows)
 {
     placement_env();
     return (G.world == 1 || rows * sizeof(u64) <= G.replicate_bytes) ? 1 : 0;
+}
+/* Placement of a batch's columns (several ranks): every rank holds whole the columns that fit, taken
+ * smallest first, into QCE_REPLICATE_FRACTION (default 0.45) of the device memory; larger relations are
+ * row-sharded.  *cap_bytes = the largest column size that is still replicated (pass it to
+ * qce_set_replicate_bytes before the uploads).  An explicit QCE_REPLICATE_BYTES wins. */
+int qce_placement_cap(const uint64_t *col_rows, uint32_t ncols, uint64_t *cap_bytes)
+{
+    NEED_INIT();
+    if (!cap_bytes || (ncols && !col_rows)) return fail("null argument");
+    placement_env();
+    if (G.replicate_forced) { *cap_bytes = G.replicate_bytes; return 0; }
+    static size_t total_b = 0;
+    if (total_b == 0) {
+        size_t free_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+    }
+    double frac = 0.45;
+    if (const char *e = getenv("QCE_REPLICATE_FRACTION")) frac = atof(e);
+    const u64 budget = (u64)(frac * (double)total_b);
+    std::vector<u64> bytes(col_rows, col_rows + ncols);
+    for (auto &b : bytes) b *= sizeof(u64);
+    std::sort(bytes.begin(), bytes.end());
+    u64 sum = 0, cap = 0;
+    for (u64 b : bytes) {
+        if (sum + b > budget) break;
+        sum += b;
+        cap = b;
+    }
+    // columns of one size share one fate: do not split a group at the budget's edge
+    u64 group = 0;
+    for (u64 b : bytes) if (b <= cap) group += b;
+    while (group > budget && cap) {
+        u64 next = 0;
+        for (u64 b : bytes) if (b < cap) next = std::max(next, b);
+        cap = next;
+        group = 0;
+        for (u64 b : bytes) if (b <= cap) group += b;
+    }
+    *cap_bytes = cap;
+    return 0;
 }
 int qce_set_replicate_bytes(uint64_t bytes)
 {
@@ -1801,13 +1854,32 @@ int qce_build_tuples_positions(uint32_t rel, uint32_t col, const qce_rowids *ids
     NEED_INIT();
     const Column *cl;
     if (!ids) return fail("null row-id column");
-    if (sharded()) return fail("position-carrying runs are not exchanged between ranks");
     if (get_column(rel, col, &cl) != 0) return -1;
     if (bitlen(cl->maxv) > 32) return fail("position-carrying runs need keys below 2^32");
     if (build_tuples(cl, ids, out, 0, ~0ull, true) != 0) return -1;
     (*out)->src_rel = rel;
     (*out)->src_col = col;
     (*out)->id_bound = (u32)ids->n;
+    (*out)->positions = true;
+    (*out)->n_others = ids->n_others;
+    (*out)->dist.kind = G.world > 1 && !cx().solo ? (int)Dist::ANY : (int)Dist::LOCAL;
+    return 0;
+}
+/* The row-id columns aligned with a position-carrying run (the joined column itself and its
+ * entity's bystanders).  One rank: nothing to do, the positions index the caller's arrays.
+ * Several ranks: the columns travel with the tuples when the run is exchanged (k_push carries up
+ * to QCE_PUSH_MAX_COLS), and qce_rowids_gather then reads the received copies. */
+int qce_tuples_attach(qce_tuples *t, uint32_t ncols, const qce_rowids *const *cols)
+{
+    NEED_INIT();
+    if (!t || (ncols && !cols)) return fail("null argument");
+    if (!t->positions) return fail("columns attach to position-carrying runs only");
+    if (ncols > QCE_PUSH_MAX_COLS) return fail("at most %d columns travel with one run", QCE_PUSH_MAX_COLS);
+    t->attached.clear();
+    for (u32 c = 0; c < ncols; c++) {
+        if (!cols[c] || cols[c]->n < t->n) return fail("attached column %u is shorter than the run", c);
+        t->attached.push_back(cols[c]);
+    }
     return 0;
 }
 int qce_elision_supported(void)
@@ -1815,7 +1887,7 @@ int qce_elision_supported(void)
     if (!G.inited && qce_init(-1) != 0) return 0;
     static int on = -1; // QCE_ELIDE=0: always replay join_payloads
     if (on < 0) { const char *e = getenv("QCE_ELIDE"); on = e ? atoi(e) : 1; }
-    return on && !sharded();
+    return on;
 }
 /* qce_merge_join that also reports the smallest and largest number of matches of an outer (R)
  * tuple: min == max means uniform multiplicity, under which join_payloads' positional pairing
@@ -1825,7 +1897,7 @@ int qce_merge_join_stats(const qce_tuples *R, const qce_tuples *S, qce_rowids **
 {
     NEED_INIT();
     if (!R || !S || !outR || !outS || !min_matches || !max_matches) return fail("null argument");
-    if (sharded()) return fail("merge statistics are per rank");
+    if (sharded()) return sh_merge_join_stats(R, S, outR, outS, min_matches, max_matches);
     u32 st[2] = {0, 0};
     if (R->n && S->n) tl_join_stats = st;
     const int rc = merge_join_any(R, S, true, true, outR, outS);
@@ -2661,8 +2733,19 @@ int qce_rowids_gather(const qce_rowids *src, const qce_rowids *index, qce_rowids
 {
     NEED_INIT();
     if (!src || !index || !out) return fail("null argument");
+    const u32 *from = src->d;
+    if (index->attach_gen && index->attach_gen == cx().attach_gen) {
+        // the positions index the copy of `src` that travelled with the tuples of the last exchange
+        from = nullptr;
+        for (auto &kv : cx().recv_cols)
+            if (kv.first == src) from = kv.second->d;
+        if (!from) return fail("this column did not travel with the exchanged run");
+    }
     if (new_rowids(index->n, src->id_bound, out) != 0) return -1;
-    if (index->n) LAUNCH("gather_ids", k_gather_u32, grid_for(2048, index->n), 256, 0, src->d, index->d, index->n, (*out)->d);
+    if (index->n) LAUNCH("gather_ids", k_gather_u32, grid_for(2048, index->n), 256, 0, from, index->d, index->n, (*out)->d);
+    (*out)->n_others = index->n_others;
+    (*out)->dist = index->dist;
+    if ((*out)->dist.kind == Dist::KEYS) (*out)->dist.kind = Dist::ANY; // key order of another column
     return 0;
 }
 

@@ -193,6 +193,7 @@ int exchange_plan_impl(const uint64_t *hists, uint32_t world, uint32_t rank, uin
 
 struct XRecv {
     qce_tuples *run = nullptr; // a view of this rank's window: valid until the window is written again
+    bool travelled = false;    // its attached columns came along (cx().recv_cols, generation cx().attach_gen)
 };
 int exchange_runs(const std::vector<const qce_tuples *> &sides, int key_bits, u64 key_max, const Dist *fixed,
                   std::vector<XRecv> *out, Dist *dist_out)
@@ -203,7 +204,10 @@ int exchange_runs(const std::vector<const qce_tuples *> &sides, int key_bits, u6
         if (qce_key_histogram(sides[k], (u32)key_bits, hists.data() + (size_t)k * 256) != 0) { qcecomm::abort_all(); return -1; }
     CQ(qcecomm::allgather(hists.data(), hists.size() * sizeof(uint64_t), all.data()));
     std::vector<uint32_t> ncols(ns, 0);
-    std::vector<uint64_t> splitters(W), recv((size_t)ns * W), before((size_t)ns * W), run_off((size_t)ns * W), col_off(1), sent(ns);
+    size_t total_cols = 0;
+    for (u32 k = 0; k < ns; k++) { ncols[k] = (u32)sides[k]->attached.size(); total_cols += ncols[k]; }
+    std::vector<uint64_t> splitters(W), recv((size_t)ns * W), before((size_t)ns * W), run_off((size_t)ns * W),
+        col_off((total_cols ? total_cols : 1) * W), sent(ns);
     uint64_t need = 0;
     if (exchange_plan_impl(all.data(), W, me, ns, ncols.data(), (u32)key_bits, fixed ? fixed->split.data() : nullptr,
                            splitters.data(), recv.data(), before.data(), run_off.data(), col_off.data(), &need, sent.data()) != 0) {
@@ -211,13 +215,30 @@ int exchange_runs(const std::vector<const qce_tuples *> &sides, int key_bits, u6
         return -1;
     }
     if (ensure_window(need) != 0) return -1;
+    // the views of the previous exchange's travelling columns die with the window's old contents
+    for (auto &kv : cx().recv_cols) qce_rowids_free(kv.second);
+    cx().recv_cols.clear();
+    cx().attach_gen++;
+    size_t col_at = 0;
     for (u32 k = 0; k < ns; k++) {
         std::vector<uint64_t> dst_words(W);
         for (u32 d = 0; d < W; d++) dst_words[d] = run_off[(size_t)k * W + d] / 8 + before[(size_t)k * W + d];
-        if (qce_push_tuples(sides[k], (u32)key_bits, splitters.data(), W, dst_words.data(), nullptr, nullptr) != 0) {
-            qcecomm::abort_all();
-            return -1;
+        int rc;
+        if (ncols[k] == 0) {
+            rc = qce_push_tuples(sides[k], (u32)key_bits, splitters.data(), W, dst_words.data(), nullptr, nullptr);
+        } else {
+            // payload := index in the receiver's run; the attached columns follow in the same kernel, laid
+            // out like the run (segment of rank s after the segments of ranks < s)
+            std::vector<uint32_t> run_index(W);
+            std::vector<uint64_t> regions((size_t)ncols[k] * W);
+            for (u32 d = 0; d < W; d++) run_index[d] = (u32)before[(size_t)k * W + d];
+            for (u32 c = 0; c < ncols[k]; c++)
+                for (u32 d = 0; d < W; d++) regions[(size_t)c * W + d] = col_off[(col_at + c) * W + d] / 4 + before[(size_t)k * W + d];
+            rc = qce_push_tuples_cols(sides[k], (u32)key_bits, splitters.data(), W, dst_words.data(), run_index.data(), ncols[k],
+                                      sides[k]->attached.data(), regions.data());
         }
+        if (rc != 0) { qcecomm::abort_all(); return -1; }
+        col_at += ncols[k];
     }
     if (fence_barrier() != 0) return -1; // every peer's stores into this rank's window have completed
     const u64 lo = me > 0 ? splitters[me - 1] : 0;
@@ -235,6 +256,20 @@ int exchange_runs(const std::vector<const qce_tuples *> &sides, int key_bits, u6
         u64 tot = 0;
         for (u32 d = 0; d < W; d++) tot += recv[(size_t)k * W + d];
         (*out)[k].run->n_others = tot - n;
+    }
+    col_at = 0;
+    for (u32 k = 0; k < ns; k++) {
+        const u64 n = recv[(size_t)k * W + me];
+        for (u32 c = 0; c < ncols[k]; c++) {
+            qce_rowids *view = nullptr;
+            if (qce_rowids_from_window(col_off[(col_at + c) * W + me] / 4, n, 0, sides[k]->attached[c]->id_bound, 0, &view) != 0) {
+                qcecomm::abort_all();
+                return -1;
+            }
+            cx().recv_cols.push_back({sides[k]->attached[c], view});
+        }
+        (*out)[k].travelled = ncols[k] != 0;
+        col_at += ncols[k];
     }
     dist_out->kind = Dist::KEYS;
     dist_out->key_bits = key_bits;
@@ -265,9 +300,13 @@ int sh_join_runs(qce_tuples *R, qce_tuples *S, bool want_r, bool want_s, qce_row
     const bool root_only = walk || R->wide || S->wide;
     int rc = -1;
     qce_tuples *lr = nullptr, *ls = nullptr;  // the local inputs of the merge
-    bool own_r = false, own_s = false;
+    bool own_r = false, own_s = false, travelled_r = false, travelled_s = false;
     Dist dist;
     dist.kind = Dist::ANY;
+    if (root_only && (!R->attached.empty() || !S->attached.empty())) {
+        qcecomm::abort_all();
+        return fail("position-carrying runs cannot take the rank-0 fallback");
+    }
     if (R->n + R->n_others == 0 || S->n + S->n_others == 0) {
         // an empty side: the pointer walk never starts (src/join.c:342), whatever the other side holds
         qce_tuples empty_r = *R, empty_s = *S;
@@ -303,8 +342,8 @@ int sh_join_runs(qce_tuples *R, qce_tuples *S, bool want_r, bool want_s, qce_row
             return -1;
         }
         size_t at = 0;
-        lr = push_r ? got[at++].run : R;
-        ls = push_s ? got[at++].run : S;
+        if (push_r) { travelled_r = got[at].travelled; lr = got[at++].run; } else lr = R;
+        if (push_s) { travelled_s = got[at].travelled; ls = got[at++].run; } else ls = S;
         own_r = push_r;
         own_s = push_s;
         LocalScope ls_;
@@ -323,8 +362,10 @@ int sh_join_runs(qce_tuples *R, qce_tuples *S, bool want_r, bool want_s, qce_row
     uint64_t v = outs[0] ? outs[0]->n : (outs[1] ? outs[1]->n : 0);
     const u64 local = v;
     CQ(qcecomm::allreduce_sum(&v, 1));
+    const bool travelled[2] = {travelled_r, travelled_s};
     for (int k = 0; k < 2; k++) {
         if (!outs[k]) continue;
+        if (travelled[k]) outs[k]->attach_gen = cx().attach_gen;
         outs[k]->n_others = v - local;
         outs[k]->dist = dist;
         outs[k]->dist.rel = src[k]->src_rel;
@@ -442,6 +483,22 @@ int sh_distinct_pairs(const qce_rowids *pr, const qce_rowids *ps, qce_rowids **d
     (*ds)->dist.kind = Dist::ANY;
     if (others_of((*dr)->n, &(*dr)->n_others) != 0) return -1;
     (*ds)->n_others = (*dr)->n_others;
+    return 0;
+}
+
+// qce_merge_join_stats over the ranks: min / max matches per outer tuple, all-reduced
+int sh_merge_join_stats(const qce_tuples *R, const qce_tuples *S, qce_rowids **outR, qce_rowids **outS, uint32_t *lo, uint32_t *hi)
+{
+    u32 st[2] = {0xffffffffu, 0u};
+    tl_join_stats = st; // filled by the local merge when both of this rank's runs are non-empty
+    const int rc = sh_join_runs(const_cast<qce_tuples *>(R), const_cast<qce_tuples *>(S), true, true, outR, outS, false);
+    tl_join_stats = nullptr;
+    if (rc != 0) return -1;
+    uint64_t v[2] = {(uint64_t)(0xffffffffu - st[0]), st[1]}; // min as a max
+    CQ(qcecomm::allreduce_max(v, 2));
+    *lo = 0xffffffffu - (u32)v[0];
+    *hi = (u32)v[1];
+    if (*lo == 0xffffffffu) *lo = 0; // no rank merged anything
     return 0;
 }
 

@@ -37,7 +37,7 @@ SYMBOLS = [
     "qce_comm_barrier", "qce_comm_allreduce_sum_u64", "qce_comm_allreduce_max_u64", "qce_comm_gatherv", "qce_comm_abort",
     "qce_comm_finish", "qce_upload_column_window", "qce_upload_column_window_device", "qce_row_share",
     "qce_set_replicate_bytes", "qce_column_would_be_whole", "qce_column_is_whole", "qce_rowids_count_local", "qce_xwin_unmap_peers", "qce_build_tuples_positions", "qce_merge_join_stats",
-    "qce_elision_supported",
+    "qce_elision_supported", "qce_tuples_attach", "qce_placement_cap",
 ]
 
 
@@ -107,7 +107,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "qce_column_would_be_whole": (i32, [u64]), "qce_column_is_whole": (i32, [u32, u32]),
         "qce_rowids_count_local": (u64, [vp]), "qce_xwin_unmap_peers": (i32, []),
         "qce_build_tuples_positions": (i32, [u32, u32, vp, P(vp)]),
-        "qce_merge_join_stats": (i32, [vp, vp, P(vp), P(vp), P(u32), P(u32)]), "qce_elision_supported": (i32, []),
+        "qce_merge_join_stats": (i32, [vp, vp, P(vp), P(vp), P(u32), P(u32)]), "qce_elision_supported": (i32, []), "qce_tuples_attach": (i32, [vp, u32, vp]), "qce_placement_cap": (i32, [vp, u32, P(u64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -405,6 +405,20 @@ static int elided_join(const join_plan *plan, DArray *entities)
     int rc = -1;
     if (qce_build_tuples_positions(sides[s]->rel, sides[s]->col, sides[s]->source->payloads, &t[s]) != 0)
         return 0; /* keys >= 2^32: the faithful path handles them */
+    {
+        /* every column that will follow the positions (the joined one and the bystanders, by the
+         * relation-id test of src/join.c:495); with several ranks they travel with the tuples */
+        const struct qce_rowids *cols[8];
+        uint32_t nc = 0;
+        for (size_t i = 0; i < DArray_count(ent[s]); i++) {
+            const mid_result *m = (const mid_result *)DArray_get(ent[s], i);
+            const int joined = m == sides[s]->source;
+            if (!joined && (m->relation == plan->lhs.rel || m->relation == plan->rhs.rel)) continue;
+            if (nc == 6 || qce_rowids_count(m->payloads) < qce_rowids_count(sides[s]->source->payloads)) { rc = QCE_JOIN_UNSAFE; goto done; }
+            cols[nc++] = m->payloads;
+        }
+        if (qce_tuples_attach(t[s], nc, cols) != 0) { rc = QCE_JOIN_UNSAFE; goto done; }
+    }
     if (qce_build_tuples_base(sides[o]->rel, sides[o]->col, &t[o]) != 0) {
         log_err("Couldn't allocate relations: %s", qce_last_error());
         goto done;

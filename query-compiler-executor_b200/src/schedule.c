@@ -336,6 +336,13 @@ int qce_run_queries(DArray *q_list, DArray *metadata_arr, FILE *out, int *failed
         for_each_col(b.jobs[i].q, note_cb, &nc);
     }
 
+    /* placement (several ranks): replicate what fits, smallest relations first; shard the rest by rows */
+    if (world > 1 && b.ncols) {
+        uint64_t *rows = (uint64_t *)calloc(b.ncols, sizeof(uint64_t)), cap = 0;
+        for (size_t i = 0; rows && i < b.ncols; i++) rows[i] = qce_host_file_rows(b.cols[i].rel);
+        if (rows && qce_placement_cap(rows, (uint32_t)b.ncols, &cap) == 0) qce_set_replicate_bytes(cap);
+        free(rows);
+    }
     /* row-sharded columns are loaded by all ranks together (their windows are mapped into every
      * peer: a collective), before anything runs; whole columns stream in behind the first queries */
     int later = 0;

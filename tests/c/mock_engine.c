@@ -102,6 +102,8 @@ int qce_comm_gatherv(const void *mine, uint64_t bytes, char **out, uint64_t *len
     if (out) { *out = xalloc(bytes ? bytes : 1, 1); memcpy(*out, mine, bytes); }
     return 0;
 }
+int qce_placement_cap(const uint64_t *col_rows, uint32_t ncols, uint64_t *cap_bytes) { (void)col_rows; (void)ncols; *cap_bytes = ~0ull; return 0; }
+int qce_set_replicate_bytes(uint64_t bytes) { (void)bytes; return 0; }
 int qce_column_would_be_whole(uint64_t rows) { (void)rows; return 1; }
 int qce_column_is_whole(uint32_t rel, uint32_t col)
 {
@@ -282,6 +284,11 @@ int qce_build_tuples_positions(uint32_t rel, uint32_t col, const qce_rowids *ids
         if ((*out)->k[i] >> 32) { qce_tuples_free(*out); return fail("position-carrying runs need keys below 2^32"); }
         (*out)->p[i] = i;
     }
+    return 0;
+}
+int qce_tuples_attach(qce_tuples *t, uint32_t ncols, const qce_rowids *const *cols)
+{
+    (void)t; (void)ncols; (void)cols; /* one rank: the positions index the caller's arrays */
     return 0;
 }
 int qce_merge_join_stats(const qce_tuples *R, const qce_tuples *S, qce_rowids **outR, qce_rowids **outS,

@@ -30,7 +30,7 @@ def _paths(db):
 @pytest.mark.parametrize("world", [2, 3])
 @pytest.mark.parametrize("db_name,batch", [("ops_db.npz", "ops.json"), ("small_db.npz", "small_batch.json"),
                                            ("edge_db.npz", "edge.json")])
-def test_golden_batches_row_sharded(world, db_name, batch):
+def test_golden_batches_row_sharded(world, db_name, batch, elide=1):
     """Every PDQ query of the golden batches with all relations row-sharded over `world` ranks:
     the recorded reference stdout, byte for byte (PDQ-D may be refused, never answered differently)."""
     db = load_db(db_name)
@@ -71,11 +71,14 @@ def test_reference_main_unchanged_sharded():
     assert out == orc.run_batch(db, q)
 
 
+@pytest.mark.parametrize("elide", [1, 0])
 @pytest.mark.parametrize("world", [2, 3])
-def test_scaled_twins_row_sharded(world):
+def test_scaled_twins_row_sharded(world, elide):
     """C2 / C3 / C4 shapes (filter + join, PK-FK chain with a self-join predicate, Zipf FK side)
-    at sizes where the exchange takes the MSD path, against the oracle."""
-    env = dict(SHARD_ALL, QCE_GPUS=world)
+    at sizes where the exchange takes the MSD path, against the oracle -- with the bystander
+    re-joins elided (the entity's columns travel with the exchanged tuples) and replayed faithfully
+    (join_payloads' two runs exchanged by row-id range)."""
+    env = dict(SHARD_ALL, QCE_GPUS=world, QCE_ELIDE=elide)
     db = wl.gen_pair_db(3_000_000, 3_000_000)
     q = "0 1|0.1=1.1&0.2>500000|0.0 1.0 1.2\n"
     out, err, rc = run_queries_bin(QUERIES_BIN, _paths(db), q, env=env)
@@ -99,3 +102,13 @@ def test_abort_is_mirrored_sharded():
     rec = [r for r in load_json("edge.json") if r["query"] == "2 2|0.0=1.0&0.2<8|0.2 1.2"][0]
     out, err, rc = run_queries_bin(QUERIES_BIN, _paths(edge), rec["query"] + "\n", env=dict(SHARD_ALL, QCE_GPUS=2))
     assert rc != 0 and out == rec["stdout"] == "18 " and "Something went really wrong" in err
+
+
+def test_golden_batch_row_sharded_faithful_replay():
+    """The golden batch with elided mode switched off: every bystander re-join is the exchanged replay."""
+    db = load_db("small_db.npz")
+    recs = [r for r in load_json("small_batch.json") if r["class"] == "PDQ-T"]
+    text = "".join(r["query"] + "\n" for r in recs)
+    out, err, rc = run_queries_bin(QUERIES_BIN, _paths(db), text, env=dict(SHARD_ALL, QCE_GPUS=2, QCE_ELIDE=0), timeout=600)
+    assert rc == 0, err[-2000:]
+    assert out == "".join(r["stdout"] for r in recs)
