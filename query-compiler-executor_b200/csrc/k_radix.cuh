@@ -1017,13 +1017,14 @@ k_msd_local_sort(u64 *__restrict__ keys, const u32 *__restrict__ seg_off, const 
 // remaining key bits (2^R shared-memory counters).  Equal digits are now equal
 // keys, so no stability is needed: a key's slot inside its digit comes from
 // atomicAdd-with-return on the digit's counter -- no ballots, one pass.
-template <int THREADS, int ITEMS, int MIN_CTAS>
+// MAXB = counters cleared and scanned per sub-bucket (>= 2^rbits): with 11 remaining bits half of the
+// 4096 is dead work that costs as much as ranking the ~2300 tuples themselves.
+template <int THREADS, int ITEMS, int MIN_CTAS, int MAXB = 4096>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 k_msd_count_sort(u64 *__restrict__ keys, const u32 *__restrict__ seg_off, const u32 *__restrict__ seg_size,
                  u64 key_base, int rbits)
 {
     constexpr int TILE = THREADS * ITEMS;
-    constexpr int MAXB = 4096;
     constexpr int BPT = MAXB / THREADS; // counters per thread in the scan (consecutive)
     static_assert(BPT % 4 == 0, "the counter scan works on uint4 groups");
     extern __shared__ __align__(16) unsigned char smem_raw[]; // TILE*8 + MAXB*4 + 33*4 bytes

@@ -739,8 +739,26 @@ int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done, const u32 
                 CK(cudaFuncSetAttribute(k_msd_count_sort<512, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16));
                 attr_set = true;
             }
-            if (max_sub <= 256 * 8)
+            static int small_counters = -1; // QCE_COUNT_SORT_SMALL=0: always clear and scan 4096 counters
+            if (small_counters < 0) {
+                const char *e = getenv("QCE_COUNT_SORT_SMALL");
+                small_counters = e ? atoi(e) : 1;
+                CK(cudaFuncSetAttribute((k_msd_count_sort<256, 12, 4, 2048>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm12));
+                CK(cudaFuncSetAttribute((k_msd_count_sort<256, 12, 4, 1024>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm12));
+                CK(cudaFuncSetAttribute((k_msd_count_sort<256, 8, 4, 2048>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm8));
+                CK(cudaFuncSetAttribute((k_msd_count_sort<256, 8, 4, 1024>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm8));
+            }
+            const size_t cut11 = 2048 * sizeof(u32), cut10 = 3072 * sizeof(u32); // counters not needed below 12 / 11 bits
+            if (max_sub <= 256 * 8 && small_counters && R <= 10)
+                LAUNCH("msd_count_sort", (k_msd_count_sort<256, 8, 4, 1024>), nsub, 256, sm8 - cut10, *keys, suboff, histB, base, R);
+            else if (max_sub <= 256 * 8 && small_counters && R == 11)
+                LAUNCH("msd_count_sort", (k_msd_count_sort<256, 8, 4, 2048>), nsub, 256, sm8 - cut11, *keys, suboff, histB, base, R);
+            else if (max_sub <= 256 * 8)
                 LAUNCH("msd_count_sort", (k_msd_count_sort<256, 8, 4>), nsub, 256, sm8, *keys, suboff, histB, base, R);
+            else if (mid_shape && max_sub <= 256 * 12 && small_counters && R <= 10)
+                LAUNCH("msd_count_sort", (k_msd_count_sort<256, 12, 4, 1024>), nsub, 256, sm12 - cut10, *keys, suboff, histB, base, R);
+            else if (mid_shape && max_sub <= 256 * 12 && small_counters && R == 11)
+                LAUNCH("msd_count_sort", (k_msd_count_sort<256, 12, 4, 2048>), nsub, 256, sm12 - cut11, *keys, suboff, histB, base, R);
             else if (mid_shape && max_sub <= 256 * 12) // sparse key ranges leave sub-buckets of 2-3 K tuples
                 LAUNCH("msd_count_sort", (k_msd_count_sort<256, 12, 4>), nsub, 256, sm12, *keys, suboff, histB, base, R);
             else if (shape == 1)
@@ -2114,9 +2132,14 @@ int qce_checksum(const qce_rowids *ids, uint32_t rel, const uint32_t *cols, uint
             src = bucketed;
         }
         static int waves = -1, per_col = -1; // QCE_CHECKSUM_WAVES / QCE_CHECKSUM_PER_COL: experiment switches
-        if (waves < 0) { const char *e = getenv("QCE_CHECKSUM_WAVES"); waves = e ? atoi(e) : 8; if (waves < 1) waves = 1; }
+        if (waves < 0) { const char *e = getenv("QCE_CHECKSUM_WAVES"); waves = e ? atoi(e) : 0; if (waves < 0) waves = 0; }
         if (per_col < 0) { const char *e = getenv("QCE_CHECKSUM_PER_COL"); per_col = e ? atoi(e) : 0; }
-        const int grid = grid_for(1024, ids->n, waves);
+        // Bucketed ids sweep the column region by region; the regions in flight must stay in L2.  With 8 waves
+        // of CTAs the front spans ~6 regions x NC columns and thrashes (ncu: 5.3 GB read for the 1.8 GB two
+        // columns + ids need, 0.86 ms); 3 waves keep it to ~2 regions: 0.33 ms (sweep in profiles/).
+        // Unbucketed ids gather at random anyway and want the parallelism.
+        const bool swept = bucketed != nullptr || ids->bucketed;
+        const int grid = grid_for(1024, ids->n, waves ? waves : (swept ? 3 : 8));
         if (per_col && ncols > 1) {
             // one pass over the (bucketed) ids per column: half the working set in L2 at any time
             for (u32 k = 0; k < ncols; k++) {

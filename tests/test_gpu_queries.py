@@ -217,3 +217,25 @@ def test_elided_rejoins_equal_the_faithful_replay(binaries, kind):
     assert a == b
     if kind != "small":
         assert a == orc.run_batch(db, text)
+
+
+def test_heavy_key_on_the_inner_side(binaries):
+    """SURVEY 8e / config 4's other half: 20 % of the INNER (S) side carries one key, at 10 M rows.  The
+    S window of the outer tiles that hold that key is 2 M tuples long and the output of those tuples is
+    split over many CTAs (two-phase count / write).  Checked against the bincount closed form
+    (sum of col[id] x multiplicity on the other side), which needs no join."""
+    n, heavy = 10_000_000, 4_242_424
+    rng = np.random.default_rng(44)
+    k0 = rng.integers(0, n, n, dtype=np.uint64)
+    k0[rng.choice(n, 12, replace=False)] = heavy          # a dozen outer tuples meet the heavy group
+    k1 = rng.integers(0, n, n, dtype=np.uint64)
+    k1[rng.random(n) < 0.2] = heavy
+    db = [[np.arange(n, dtype=np.uint64), k0, rng.integers(0, 1000, n, dtype=np.uint64)],
+          [np.arange(n, dtype=np.uint64), k1, rng.integers(0, 1000, n, dtype=np.uint64)]]
+    c0, c1 = np.bincount(k0.astype(np.int64), minlength=n), np.bincount(k1.astype(np.int64), minlength=n)
+    with np.errstate(over="ignore"):
+        s0 = int(np.sum(db[0][0] * c1[k0.astype(np.int64)].astype(np.uint64), dtype=np.uint64))
+        s1 = int(np.sum(db[1][2] * c0[k1.astype(np.int64)].astype(np.uint64), dtype=np.uint64))
+    out, err, rc = run_queries_bin(binaries[0], _paths(db), "0 1|0.1=1.1|0.0 1.2\n", timeout=600)
+    assert rc == 0, err[-1500:]
+    assert out == "%d %d \n" % (s0, s1)
