@@ -221,14 +221,25 @@ k_tile_keymax(TupleView R, u32 nR, u64 *__restrict__ tile_max)
     }
 }
 // exclusive prefix max over the tiles; has_prev[t] = 0 for the first tile
-__global__ void k_scan_excl_max(const u64 *__restrict__ tile_max, u64 *__restrict__ tile_pm, u32 ntiles)
+// exclusive prefix MAXIMUM over the tiles' largest keys (one warp, 32 tiles per step: shuffles instead
+// of the serial loop a single thread used to run over up to ~50 K tiles)
+__global__ void __launch_bounds__(32) k_scan_excl_max(const u64 *__restrict__ tile_max, u64 *__restrict__ tile_pm, u32 ntiles)
 {
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        u64 run = 0;
-        for (u32 t = 0; t < ntiles; t++) {
-            tile_pm[t] = run;
-            run = max(run, tile_max[t]);
+    const u32 lane = threadIdx.x;
+    u64 run = 0;
+    for (u32 base = 0; base < ntiles; base += 32) {
+        const u32 t = base + lane;
+        const u64 v = t < ntiles ? tile_max[t] : 0ull;
+        u64 incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u64 n = __shfl_up_sync(QCE_FULL_MASK, incl, o);
+            if (lane >= (u32)o) incl = max(incl, n);
         }
+        u64 excl = __shfl_up_sync(QCE_FULL_MASK, incl, 1);
+        if (lane == 0) excl = 0;
+        if (t < ntiles) tile_pm[t] = max(run, excl);
+        run = max(run, __shfl_sync(QCE_FULL_MASK, incl, 31));
     }
 }
 template <bool WR, bool WS>

@@ -324,6 +324,19 @@ template <typename T> int dalloc(T **p, u64 count)
     return cx().arena.alloc((void **)p, (count ? count : 1) * sizeof(T));
 }
 template <typename T> void dfree(T *p) { cx().arena.free((void *)p); }
+// Scratch buffers of one operator: whatever path the function leaves by (every `return -1` of a
+// failed allocation or launch included) they go back to the arena -- an out-of-memory error used
+// to leave the arena permanently smaller.  Buffers that outlive the call are allocated with dalloc.
+struct Scratch {
+    std::vector<void *> owned;
+    ~Scratch() { for (void *p : owned) cx().arena.free(p); }
+    template <typename T> int get(T **p, u64 count)
+    {
+        if (dalloc(p, count) != 0) return -1;
+        owned.push_back((void *)*p);
+        return 0;
+    }
+};
 
 void prof_begin(const char *tag)
 {
@@ -410,8 +423,9 @@ int compact_from_mask(int layout, int mode, const u32 *mask, const u32 *tile_cou
                       const void *src0, const u32 *src1, u32 id_bound0, u32 id_bound1,
                       qce_rowids **out0, qce_rowids **out1, u32 id_base = 0)
 {
+    Scratch sc;
     u32 *tile_off = nullptr;
-    if (dalloc(&tile_off, ntiles) != 0) return -1;
+    if (sc.get(&tile_off, ntiles) != 0) return -1;
     if (ntiles <= 512)
         LAUNCH("scan_tiles", (k_scan_excl_warp<u32, u32>), 1, 32, 0, tile_count, tile_off, ntiles, cx().d_scalars);
     else
@@ -438,7 +452,6 @@ int compact_from_mask(int layout, int mode, const u32 *mask, const u32 *tile_cou
         else
             return fail("internal: unsupported compaction layout/mode %d/%d", layout, mode);
     }
-    dfree(tile_off);
     return 0;
 }
 
@@ -531,12 +544,12 @@ int radix_sort(u64 **keys, u32 **vals, u64 n, const RadixShifts &rs, int digit_b
     const u32 ntiles = (u32)ceil_div(n, onesweep_tile_size());
     u64 *alt_k = nullptr;
     u32 *alt_v = nullptr, *ghist = nullptr, *gbase = nullptr, *status = nullptr, *counters = nullptr;
+    Scratch sc; // the ping-pong buffers change hands with *keys / *vals and are released by hand
+    if (sc.get(&ghist, (u64)rs.npass * bins) != 0 || sc.get(&gbase, (u64)rs.npass * bins) != 0 ||
+        sc.get(&status, (u64)rs.npass * ntiles * bins) != 0 || sc.get(&counters, (u64)rs.npass) != 0)
+        return -1;
     if (dalloc(&alt_k, n) != 0) return -1;
-    if (vals && dalloc(&alt_v, n) != 0) return -1;
-    if (dalloc(&ghist, (u64)rs.npass * bins) != 0) return -1;
-    if (dalloc(&gbase, (u64)rs.npass * bins) != 0) return -1;
-    if (dalloc(&status, (u64)rs.npass * ntiles * bins) != 0) return -1;
-    if (dalloc(&counters, (u64)rs.npass) != 0) return -1;
+    if (vals && dalloc(&alt_v, n) != 0) { dfree(alt_k); return -1; }
     CK(cudaMemsetAsync(ghist, 0, (u64)rs.npass * bins * sizeof(u32), cx().stream));
     CK(cudaMemsetAsync(status, 0, (u64)rs.npass * ntiles * bins * sizeof(u32), cx().stream));
     CK(cudaMemsetAsync(counters, 0, (u64)rs.npass * sizeof(u32), cx().stream));
@@ -568,10 +581,6 @@ int radix_sort(u64 **keys, u32 **vals, u64 n, const RadixShifts &rs, int digit_b
     if (vals) dfree(vout);
     *keys = kin;
     if (vals) *vals = vin;
-    dfree(ghist);
-    dfree(gbase);
-    dfree(status);
-    dfree(counters);
     return 0;
 }
 
@@ -635,8 +644,9 @@ int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done, const u32 
     u64 *alt = nullptr;
     u32 *lvl0 = nullptr, *histA = nullptr, *offA = nullptr, *curA = nullptr, *tstart1 = nullptr, *histB = nullptr,
         *suboff = nullptr, *curB = nullptr;
-    if (dalloc(&alt, n) || dalloc(&lvl0, 4) || dalloc(&histA, nbA) || dalloc(&offA, nbA) || dalloc(&curA, nbA) ||
-        dalloc(&tstart1, nbA + 1) || dalloc(&histB, nsub) || dalloc(&suboff, nsub) || dalloc(&curB, nsub))
+    Scratch sc; // level A scatters into alt, level B back into *keys: every buffer here is a temporary
+    if (sc.get(&alt, n) || sc.get(&lvl0, 4) || sc.get(&histA, nbA) || sc.get(&offA, nbA) || sc.get(&curA, nbA) ||
+        sc.get(&tstart1, nbA + 1) || sc.get(&histB, nsub) || sc.get(&suboff, nsub) || sc.get(&curB, nsub))
         return -1;
     // level 0: one bucket = the whole run.  lvl0 = {tile_start[0], tile_start[1], bucket_off, bucket_size}
     const u32 h_lvl0[4] = {0u, ntiles0, 0u, (u32)n};
@@ -671,7 +681,7 @@ int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done, const u32 
     const u32 ntiles_cap = ntiles0 + nbA;
     const int bulk_grid = G.sms * 3;
     if (bulk) {
-        if (dalloc(&tdesc, ntiles_cap) != 0) return -1;
+        if (sc.get(&tdesc, ntiles_cap) != 0) return -1;
         LAUNCH("msd_tiles", k_msd_tile_desc, (int)ceil_div(ntiles0, 256), 256, 0, lvl0, lvl0 + 2, lvl0 + 3, 1u, ntiles0, tdesc);
         LAUNCH("msd_partition", k_msd_partition_bulk, (int)std::min<u32>(ntiles0, (u32)bulk_grid), QCE_MSDB_THREADS, QCE_MSDB_SMEM, *keys, alt,
                tdesc, ntiles0, base, shiftA, nbA, curA);
@@ -786,8 +796,6 @@ int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done, const u32 
         }
         *done = true;
     }
-    dfree(alt); dfree(lvl0); dfree(histA); dfree(offA); dfree(curA); dfree(tstart1); dfree(histB); dfree(suboff);
-    dfree(curB); dfree(tdesc);
     return 0;
 }
 
@@ -825,19 +833,18 @@ int merge_join_t(const qce_tuples *R, const qce_tuples *S, bool want_r, bool wan
     uint2 *win = nullptr;
     u32 *lb = nullptr, *cnt = nullptr, *tile_chunks = nullptr, *chunk_off = nullptr;
     u64 *tile_total = nullptr, *tile_off = nullptr;
-    if (dalloc(&win, ntiles) || dalloc(&lb, nR) || dalloc(&cnt, nR) || dalloc(&tile_chunks, ntiles) ||
-        dalloc(&chunk_off, ntiles) || dalloc(&tile_total, ntiles) || dalloc(&tile_off, ntiles))
+    Scratch sc;
+    if (sc.get(&win, ntiles) || sc.get(&lb, nR) || sc.get(&cnt, nR) || sc.get(&tile_chunks, ntiles) ||
+        sc.get(&chunk_off, ntiles) || sc.get(&tile_total, ntiles) || sc.get(&tile_off, ntiles))
         return -1;
     TupleView vr = view_of(R), vs = view_of(S);
     if (walk) {
         u64 *tile_max = nullptr, *tile_pm = nullptr;
-        if (dalloc(&tile_max, ntiles) || dalloc(&tile_pm, ntiles)) return -1;
+        if (sc.get(&tile_max, ntiles) || sc.get(&tile_pm, ntiles)) return -1;
         LAUNCH("join_keymax", (k_tile_keymax<WR>), (int)ntiles, QCE_JTHREADS, 0, vr, nR, tile_max);
         LAUNCH("join_keymax", k_scan_excl_max, 1, 32, 0, tile_max, tile_pm, ntiles);
         LAUNCH("join_bounds_walk", (k_join_bounds_walk<WR, WS>), (int)ntiles, QCE_JTHREADS, 0, vr, nR, vs, nS,
                tile_pm, lb, cnt, tile_total, tile_chunks);
-        dfree(tile_max);
-        dfree(tile_pm);
     } else {
         LAUNCH("join_partition", (k_join_partition<WR, WS>), (int)ceil_div(ntiles, 256), 256, 0, vr, nR, vs, nS,
                ntiles, win);
@@ -873,7 +880,7 @@ int merge_join_t(const qce_tuples *R, const qce_tuples *S, bool want_r, bool wan
     if (m >= (1ull << 32)) return fail("join output of %llu pairs exceeds the 2^32 row-id column limit", (unsigned long long)m);
     qce_rowids *oR = nullptr, *oS = nullptr;
     if (want_r && new_rowids(m, R->id_bound, &oR) != 0) return -1;
-    if (want_s && new_rowids(m, S->id_bound, &oS) != 0) return -1;
+    if (want_s && new_rowids(m, S->id_bound, &oS) != 0) { qce_rowids_free(oR); return -1; }
     if (m > 0) {
         u32 *pr = oR ? oR->d : nullptr, *ps = oS ? oS->d : nullptr;
         if (want_r && want_s)
@@ -886,7 +893,6 @@ int merge_join_t(const qce_tuples *R, const qce_tuples *S, bool want_r, bool wan
             LAUNCH("join_write", (k_join_write<WR, WS, false, true>), (int)nchunks, QCE_JTHREADS, 0, vr, nR, vs, lb,
                    cnt, tile_off, chunk_off, ntiles, pr, ps);
     }
-    dfree(win); dfree(lb); dfree(cnt); dfree(tile_chunks); dfree(chunk_off); dfree(tile_total); dfree(tile_off);
     if (outR) *outR = oR;
     if (outS) *outS = oS;
     return 0;

@@ -367,3 +367,29 @@ def test_large_sort_msd_and_fallback(engine, n, kind):
     k, p = engine.tuples_to_host(t)
     _assert_sorted_run(k, p, keys, ids)
     engine.tuples_free(t)
+
+
+def test_arena_returns_to_empty(engine):
+    """Every temporary of the operators goes back to the engine's HBM arena (Scratch scopes cover the
+    error paths too): after the handles are freed nothing is in use."""
+    e = engine
+    rng = np.random.default_rng(9)
+    n = 1_500_000
+    e.upload_column(70, 0, np.arange(n, dtype=np.uint64))
+    e.upload_column(70, 1, rng.integers(0, n, n, dtype=np.uint64))
+    e.upload_column(71, 1, rng.integers(0, n, n, dtype=np.uint64))
+    e.sync()
+    _, used0 = e.mempool_stats()
+    ids = e.filter_scan(70, 0, "<", n // 2)
+    tl, tr = e.build_tuples(70, 1, ids), e.build_tuples(71, 1)
+    e.sort_tuples(tl); e.sort_tuples(tr)
+    a, b = e.merge_join(tl, tr)
+    da, db = e.distinct_pairs(a, b)
+    sums = e.checksum(a, 70, [0, 1])
+    assert len(sums) == 2
+    for h in (ids, a, b, da, db):
+        e.rowids_free(h)
+    e.tuples_free(tl); e.tuples_free(tr)
+    e.sync()
+    _, used1 = e.mempool_stats()
+    assert used1 == used0
