@@ -313,6 +313,12 @@ struct Ctx {
     // columns that travelled with the last exchange: caller's handle -> view of the received copy
     u64 attach_gen = 0;
     std::vector<std::pair<const qce_rowids *, qce_rowids *>> recv_cols;
+    // exchange overlap: the first received run is sorted on `aux` while the second side's push is
+    // still crossing NVLink on `stream`; scratch the in-flight push reads is freed after it
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_side[2] = {nullptr, nullptr}, ev_aux = nullptr;
+    bool defer_frees = false;
+    std::vector<void *> deferred;
 };
 Ctx g_main;
 thread_local Ctx *tl_ctx = nullptr;
@@ -324,6 +330,17 @@ template <typename T> int dalloc(T **p, u64 count)
     return cx().arena.alloc((void **)p, (count ? count : 1) * sizeof(T));
 }
 template <typename T> void dfree(T *p) { cx().arena.free((void *)p); }
+// scratch of a kernel that may still be in flight while another stream of this context allocates
+template <typename T> void dfree_after_push(T *p)
+{
+    if (cx().defer_frees) cx().deferred.push_back((void *)p);
+    else cx().arena.free((void *)p);
+}
+inline void release_deferred()
+{
+    for (void *p : cx().deferred) cx().arena.free(p);
+    cx().deferred.clear();
+}
 // Scratch buffers of one operator: whatever path the function leaves by (every `return -1` of a
 // failed allocation or launch included) they go back to the arena -- an out-of-memory error used
 // to leave the arena permanently smaller.  Buffers that outlive the call are allocated with dalloc.
@@ -1024,6 +1041,10 @@ static int ctx_open(Ctx *c)
     CK(cudaMallocHost((void **)&c->h_scalars, 16 * sizeof(u64)));
     CK(cudaEventCreate(&c->t0));
     CK(cudaEventCreate(&c->t1));
+    CK(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_side[0], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_side[1], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_aux, cudaEventDisableTiming));
     return 0;
 }
 static void ctx_close(Ctx *c)
@@ -1039,6 +1060,10 @@ static void ctx_close(Ctx *c)
     cudaFreeHost(c->h_scalars);
     cudaEventDestroy(c->t0);
     cudaEventDestroy(c->t1);
+    cudaEventDestroy(c->ev_side[0]);
+    cudaEventDestroy(c->ev_side[1]);
+    cudaEventDestroy(c->ev_aux);
+    cudaStreamDestroy(c->aux);
     cudaStreamDestroy(c->stream);
     c->stream = nullptr;
 }
@@ -2587,7 +2612,7 @@ static int push_tuples_impl(const qce_tuples *t, uint32_t key_bits, const uint64
         LAUNCH("push_tuples", (k_push<u64, true, true>), grid, QCE_PUSH_THREADS, 0, (const u64 *)t->a, n, dg, plan, G.peers, dbits, so, pc);
     else
         LAUNCH("push_tuples", (k_push<u64, true, false>), grid, QCE_PUSH_THREADS, 0, (const u64 *)t->a, n, dg, plan, G.peers, dbits, so, pc);
-    dfree(d_seg); dfree(d_cur); dfree(d_run); dfree(dlut);
+    dfree_after_push(d_seg); dfree_after_push(d_cur); dfree_after_push(d_run); dfree_after_push(dlut);
     return 0;
 }
 

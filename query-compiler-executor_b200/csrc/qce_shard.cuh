@@ -195,9 +195,13 @@ struct XRecv {
     qce_tuples *run = nullptr; // a view of this rank's window: valid until the window is written again
     bool travelled = false;    // its attached columns came along (cx().recv_cols, generation cx().attach_gen)
 };
+// sort_received: the received runs are sorted here, the first one on the context's aux stream as
+// soon as ITS tuples have landed everywhere -- while the second side's push still crosses NVLink.
 int exchange_runs(const std::vector<const qce_tuples *> &sides, int key_bits, u64 key_max, const Dist *fixed,
-                  std::vector<XRecv> *out, Dist *dist_out)
+                  std::vector<XRecv> *out, Dist *dist_out, bool sort_received = false)
 {
+    static int overlap = -1; // QCE_OVERLAP_PUSH=0: one barrier after all pushes, sorts afterwards
+    if (overlap < 0) { const char *e = getenv("QCE_OVERLAP_PUSH"); overlap = e ? atoi(e) : 1; }
     const u32 W = G.world, me = G.rank, ns = (u32)sides.size();
     std::vector<uint64_t> hists((size_t)ns * 256), all((size_t)W * ns * 256);
     for (u32 k = 0; k < ns; k++)
@@ -220,6 +224,8 @@ int exchange_runs(const std::vector<const qce_tuples *> &sides, int key_bits, u6
     cx().recv_cols.clear();
     cx().attach_gen++;
     size_t col_at = 0;
+    const bool split = sort_received && overlap && ns == 2;
+    cx().defer_frees = split;
     for (u32 k = 0; k < ns; k++) {
         std::vector<uint64_t> dst_words(W);
         for (u32 d = 0; d < W; d++) dst_words[d] = run_off[(size_t)k * W + d] / 8 + before[(size_t)k * W + d];
@@ -237,16 +243,25 @@ int exchange_runs(const std::vector<const qce_tuples *> &sides, int key_bits, u6
             rc = qce_push_tuples_cols(sides[k], (u32)key_bits, splitters.data(), W, dst_words.data(), run_index.data(), ncols[k],
                                       sides[k]->attached.data(), regions.data());
         }
-        if (rc != 0) { qcecomm::abort_all(); return -1; }
+        if (rc != 0) { cx().defer_frees = false; qcecomm::abort_all(); return -1; }
+        if (split) CK(cudaEventRecord(cx().ev_side[k], cx().stream));
         col_at += ncols[k];
     }
-    if (fence_barrier() != 0) return -1; // every peer's stores into this rank's window have completed
+    cx().defer_frees = false;
+    if (!split && fence_barrier() != 0) return -1; // every peer's stores into this rank's window have completed
     const u64 lo = me > 0 ? splitters[me - 1] : 0;
     // the last rank's range ends at the largest key that exists, not at 2^key_bits - 1: the
     // local sort sizes its MSD buckets from this range
     const u64 hi = me < W - 1 ? splitters[me] - 1 : key_max;
     out->assign(ns, XRecv());
+    cudaStream_t main_stream = cx().stream;
     for (u32 k = 0; k < ns; k++) {
+        if (split) {
+            // side k has landed on every rank: this rank's push of it is done, and so is everybody else's
+            cudaError_t e = cudaEventSynchronize(cx().ev_side[k]);
+            if (e != cudaSuccess) { qcecomm::abort_all(); return fail("push of side %u: %s", k, cudaGetErrorString(e)); }
+            CQ(qcecomm::barrier());
+        }
         const u64 n = recv[(size_t)k * W + me];
         if (qce_tuples_from_window(run_off[(size_t)k * W + me] / 8, n, (u32)key_bits, sides[k]->id_bound, lo, std::max(lo, hi),
                                    &(*out)[k].run) != 0) {
@@ -256,7 +271,25 @@ int exchange_runs(const std::vector<const qce_tuples *> &sides, int key_bits, u6
         u64 tot = 0;
         for (u32 d = 0; d < W; d++) tot += recv[(size_t)k * W + d];
         (*out)[k].run->n_others = tot - n;
+        if (sort_received) {
+            const bool early = split && k + 1 < ns; // the next side's push is still in flight on the main stream
+            if (early) cx().stream = cx().aux;
+            // the arena hands freed blocks out again at once (one stream per context): the last side's sort
+            // must not start before the early one has finished with its temporaries -- and the merge reads both
+            else if (split) cudaStreamWaitEvent(main_stream, cx().ev_aux, 0);
+            int rc;
+            {
+                LocalScope ls;
+                rc = qce_sort_tuples((*out)[k].run);
+            }
+            if (early) {
+                cudaEventRecord(cx().ev_aux, cx().aux);
+                cx().stream = main_stream;
+            }
+            if (rc != 0) { qcecomm::abort_all(); return -1; }
+        }
     }
+    if (split) release_deferred(); // the pushes that read this scratch have completed (ev_side[1])
     col_at = 0;
     for (u32 k = 0; k < ns; k++) {
         const u64 n = recv[(size_t)k * W + me];
@@ -338,7 +371,7 @@ int sh_join_runs(qce_tuples *R, qce_tuples *S, bool want_r, bool want_s, qce_row
         std::vector<XRecv> got;
         if (sides.empty()) {
             dist = R->dist;
-        } else if (exchange_runs(sides, key_bits, key_max, fixed, &got, &dist) != 0) {
+        } else if (exchange_runs(sides, key_bits, key_max, fixed, &got, &dist, true) != 0) {
             return -1;
         }
         size_t at = 0;
@@ -346,12 +379,8 @@ int sh_join_runs(qce_tuples *R, qce_tuples *S, bool want_r, bool want_s, qce_row
         if (push_s) { travelled_s = got[at].travelled; ls = got[at++].run; } else ls = S;
         own_r = push_r;
         own_s = push_s;
-        LocalScope ls_;
-        if ((push_r && qce_sort_tuples(lr) != 0) || (push_s && qce_sort_tuples(ls) != 0)) {
-            qcecomm::abort_all();
-        } else {
-            rc = merge_join_any(lr, ls, want_r, want_s, outR, outS, false);
-        }
+        LocalScope ls_; // the received runs were sorted inside the exchange
+        rc = merge_join_any(lr, ls, want_r, want_s, outR, outS, false);
     }
     if (own_r) qce_tuples_free(lr);
     if (own_s) qce_tuples_free(ls);
