@@ -428,7 +428,8 @@ C2_MODELS = {
     "onesweep_k": lambda s: (16.0 * s["sort"] * s["passes"], "16 B per tuple per pass"),
     "checksum": lambda s: (12.0 * s["pairs"] * 3, "4 B row id + 8 B value per row per projected column"),
     "join_bounds": lambda s: (8.0 * s["sort"] + 8.0 * s["lhs"], "8 B per input tuple + 8 B (lb,cnt) per lhs tuple"),
-    "join_write": lambda s: (8.0 * s["lhs"] + 12.0 * s["pairs"], "8 B (lb,cnt) per lhs tuple + 8 B per pair written + 4 B rhs id per pair"),
+    "join_write": lambda s: (16.0 * s["lhs"] + 8.0 * (s["sort"] - s["lhs"]) + 8.0 * s["pairs"],
+                             "8 B (lb,cnt) + 8 B tuple per lhs tuple, the rhs run's 8 B tuples (row ids of the matches), 8 B per pair written"),
     "build_tuples": lambda s: (8.0 * s["rows"] + 12.0 * s["lhs"] + 8.0 * s["sort"], "8 B key (+4 B id) in, 8 B packed tuple out"),
     "filter_scan": lambda s: (8.0 * s["rows"] + s["rows"] / 8.0, "8 B per row in + 1 bit per row out"),
     "push_tuples": lambda s: (16.0 * s["sort"], "8 B read + 8 B stored (locally or over NVLink) per tuple"),

@@ -1041,7 +1041,13 @@ static int ctx_open(Ctx *c)
     CK(cudaMallocHost((void **)&c->h_scalars, 16 * sizeof(u64)));
     CK(cudaEventCreate(&c->t0));
     CK(cudaEventCreate(&c->t1));
-    CK(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
+    {
+        // the early sort must get SM slots while the other side's push (a grid of thousands of CTAs,
+        // launched first) is still draining: blocks of a higher-priority stream are dispatched first
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&c->aux, cudaStreamNonBlocking, hi));
+    }
     CK(cudaEventCreateWithFlags(&c->ev_side[0], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_side[1], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_aux, cudaEventDisableTiming));
@@ -2586,6 +2592,20 @@ static int push_tuples_impl(const qce_tuples *t, uint32_t key_bits, const uint64
             if (((u64)b << bin_shift) >= splitters[k]) part++;
         }
         lut[b] = (unsigned char)part;
+    }
+    // a wrong plan must not scribble over a peer's memory: with the run's histogram at hand (the exchange
+    // always has it) every destination segment is checked against the window before anything is stored
+    if (t->hist_key_bits == (int)key_bits && t->hist_host.size() == QCE_RADIX_BINS) {
+        u64 per_dst[QCE_MAX_RANKS] = {0};
+        for (u32 b = 0; b < 256; b++) per_dst[lut[b]] += t->hist_host[b];
+        const u64 window_words = (G.xworld && G.peers.base[0] && G.xworld > 1 && G.peers.base[1] &&
+                                  (u64)(G.peers.base[1] - G.peers.base[0]) < G.xwin_bytes && G.peers.base[1] > G.peers.base[0])
+                                     ? (u64)(G.peers.base[1] - G.peers.base[0]) / 8   // loopback: each fake rank owns a slice
+                                     : G.xwin_bytes / 8;
+        for (u32 p = 0; p < nparts; p++)
+            if (per_dst[p] && dst_word_offset[p] + per_dst[p] > window_words)
+                return fail("push would overrun rank %u's window: words [%llu, +%llu) of %llu", p,
+                            (unsigned long long)dst_word_offset[p], (unsigned long long)per_dst[p], (unsigned long long)window_words);
     }
     if (slots_out && new_rowids(t->n, 0, slots_out) != 0) return -1;
     if (t->n == 0) return 0;
