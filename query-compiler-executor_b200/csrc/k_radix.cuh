@@ -1094,6 +1094,125 @@ k_msd_count_sort(u64 *__restrict__ keys, const u32 *__restrict__ seg_off, const 
     }
 }
 
+// ---- the same finish with Blackwell-native data movement ------------------------------------------
+// Persistent CTAs walk the sub-buckets; sub-bucket k+1 (and k+2) land in shared memory through the
+// bulk-copy engine (cp.async.bulk + mbarrier, as in k_msd_partition_bulk) while sub-bucket k is counted,
+// scanned and scattered -- the plain kernel above spends a third of every sub-bucket waiting for its own
+// loads (ncu: long + short scoreboard, issue 27 %).  The landing buffer is the staging buffer.
+template <int THREADS, int ITEMS, int MAXB>
+__global__ void __launch_bounds__(THREADS, 3)
+k_msd_count_sort_bulk(u64 *__restrict__ keys, const u32 *__restrict__ seg_off, const u32 *__restrict__ seg_size, u32 nsub,
+                      u64 key_base, int rbits)
+{
+    constexpr int TILE = THREADS * ITEMS, SLOTS = TILE + 2;
+    constexpr int BPT = MAXB / THREADS;
+    static_assert(BPT % 4 == 0, "the counter scan works on uint4 groups");
+    extern __shared__ __align__(128) unsigned char csb_smem[]; // 2 * SLOTS * 8 + MAXB * 4 bytes
+    u64 *const buf0 = reinterpret_cast<u64 *>(csb_smem);
+    u32 *const cnt = reinterpret_cast<u32 *>(buf0 + 2 * SLOTS);
+    __shared__ __align__(8) u64 bar[2];
+    __shared__ u32 scratch[33];
+    __shared__ u32 sseg[2][2]; // offset, size of the sub-bucket in each buffer
+    const int tid = threadIdx.x;
+    const u32 nb = 1u << rbits, mask = nb - 1;
+#define CSB_BUF(b) (buf0 + (b) * SLOTS)
+    auto fetch = [&](u32 s, int b) {
+        const u32 off = seg_off[s], n = seg_size[s];
+        sseg[b][0] = off;
+        sseg[b][1] = n;
+        if (n <= 1) return; // nothing to sort, nothing to fetch
+        const u32 first = off & ~1u, last = (off + n + 1u) & ~1u;
+        const u32 bytes = (last - first) * (u32)sizeof(u64);
+        mbar_expect_tx(&bar[b], bytes);
+        bulk_g2s(CSB_BUF(b), keys + first, bytes, &bar[b]);
+    };
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {
+        uint4 *c4 = reinterpret_cast<uint4 *>(cnt);
+#pragma unroll
+        for (int q = 0; q < BPT / 4; q++) c4[tid + q * THREADS] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+    const u32 s0 = blockIdx.x, stride = gridDim.x;
+    if (tid == 0) {
+        if (s0 < nsub) fetch(s0, 0);
+        if (s0 + stride < nsub) fetch(s0 + stride, 1);
+    }
+    __syncthreads();
+    u32 uses[2] = {0u, 0u}; // completed phases of each buffer's barrier (only sub-buckets with n > 1 use it)
+    u32 it = 0;
+    for (u32 s = s0; s < nsub; s += stride, it++) {
+        const int b = it & 1;
+        const u32 off = sseg[b][0], n = sseg[b][1];
+        if (n > 1) {
+            mbar_wait(&bar[b], uses[b] & 1u);
+            uses[b]++;
+            u64 key[ITEMS];
+            u32 slot[ITEMS];
+            const u64 *src = CSB_BUF(b) + (off & 1u);
+#pragma unroll
+            for (int j = 0; j < ITEMS; j++) {
+                const u32 i = tid + j * THREADS;
+                if (i < n) {
+                    key[j] = src[i];
+                    slot[j] = atomicAdd(&cnt[(u32)((key[j] - key_base) >> 32) & mask], 1u);
+                }
+            }
+            __syncthreads(); // keys in registers, counters complete
+            {
+                uint4 *c4 = reinterpret_cast<uint4 *>(cnt) + tid * (BPT / 4);
+                uint4 v[BPT / 4];
+                u32 sum = 0;
+#pragma unroll
+                for (int q = 0; q < BPT / 4; q++) {
+                    v[q] = c4[q];
+                    sum += v[q].x + v[q].y + v[q].z + v[q].w;
+                }
+                u32 tot;
+                u32 ex = block_scan_excl<u32, THREADS>(sum, scratch, &tot);
+#pragma unroll
+                for (int q = 0; q < BPT / 4; q++) {
+                    uint4 o;
+                    o.x = ex; ex += v[q].x;
+                    o.y = ex; ex += v[q].y;
+                    o.z = ex; ex += v[q].z;
+                    o.w = ex; ex += v[q].w;
+                    c4[q] = o;
+                }
+            }
+            __syncthreads();
+            u64 *stage = CSB_BUF(b);
+#pragma unroll
+            for (int j = 0; j < ITEMS; j++) {
+                const u32 i = tid + j * THREADS;
+                if (i < n) stage[cnt[(u32)((key[j] - key_base) >> 32) & mask] + slot[j]] = key[j];
+            }
+            __syncthreads();
+            u64 *dst = keys + off;
+#pragma unroll
+            for (int j = 0; j < ITEMS; j++) {
+                const u32 i = tid + j * THREADS;
+                if (i < n) dst[i] = stage[i];
+            }
+            {
+                uint4 *c4 = reinterpret_cast<uint4 *>(cnt);
+#pragma unroll
+                for (int q = 0; q < BPT / 4; q++) c4[tid + q * THREADS] = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+        __syncthreads(); // staging reads done, counters clear: the buffer may take the sub-bucket after next
+        if (tid == 0 && s + 2 * stride < nsub) {
+            fence_proxy_async();
+            fetch(s + 2 * stride, b);
+        }
+    }
+#undef CSB_BUF
+}
+
 // 1 if keys[i-1] > keys[i] anywhere (checks the "already sorted" assumption of
 // JOIN_SORT_LHS / JOIN_SORT_RHS, src/join.c:647-658).
 template <bool WIDE>

@@ -775,6 +775,25 @@ int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done, const u32 
                 CK(cudaFuncSetAttribute((k_msd_count_sort<256, 8, 4, 2048>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm8));
                 CK(cudaFuncSetAttribute((k_msd_count_sort<256, 8, 4, 1024>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm8));
             }
+            // persistent, bulk-copy pipelined variant (QCE_COUNT_SORT_BULK=0: the plain kernels below)
+            static int cs_bulk = -1;
+            constexpr size_t csb_tile = (256 * 12 + 2) * sizeof(u64) * 2;
+            if (cs_bulk < 0) {
+                const char *e = getenv("QCE_COUNT_SORT_BULK");
+                cs_bulk = e ? atoi(e) : 1;
+                CK(cudaFuncSetAttribute((k_msd_count_sort_bulk<256, 12, 1024>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(csb_tile + 1024 * 4)));
+                CK(cudaFuncSetAttribute((k_msd_count_sort_bulk<256, 12, 2048>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(csb_tile + 2048 * 4)));
+                CK(cudaFuncSetAttribute((k_msd_count_sort_bulk<256, 12, 4096>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(csb_tile + 4096 * 4)));
+            }
+            if (cs_bulk && max_sub <= 256 * 12) {
+                const int cgrid = (int)std::min<u32>(nsub, (u32)G.sms * 3);
+                if (R <= 10)
+                    LAUNCH("msd_count_sort", (k_msd_count_sort_bulk<256, 12, 1024>), cgrid, 256, csb_tile + 1024 * 4, *keys, suboff, histB, nsub, base, R);
+                else if (R == 11)
+                    LAUNCH("msd_count_sort", (k_msd_count_sort_bulk<256, 12, 2048>), cgrid, 256, csb_tile + 2048 * 4, *keys, suboff, histB, nsub, base, R);
+                else
+                    LAUNCH("msd_count_sort", (k_msd_count_sort_bulk<256, 12, 4096>), cgrid, 256, csb_tile + 4096 * 4, *keys, suboff, histB, nsub, base, R);
+            } else {
             const size_t cut11 = 2048 * sizeof(u32), cut10 = 3072 * sizeof(u32); // counters not needed below 12 / 11 bits
             if (max_sub <= 256 * 8 && small_counters && R <= 10)
                 LAUNCH("msd_count_sort", (k_msd_count_sort<256, 8, 4, 1024>), nsub, 256, sm8 - cut10, *keys, suboff, histB, base, R);
@@ -796,6 +815,7 @@ int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done, const u32 
                 LAUNCH("msd_count_sort", (k_msd_count_sort<512, 8, 4>), nsub, 512, sm16, *keys, suboff, histB, base, R);
             else
                 LAUNCH("msd_count_sort", (k_msd_count_sort<256, 16, 3>), nsub, 256, sm16, *keys, suboff, histB, base, R);
+            }
         } else if (R > 0) {
             LocalPlan plan;
             plan.npass = (R + 7) / 8;

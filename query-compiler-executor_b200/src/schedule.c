@@ -406,7 +406,7 @@ int qce_run_queries(DArray *q_list, DArray *metadata_arr, FILE *out, int *failed
         if (g_loader_ctx && pthread_create(&loader, NULL, loader_main, &b) == 0) have_loader = 1;
         else loader_main(&b);
     }
-    long streams = env_long("QCE_STREAMS", 4);
+    long streams = env_long("QCE_STREAMS", 8);
     if (streams > MAX_STREAMS) streams = MAX_STREAMS;
     if (b.nlight < 2) streams = 0; /* nothing to overlap */
     if ((size_t)streams > b.nlight) streams = (long)b.nlight;
