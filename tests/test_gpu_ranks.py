@@ -48,7 +48,17 @@ def test_golden_batches_row_sharded(world, db_name, batch, elide=1):
             assert o == r["stdout"] or (r["class"] == "PDQ-D" and refused), (r, o, e[-1500:])
 
 
-@pytest.mark.parametrize("world", [2, 4])
+def test_golden_batch_row_sharded_eight_ranks():
+    """QCE_GPUS=8 (the node's size): eight ranks, every relation row-sharded, the operational golden batch."""
+    db = load_db("ops_db.npz")
+    recs = [r for r in load_json("ops.json") if r["class"] in ("PDQ-T", "PDQ-D")]
+    text = "".join(r["query"] + "\n" for r in recs)
+    out, err, rc = run_queries_bin(QUERIES_BIN, _paths(db), text, env=dict(SHARD_ALL, QCE_GPUS=8, QCE_COMM_TIMEOUT_S=120), timeout=900)
+    assert rc == 0, err[-2000:]
+    assert out == "".join(r["stdout"] for r in recs)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_golden_batch_replicas(world):
     """Default placement: the small relations are held whole by every rank, whole queries are
     dealt to the ranks (and to several streams per rank), stdout comes back in query order."""
