@@ -1032,7 +1032,7 @@ k_msd_count_sort(u64 *__restrict__ keys, const u32 *__restrict__ seg_off, const 
     u32 *cnt = reinterpret_cast<u32 *>(skeys + TILE);
     u32 *scratch = cnt + MAXB;
     const u32 n = seg_size[blockIdx.x];
-    if (n <= 1) return;
+    if (n <= 1 || n > (u32)TILE) return; // oversized sub-buckets (a heavy key) take the k_big_* route
     u64 *base = keys + seg_off[blockIdx.x];
     const int tid = threadIdx.x;
     const u32 nb = 1u << rbits, mask = nb - 1;
@@ -1119,8 +1119,8 @@ k_msd_count_sort_bulk(u64 *__restrict__ keys, const u32 *__restrict__ seg_off, c
     auto fetch = [&](u32 s, int b) {
         const u32 off = seg_off[s], n = seg_size[s];
         sseg[b][0] = off;
-        sseg[b][1] = n;
-        if (n <= 1) return; // nothing to sort, nothing to fetch
+        sseg[b][1] = n > (u32)TILE ? 0u : n; // oversized sub-buckets (a heavy key) take the k_big_* route
+        if (n <= 1 || n > (u32)TILE) return; // nothing to sort here, nothing to fetch
         const u32 first = off & ~1u, last = (off + n + 1u) & ~1u;
         const u32 bytes = (last - first) * (u32)sizeof(u64);
         mbar_expect_tx(&bar[b], bytes);
@@ -1211,6 +1211,161 @@ k_msd_count_sort_bulk(u64 *__restrict__ keys, const u32 *__restrict__ seg_off, c
         }
     }
 #undef CSB_BUF
+}
+
+// ---- skew: sub-buckets a heavy key overflows ----------------------------------------------------------
+// A sub-bucket larger than the finish kernel's tile (a key that alone has more than ~3000 tuples: config 4's
+// Zipf side has ~1000 of them holding 78 % of the run) used to send the WHOLE run down four LSD passes.
+// Only those sub-buckets now take another route: one more counting pass on ALL their remaining key bits
+// (<= 12 bits -> <= 4096 bins, so equal digits are equal keys and nothing has to be stable): a
+// multi-CTA histogram, a per-bucket scan, an unstable scatter into the ping-pong buffer, and a copy back.
+// 40 B per tuple of the big sub-buckets instead of 72 B per tuple of everything.
+__global__ void __launch_bounds__(256)
+k_big_list(const u32 *__restrict__ sub_size, const u32 *__restrict__ sub_off, u32 nsub, u32 cap, u32 max_list,
+           u32 *__restrict__ nbig, u32 *__restrict__ big_off, u32 *__restrict__ big_size, u32 *__restrict__ big_tiles)
+{
+    const u32 s = blockIdx.x * 256 + threadIdx.x;
+    if (s >= nsub) return;
+    const u32 n = sub_size[s];
+    if (n <= cap) return;
+    const u32 at = atomicAdd(nbig, 1u);
+    if (at >= max_list) return; // the caller sees nbig > max_list and falls back
+    big_off[at] = sub_off[s];
+    big_size[at] = n;
+    big_tiles[at] = (n + QCE_MSD_TILE - 1) / QCE_MSD_TILE;
+}
+__global__ void k_big_tile_total(u32 *__restrict__ tile_start, u32 nbig, const u64 *__restrict__ total)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) tile_start[nbig] = (u32)*total;
+}
+// ghist[bucket * nb + (low rbits of the key)] over the tiles of the big sub-buckets
+template <int MAXB>
+__global__ void __launch_bounds__(512)
+k_big_hist(const u64 *__restrict__ keys, const MsdTileDesc *__restrict__ desc, u64 key_base, int rbits, u32 *__restrict__ ghist)
+{
+    __shared__ u32 sh[MAXB];
+    const MsdTileDesc d = desc[blockIdx.x];
+    if (d.count == 0) return;
+    const u32 nb = 1u << rbits, mask = nb - 1;
+    for (u32 b = threadIdx.x; b < nb; b += 512) sh[b] = 0;
+    __syncthreads();
+    // a heavy key's tiles are one bin: warps whose lanes agree count once (32 atomics on one shared
+    // address serialise)
+    for (u32 i0 = (threadIdx.x & ~31u); i0 < d.count; i0 += 512) {
+        const u32 i = i0 + (threadIdx.x & 31u);
+        const bool valid = i < d.count;
+        const u32 bin = valid ? (u32)((ld_stream_u64(keys + d.begin + i) - key_base) >> 32) & mask : 0xffffffffu;
+        const u32 live = __ballot_sync(QCE_FULL_MASK, valid);
+        const u32 first = __shfl_sync(QCE_FULL_MASK, bin, 0);
+        if (__all_sync(QCE_FULL_MASK, bin == first || !valid)) {
+            if ((threadIdx.x & 31u) == 0 && live) atomicAdd(&sh[first], (u32)__popc(live));
+        } else if (valid) {
+            atomicAdd(&sh[bin], 1u);
+        }
+    }
+    __syncthreads();
+    for (u32 b = threadIdx.x; b < nb; b += 512)
+        if (sh[b]) atomicAdd(&ghist[(size_t)d.bucket * nb + b], sh[b]);
+}
+// in place: ghist[bucket][bin] -> exclusive prefix inside the bucket (one CTA per big sub-bucket)
+__global__ void __launch_bounds__(1024) k_big_scan(u32 *__restrict__ ghist, u32 nb)
+{
+    __shared__ u32 scratch[33];
+    u32 *h = ghist + (size_t)blockIdx.x * nb;
+    u32 running = 0;
+    for (u32 base = 0; base < nb; base += 1024) {
+        const u32 b = base + threadIdx.x;
+        const u32 v = b < nb ? h[b] : 0u;
+        u32 tot;
+        const u32 ex = block_scan_excl<u32, 1024>(v, scratch, &tot);
+        if (b < nb) h[b] = running + ex;
+        running += tot;
+    }
+}
+// scatter the tiles of the big sub-buckets by the low rbits: out[bucket_off + cursor[bucket][bin]++]
+template <int MAXB>
+__global__ void __launch_bounds__(512, 2)
+k_big_partition(const u64 *__restrict__ in, u64 *__restrict__ out, const MsdTileDesc *__restrict__ desc,
+                const u32 *__restrict__ big_off, u64 key_base, int rbits, u32 *__restrict__ cursor)
+{
+    constexpr int THREADS = 512, ITEMS = QCE_MSD_TILE / THREADS;
+    extern __shared__ __align__(16) unsigned char bigp_smem[]; // TILE * 8 + 3 * MAXB * 4 bytes
+    u64 *skeys = reinterpret_cast<u64 *>(bigp_smem);
+    u32 *cnt = reinterpret_cast<u32 *>(skeys + QCE_MSD_TILE), *excl = cnt + MAXB, *goff = excl + MAXB;
+    __shared__ u32 scratch[33];
+    const MsdTileDesc d = desc[blockIdx.x];
+    if (d.count == 0) return;
+    const int tid = threadIdx.x;
+    const u32 nb = 1u << rbits, mask = nb - 1;
+    for (u32 b = tid; b < nb; b += THREADS) cnt[b] = 0;
+    __syncthreads();
+    u64 key[ITEMS];
+    u32 slot[ITEMS];
+    const u32 lt = lanemask_lt();
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+        const u32 i = tid + j * THREADS; // whole warps share `valid` except in the tail warp
+        const bool valid = i < d.count;
+        key[j] = valid ? ld_stream_u64(in + d.begin + i) : 0ull;
+        const u32 bin = (u32)((key[j] - key_base) >> 32) & mask;
+        const u32 live = __ballot_sync(QCE_FULL_MASK, valid);
+        const u32 first = __shfl_sync(QCE_FULL_MASK, bin, __ffs(live) - 1 < 0 ? 0 : __ffs(live) - 1);
+        if (__all_sync(QCE_FULL_MASK, !valid || bin == first)) {
+            // the whole warp holds one key (a heavy hitter's tile): one shared atomic instead of 32 on one address
+            u32 b0 = 0;
+            if ((tid & 31) == 0 && live) b0 = atomicAdd(&cnt[first], (u32)__popc(live));
+            b0 = __shfl_sync(QCE_FULL_MASK, b0, 0);
+            slot[j] = b0 + (u32)__popc(live & lt);
+        } else if (valid) {
+            slot[j] = atomicAdd(&cnt[bin], 1u);
+        }
+    }
+    __syncthreads();
+    // exclusive scan of the tile's counters (MAXB / THREADS consecutive ones per thread) and the
+    // reservation of the tile's output range per populated bin
+    {
+        constexpr int BPT = MAXB / THREADS;
+        u32 v[BPT], sum = 0;
+#pragma unroll
+        for (int q = 0; q < BPT; q++) {
+            const u32 b = tid * BPT + q;
+            v[q] = b < nb ? cnt[b] : 0u;
+            sum += v[q];
+        }
+        u32 tot;
+        u32 ex = block_scan_excl<u32, THREADS>(sum, scratch, &tot);
+#pragma unroll
+        for (int q = 0; q < BPT; q++) {
+            const u32 b = tid * BPT + q;
+            if (b < nb) {
+                excl[b] = ex;
+                goff[b] = (v[q] ? atomicAdd(&cursor[(size_t)d.bucket * nb + b], v[q]) : 0u) - ex;
+            }
+            ex += v[q];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+        const u32 i = tid + j * THREADS;
+        if (i < d.count) skeys[excl[(u32)((key[j] - key_base) >> 32) & mask] + slot[j]] = key[j];
+    }
+    __syncthreads();
+    u64 *dst = out + big_off[d.bucket];
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+        const u32 p = tid + j * THREADS;
+        if (p < d.count) {
+            const u64 k = skeys[p];
+            dst[goff[(u32)((k - key_base) >> 32) & mask] + p] = k;
+        }
+    }
+}
+__global__ void __launch_bounds__(512)
+k_big_copyback(const u64 *__restrict__ from, u64 *__restrict__ to, const MsdTileDesc *__restrict__ desc)
+{
+    const MsdTileDesc d = desc[blockIdx.x];
+    for (u32 i = threadIdx.x; i < d.count; i += 512) to[d.begin + i] = ld_stream_u64(from + d.begin + i);
 }
 
 // 1 if keys[i-1] > keys[i] anywhere (checks the "already sorted" assumption of

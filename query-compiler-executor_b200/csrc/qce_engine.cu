@@ -725,10 +725,27 @@ int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done, const u32 
            histB);
     LAUNCH("scan_tiles", (k_scan_excl<u32, u32>), 1, 1024, 0, histB, suboff, (u64)nsub, cx().d_scalars + 11);
     LAUNCH("msd_max", k_max_u32, grid_for(256, nsub, 1), 256, 0, histB, nsub, (u32 *)(cx().d_scalars + 10));
-    CK(cudaMemcpyAsync(cx().h_scalars + 10, cx().d_scalars + 10, sizeof(u64), cudaMemcpyDeviceToHost, cx().stream));
+    // skew: the sub-buckets a heavy key overflows are listed on the way (k_big_* below)
+    constexpr u32 BIG_CAP = 256 * 12, BIG_MAX = 8192;
+    static int big_path = -1; // QCE_MSD_BIG=0: any overflowing sub-bucket sends the whole run to the LSD passes
+    if (big_path < 0) {
+        const char *e = getenv("QCE_MSD_BIG");
+        big_path = e ? atoi(e) : 1;
+        CK(cudaFuncSetAttribute(k_big_partition<4096>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(QCE_MSD_TILE * sizeof(u64) + 3 * 4096 * sizeof(u32))));
+    }
+    u32 *big_off = nullptr, *big_size = nullptr, *big_tiles = nullptr;
+    if (sc.get(&big_off, BIG_MAX) || sc.get(&big_size, BIG_MAX) || sc.get(&big_tiles, BIG_MAX)) return -1;
+    CK(cudaMemsetAsync(cx().d_scalars + 12, 0, sizeof(u64), cx().stream));
+    LAUNCH("msd_big_list", k_big_list, (int)ceil_div(nsub, 256), 256, 0, histB, suboff, nsub, BIG_CAP, BIG_MAX,
+           (u32 *)(cx().d_scalars + 12), big_off, big_size, big_tiles);
+    CK(cudaMemcpyAsync(cx().h_scalars + 10, cx().d_scalars + 10, 3 * sizeof(u64), cudaMemcpyDeviceToHost, cx().stream));
     CK(cudaStreamSynchronize(cx().stream));
     const u32 max_sub = (u32)(cx().h_scalars[10] & 0xffffffffu);
-    if (max_sub <= MSD_LOCAL_CAP) {
+    const u32 nbig = (u32)(cx().h_scalars[12] & 0xffffffffu);
+    // R == 0: the partition levels consumed every key bit, a sub-bucket is one key however large it is
+    const bool big_route = max_sub > MSD_LOCAL_CAP && big_path && R > 0 && R <= 12 && nbig <= BIG_MAX;
+    if (max_sub <= MSD_LOCAL_CAP || R == 0 || big_route) {
         CK(cudaMemcpyAsync(curB, suboff, nsub * sizeof(u32), cudaMemcpyDeviceToDevice, cx().stream));
         if (bulk) {
             LAUNCH("msd_tiles", k_msd_tile_desc, (int)ceil_div(ntiles1, 256), 256, 0, tstart1, offA, histA, nbA, ntiles1, tdesc);
@@ -785,7 +802,7 @@ int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done, const u32 
                 CK(cudaFuncSetAttribute((k_msd_count_sort_bulk<256, 12, 2048>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(csb_tile + 2048 * 4)));
                 CK(cudaFuncSetAttribute((k_msd_count_sort_bulk<256, 12, 4096>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(csb_tile + 4096 * 4)));
             }
-            if (cs_bulk && max_sub <= 256 * 12) {
+            if (cs_bulk && (max_sub <= 256 * 12 || big_route)) {
                 const int cgrid = (int)std::min<u32>(nsub, (u32)G.sms * 3);
                 if (R <= 10)
                     LAUNCH("msd_count_sort", (k_msd_count_sort_bulk<256, 12, 1024>), cgrid, 256, csb_tile + 1024 * 4, *keys, suboff, histB, nsub, base, R);
@@ -801,6 +818,8 @@ int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done, const u32 
                 LAUNCH("msd_count_sort", (k_msd_count_sort<256, 8, 4, 2048>), nsub, 256, sm8 - cut11, *keys, suboff, histB, base, R);
             else if (max_sub <= 256 * 8)
                 LAUNCH("msd_count_sort", (k_msd_count_sort<256, 8, 4>), nsub, 256, sm8, *keys, suboff, histB, base, R);
+            else if (big_route)
+                LAUNCH("msd_count_sort", (k_msd_count_sort<256, 12, 4>), nsub, 256, sm12, *keys, suboff, histB, base, R);
             else if (mid_shape && max_sub <= 256 * 12 && small_counters && R <= 10)
                 LAUNCH("msd_count_sort", (k_msd_count_sort<256, 12, 4, 1024>), nsub, 256, sm12 - cut10, *keys, suboff, histB, base, R);
             else if (mid_shape && max_sub <= 256 * 12 && small_counters && R == 11)
@@ -816,7 +835,24 @@ int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done, const u32 
             else
                 LAUNCH("msd_count_sort", (k_msd_count_sort<256, 16, 3>), nsub, 256, sm16, *keys, suboff, histB, base, R);
             }
+            if (big_route && nbig > 0) {
+                // the oversized sub-buckets: one more counting pass on all their remaining bits, through alt
+                const u32 nbR = 1u << R, ntiles_big = ntiles0 + nbig; // upper bound; surplus CTAs exit
+                u32 *tstartB = nullptr, *bhist = nullptr;
+                MsdTileDesc *bdesc = nullptr;
+                if (sc.get(&tstartB, nbig + 1) || sc.get(&bhist, (u64)nbig * nbR) || sc.get(&bdesc, ntiles_big)) return -1;
+                CK(cudaMemsetAsync(bhist, 0, (u64)nbig * nbR * sizeof(u32), cx().stream));
+                LAUNCH("scan_tiles", (k_scan_excl<u32, u32>), 1, 1024, 0, big_tiles, tstartB, (u64)nbig, cx().d_scalars + 13);
+                LAUNCH("msd_tiles", k_big_tile_total, 1, 1, 0, tstartB, nbig, cx().d_scalars + 13);
+                LAUNCH("msd_tiles", k_msd_tile_desc, (int)ceil_div(ntiles_big, 256), 256, 0, tstartB, big_off, big_size, nbig, ntiles_big, bdesc);
+                LAUNCH("msd_big_hist", k_big_hist<4096>, (int)ntiles_big, 512, 0, *keys, bdesc, base, R, bhist);
+                LAUNCH("msd_big_scan", k_big_scan, (int)nbig, 1024, 0, bhist, nbR);
+                LAUNCH("msd_big_partition", k_big_partition<4096>, (int)ntiles_big, 512,
+                       QCE_MSD_TILE * sizeof(u64) + 3 * 4096 * sizeof(u32), *keys, alt, bdesc, big_off, base, R, bhist);
+                LAUNCH("msd_big_copy", k_big_copyback, (int)ntiles_big, 512, 0, alt, *keys, bdesc);
+            }
         } else if (R > 0) {
+            if (max_sub > MSD_LOCAL_CAP) return 0; // 13..16 remaining bits and a heavy key: the LSD passes
             LocalPlan plan;
             plan.npass = (R + 7) / 8;
             int at = 32;

@@ -343,10 +343,11 @@ def test_row_window_scan_and_build(engine, begin, count):
 
 
 @pytest.mark.parametrize("n,kind", [(3_000_000, "uniform27"), (2_500_001, "uniform20"), (3_000_000, "zipf"),
-                                    (2_000_000, "few_keys"), (1_048_576, "dense"), (5_000_000, "uniform32")])
+                                    (2_000_000, "few_keys"), (1_048_576, "dense"), (5_000_000, "uniform32"),
+                                    (4_000_000, "heavy_in_sparse"), (6_000_000, "zipf_dense"), (3_000_000, "one_key_plus")])
 def test_large_sort_msd_and_fallback(engine, n, kind):
-    """Large packed runs: MSD partition + shared-memory finish for non-skewed keys,
-    LSD fallback for skewed ones (a sub-bucket over the finish kernel's capacity)."""
+    """Large packed runs: MSD partition + shared-memory finish for non-skewed keys; sub-buckets a heavy
+    key overflows take one more multi-CTA counting pass (k_big_*); what neither covers falls back to LSD."""
     rng = np.random.default_rng(n)
     if kind == "uniform27":
         keys = rng.integers(0, 1 << 27, n, dtype=np.uint64)
@@ -358,6 +359,17 @@ def test_large_sort_msd_and_fallback(engine, n, kind):
         keys = (rng.zipf(1.2, n) % (1 << 27)).astype(np.uint64)
     elif kind == "few_keys":
         keys = rng.integers(0, 100, n, dtype=np.uint64)
+    elif kind == "heavy_in_sparse":   # 30 % one key, a few keys of 5-20 K tuples, the rest uniform over 2^27
+        keys = rng.integers(0, 1 << 27, n, dtype=np.uint64)
+        keys[rng.random(n) < 0.3] = 77_777_777
+        for k in range(12):
+            keys[rng.choice(n, 5000 + 1500 * k, replace=False)] = 1_000_003 * (k + 1)
+    elif kind == "zipf_dense":        # config 4's shape: Zipf(1.2) ranks scattered over the key range
+        perm_mul = 48_271
+        keys = ((rng.zipf(1.2, n) % n) * perm_mul % (1 << 26)).astype(np.uint64)
+    elif kind == "one_key_plus":      # 99 % one key
+        keys = rng.integers(0, 1 << 24, n, dtype=np.uint64)
+        keys[rng.random(n) < 0.99] = 123_456
     else:
         keys = rng.permutation(n).astype(np.uint64)
     ids = np.arange(n, dtype=U64)
