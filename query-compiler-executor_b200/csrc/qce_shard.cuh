@@ -584,9 +584,7 @@ int sh_scan_join_base(const Column *cr, const Column *cs, qce_rowids **outR, qce
     const int rc = scan_join_impl(cr, pos, cs, pos, outR, outS);
     qce_rowids_free(pos);
     if (rc != 0) { qcecomm::abort_all(); return -1; }
-    (*outR)->dist.kind = Dist::ROWS;
-    (*outR)->dist.rel = 0xffffffffu; // ascending row ids, but the relation is recorded by the caller
-    (*outR)->dist.kind = Dist::ANY;
+    (*outR)->dist.kind = Dist::ANY; // ascending positions; which relation's rows they are is the caller's knowledge
     (*outS)->dist.kind = Dist::ANY;
     if (others_of((*outR)->n, &(*outR)->n_others) != 0) return -1;
     (*outS)->n_others = (*outR)->n_others;
