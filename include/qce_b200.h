@@ -19,6 +19,14 @@
  * below 2^31 tuples (`int start,size`, src/utilities.c:20; int32 histogram,
  * src/histogram.h:5).  At the ABI they are widened to uint64_t.
  *
+ * Several ranks (one process per GPU; "ranks of the node" below): a handle is THIS
+ * RANK'S SHARE of a distributed object -- base columns are replicated or split by
+ * row range, filter outputs follow the row windows, join outputs follow the key
+ * ranges of the exchange -- while every count the host layer sees
+ * (qce_rowids_count, qce_tuples_count, the survivors of a refine) and every
+ * checksum is global and identical on all ranks.  The host layer is the same code
+ * on one GPU and on eight.
+ *
  * There is no CPU fallback: every compute entry point fails with -1 when no
  * CUDA device is usable.
  */

@@ -123,8 +123,9 @@ k_join_bounds(TupleView R, u32 nR, TupleView S, const uint2 *__restrict__ win,
             const u32 i = tbase + k * QCE_JTHREADS + tid;
             if (i < nR) { lb_out[i] = w.x; cnt_out[i] = 0; }
         }
-    } else if (khi - klo < QCE_JTAB) {
-        // ---- table path
+    } else if (khi - klo < QCE_JTAB && wn <= 16u * QCE_JTILE) {
+        // ---- table path (not for a window dominated by a heavy inner key: histogramming 2 M equal keys is
+        // 2 M atomics on one shared address by ONE CTA, where two binary searches per outer tuple do)
         u32 *tab = reinterpret_cast<u32 *>(skeys); // range + 1 entries
         const u32 range = (u32)(khi - klo) + 1;
         for (u32 v = tid; v <= range; v += QCE_JTHREADS) tab[v] = 0;
