@@ -405,3 +405,77 @@ def test_arena_returns_to_empty(engine):
     e.sync()
     _, used1 = e.mempool_stats()
     assert used1 == used0
+
+
+def test_worker_contexts_run_concurrently(engine):
+    """engine contexts (stream + scratch + arena each), one bound per host thread; the same
+    operators from four threads at once give the single-threaded answers."""
+    import ctypes as C
+    import threading
+    e = engine
+    rng = np.random.default_rng(5)
+    n = 400_000
+    for c in range(2):
+        e.upload_column(80, c, rng.integers(0, 1000, n, dtype=np.uint64))
+        e.upload_column(81, c, rng.integers(0, 1000, n, dtype=np.uint64))
+    col = [rng.integers(0, 1000, n, dtype=np.uint64) for _ in range(4)]  # not used on the device: reference answers
+    want = {}
+    for thr in (100, 300, 500, 700):
+        ids = e.filter_scan(80, 0, "<", thr)
+        want[thr] = (e.rowids_count(ids), e.checksum(ids, 80, [0, 1]))
+        e.rowids_free(ids)
+    ctxs = [e.lib.qce_ctx_create() for _ in range(4)]
+    assert all(ctxs)
+    got, errs = {}, []
+
+    def work(ctx, thr):
+        try:
+            assert e.lib.qce_ctx_bind(ctx) == 0
+            for _ in range(20):
+                ids = e.filter_scan(80, 0, "<", thr)
+                got[thr] = (e.rowids_count(ids), e.checksum(ids, 80, [0, 1]))
+                e.rowids_free(ids)
+            e.lib.qce_ctx_bind(None)
+        except Exception as ex:  # noqa: BLE001
+            errs.append(repr(ex))
+    ts = [threading.Thread(target=work, args=(ctxs[i], thr)) for i, thr in enumerate((100, 300, 500, 700))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for c in ctxs:
+        e.lib.qce_ctx_destroy(c)
+    assert not errs, errs
+    assert got == want
+
+
+def test_sorted_run_cache_is_per_batch(engine):
+    """Inside one batch the sorted run of a whole base column is built once and borrowed afterwards;
+    nothing survives qce_batch_end."""
+    import ctypes as C
+    e = engine
+    rng = np.random.default_rng(6)
+    n = 300_000
+    e.upload_column(82, 0, rng.integers(0, n, n, dtype=np.uint64))
+    h0, m0 = C.c_uint64(), C.c_uint64()
+    e.lib.qce_batch_cache_stats(C.byref(h0), C.byref(m0))
+    assert e.lib.qce_batch_begin() == 0
+    runs = []
+    for _ in range(3):
+        t = e.build_tuples(82, 0)
+        e.sort_tuples(t)
+        assert e.is_sorted(t)
+        runs.append(t)
+    k0, p0 = e.tuples_to_host(runs[0])
+    k2, p2 = e.tuples_to_host(runs[2])
+    np.testing.assert_array_equal(k0, k2)
+    np.testing.assert_array_equal(p0, p2)
+    for t in runs:
+        e.tuples_free(t)
+    assert e.lib.qce_batch_end() == 0
+    h1, m1 = C.c_uint64(), C.c_uint64()
+    e.lib.qce_batch_cache_stats(C.byref(h1), C.byref(m1))
+    assert h1.value - h0.value == 2 and m1.value - m0.value == 1
+    t = e.build_tuples(82, 0)   # outside a batch: built afresh, not sorted yet
+    assert not e.is_sorted(t) or n < 2
+    e.tuples_free(t)
