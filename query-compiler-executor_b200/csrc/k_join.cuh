@@ -134,7 +134,7 @@ k_join_bounds(TupleView R, u32 nR, TupleView S, const uint2 *__restrict__ win,
         for (u32 i = tid; i < wn; i += QCE_JTHREADS) atomicAdd(&tab[(u32)(tv_key<WS>(S, w.x + i) - klo)], 1u);
         __syncthreads();
         {   // exclusive scan in place; thread t owns `per` consecutive entries
-            const u32 per = (range + 1 + QCE_JTHREADS - 1) / QCE_JTHREADS; // <= 33
+            const u32 per = ((range + 1 + QCE_JTHREADS - 1) / QCE_JTHREADS) | 1u; // <= 33, odd: lane strides on distinct banks
             const u32 b0 = tid * per;
             u32 local = 0;
             for (u32 q = 0; q < per; q++)
@@ -190,6 +190,247 @@ k_join_bounds(TupleView R, u32 nR, TupleView S, const uint2 *__restrict__ win,
     if (tid == 0) {
         tile_total[blockIdx.x] = tot;
         tile_chunks[blockIdx.x] = (u32)((tot + QCE_JCHUNK - 1) / QCE_JCHUNK);
+    }
+}
+
+// ---- single pass: bounds and pairs in one kernel ------------------------------------------------
+// The two-phase join above reads both runs twice and round-trips lb/cnt through HBM (3.6 GB for
+// config 2's 150 M input tuples and 50 M pairs, where the runs and the pairs are 1.6 GB).  The only
+// thing phase 2 waits for is each tile's output offset -- a prefix sum over the tiles' pair totals.
+// Here the tiles are claimed in order through a ticket and a tile gets its offset from a decoupled
+// look-back over per-tile status words (flag | total in one 64-bit word, so a relaxed load either
+// sees nothing or the value), then writes its pairs straight from the registers that hold its
+// bounds.  The host sizes the outputs with a guess (`cap`); a tile that would cross it, or that
+// produces more than QCE_JFUSE_MAX pairs (a heavy key: its pairs are better spread over many CTAs),
+// stores lb/cnt instead and leaves its pairs to k_join_write's chunks (tile_chunks[t] > 0).
+// Output order is unchanged: R-major, S in run order inside a key group.
+#define QCE_JFUSE_MAX 16384u
+#define QCE_JST_AGG (1ull << 62)   // the tile's own total
+#define QCE_JST_INCL (2ull << 62)  // total of this tile and every tile before it
+#define QCE_JST_VAL ((1ull << 62) - 1)
+template <bool WR, bool WS, bool WRITE_R, bool WRITE_S, int MIN_CTAS>
+__global__ void __launch_bounds__(QCE_JTHREADS, MIN_CTAS)
+k_join_fused(TupleView R, u32 nR, TupleView S, const uint2 *__restrict__ win, u32 ntiles, u32 *__restrict__ ticket,
+             u64 *__restrict__ status, u64 cap, u32 *__restrict__ outR, u32 *__restrict__ outS,
+             u32 *__restrict__ lb_out, u32 *__restrict__ cnt_out, u64 *__restrict__ tile_off,
+             u32 *__restrict__ tile_chunks, u64 *__restrict__ total_out, u64 *__restrict__ deferred_chunks,
+             u32 *__restrict__ stats)
+{
+    constexpr int PER = QCE_JTILE / QCE_JTHREADS;
+    extern __shared__ __align__(16) u64 skeys[]; // QCE_JSMEM_BYTES: count table or staged S keys, then offsets / lb / row ids
+    __shared__ u64 scratch[33];
+    __shared__ u32 s_tile;
+    __shared__ u64 s_gbase;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // tiles in launch order: a look-back only ever waits for tiles that are resident or done.  CTAs are
+    // dispatched in blockIdx order; with a ticket the order holds whatever the dispatcher does.
+    if (ticket) {
+        if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+    }
+    const u32 t = ticket ? s_tile : blockIdx.x;
+    const u32 tbase = t * QCE_JTILE;
+    const uint2 w = win[t];
+    const u32 wn = w.y - w.x;
+    u64 key[PER];
+    u32 lo[PER], c[PER];
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        const u32 i = tbase + k * QCE_JTHREADS + tid;
+        key[k] = (i < nR) ? tv_key<WR>(R, i) : ~0ull;
+        lo[k] = w.x;
+        c[k] = 0;
+    }
+    const u32 last = min(tbase + QCE_JTILE, nR) - 1;
+    const u64 klo = tv_key<WR>(R, tbase), khi = tv_key<WR>(R, last);
+    if (wn == 0) {
+        // nothing in S inside the tile's key range
+    } else if (khi - klo < QCE_JTAB && wn <= 16u * QCE_JTILE) {
+        u32 *tab = reinterpret_cast<u32 *>(skeys);
+        const u32 range = (u32)(khi - klo) + 1;
+        for (u32 v = tid; v <= range; v += QCE_JTHREADS) tab[v] = 0;
+        __syncthreads();
+        for (u32 i = tid; i < wn; i += QCE_JTHREADS) atomicAdd(&tab[(u32)(tv_key<WS>(S, w.x + i) - klo)], 1u);
+        __syncthreads();
+        {   // exclusive scan in place; thread t owns `per` consecutive entries (odd: the lanes' strides then
+            // fall on different banks)
+            const u32 per = ((range + 1 + QCE_JTHREADS - 1) / QCE_JTHREADS) | 1u;
+            const u32 b0 = tid * per;
+            u32 local = 0;
+            for (u32 q = 0; q < per; q++)
+                if (b0 + q <= range) local += tab[b0 + q];
+            u32 tot32;
+            u32 ex = block_scan_excl<u32, QCE_JTHREADS>(local, reinterpret_cast<u32 *>(scratch), &tot32);
+            for (u32 q = 0; q < per; q++) {
+                if (b0 + q <= range) {
+                    const u32 cc = tab[b0 + q];
+                    tab[b0 + q] = ex;
+                    ex += cc;
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const u32 i = tbase + k * QCE_JTHREADS + tid;
+            if (i < nR) {
+                const u32 v = (u32)(key[k] - klo);
+                const u32 l = tab[v];
+                lo[k] = w.x + l;
+                c[k] = tab[v + 1] - l;
+            }
+        }
+    } else {
+        const bool staged = wn <= QCE_JWIN;
+        if (staged) {
+            for (u32 i = tid; i < wn; i += QCE_JTHREADS) skeys[i] = tv_key<WS>(S, w.x + i);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const u32 i = tbase + k * QCE_JTHREADS + tid;
+            if (i < nR) {
+                u32 lb, ub;
+                if (staged) {
+                    lb = bound_s<true>(skeys, wn, key[k]) + w.x;
+                    ub = bound_s<false>(skeys, wn, key[k]) + w.x;
+                } else {
+                    lb = lower_bound_g<WS>(S, w.x, w.y, key[k]);
+                    ub = upper_bound_g<WS>(S, lb, w.y, key[k]);
+                }
+                lo[k] = lb;
+                c[k] = ub - lb;
+            }
+        }
+    }
+    __syncthreads(); // every lookup is done: the table's memory is reused
+    u32 *soff = reinterpret_cast<u32 *>(skeys); // [QCE_JTILE] match counts, then tile-local exclusive offsets
+    u32 *slo = soff + QCE_JTILE, *srid = slo + QCE_JTILE;
+    u32 cmax = 0, cmin = 0xffffffffu;
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        soff[k * QCE_JTHREADS + tid] = c[k];
+        slo[k * QCE_JTHREADS + tid] = lo[k]; // the bounds wait in shared memory for the paths that need them again
+        cmax = max(cmax, c[k]);
+        if (tbase + k * QCE_JTHREADS + tid < nR) cmin = min(cmin, c[k]);
+    }
+    __syncthreads();
+    const uint4 a = reinterpret_cast<const uint4 *>(soff)[2 * tid], b = reinterpret_cast<const uint4 *>(soff)[2 * tid + 1];
+    const u64 mine = (u64)a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+    u64 tot;
+    const u64 ex = block_scan_excl<u64, QCE_JTHREADS>(mine, scratch, &tot);
+    const bool small_tot = tot <= QCE_JFUSE_MAX;
+    if (small_tot) {
+        u32 x = (u32)ex;
+        uint4 a2, b2;
+        a2.x = x; x += a.x; a2.y = x; x += a.y; a2.z = x; x += a.z; a2.w = x; x += a.w;
+        b2.x = x; x += b.x; b2.y = x; x += b.y; b2.z = x; x += b.z; b2.w = x;
+        reinterpret_cast<uint4 *>(soff)[2 * tid] = a2;
+        reinterpret_cast<uint4 *>(soff)[2 * tid + 1] = b2;
+    }
+    const int heavy = __syncthreads_or(cmax > 16u);
+    // The first match of all eight tuples is fetched now, in one batch, and the fetch is in flight while
+    // warp 0 publishes the tile's total and looks back for its offset (two global round trips that the
+    // other warps would otherwise sit out at the barrier).
+    // (the outer tuples' row ids come from L2 with them: holding them since the first read costs a CTA per SM)
+    u32 sid[PER], rid[PER];
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        const u32 i = tbase + k * QCE_JTHREADS + tid;
+        sid[k] = (WRITE_S && small_tot && !heavy && c[k]) ? tv_id<WS>(S, lo[k]) : 0u;
+        rid[k] = (WRITE_R && small_tot && i < nR && (c[k] || heavy)) ? tv_id<WR>(R, i) : 0u;
+    }
+    if (tid < 32) {
+        if (lane == 0) st_relaxed_gpu_u64(&status[t], (t == 0 ? QCE_JST_INCL : QCE_JST_AGG) | tot);
+        u64 before = 0;
+        if (t > 0) {
+            int look = (int)t - 1;
+            while (true) {
+                const int idx = look - lane;
+                u64 v = QCE_JST_INCL; // in front of the first tile: an inclusive total of zero
+                if (idx >= 0) {
+                    do { v = ld_relaxed_gpu_u64(&status[idx]); } while ((v >> 62) == 0);
+                }
+                const u32 incl = __ballot_sync(QCE_FULL_MASK, (v >> 62) == 2);
+                u64 val = v & QCE_JST_VAL;
+                if (incl && lane > __ffs(incl) - 1) val = 0; // beyond the nearest inclusive total
+                before += warp_sum_u64(val);
+                if (incl) break;
+                look -= 32;
+            }
+            if (lane == 0) st_relaxed_gpu_u64(&status[t], QCE_JST_INCL | (before + tot));
+        }
+        if (lane == 0) {
+            s_gbase = before;
+            if (t == ntiles - 1) *total_out = before + tot;
+        }
+    }
+    __syncthreads();
+    const u64 gbase = s_gbase;
+    const bool fused = small_tot && gbase + tot <= cap;
+    if (tid == 0) {
+        const u32 chunks = fused ? 0u : (u32)((tot + QCE_JCHUNK - 1) / QCE_JCHUNK);
+        tile_off[t] = gbase;
+        tile_chunks[t] = chunks;
+        if (chunks) atomicAdd(deferred_chunks, (u64)chunks);
+    }
+    if (stats) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            cmin = min(cmin, __shfl_xor_sync(QCE_FULL_MASK, cmin, o));
+            cmax = max(cmax, __shfl_xor_sync(QCE_FULL_MASK, cmax, o));
+        }
+        if (lane == 0) {
+            atomicMin(&stats[0], cmin);
+            atomicMax(&stats[1], cmax);
+        }
+    }
+    if (!fused) {
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const u32 i = tbase + k * QCE_JTHREADS + tid;
+            if (i < nR) { lb_out[i] = slo[k * QCE_JTHREADS + tid]; cnt_out[i] = c[k]; }
+        }
+        return;
+    }
+    if (tot == 0) return;
+    if (!heavy) {
+        // at most 16 matches per outer tuple: every thread writes the pairs of its own tuples; consecutive
+        // lanes hold consecutive tuples, so their pairs are neighbours in the output
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            if (c[k]) {
+                const u64 o = gbase + soff[k * QCE_JTHREADS + tid];
+                if (WRITE_R) outR[o] = rid[k];
+                if (WRITE_S) outS[o] = sid[k];
+            }
+        }
+        if (__any_sync(QCE_FULL_MASK, cmax > 1u)) {
+#pragma unroll
+            for (int k = 0; k < PER; k++) {
+                const u64 o = gbase + soff[k * QCE_JTHREADS + tid];
+                const u32 l = slo[k * QCE_JTHREADS + tid];
+                for (u32 q = 1; q < c[k]; q++) {
+                    if (WRITE_R) outR[o + q] = rid[k];
+                    if (WRITE_S) outS[o + q] = tv_id<WS>(S, l + q);
+                }
+            }
+        }
+    } else {
+        // a few outer tuples carry most of the tile's pairs: one output slot per thread and step, mapped back
+        // to its outer tuple by binary search over the offsets
+#pragma unroll
+        for (int k = 0; k < PER; k++) srid[k * QCE_JTHREADS + tid] = rid[k];
+        __syncthreads();
+        for (u32 o = tid; o < (u32)tot; o += QCE_JTHREADS) {
+            u32 l = 0, h = QCE_JTILE; // largest e with soff[e] <= o (tuples without matches share their successor's offset)
+            while (h - l > 1) {
+                const u32 mid = (l + h) >> 1;
+                if (soff[mid] <= o) l = mid; else h = mid;
+            }
+            if (WRITE_R) outR[gbase + o] = srid[l];
+            if (WRITE_S) outS[gbase + o] = tv_id<WS>(S, slo[l] + (o - soff[l]));
+        }
     }
 }
 

@@ -68,6 +68,17 @@ __device__ __forceinline__ void st_relaxed_gpu_u32(u32 *p, u32 a)
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(a) : "memory");
 }
 
+__device__ __forceinline__ u64 ld_relaxed_gpu_u64(const u64 *p)
+{
+    u64 a;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(a) : "l"(p) : "memory");
+    return a;
+}
+__device__ __forceinline__ void st_relaxed_gpu_u64(u64 *p, u64 a)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(a) : "memory");
+}
+
 __device__ __forceinline__ u32 lanemask_lt()
 {
     u32 m;

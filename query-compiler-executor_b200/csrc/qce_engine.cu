@@ -65,6 +65,7 @@ struct qce_tuples {
     u64 key_max;   // range after an exchange); they size the MSD buckets
     u32 id_bound;
     bool sorted;
+    bool skewed = false;    // the sort met a heavy key (a sub-bucket over the finish tile): joins take the two-phase route
     u32 *hist256 = nullptr; // device: 256-bin histogram of the top 8 of hist_key_bits key bits (taken by the build
     int hist_key_bits = 0;  // kernels, or by qce_key_histogram); valid while the run is unsorted and unmodified
     std::vector<unsigned int> hist_host; // the same 256 counts on the host
@@ -146,6 +147,7 @@ struct Global {
         u64 *a; u64 n; int key_bits; u64 key_min, key_max; u32 id_bound;
         cudaEvent_t ready;      // recorded on the producer's stream after the sort
         class Arena *owner;
+        bool skewed = false;
     };
     std::map<u64, CachedRun> run_cache;
     bool cache_on = false;
@@ -251,6 +253,25 @@ class Arena {
                 by_size_.erase({prev->second, prev->first});
                 by_addr_.erase(prev);
             }
+        }
+        insert_free(addr, size);
+    }
+    // give the tail of a live block back (an output sized by a guess, once its real size is known)
+    void shrink(void *p, u64 bytes)
+    {
+        auto it = live_.find((u64)p);
+        if (it == live_.end()) return;
+        bytes = (bytes + kAlign - 1) / kAlign * kAlign;
+        if (bytes == 0) bytes = kAlign;
+        if (bytes >= it->second) return;
+        u64 addr = it->first + bytes, size = it->second - bytes;
+        used_ -= size;
+        it->second = bytes;
+        auto next = by_addr_.find(addr + size);
+        if (next != by_addr_.end() && !slab_starts_.count(addr + size)) {
+            size += next->second;
+            by_size_.erase({next->second, next->first});
+            by_addr_.erase(next);
         }
         insert_free(addr, size);
     }
@@ -631,6 +652,7 @@ RadixShifts shifts_for(int base_shift, int bits, int digit_bits = QCE_RADIX_BITS
 // For large packed runs.  *done = false means "not applicable or skewed": the
 // caller sorts with the LSD passes instead (the run is left untouched).
 constexpr u32 MSD_LOCAL_CAP = 256 * 16; // tuples the largest k_msd_local_sort shape can hold
+thread_local bool tl_sort_skewed = false; // set by msd_sort: some sub-bucket holds more than the finish tile (a heavy key)
 int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done, const u32 *hist_top8 = nullptr,
              int hist_key_bits = 0)
 {
@@ -646,13 +668,14 @@ int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done, const u32 
     const u64 base = key_min << 32;
     key_max -= key_min;
     const int key_bits = bitlen(key_max);
+    if (key_bits < 9) tl_sort_skewed = true; // a million tuples over fewer than 512 keys
     if (key_bits < 9 || key_bits > 32) return 0;
     // Partition bits P: the smallest count for which a populated sub-bucket holds
     // at most ~2700 tuples on average (finish capacity 4096), assuming keys spread
     // over [0, key_max]; anything denser is caught by the max-bucket check below.
     int P = 9;
     while (P < 16 && P < key_bits && n / (((key_max >> (key_bits - P)) + 1)) > 2700) P++;
-    if (n / (((key_max >> (key_bits - P)) + 1)) > 2700) return 0; // too dense for 16 partition bits: LSD
+    if (n / (((key_max >> (key_bits - P)) + 1)) > 2700) { tl_sort_skewed = true; return 0; } // too dense for 16 partition bits: LSD
     const int P1 = 8, P2 = P - 8, R = key_bits - P;
     const int shiftA = 32 + key_bits - P1, shiftB = 32 + key_bits - P;
     const u32 nbA = 256, nbB = 1u << P2, nsub = nbA * nbB;
@@ -694,10 +717,21 @@ int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done, const u32 
         bulk = e ? atoi(e) : 1;
         if (bulk) CK(cudaFuncSetAttribute(k_msd_partition_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QCE_MSDB_SMEM));
     }
+    static int slots = -1; // QCE_MSD_SLOTS=0: the bulk-copy / plain kernels with contiguous staging (for comparison)
+    if (slots < 0) {
+        const char *e = getenv("QCE_MSD_SLOTS");
+        slots = e ? atoi(e) : 0;
+        CK(cudaFuncSetAttribute((k_msd_partition_slots<u64, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MsdsSmem<u64>::bytes));
+    }
     MsdTileDesc *tdesc = nullptr;
     const u32 ntiles_cap = ntiles0 + nbA;
     const int bulk_grid = G.sms * 3;
-    if (bulk) {
+    if (slots) {
+        if (sc.get(&tdesc, ntiles_cap) != 0) return -1;
+        LAUNCH("msd_tiles", k_msd_tile_desc, (int)ceil_div(ntiles0, 256), 256, 0, lvl0, lvl0 + 2, lvl0 + 3, 1u, ntiles0, tdesc);
+        LAUNCH("msd_partition", (k_msd_partition_slots<u64, 3>), (int)ntiles0, QCE_MSDS_THREADS, MsdsSmem<u64>::bytes, *keys, alt, tdesc,
+               base, shiftA, nbA, 8, curA);
+    } else if (bulk) {
         if (sc.get(&tdesc, ntiles_cap) != 0) return -1;
         LAUNCH("msd_tiles", k_msd_tile_desc, (int)ceil_div(ntiles0, 256), 256, 0, lvl0, lvl0 + 2, lvl0 + 3, 1u, ntiles0, tdesc);
         LAUNCH("msd_partition", k_msd_partition_bulk, (int)std::min<u32>(ntiles0, (u32)bulk_grid), QCE_MSDB_THREADS, QCE_MSDB_SMEM, *keys, alt,
@@ -743,11 +777,16 @@ int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done, const u32 
     CK(cudaStreamSynchronize(cx().stream));
     const u32 max_sub = (u32)(cx().h_scalars[10] & 0xffffffffu);
     const u32 nbig = (u32)(cx().h_scalars[12] & 0xffffffffu);
+    if (max_sub > 256 * 12) tl_sort_skewed = true;
     // R == 0: the partition levels consumed every key bit, a sub-bucket is one key however large it is
     const bool big_route = max_sub > MSD_LOCAL_CAP && big_path && R > 0 && R <= 12 && nbig <= BIG_MAX;
     if (max_sub <= MSD_LOCAL_CAP || R == 0 || big_route) {
         CK(cudaMemcpyAsync(curB, suboff, nsub * sizeof(u32), cudaMemcpyDeviceToDevice, cx().stream));
-        if (bulk) {
+        if (slots) {
+            LAUNCH("msd_tiles", k_msd_tile_desc, (int)ceil_div(ntiles1, 256), 256, 0, tstart1, offA, histA, nbA, ntiles1, tdesc);
+            LAUNCH("msd_partition", (k_msd_partition_slots<u64, 3>), (int)ntiles1, QCE_MSDS_THREADS, MsdsSmem<u64>::bytes, alt, *keys, tdesc,
+                   base, shiftB, nbB, P2, curB);
+        } else if (bulk) {
             LAUNCH("msd_tiles", k_msd_tile_desc, (int)ceil_div(ntiles1, 256), 256, 0, tstart1, offA, histA, nbA, ntiles1, tdesc);
             LAUNCH("msd_partition", k_msd_partition_bulk, (int)std::min<u32>(ntiles1, (u32)bulk_grid), QCE_MSDB_THREADS, QCE_MSDB_SMEM, alt,
                    *keys, tdesc, ntiles1, base, shiftB, nbB, curB);
@@ -897,10 +936,124 @@ TupleView view_of(const qce_tuples *t)
 // ---- merge join driver -------------------------------------------------------
 thread_local u32 *tl_join_stats = nullptr; // when set: {min, max} match count per outer tuple of the next merge
 
+// Single-pass join (k_join_fused): the outputs are sized by a guess -- an equi-join along a key /
+// foreign-key pair cannot produce more pairs than its larger input has tuples -- and trimmed once the
+// pair count is known.  Tiles the guess cannot hold, and tiles dominated by a heavy key, come back as
+// a chunk list for k_join_write.  Returns 1 when the guess cannot be allocated: the caller then runs
+// the two-phase join, which sizes its outputs exactly.
+struct OutGuard {
+    qce_rowids *r = nullptr, *s = nullptr;
+    ~OutGuard() { qce_rowids_free(r); qce_rowids_free(s); }
+};
+template <bool WR, bool WS>
+int merge_join_fused_t(const qce_tuples *R, const qce_tuples *S, bool want_r, bool want_s, qce_rowids **outR,
+                       qce_rowids **outS)
+{
+    const u32 nR = (u32)R->n, nS = (u32)S->n;
+    const u32 ntiles = (u32)ceil_div(nR, QCE_JTILE);
+    u64 cap = std::max<u64>(nR, nS);
+    static long long cap_env = -1; // QCE_JOIN_CAP: force the guess (tests: 1 = every tile past the first pair is deferred)
+    if (cap_env < 0) { const char *e = getenv("QCE_JOIN_CAP"); cap_env = e ? atoll(e) : 0; }
+    if (cap_env > 0) cap = (u64)cap_env;
+    uint2 *win = nullptr;
+    u32 *lb = nullptr, *cnt = nullptr, *tile_chunks = nullptr, *chunk_off = nullptr;
+    u64 *tile_off = nullptr, *status = nullptr;
+    Scratch sc;
+    OutGuard og;
+    if (sc.get(&win, ntiles) || sc.get(&lb, nR) || sc.get(&cnt, nR) || sc.get(&tile_chunks, ntiles) ||
+        sc.get(&chunk_off, ntiles) || sc.get(&tile_off, ntiles) || sc.get(&status, (u64)ntiles + 1) ||
+        (want_r && new_rowids(cap, R->id_bound, &og.r) != 0) || (want_s && new_rowids(cap, S->id_bound, &og.s) != 0))
+        return 1;
+    TupleView vr = view_of(R), vs = view_of(S);
+    static int use_ticket = -1; // QCE_JOIN_TICKET=1: claim the tiles through an atomic counter instead of blockIdx
+    if (use_ticket < 0) { const char *e = getenv("QCE_JOIN_TICKET"); use_ticket = e ? atoi(e) : 0; }
+    u32 *ticket = use_ticket ? reinterpret_cast<u32 *>(status + ntiles) : nullptr;
+    CK(cudaMemsetAsync(status, 0, ((u64)ntiles + 1) * sizeof(u64), cx().stream));
+    const u64 init3[3] = {0ull, 0ull, 0x00000000ffffffffull}; // pairs, deferred chunks, {min, max} matches
+    CK(cudaMemcpyAsync(cx().d_scalars, init3, sizeof init3, cudaMemcpyHostToDevice, cx().stream));
+    LAUNCH("join_partition", (k_join_partition<WR, WS>), (int)ceil_div(ntiles, 256), 256, 0, vr, nR, vs, nS, ntiles, win);
+    u32 *stats = tl_join_stats ? (u32 *)(cx().d_scalars + 2) : nullptr;
+    u32 *pr = og.r ? og.r->d : nullptr, *ps = og.s ? og.s->d : nullptr;
+#define QCE_FUSED_LAUNCH_M(WRF, WSF, M)                                                                              \
+    do {                                                                                                             \
+        static bool attr_set = false;                                                                                \
+        if (!attr_set) {                                                                                             \
+            CK(cudaFuncSetAttribute((k_join_fused<WR, WS, WRF, WSF, M>), cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    (int)QCE_JSMEM_BYTES));                                                          \
+            attr_set = true;                                                                                         \
+        }                                                                                                            \
+        LAUNCH("join_fused", (k_join_fused<WR, WS, WRF, WSF, M>), (int)ntiles, QCE_JTHREADS, QCE_JSMEM_BYTES, vr, nR, vs, \
+               win, ntiles, ticket, status, cap, pr, ps, lb, cnt, tile_off, tile_chunks, cx().d_scalars,             \
+               cx().d_scalars + 1, stats);                                                                           \
+    } while (0)
+    static int minb = -1; // QCE_JOIN_MINB=4: 64 registers, 4 CTAs per SM (default 5: 48 registers)
+    if (minb < 0) { const char *e = getenv("QCE_JOIN_MINB"); minb = e ? atoi(e) : 5; }
+#define QCE_FUSED_LAUNCH(WRF, WSF)                                                                                   \
+    do {                                                                                                             \
+        if (minb == 4) QCE_FUSED_LAUNCH_M(WRF, WSF, 4);                                                              \
+        else QCE_FUSED_LAUNCH_M(WRF, WSF, 5);                                                                        \
+    } while (0)
+    if (want_r && want_s) QCE_FUSED_LAUNCH(true, true);
+    else if (want_r) QCE_FUSED_LAUNCH(true, false);
+    else QCE_FUSED_LAUNCH(false, true);
+#undef QCE_FUSED_LAUNCH
+#undef QCE_FUSED_LAUNCH_M
+    if (read_scalars(3) != 0) return -1;
+    const u64 m = cx().h_scalars[0], nchunks = cx().h_scalars[1];
+    if (tl_join_stats) {
+        tl_join_stats[0] = (u32)(cx().h_scalars[2] & 0xffffffffu);
+        tl_join_stats[1] = (u32)(cx().h_scalars[2] >> 32);
+    }
+    if (m >= (1ull << 32)) return fail("join output of %llu pairs exceeds the 2^32 row-id column limit", (unsigned long long)m);
+    if (m > cap) {
+        // the guess was too small: tiles below it wrote their pairs, move those into outputs of the real size
+        OutGuard big;
+        if (want_r && new_rowids(m, R->id_bound, &big.r) != 0) return -1;
+        if (want_s && new_rowids(m, S->id_bound, &big.s) != 0) return -1;
+        if (big.r) CK(cudaMemcpyAsync(big.r->d, og.r->d, cap * sizeof(u32), cudaMemcpyDeviceToDevice, cx().stream));
+        if (big.s) CK(cudaMemcpyAsync(big.s->d, og.s->d, cap * sizeof(u32), cudaMemcpyDeviceToDevice, cx().stream));
+        std::swap(big.r, og.r);
+        std::swap(big.s, og.s);
+        pr = og.r ? og.r->d : nullptr;
+        ps = og.s ? og.s->d : nullptr;
+    } else {
+        if (og.r) { cx().arena.shrink(og.r->d, m * sizeof(u32)); og.r->n = m; }
+        if (og.s) { cx().arena.shrink(og.s->d, m * sizeof(u32)); og.s->n = m; }
+    }
+    if (nchunks > 0) {
+        if (ntiles <= 512)
+            LAUNCH("scan_tiles", (k_scan_excl_warp<u32, u32>), 1, 32, 0, tile_chunks, chunk_off, (u64)ntiles, cx().d_scalars + 1);
+        else
+            LAUNCH("scan_tiles", (k_scan_excl<u32, u32>), 1, 1024, 0, tile_chunks, chunk_off, (u64)ntiles, cx().d_scalars + 1);
+        if (want_r && want_s)
+            LAUNCH("join_write", (k_join_write<WR, WS, true, true>), (int)nchunks, QCE_JTHREADS, 0, vr, nR, vs, lb, cnt,
+                   tile_off, chunk_off, ntiles, pr, ps);
+        else if (want_r)
+            LAUNCH("join_write", (k_join_write<WR, WS, true, false>), (int)nchunks, QCE_JTHREADS, 0, vr, nR, vs, lb, cnt,
+                   tile_off, chunk_off, ntiles, pr, ps);
+        else
+            LAUNCH("join_write", (k_join_write<WR, WS, false, true>), (int)nchunks, QCE_JTHREADS, 0, vr, nR, vs, lb, cnt,
+                   tile_off, chunk_off, ntiles, pr, ps);
+    }
+    if (outR) *outR = og.r;
+    if (outS) *outS = og.s;
+    og.r = og.s = nullptr;
+    return 0;
+}
+
 template <bool WR, bool WS>
 int merge_join_t(const qce_tuples *R, const qce_tuples *S, bool want_r, bool want_s, qce_rowids **outR,
                  qce_rowids **outS, bool walk)
 {
+    static int fused_on = -1; // QCE_JOIN_FUSED=0: always the two-phase join
+    if (fused_on < 0) { const char *e = getenv("QCE_JOIN_FUSED"); fused_on = e ? atoi(e) : 1; }
+    // a look-back chain runs at the pace of its slowest tile: a heavy key's tile (a window of millions of inner
+    // tuples, searched instead of tabulated) would hold every later tile up -- such joins stay two-phase
+    if (!walk && fused_on && !R->skewed && !S->skewed) {
+        const int rc = merge_join_fused_t<WR, WS>(R, S, want_r, want_s, outR, outS);
+        if (rc <= 0) return rc;
+        g_err[0] = 0; // the guess did not fit: size the outputs exactly
+    }
     const u32 nR = (u32)R->n, nS = (u32)S->n;
     const u32 ntiles = (u32)ceil_div(nR, QCE_JTILE);
     uint2 *win = nullptr;
@@ -1918,6 +2071,7 @@ int qce_build_tuples_base(uint32_t rel, uint32_t col, qce_tuples **out)
             t->a = c.a; t->ids = nullptr; t->n = c.n; t->wide = false; t->key_bits = c.key_bits;
             t->key_min = c.key_min; t->key_max = c.key_max; t->id_bound = c.id_bound;
             t->sorted = true; t->borrowed = true; t->src_rel = rel; t->src_col = col; t->whole_base = true;
+            t->skewed = c.skewed;
             CK(cudaStreamWaitEvent(cx().stream, c.ready, 0)); // sorted on another context's stream
             *out = t;
             return 0;
@@ -2028,6 +2182,7 @@ int qce_sort_tuples(qce_tuples *t)
     }
     if (t->borrowed && t->sorted) return 0; // a cached sorted base run
     int rc;
+    tl_sort_skewed = false;
     if (t->wide) {
         RadixShifts rs = shifts_for(0, t->key_bits, 8);
         rc = radix_sort(&t->a, &t->ids, t->n, rs);
@@ -2037,13 +2192,13 @@ int qce_sort_tuples(qce_tuples *t)
         rc = sort_packed(&t->a, t->n, t->key_bits, t->key_min, t->key_max, t->hist256,
                          bitlen(t->key_max) == t->hist_key_bits ? t->hist_key_bits : -1);
     }
-    if (rc == 0) t->sorted = true;
+    if (rc == 0) { t->sorted = true; t->skewed = tl_sort_skewed; }
     if (rc == 0 && G.cache_on && t->whole_base && !t->wide && !t->borrowed && t->n >= 1024) {
         // hand the run to the batch's cache; this handle (and later ones) borrow it
         std::lock_guard<std::mutex> lk(G.mu);
         const u64 bytes = t->n * sizeof(u64);
         if (!G.run_cache.count(col_key(t->src_rel, t->src_col)) && G.cache_bytes + bytes <= G.cache_budget) {
-            Global::CachedRun c{t->a, t->n, t->key_bits, t->key_min, t->key_max, t->id_bound, nullptr, &cx().arena};
+            Global::CachedRun c{t->a, t->n, t->key_bits, t->key_min, t->key_max, t->id_bound, nullptr, &cx().arena, t->skewed};
             if (cudaEventCreateWithFlags(&c.ready, cudaEventDisableTiming) == cudaSuccess) {
                 cudaEventRecord(c.ready, cx().stream);
                 G.run_cache[col_key(t->src_rel, t->src_col)] = c;
