@@ -428,6 +428,7 @@ C2_MODELS = {
     "onesweep_k": lambda s: (16.0 * s["sort"] * s["passes"], "16 B per tuple per pass"),
     "checksum": lambda s: (12.0 * s["pairs"] * 3, "4 B row id + 8 B value per row per projected column"),
     "join_bounds": lambda s: (8.0 * s["sort"] + 8.0 * s["lhs"], "8 B per input tuple + 8 B (lb,cnt) per lhs tuple"),
+    "join_fused": lambda s: (8.0 * s["sort"] + 8.0 * s["pairs"], "8 B per input tuple (both runs, read once) + 8 B per pair written"),
     "join_write": lambda s: (16.0 * s["lhs"] + 8.0 * (s["sort"] - s["lhs"]) + 8.0 * s["pairs"],
                              "8 B (lb,cnt) + 8 B tuple per lhs tuple, the rhs run's 8 B tuples (row ids of the matches), 8 B per pair written"),
     "build_tuples": lambda s: (8.0 * s["rows"] + 12.0 * s["lhs"] + 8.0 * s["sort"], "8 B key (+4 B id) in, 8 B packed tuple out"),
@@ -439,7 +440,7 @@ C2_MODELS = {
 # kernels no longer flips the headline kernel)
 C2_STAGES = {"sort": ["msd_partition", "msd_count_sort", "msd_hist", "onesweep_k", "radix_hist", "msd_tiles", "msd_max"],
              "projection": ["checksum", "hist_u32", "partition_u32", "join_write", "push_rowids", "hist_ids"],
-             "join": ["join_bounds", "join_partition"], "build": ["build_tuples", "filter_scan", "compact_ids"],
+             "join": ["join_fused", "join_bounds", "join_partition"], "build": ["build_tuples", "filter_scan", "compact_ids"],
              "exchange": ["push_tuples", "radix_hist"]}
 
 

@@ -99,7 +99,7 @@ template <bool WR, bool WS>
 __global__ void __launch_bounds__(QCE_JTHREADS)
 k_join_bounds(TupleView R, u32 nR, TupleView S, const uint2 *__restrict__ win,
               u32 *__restrict__ lb_out, u32 *__restrict__ cnt_out, u64 *__restrict__ tile_total,
-              u32 *__restrict__ tile_chunks)
+              u32 *__restrict__ tile_chunks, u32 *__restrict__ stats)
 {
     extern __shared__ __align__(16) u64 skeys[]; // QCE_JSMEM_BYTES: S keys (search path) or the count table
     __shared__ u64 scratch[33];
@@ -117,11 +117,12 @@ k_join_bounds(TupleView R, u32 nR, TupleView S, const uint2 *__restrict__ win,
     const u32 last = min(tbase + QCE_JTILE, nR) - 1;
     const u64 klo = tv_key<WR>(R, tbase), khi = tv_key<WR>(R, last);
     u64 sum = 0;
+    u32 cmin = 0xffffffffu, cmax = 0; // smallest / largest match count of an outer tuple (stats != nullptr: the 8f-2 test)
     if (wn == 0) {
 #pragma unroll
         for (int k = 0; k < QCE_JTILE / QCE_JTHREADS; k++) {
             const u32 i = tbase + k * QCE_JTHREADS + tid;
-            if (i < nR) { lb_out[i] = w.x; cnt_out[i] = 0; }
+            if (i < nR) { lb_out[i] = w.x; cnt_out[i] = 0; cmin = 0; }
         }
     } else if (khi - klo < QCE_JTAB && wn <= 16u * QCE_JTILE) {
         // ---- table path (not for a window dominated by a heavy inner key: histogramming 2 M equal keys is
@@ -159,6 +160,8 @@ k_join_bounds(TupleView R, u32 nR, TupleView S, const uint2 *__restrict__ win,
                 lb_out[i] = w.x + lo;
                 cnt_out[i] = c;
                 sum += c;
+                cmin = min(cmin, c);
+                cmax = max(cmax, c);
             }
         }
     } else {
@@ -183,7 +186,20 @@ k_join_bounds(TupleView R, u32 nR, TupleView S, const uint2 *__restrict__ win,
                 lb_out[i] = lb;
                 cnt_out[i] = ub - lb;
                 sum += ub - lb;
+                cmin = min(cmin, ub - lb);
+                cmax = max(cmax, ub - lb);
             }
+        }
+    }
+    if (stats) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            cmin = min(cmin, __shfl_xor_sync(QCE_FULL_MASK, cmin, o));
+            cmax = max(cmax, __shfl_xor_sync(QCE_FULL_MASK, cmax, o));
+        }
+        if ((tid & 31) == 0) {
+            atomicMin(&stats[0], cmin);
+            atomicMax(&stats[1], cmax);
         }
     }
     u64 tot = block_sum<u64, QCE_JTHREADS>(sum, scratch);

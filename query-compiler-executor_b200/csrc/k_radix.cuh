@@ -911,153 +911,6 @@ k_msd_partition_bulk(const u64 *__restrict__ in, u64 *__restrict__ out, const Ms
 #undef MSDB_BUF
 }
 
-// ---- the same pass with slotted staging ------------------------------------------------------
-// ncu of the two kernels above (profiles/ncu_summary_r2b.json): the shared-memory data pipe is
-// 77-80 % busy, DRAM 50 % -- the pass is bound by shared-memory wavefronts, ~27 per 32 tuples:
-// rank (atomic), look up the digit's exclusive offset, scatter into the staging buffer, read it
-// back in order, look up the digit's global offset.  Here every digit owns a fixed window of
-// CAP = 8192 / bins staging slots (twice its expected share of a 4096-tuple tile), so a tuple's
-// staging slot is known the moment its rank is: digit * CAP + rank.  No scan, no offset lookups,
-// one barrier less; the write-out walks the windows, one warp per 32 slots (the per-window fill
-// and global base are fetched once per warp and passed round by shuffles).  The slot inside a
-// window is rotated by the digit, otherwise every window's first slots share a bank.
-// A tile whose digits do not fit their windows (skew) is redone the classic way by the same CTA
-// (ranks -> scan -> contiguous staging), with the staging buffer reused as 4096 flat slots; a
-// warp that sees half of its lanes on one digit raises the flag before it has ranked anything.
-constexpr int QCE_MSDS_THREADS = 512, QCE_MSDS_ITEMS = 8;
-constexpr int QCE_MSDS_SLOTS_LOG2 = 13;                              // 8192 staging slots per tile
-template <typename KeyT> struct MsdsSmem {
-    static constexpr size_t bytes = (size_t(1) << QCE_MSDS_SLOTS_LOG2) * sizeof(KeyT);
-};
-template <typename KeyT, int MIN_CTAS>
-__global__ void __launch_bounds__(QCE_MSDS_THREADS, MIN_CTAS)
-k_msd_partition_slots(const KeyT *__restrict__ in, KeyT *__restrict__ out, const MsdTileDesc *__restrict__ desc,
-                      KeyT base, int shift, u32 bins, int bins_log2, u32 *__restrict__ cursor)
-{
-    constexpr int THREADS = QCE_MSDS_THREADS, ITEMS = QCE_MSDS_ITEMS, WARPS = THREADS / 32;
-    extern __shared__ __align__(128) unsigned char msds_smem[];
-    KeyT *const stage = reinterpret_cast<KeyT *>(msds_smem);
-    __shared__ u32 cnt[256], goff[256], excl[256];
-    __shared__ u32 scratch[33];
-    __shared__ u32 s_redo;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const MsdTileDesc d = desc[blockIdx.x];
-    const u32 count = d.count;
-    if (count == 0) return;
-    const u32 mask = bins - 1;
-    const int cap_log2 = QCE_MSDS_SLOTS_LOG2 - bins_log2; // >= 5: bins <= 256
-    const u32 cap = 1u << cap_log2, cmask = cap - 1;
-
-    KeyT key[ITEMS];
-#pragma unroll
-    for (int j = 0; j < ITEMS; j++) {
-        const u32 i = tid + j * THREADS;
-        key[j] = i < count ? ld_stream_key<KeyT>(in + d.begin + i) : (KeyT)0;
-    }
-    if (tid < 256) cnt[tid] = 0;
-    if (tid == 0) s_redo = 0;
-    __syncthreads();
-
-    bool redo = false;
-    {   // half of this warp's first 32 keys on one digit: the windows will not hold this tile
-        const u32 dg0 = (u32)((key[0] - base) >> shift) & mask;
-        const u32 lead = __shfl_sync(QCE_FULL_MASK, dg0, 0);
-        redo = count >= THREADS && bins >= 8 && __popc(__ballot_sync(QCE_FULL_MASK, dg0 == lead)) >= 16;
-    }
-    if (!redo) {
-#pragma unroll
-        for (int j = 0; j < ITEMS; j++) {
-            const u32 i = tid + j * THREADS;
-            if (i < count) {
-                const u32 dg = (u32)((key[j] - base) >> shift) & mask;
-                const u32 s = atomicAdd(&cnt[dg], 1u);
-                if (s < cap) stage[(dg << cap_log2) + ((s + dg) & cmask)] = key[j];
-                else redo = true;
-            }
-        }
-    }
-    if (redo) s_redo = 1;
-    __syncthreads();
-
-    if (!s_redo) {
-        if (tid < (int)bins) {
-            const u32 c = cnt[tid];
-            goff[tid] = c ? atomicAdd(&cursor[d.bucket * bins + tid], c) : 0u;
-        }
-        __syncthreads();
-        // 256 units of 32 slots; warp w takes units w, w + 16, ...; lane i holds unit w + 16 i
-        u32 u_fill = 0, u_src = 0, u_dst = 0;
-        if (lane < 256 / WARPS) {
-            const u32 u = warp + WARPS * lane;
-            const u32 dg = u >> (cap_log2 - 5), k = (u & ((1u << (cap_log2 - 5)) - 1)) << 5;
-            const u32 c = cnt[dg];
-            u_fill = c > k ? min(c - k, 32u) : 0u;
-            u_src = dg; // the window base and the rotation both follow from the digit
-            u_dst = goff[dg] + k;
-        }
-#pragma unroll 4
-        for (int i = 0; i < 256 / WARPS; i++) {
-            const u32 fill = __shfl_sync(QCE_FULL_MASK, u_fill, i);
-            const u32 dg = __shfl_sync(QCE_FULL_MASK, u_src, i);
-            const u32 dst = __shfl_sync(QCE_FULL_MASK, u_dst, i);
-            if ((u32)lane < fill) {
-                const u32 u = warp + WARPS * i;
-                const u32 k = (u & ((1u << (cap_log2 - 5)) - 1)) << 5;
-                out[dst + lane] = stage[(dg << cap_log2) + ((k + lane + dg) & cmask)];
-            }
-        }
-        return;
-    }
-
-    // ---- skewed tile: ranks, scan, contiguous staging (the keys are still in registers)
-    if (tid < 256) cnt[tid] = 0;
-    __syncthreads();
-    u32 slot[ITEMS];
-#pragma unroll
-    for (int j = 0; j < ITEMS; j++) {
-        const u32 i = tid + j * THREADS;
-        const bool live = i < count;
-        const u32 dg = live ? (u32)((key[j] - base) >> shift) & mask : 0xffffffffu;
-        // a warp that sits on one digit counts once instead of 32 times on one shared address
-        const u32 lead = __shfl_sync(QCE_FULL_MASK, dg, 0);
-        const u32 same = __ballot_sync(QCE_FULL_MASK, dg == lead);
-        if (lead != 0xffffffffu && __popc(same) >= 8) {
-            u32 b = 0;
-            if (lane == 0) b = atomicAdd(&cnt[lead], (u32)__popc(same));
-            b = __shfl_sync(QCE_FULL_MASK, b, 0);
-            if (dg == lead) slot[j] = (dg << 16) | (b + __popc(same & lanemask_lt()));
-            else if (live) slot[j] = (dg << 16) | atomicAdd(&cnt[dg], 1u);
-        } else if (live) {
-            slot[j] = (dg << 16) | atomicAdd(&cnt[dg], 1u);
-        }
-    }
-    __syncthreads();
-    {
-        const u32 c = tid < 256 ? cnt[tid] : 0u;
-        u32 tot;
-        const u32 ex = block_scan_excl<u32, THREADS>(c, scratch, &tot);
-        if (tid < 256) {
-            excl[tid] = ex;
-            goff[tid] = (c ? atomicAdd(&cursor[d.bucket * bins + tid], c) : 0u) - ex;
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < ITEMS; j++) {
-        const u32 i = tid + j * THREADS;
-        if (i < count) stage[excl[slot[j] >> 16] + (slot[j] & 0xffffu)] = key[j];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < ITEMS; j++) {
-        const u32 p = tid + j * THREADS;
-        if (p < count) {
-            const KeyT k = stage[p];
-            out[goff[(u32)((k - base) >> shift) & mask] + p] = k;
-        }
-    }
-}
-
 // Largest segment length (to decide whether every sub-bucket fits the finish kernel).
 // min and max of the per-tuple match counts of a merge (uniform multiplicity test, 8f-2)
 __global__ void __launch_bounds__(256) k_minmax_u32(const u32 *__restrict__ v, u32 n, u32 *__restrict__ out_min, u32 *__restrict__ out_max)

@@ -717,21 +717,10 @@ int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done, const u32 
         bulk = e ? atoi(e) : 1;
         if (bulk) CK(cudaFuncSetAttribute(k_msd_partition_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QCE_MSDB_SMEM));
     }
-    static int slots = -1; // QCE_MSD_SLOTS=0: the bulk-copy / plain kernels with contiguous staging (for comparison)
-    if (slots < 0) {
-        const char *e = getenv("QCE_MSD_SLOTS");
-        slots = e ? atoi(e) : 0;
-        CK(cudaFuncSetAttribute((k_msd_partition_slots<u64, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MsdsSmem<u64>::bytes));
-    }
     MsdTileDesc *tdesc = nullptr;
     const u32 ntiles_cap = ntiles0 + nbA;
     const int bulk_grid = G.sms * 3;
-    if (slots) {
-        if (sc.get(&tdesc, ntiles_cap) != 0) return -1;
-        LAUNCH("msd_tiles", k_msd_tile_desc, (int)ceil_div(ntiles0, 256), 256, 0, lvl0, lvl0 + 2, lvl0 + 3, 1u, ntiles0, tdesc);
-        LAUNCH("msd_partition", (k_msd_partition_slots<u64, 3>), (int)ntiles0, QCE_MSDS_THREADS, MsdsSmem<u64>::bytes, *keys, alt, tdesc,
-               base, shiftA, nbA, 8, curA);
-    } else if (bulk) {
+    if (bulk) {
         if (sc.get(&tdesc, ntiles_cap) != 0) return -1;
         LAUNCH("msd_tiles", k_msd_tile_desc, (int)ceil_div(ntiles0, 256), 256, 0, lvl0, lvl0 + 2, lvl0 + 3, 1u, ntiles0, tdesc);
         LAUNCH("msd_partition", k_msd_partition_bulk, (int)std::min<u32>(ntiles0, (u32)bulk_grid), QCE_MSDB_THREADS, QCE_MSDB_SMEM, *keys, alt,
@@ -782,11 +771,7 @@ int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done, const u32 
     const bool big_route = max_sub > MSD_LOCAL_CAP && big_path && R > 0 && R <= 12 && nbig <= BIG_MAX;
     if (max_sub <= MSD_LOCAL_CAP || R == 0 || big_route) {
         CK(cudaMemcpyAsync(curB, suboff, nsub * sizeof(u32), cudaMemcpyDeviceToDevice, cx().stream));
-        if (slots) {
-            LAUNCH("msd_tiles", k_msd_tile_desc, (int)ceil_div(ntiles1, 256), 256, 0, tstart1, offA, histA, nbA, ntiles1, tdesc);
-            LAUNCH("msd_partition", (k_msd_partition_slots<u64, 3>), (int)ntiles1, QCE_MSDS_THREADS, MsdsSmem<u64>::bytes, alt, *keys, tdesc,
-                   base, shiftB, nbB, P2, curB);
-        } else if (bulk) {
+        if (bulk) {
             LAUNCH("msd_tiles", k_msd_tile_desc, (int)ceil_div(ntiles1, 256), 256, 0, tstart1, offA, histA, nbA, ntiles1, tdesc);
             LAUNCH("msd_partition", k_msd_partition_bulk, (int)std::min<u32>(ntiles1, (u32)bulk_grid), QCE_MSDB_THREADS, QCE_MSDB_SMEM, alt,
                    *keys, tdesc, ntiles1, base, shiftB, nbB, curB);
@@ -1080,8 +1065,12 @@ int merge_join_t(const qce_tuples *R, const qce_tuples *S, bool want_r, bool wan
                                     (int)QCE_JSMEM_BYTES));
             attr_set = true;
         }
+        if (tl_join_stats) {
+            const u32 init[4] = {0xffffffffu, 0u, 0u, 0u}; // d_scalars[2] = {min, max}
+            CK(cudaMemcpyAsync(cx().d_scalars + 2, init, sizeof init, cudaMemcpyHostToDevice, cx().stream));
+        }
         LAUNCH("join_bounds", (k_join_bounds<WR, WS>), (int)ntiles, QCE_JTHREADS, QCE_JSMEM_BYTES, vr, nR, vs, win,
-               lb, cnt, tile_total, tile_chunks);
+               lb, cnt, tile_total, tile_chunks, tl_join_stats ? (u32 *)(cx().d_scalars + 2) : nullptr);
     }
     if (ntiles <= 512) {
         LAUNCH("scan_tiles", (k_scan_excl_warp<u64, u64>), 1, 32, 0, tile_total, tile_off, (u64)ntiles, cx().d_scalars);
@@ -1092,7 +1081,7 @@ int merge_join_t(const qce_tuples *R, const qce_tuples *S, bool want_r, bool wan
         LAUNCH("scan_tiles", (k_scan_excl<u32, u32>), 1, 1024, 0, tile_chunks, chunk_off, (u64)ntiles,
                cx().d_scalars + 1);
     }
-    if (tl_join_stats) {
+    if (tl_join_stats && walk) {
         const u32 init[4] = {0xffffffffu, 0u, 0u, 0u}; // d_scalars[2] = {min, max}
         CK(cudaMemcpyAsync(cx().d_scalars + 2, init, sizeof init, cudaMemcpyHostToDevice, cx().stream));
         LAUNCH("join_stats", k_minmax_u32, grid_for(1024, nR, 4), 256, 0, cnt, nR, (u32 *)(cx().d_scalars + 2), (u32 *)(cx().d_scalars + 2) + 1);
