@@ -52,6 +52,69 @@ __device__ __forceinline__ u32 upper_bound_g(const TupleView &t, u32 lo, u32 hi,
     return lo;
 }
 
+// lower / upper bound of `key` in the sorted run S[lo, hi), starting from a guess g in [lo, hi):
+// gallop away from the guess (steps 1, 2, 4, ...) until the answer is bracketed, then bisect the
+// bracket.  With a good guess this is two or three probes in one or two neighbouring sectors where
+// the plain bisection of a 10^5-tuple window is ~17 dependent misses -- the case of a selective
+// filter on the outer side of a key / foreign-key join, whose tiles span windows far larger than
+// the count table or the staging buffer can hold.
+template <bool WIDE, bool UPPER>
+__device__ __forceinline__ u32 bound_from_guess(const TupleView &t, u32 lo, u32 hi, u32 g, u64 key)
+{
+    // invariant: every index < lo is "left" (key' < key, or <= for UPPER), every index >= hi is not
+#define QCE_LEFT(i) (UPPER ? (tv_key<WIDE>(t, (i)) <= key) : (tv_key<WIDE>(t, (i)) < key))
+    if (lo >= hi) return lo;
+    if (QCE_LEFT(g)) {
+        lo = g + 1;
+        for (u32 step = 1;; step <<= 1) {
+            const u32 q = lo + step - 1;
+            if (q >= hi || q < lo) break;
+            if (QCE_LEFT(q)) lo = q + 1;
+            else { hi = q; break; }
+        }
+    } else {
+        hi = g;
+        for (u32 step = 1;; step <<= 1) {
+            if (step == 0 || hi - lo < step) break;
+            const u32 q = hi - step;
+            if (!QCE_LEFT(q)) hi = q;
+            else { lo = q + 1; break; }
+        }
+    }
+    while (lo < hi) {
+        const u32 mid = lo + ((hi - lo) >> 1);
+        if (QCE_LEFT(mid)) lo = mid + 1;
+        else hi = mid;
+    }
+#undef QCE_LEFT
+    return lo;
+}
+// [lb, ub) of `key` in the window S[w.x, w.y) whose first and last keys are ks0 <= ks1: the guess
+// interpolates the key's position between them (exact for a dense key column); scale = (wn - 1) /
+// (ks1 - ks0), computed once per tile.  Windows below QCE_JINTERP_MIN tuples are bisected: they stay in
+// L1 / L2 while a tile's 2048 lookups run over them, and a dozen cached probes beat the guess's
+// arithmetic and galloping there (config 3 lost 4 % with the guess on every window).
+// (not inlined: the rare path of the join kernels, and inlined its registers cost the common path spills)
+// Returns lb | ub << 32.
+#define QCE_JINTERP_MIN 65536u
+template <bool WIDE>
+__device__ __noinline__ u64 window_bounds_g(TupleView S, uint2 w, u64 ks0, u64 ks1, double scale, u64 key)
+{
+    u32 lb, ub;
+    if (key < ks0) return (u64)w.x | ((u64)w.x << 32);
+    if (key > ks1) return (u64)w.y | ((u64)w.y << 32);
+    const u32 wn = w.y - w.x;
+    if (wn < QCE_JINTERP_MIN) {
+        lb = lower_bound_g<WIDE>(S, w.x, w.y, key);
+        ub = upper_bound_g<WIDE>(S, lb, w.y, key);
+    } else {
+        const u32 g = w.x + min(wn - 1, (u32)((double)(key - ks0) * scale));
+        lb = bound_from_guess<WIDE, false>(S, w.x, w.y, g, key);
+        ub = bound_from_guess<WIDE, true>(S, lb, w.y, min(lb, w.y - 1), key);
+    }
+    return (u64)lb | ((u64)ub << 32);
+}
+
 // One thread per R tile: the S window [lo, hi) its key range can match.
 template <bool WR, bool WS>
 __global__ void __launch_bounds__(256)
@@ -166,6 +229,8 @@ k_join_bounds(TupleView R, u32 nR, TupleView S, const uint2 *__restrict__ win,
         }
     } else {
         const bool staged = wn <= QCE_JWIN;
+        const u64 ks0 = staged ? 0ull : tv_key<WS>(S, w.x), ks1 = staged ? 0ull : tv_key<WS>(S, w.y - 1);
+        const double scale = ks1 > ks0 ? (double)(wn - 1) / (double)(ks1 - ks0) : 0.0;
         if (staged) {
             for (u32 i = tid; i < wn; i += QCE_JTHREADS) skeys[i] = tv_key<WS>(S, w.x + i);
         }
@@ -179,9 +244,10 @@ k_join_bounds(TupleView R, u32 nR, TupleView S, const uint2 *__restrict__ win,
                     lb = bound_s<true>(skeys, wn, key[k]) + w.x;
                     ub = bound_s<false>(skeys, wn, key[k]) + w.x;
                 } else {
-                    // S is much denser than R here (or one key is very heavy)
-                    lb = lower_bound_g<WS>(S, w.x, w.y, key[k]);
-                    ub = upper_bound_g<WS>(S, lb, w.y, key[k]);
+                    // a window too large to stage: R is sparse against S (a selective filter), or one key is very heavy
+                    const u64 b2 = window_bounds_g<WS>(S, w, ks0, ks1, scale, key[k]);
+                    lb = (u32)b2;
+                    ub = (u32)(b2 >> 32);
                 }
                 lb_out[i] = lb;
                 cnt_out[i] = ub - lb;
@@ -296,27 +362,38 @@ k_join_fused(TupleView R, u32 nR, TupleView S, const uint2 *__restrict__ win, u3
                 c[k] = tab[v + 1] - l;
             }
         }
-    } else {
-        const bool staged = wn <= QCE_JWIN;
-        if (staged) {
-            for (u32 i = tid; i < wn; i += QCE_JTHREADS) skeys[i] = tv_key<WS>(S, w.x + i);
-        }
+    } else if (wn <= QCE_JWIN) {
+        for (u32 i = tid; i < wn; i += QCE_JTHREADS) skeys[i] = tv_key<WS>(S, w.x + i);
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < PER; k++) {
             const u32 i = tbase + k * QCE_JTHREADS + tid;
             if (i < nR) {
-                u32 lb, ub;
-                if (staged) {
-                    lb = bound_s<true>(skeys, wn, key[k]) + w.x;
-                    ub = bound_s<false>(skeys, wn, key[k]) + w.x;
-                } else {
-                    lb = lower_bound_g<WS>(S, w.x, w.y, key[k]);
-                    ub = upper_bound_g<WS>(S, lb, w.y, key[k]);
-                }
-                lo[k] = lb;
-                c[k] = ub - lb;
+                const u32 lb = bound_s<true>(skeys, wn, key[k]);
+                lo[k] = lb + w.x;
+                c[k] = bound_s<false>(skeys, wn, key[k]) - lb;
             }
+        }
+    } else {
+        // a window too large to stage: R is sparse against S (a selective filter), or one key is very heavy.
+        // The bounds go through shared memory (unused on this path): held in registers across the calls they
+        // would spill.
+        const u64 ks0 = tv_key<WS>(S, w.x), ks1 = tv_key<WS>(S, w.y - 1);
+        const double scale = ks1 > ks0 ? (double)(wn - 1) / (double)(ks1 - ks0) : 0.0;
+        u32 *tlo = reinterpret_cast<u32 *>(skeys), *tc = tlo + QCE_JTILE;
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const u32 i = tbase + k * QCE_JTHREADS + tid;
+            if (i < nR) {
+                const u64 b2 = window_bounds_g<WS>(S, w, ks0, ks1, scale, key[k]);
+                tlo[k * QCE_JTHREADS + tid] = (u32)b2;
+                tc[k * QCE_JTHREADS + tid] = (u32)(b2 >> 32) - (u32)b2;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const u32 i = tbase + k * QCE_JTHREADS + tid;
+            if (i < nR) { lo[k] = tlo[k * QCE_JTHREADS + tid]; c[k] = tc[k * QCE_JTHREADS + tid]; }
         }
     }
     __syncthreads(); // every lookup is done: the table's memory is reused
@@ -662,20 +739,26 @@ k_checksum(const u32 *__restrict__ ids, u64 n, ChecksumCols cols, u64 *__restric
 // never happens in the reference -- every projected binding has a mid result --
 // but the sharded driver uses it for load-time fingerprints).
 __global__ void __launch_bounds__(256)
-k_column_stats(const u64 *__restrict__ col, u64 n, u64 *__restrict__ max_out)
+k_column_stats(const u64 *__restrict__ col, u64 n, u64 *__restrict__ max_out, u32 *__restrict__ unordered)
 {
+    // max(column) sizes the sort passes; *unordered stays 0 when the column is stored in ascending order (a primary
+    // key usually is): a run built from it is sorted as it stands and its sort is skipped (qce_sort_tuples)
     __shared__ u64 smax[8];
     u64 m = 0;
+    bool bad = false;
     const u64 stride = (u64)gridDim.x * 512;
     for (u64 e = ((u64)blockIdx.x * 256 + threadIdx.x) * 2; e < n; e += stride) {
         if (e + 1 < n) {
             u64 a, b;
             ld_stream_u64x2(col + e, a, b);
             m = max(m, max(a, b));
+            bad |= a > b;
+            if (e + 2 < n) bad |= b > col[e + 2];
         } else {
             m = max(m, col[e]);
         }
     }
+    if (__any_sync(QCE_FULL_MASK, bad) && (threadIdx.x & 31) == 0) atomicOr(unordered, 1u);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(QCE_FULL_MASK, m, o));
     if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = m;

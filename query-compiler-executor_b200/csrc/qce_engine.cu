@@ -65,6 +65,7 @@ struct qce_tuples {
     u64 key_max;   // range after an exchange); they size the MSD buckets
     u32 id_bound;
     bool sorted;
+    bool in_order = false;  // built from a whole base column that is stored in ascending order (Column::in_order)
     bool skewed = false;    // the sort met a heavy key (a sub-bucket over the finish tile): joins take the two-phase route
     u32 *hist256 = nullptr; // device: 256-bin histogram of the top 8 of hist_key_bits key bits (taken by the build
     int hist_key_bits = 0;  // kernels, or by qce_key_histogram); valid while the run is unsorted and unmodified
@@ -88,6 +89,7 @@ struct Column {
     const u64 *d = nullptr; // row-sharded column: VIRTUAL base (window pointer - win_begin), rows outside the
     u64 n = 0;              // window are not resident; n stays the relation's global row count
     u64 maxv = 0;
+    bool in_order = false;  // the whole column is resident and stored in ascending order (seen when it was loaded)
     bool owned = false;
     bool windowed = false;
     u64 win_begin = 0, win_count = 0;
@@ -668,14 +670,14 @@ int msd_sort(u64 **keys, u64 n, u64 key_min, u64 key_max, bool *done, const u32 
     const u64 base = key_min << 32;
     key_max -= key_min;
     const int key_bits = bitlen(key_max);
-    if (key_bits < 9) tl_sort_skewed = true; // a million tuples over fewer than 512 keys
+    if (n / (key_max + 1) >= 16) tl_sort_skewed = true; // 16 or more tuples per possible key: every join tile is heavy
     if (key_bits < 9 || key_bits > 32) return 0;
     // Partition bits P: the smallest count for which a populated sub-bucket holds
     // at most ~2700 tuples on average (finish capacity 4096), assuming keys spread
     // over [0, key_max]; anything denser is caught by the max-bucket check below.
     int P = 9;
     while (P < 16 && P < key_bits && n / (((key_max >> (key_bits - P)) + 1)) > 2700) P++;
-    if (n / (((key_max >> (key_bits - P)) + 1)) > 2700) { tl_sort_skewed = true; return 0; } // too dense for 16 partition bits: LSD
+    if (n / (((key_max >> (key_bits - P)) + 1)) > 2700) return 0; // too dense for 16 partition bits: LSD
     const int P1 = 8, P2 = P - 8, R = key_bits - P;
     const int shiftA = 32 + key_bits - P1, shiftB = 32 + key_bits - P;
     const u32 nbA = 256, nbB = 1u << P2, nsub = nbA * nbB;
@@ -1563,13 +1565,14 @@ static int column_buffer(u32 rel, u32 col, u64 bytes, Column *c, bool *reused)
     c->owned = true;
     return 0;
 }
-static int column_max(const u64 *d, u64 n, u64 *maxv)
+static int column_max(const u64 *d, u64 n, u64 *maxv, bool *in_order = nullptr)
 {
-    CK(cudaMemsetAsync(cx().d_scalars + 8, 0, sizeof(u64), cx().stream));
-    if (n > 0) LAUNCH("column_stats", k_column_stats, grid_for(512, n, 4), 256, 0, d, n, cx().d_scalars + 8);
-    CK(cudaMemcpyAsync(cx().h_scalars + 8, cx().d_scalars + 8, sizeof(u64), cudaMemcpyDeviceToHost, cx().stream));
+    CK(cudaMemsetAsync(cx().d_scalars + 8, 0, 2 * sizeof(u64), cx().stream));
+    if (n > 0) LAUNCH("column_stats", k_column_stats, grid_for(512, n, 4), 256, 0, d, n, cx().d_scalars + 8, (u32 *)(cx().d_scalars + 9));
+    CK(cudaMemcpyAsync(cx().h_scalars + 8, cx().d_scalars + 8, 2 * sizeof(u64), cudaMemcpyDeviceToHost, cx().stream));
     CK(cudaStreamSynchronize(cx().stream));
     *maxv = cx().h_scalars[8];
+    if (in_order) *in_order = (cx().h_scalars[9] & 0xffffffffu) == 0;
     return 0;
 }
 static void install_column(u32 rel, u32 col, const Column &c)
@@ -1732,7 +1735,8 @@ static int upload_impl(u32 rel, u32 col, const void *src, int src_kind, u64 src_
     c.windowed = !whole;
     c.win_begin = begin;
     c.win_count = count;
-    if (column_max((const u64 *)c.alloc, count, &c.maxv) != 0) return -1;
+    if (column_max((const u64 *)c.alloc, count, &c.maxv, &c.in_order) != 0) return -1;
+    if (!whole) c.in_order = false; // a row window: the runs built from it are exchanged by key range anyway
     if (!whole && share_window(&c, per, reused) != 0) return -1;
     install_column(rel, col, c);
     return 0;
@@ -1846,7 +1850,7 @@ int qce_adopt_column_device(uint32_t rel, uint32_t col, const void *dev, uint64_
     (void)reused;
     c.d = (const u64 *)dev;
     c.n = n;
-    if (column_max(c.d, n, &c.maxv) != 0) return -1;
+    if (column_max(c.d, n, &c.maxv, &c.in_order) != 0) return -1;
     install_column(rel, col, c);
     return 0;
 }
@@ -2071,6 +2075,7 @@ int qce_build_tuples_base(uint32_t rel, uint32_t col, qce_tuples **out)
     (*out)->src_rel = rel;
     (*out)->src_col = col;
     (*out)->whole_base = true;
+    (*out)->in_order = cl->in_order && !cl->windowed;
     return 0;
 }
 int qce_build_tuples_base_range(uint32_t rel, uint32_t col, uint64_t row_begin, uint64_t row_count, qce_tuples **out)
@@ -2172,7 +2177,12 @@ int qce_sort_tuples(qce_tuples *t)
     if (t->borrowed && t->sorted) return 0; // a cached sorted base run
     int rc;
     tl_sort_skewed = false;
-    if (t->wide) {
+    static int probe_on = -1; // QCE_SORT_PROBE=0: sort runs of columns that are stored in order like any other
+    if (probe_on < 0) { const char *e = getenv("QCE_SORT_PROBE"); probe_on = e ? atoi(e) : 1; }
+    const bool in_order = probe_on && t->in_order; // built from a whole column stored in key order: sorted as it stands
+    if (in_order) {
+        rc = 0;
+    } else if (t->wide) {
         RadixShifts rs = shifts_for(0, t->key_bits, 8);
         rc = radix_sort(&t->a, &t->ids, t->n, rs);
     } else {

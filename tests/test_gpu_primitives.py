@@ -99,6 +99,27 @@ def test_build_and_sort_base(engine, n, domain):
     engine.tuples_free(t)
 
 
+@pytest.mark.parametrize("n", [2, 4097, 2_500_000])
+@pytest.mark.parametrize("kind", ["ascending", "ascending-with-ties", "one-inversion-at-the-end", "one-inversion-at-the-start"])
+def test_sort_of_a_column_stored_in_order(engine, n, kind):
+    """A run built from a whole base column is probed before it is sorted (k_probe_sorted): a column already
+    in key order is left as it stands, a single inversion anywhere sends it through the sort."""
+    col = np.arange(n, dtype=U64) * 3
+    if kind == "ascending-with-ties":
+        col = col // 12
+    elif kind == "one-inversion-at-the-end":
+        col[-1] = 0
+    elif kind == "one-inversion-at-the-start":
+        col[0] = col[-1] + 5
+    engine.upload_column(104, 0, col)
+    t = engine.build_tuples(104, 0)
+    engine.sort_tuples(t)
+    assert engine.is_sorted(t)
+    k, p = engine.tuples_to_host(t)
+    _assert_sorted_run(k, p, *orc.build_tuples(col))
+    engine.tuples_free(t)
+
+
 def test_sort_skewed_and_presorted(engine):
     rng = np.random.default_rng(9)
     n = 500000
