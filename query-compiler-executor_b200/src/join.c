@@ -315,6 +315,7 @@ static int install_results(join_result *res, DArray *entities, const join_plan *
     if (plan->kind == SCAN_JOIN) {
         /* only the row-id columns are swapped in; bystanders and the sorted
          * column marker stay as they were (:607-627) */
+        mid_result *touched[2] = {NULL, NULL};
         for (int s = 0; s < 2; s++) {
             exists_info where = relation_exists(entities, sides[s]->rel, sides[s]->binding);
             if (where.index == -1) fatal_inconsistent();
@@ -322,6 +323,13 @@ static int install_results(join_result *res, DArray *entities, const join_plan *
             if (entry->payloads != res->results[0] && entry->payloads != res->results[1])
                 qce_rowids_free(entry->payloads); /* the reference leaks the old array */
             entry->payloads = res->results[s];
+            touched[s] = entry;
+        }
+        /* both sides on one binding (a predicate like 0.1=0.2): the entry now holds results[1] and results[0],
+         * the same row ids, belongs to nobody -- 4 bytes per surviving row were lost per query */
+        if (touched[0] == touched[1] && res->results[0] != res->results[1]) {
+            qce_rowids_free(res->results[0]);
+            res->results[0] = res->results[1];
         }
         return 0;
     }

@@ -239,3 +239,38 @@ def test_heavy_key_on_the_inner_side(binaries):
     out, err, rc = run_queries_bin(binaries[0], _paths(db), "0 1|0.1=1.1|0.0 1.2\n", timeout=600)
     assert rc == 0, err[-1500:]
     assert out == "%d %d \n" % (s0, s1)
+
+
+_BALANCE_CHILD = r"""
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np, torch
+import bench
+from oracle import workload as wl, qce_oracle as orc
+rig = bench.Rig(torch, None, 0, 1, 0)
+db = wl.gen_chain_db(300_000, nrel=4, seed=3)
+for r, cols in enumerate(db):
+    for c, a in enumerate(cols):
+        rig.upload_host(10 + r, c, a)
+qs = ["10 11 12 13|0.1=0.2&0.1=1.0&1.1=2.0&2.1=3.0&0.3<900|0.3 1.3 2.3 3.3\n",   # predicate on one binding (scan join)
+      "10 11|0.1=1.0&0.3<500&0.1=0.2|0.0 1.3\n", "10 11 12|0.1=1.0&1.1=2.0|0.3 2.0\n"]
+for q in qs:
+    want = orc.run_batch(db, q.replace("10 11 12 13", "0 1 2 3").replace("10 11 12", "0 1 2").replace("10 11", "0 1"))
+    used = []
+    for _ in range(4):
+        assert rig.run(q) == want
+        rig.eng.sync()
+        used.append(rig.eng.mempool_stats()[1])
+    assert used[1] == used[2] == used[3], (q, used)
+print("ok")
+"""
+
+
+def test_arena_is_balanced_over_repeated_queries(binaries):
+    """Nothing stays allocated from one run of a query to the next -- a predicate with both sides on one binding
+    (0.1=0.2) used to orphan one row-id column per query (install_results, SCAN_JOIN), 112 MB per step of config 3:
+    the arena then grows in the middle of a long run."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-c", _BALANCE_CHILD % root], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and p.stdout.strip().endswith("ok"), (p.stdout[-500:], p.stderr[-2000:])
