@@ -49,8 +49,11 @@ static void *xalloc(uint64_t count, size_t size)
     if (!p) { fprintf(stderr, "mock engine: out of memory\n"); exit(2); }
     return p;
 }
+/* handles alive: the host layer must hand every one back (QCE_MOCK_BALANCE=1 reports at shutdown) */
+static long g_live_ids, g_live_tuples;
 static qce_rowids *new_ids(uint64_t n)
 {
+    __atomic_add_fetch(&g_live_ids, 1, __ATOMIC_RELAXED);
     qce_rowids *r = xalloc(1, sizeof *r);
     r->d = xalloc(n, sizeof(uint64_t));
     r->n = n;
@@ -58,6 +61,7 @@ static qce_rowids *new_ids(uint64_t n)
 }
 static qce_tuples *new_tuples(uint64_t n)
 {
+    __atomic_add_fetch(&g_live_tuples, 1, __ATOMIC_RELAXED);
     qce_tuples *t = xalloc(1, sizeof *t);
     t->k = xalloc(n, sizeof(uint64_t));
     t->p = xalloc(n, sizeof(uint64_t));
@@ -120,7 +124,11 @@ int qce_column_info(uint32_t rel, uint32_t col, uint64_t *n, uint64_t *max_value
 }
 
 int qce_init(int device) { (void)device; return 0; }
-void qce_shutdown(void) {}
+void qce_shutdown(void)
+{
+    if (getenv("QCE_MOCK_BALANCE"))
+        fprintf(stderr, "mock engine: %ld row-id columns and %ld tuple runs were never freed\n", g_live_ids, g_live_tuples);
+}
 int qce_sync(void) { return 0; }
 const char *qce_last_error(void) { return g_err; }
 int qce_abi_version(void) { return 1; }
@@ -235,6 +243,7 @@ uint64_t qce_tuples_count(const qce_tuples *t) { return t ? t->n : 0; }
 void qce_tuples_free(qce_tuples *t)
 {
     if (!t) return;
+    __atomic_sub_fetch(&g_live_tuples, 1, __ATOMIC_RELAXED);
     free(t->k);
     free(t->p);
     free(t);
@@ -270,6 +279,7 @@ static void walk(const qce_tuples *R, const qce_tuples *S, qce_rowids **outR, qc
         pr++;
     }
     qce_rowids *r = xalloc(1, sizeof *r), *s = xalloc(1, sizeof *s);
+    __atomic_add_fetch(&g_live_ids, 2, __ATOMIC_RELAXED);
     r->d = a; r->n = m;
     s->d = b; s->n = m;
     if (outR) *outR = r; else qce_rowids_free(r);
@@ -334,6 +344,7 @@ int qce_distinct_pairs(const qce_rowids *pairsR, const qce_rowids *pairsS, qce_r
     for (uint64_t i = 0; i < n; i++)
         if (i == 0 || r[i] != r[i - 1] || s[i] != s[i - 1]) { r[m] = r[i]; s[m++] = s[i]; }
     qce_rowids *dr = xalloc(1, sizeof *dr), *ds = xalloc(1, sizeof *ds);
+    __atomic_add_fetch(&g_live_ids, 2, __ATOMIC_RELAXED);
     dr->d = r; dr->n = m;
     ds->d = s; ds->n = m;
     *distinctR = dr;
@@ -433,6 +444,7 @@ uint64_t qce_rowids_count(const qce_rowids *ids) { return ids ? ids->n : 0; }
 void qce_rowids_free(qce_rowids *ids)
 {
     if (!ids) return;
+    __atomic_sub_fetch(&g_live_ids, 1, __ATOMIC_RELAXED);
     free(ids->d);
     free(ids);
 }
