@@ -30,6 +30,7 @@
 #include "k_radix.cuh"
 #include "k_exchange.cuh"
 #include "qce_comm.cuh"
+#include "qce_arena.hpp"
 
 #define QCE_ABI_VERSION 1
 
@@ -199,126 +200,31 @@ void row_share(u64 n, u32 rank, u32 world, u64 *begin, u64 *count, u64 *per_out 
     if (per_out) *per_out = per;
 }
 
-// ---- HBM arena ----------------------------------------------------------------
-// Temporaries (tuple runs, ping-pong buffers, masks, look-back words, join
-// scratch, row-id columns) are GB-sized and short-lived.  cudaMallocAsync's pool
-// handled the steady single-query loop, but as soon as the pool ran tight it
-// defragmented by remapping virtual ranges: single allocations took 40-340 ms
-// (tools/sharded_probe.py).  The engine therefore owns its memory: large slabs
-// from cudaMalloc, a best-fit free list with coalescing on the host.  All engine
-// work is ordered on one stream, so a block freed by the host may be handed out
-// again immediately -- any kernel that still reads it was enqueued earlier.
-class Arena {
+// ---- HBM arena (qce_arena.hpp) ------------------------------------------------------------
+// Large slabs from cudaMalloc, a best-fit free list with coalescing on the host: no cudaMalloc / cudaFree on
+// the hot path once the slabs exist.
+static void *arena_slab_alloc(u64 bytes)
+{
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+static void arena_slab_free(void *p) { cudaFree(p); }
+static void arena_grow_hook(const QceArena *self, u64 grew_by, u64 need, bool failed)
+{
+    if (failed)
+        fail("out of device memory: %llu bytes requested, %llu reserved", (unsigned long long)need,
+             (unsigned long long)self->reserved());
+    else if (getenv("QCE_TRACE"))
+        fprintf(stderr, "[qce] arena %p grows by %.1f MB (need %.1f MB, reserved %.1f MB)\n", (const void *)self, grew_by / 1e6,
+                need / 1e6, self->reserved() / 1e6);
+}
+class Arena : public QceArena {
   public:
-    static constexpr u64 kAlign = 512;
-    u64 min_slab = 1ull << 30; // worker contexts (small queries) grow in smaller steps
-
-    int alloc(void **out, u64 bytes)
-    {
-        bytes = (bytes + kAlign - 1) / kAlign * kAlign;
-        if (bytes == 0) bytes = kAlign;
-        auto it = by_size_.lower_bound({bytes, 0});
-        if (it == by_size_.end()) {
-            if (grow(bytes) != 0) return -1;
-            it = by_size_.lower_bound({bytes, 0});
-        }
-        const u64 size = it->first, addr = it->second;
-        by_size_.erase(it);
-        by_addr_.erase(addr);
-        if (size > bytes) insert_free(addr + bytes, size - bytes);
-        live_[addr] = bytes;
-        used_ += bytes;
-        *out = (void *)addr;
-        return 0;
-    }
-    void free(void *p)
-    {
-        if (!p) return;
-        auto it = live_.find((u64)p);
-        if (it == live_.end()) return; // not ours (adopted buffer)
-        u64 addr = it->first, size = it->second;
-        live_.erase(it);
-        used_ -= size;
-        // coalesce with the free neighbours (never across slab boundaries)
-        auto next = by_addr_.find(addr + size);
-        if (next != by_addr_.end() && !slab_starts_.count(addr + size)) {
-            size += next->second;
-            by_size_.erase({next->second, next->first});
-            by_addr_.erase(next);
-        }
-        auto prev = by_addr_.lower_bound(addr);
-        if (prev != by_addr_.begin()) {
-            --prev;
-            if (prev->first + prev->second == addr && !slab_starts_.count(addr)) {
-                addr = prev->first;
-                size += prev->second;
-                by_size_.erase({prev->second, prev->first});
-                by_addr_.erase(prev);
-            }
-        }
-        insert_free(addr, size);
-    }
-    // give the tail of a live block back (an output sized by a guess, once its real size is known)
-    void shrink(void *p, u64 bytes)
-    {
-        auto it = live_.find((u64)p);
-        if (it == live_.end()) return;
-        bytes = (bytes + kAlign - 1) / kAlign * kAlign;
-        if (bytes == 0) bytes = kAlign;
-        if (bytes >= it->second) return;
-        u64 addr = it->first + bytes, size = it->second - bytes;
-        used_ -= size;
-        it->second = bytes;
-        auto next = by_addr_.find(addr + size);
-        if (next != by_addr_.end() && !slab_starts_.count(addr + size)) {
-            size += next->second;
-            by_size_.erase({next->second, next->first});
-            by_addr_.erase(next);
-        }
-        insert_free(addr, size);
-    }
-    void release_all()
-    {
-        for (auto &s : slabs_) cudaFree((void *)s.first);
-        slabs_.clear(); slab_starts_.clear(); by_addr_.clear(); by_size_.clear(); live_.clear();
-        reserved_ = used_ = 0;
-    }
-    u64 reserved() const { return reserved_; }
-    u64 used() const { return used_; }
-
-  private:
-    int grow(u64 need)
-    {
-        // at least as much again as is already reserved, so the slab count stays small
-        u64 bytes = std::max<u64>(std::max<u64>(need, min_slab), reserved_);
-        void *p = nullptr;
-        cudaError_t e = cudaMalloc(&p, bytes);
-        if (e != cudaSuccess && bytes > need) {
-            cudaGetLastError();
-            bytes = need;
-            e = cudaMalloc(&p, bytes);
-        }
-        if (e != cudaSuccess)
-            return fail("out of device memory: %llu bytes requested, %llu reserved (%s)", (unsigned long long)need,
-                        (unsigned long long)reserved_, cudaGetErrorString(e));
-        if (getenv("QCE_TRACE")) fprintf(stderr, "[qce] arena %p grows by %.1f MB (need %.1f MB, reserved %.1f MB)\n", (void *)this, bytes / 1e6, need / 1e6, reserved_ / 1e6);
-        slabs_.push_back({(u64)p, bytes});
-        slab_starts_.insert((u64)p);
-        reserved_ += bytes;
-        insert_free((u64)p, bytes);
-        return 0;
-    }
-    void insert_free(u64 addr, u64 size)
-    {
-        by_addr_[addr] = size;
-        by_size_.insert({size, addr});
-    }
-    std::vector<std::pair<u64, u64>> slabs_;
-    std::set<u64> slab_starts_;
-    std::map<u64, u64> by_addr_;            // free blocks: addr -> size
-    std::set<std::pair<u64, u64>> by_size_; // free blocks: (size, addr)
-    std::map<u64, u64> live_;               // handed out: addr -> size
-    u64 reserved_ = 0, used_ = 0;
+    Arena() : QceArena(arena_slab_alloc, arena_slab_free, arena_grow_hook) {}
 };
 
 struct Ctx {
