@@ -109,3 +109,69 @@ def test_hbm_arena_free_list_on_cpu(tmp_path):
                     os.path.join(ROOT, "tests", "c", "arena_test.cpp")], check=True)
     p = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
     assert p.returncode == 0 and p.stdout.decode().strip() == "arena ok", p.stderr.decode()[-2000:]
+
+
+_SEARCH_HARNESS = r"""
+#include <stdio.h>
+#include <stdlib.h>
+#include <stddef.h>
+#include <algorithm>
+#include <random>
+#include <vector>
+typedef unsigned long long u64;
+typedef unsigned int u32;
+#define __device__
+#define __forceinline__ inline
+struct TupleView { const u64 *a; const u32 *ids; };
+template <bool WIDE> u64 tv_key(const TupleView &t, size_t i) { return WIDE ? t.a[i] : (t.a[i] >> 32); }
+%s
+int main()
+{
+    std::mt19937_64 rng(3);
+    long checked = 0;
+    for (int round = 0; round < 400; round++) {
+        const u32 n = 1 + (u32)(rng() %% (round %% 7 == 0 ? 40000 : 300));
+        const u64 domain = 1 + rng() %% (round %% 3 == 0 ? 5 : (round %% 3 == 1 ? n : 4ull * n));
+        std::vector<u64> keys(n), packed(n);
+        for (auto &k : keys) k = rng() %% domain;
+        std::sort(keys.begin(), keys.end());
+        for (u32 i = 0; i < n; i++) packed[i] = (keys[i] << 32) | i;
+        TupleView wide{keys.data(), nullptr}, pk{packed.data(), nullptr};
+        for (int q = 0; q < 300; q++) {
+            u32 lo = (u32)(rng() %% n), hi = lo + (u32)(rng() %% (n - lo + 1));
+            if (q %% 5 == 0) { lo = 0; hi = n; }
+            const u64 key = q %% 11 == 0 ? domain + 3 : rng() %% (domain + 1);
+            u32 g = lo;
+            if (hi > lo) g = q %% 4 == 0 ? lo : (q %% 4 == 1 ? hi - 1 : lo + (u32)(rng() %% (hi - lo)));
+            const u32 wl = (u32)(std::lower_bound(keys.begin() + lo, keys.begin() + hi, key) - keys.begin());
+            const u32 wu = (u32)(std::upper_bound(keys.begin() + lo, keys.begin() + hi, key) - keys.begin());
+            if (bound_from_guess<true, false>(wide, lo, hi, g, key) != wl || bound_from_guess<true, true>(wide, lo, hi, g, key) != wu ||
+                bound_from_guess<false, false>(pk, lo, hi, g, key) != wl || bound_from_guess<false, true>(pk, lo, hi, g, key) != wu) {
+                fprintf(stderr, "mismatch: n %%u lo %%u hi %%u g %%u key %%llu\n", n, lo, hi, g, key);
+                return 1;
+            }
+            // the way the kernels chain the two: the upper bound starts at the lower bound
+            if (hi > lo && bound_from_guess<true, true>(wide, wl, hi, std::min(wl, hi - 1), key) != wu) return 2;
+            checked++;
+        }
+    }
+    printf("search ok %%ld\n", checked);
+    return 0;
+}
+"""
+
+
+def test_guess_and_gallop_search_on_cpu(tmp_path):
+    """bound_from_guess (csrc/k_join.cuh: the join's search over windows too large to stage -- start at an
+    interpolated guess, gallop until the answer is bracketed, bisect) is lifted from the shipped source as it
+    stands and held to std::lower_bound / std::upper_bound on random sorted runs: duplicates, sub-ranges, guesses at
+    both ends, keys outside the run, packed and wide tuples."""
+    src = open(os.path.join(ROOT, "query-compiler-executor_b200", "csrc", "k_join.cuh")).read()
+    m = re.search(r"template <bool WIDE, bool UPPER>\n__device__ __forceinline__ u32 bound_from_guess.*?\n    return lo;\n}\n", src, re.S)
+    assert m, "bound_from_guess not found in k_join.cuh"
+    cpp = tmp_path / "search_test.cpp"
+    cpp.write_text(_SEARCH_HARNESS % m.group(0))
+    exe = str(tmp_path / "search_test")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-o", exe, str(cpp)], check=True)
+    p = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+    assert p.returncode == 0 and p.stdout.decode().startswith("search ok"), (p.stdout.decode(), p.stderr.decode()[-2000:])
