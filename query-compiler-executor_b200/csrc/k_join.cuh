@@ -442,7 +442,7 @@ k_join_fused(TupleView R, u32 nR, TupleView S, const uint2 *__restrict__ win, u3
             // ~25 tiles back and one window of 32 predecessors reaches it; what the warp waits for is the slowest of
             // those predecessors to publish its own total (ncu: 23 % of the kernel's stall samples sit at the barrier
             // behind this block).  Polling 4 windows per round trip (QCE_JLOOK 4) was measured: 0.67 -> 0.71 ms on
-            // config 2, config 3 9.3 -> 11.7 ms -- four times the polling traffic on the same status lines.
+            // config 2 -- four times the polling traffic on the same status lines.
             int look = (int)t - 1;
             bool done = false;
             while (!done) {
