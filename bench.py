@@ -198,6 +198,13 @@ class Rig:
             raise RuntimeError("host layer failed %d queries: %s" % (failed.value, self.lib.qce_last_error().decode()))
         return self._buf.value.decode()
 
+    def arena(self):
+        """(reserved, in use) bytes of the engine's HBM arena, or None"""
+        try:
+            return self.eng.mempool_stats()
+        except Exception:
+            return None
+
     def share(self, rows):
         b, c = C.c_uint64(), C.c_uint64()
         self.ck(self.lib.qce_row_share(rows, self.rank, self.world, C.byref(b), C.byref(c)))
@@ -261,12 +268,21 @@ class Rig:
         for _ in range(warmup):
             out = self.run(text)
         self.sync_all()
+        arena0 = self.arena()
         self.eng.timer_reset()
         t0 = time.perf_counter()
         for _ in range(steps):
             out = self.run(text)
         ms, launches = self.eng.timer_read()
         wall = 1e3 * (time.perf_counter() - t0)
+        arena1 = self.arena()
+        # steady state allocates nothing new: the engine's HBM arena (this rank's main context) must not have
+        # grown inside the timed region, and every temporary must be back (a leak shows here long before it
+        # costs a cudaMalloc in the middle of a run)
+        self.last_arena = None
+        if arena0 is not None and arena1 is not None:
+            self.last_arena = {"reserved_mb": round(arena1[0] / 1e6, 1), "grew_during_timed_steps": arena1[0] != arena0[0],
+                               "in_use_mb_after_last_step": round(arena1[1] / 1e6, 1)}
         if want is not None and self.rank == 0:
             assert out == want, (out[:200], want[:200])
         return self.max_over_ranks(ms) / steps, launches // max(steps, 1), out, self.max_over_ranks(wall) / steps
@@ -345,6 +361,8 @@ def run_generated(rig, name, w, twin, check, rel_offset, steps, warmup, twin_fir
     }
     if clocks:
         res["clocks"] = clocks
+    if getattr(rig, "last_arena", None):
+        res["arena"] = rig.last_arena
     if len(w.queries) == 1:
         res["result"] = got.strip()
     return res
@@ -535,6 +553,7 @@ def config_c2(rig, rows, steps, warmup, args, local_rank):
     rig.sync_all()
     sampler.start()
     ms_per_step, launches, out, wall_ms = rig.timed(q, steps, 0, want=want)
+    arena_c2 = getattr(rig, "last_arena", None)
     value = 2 * n / (ms_per_step / 1e3)
     # the same K steps again with CUDA events around every kernel launch (adds ~1.5 % to a step, so it is
     # kept out of `value`): per-kernel times for the roofline
@@ -634,7 +653,7 @@ def config_c2(rig, rows, steps, warmup, args, local_rank):
         "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": 6 * col_bytes, "d2h_bytes_per_step": 3 * 8 + 5 * 16,
                 "ms_per_step": ms_e2e / steps, "note": "per rank: its six column windows from pinned host memory, statistics recomputed"},
         "gpu_launches": int(launches) * steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-        "wall_ms_per_step": wall_ms, "ms_per_step_with_kernel_events": ms_prof / steps,
+        "wall_ms_per_step": wall_ms, "ms_per_step_with_kernel_events": ms_prof / steps, "arena": arena_c2,
     })
     return line
 
