@@ -2088,6 +2088,8 @@ int qce_sort_tuples(qce_tuples *t)
     const bool in_order = probe_on && t->in_order; // built from a whole column stored in key order: sorted as it stands
     if (in_order) {
         rc = 0;
+        // the sort would have noticed a run of few distinct keys (msd_sort); here the statistics have to
+        if (t->key_max < ~0ull && t->n / (t->key_max + 1) >= 16) tl_sort_skewed = true;
     } else if (t->wide) {
         RadixShifts rs = shifts_for(0, t->key_bits, 8);
         rc = radix_sort(&t->a, &t->ids, t->n, rs);
