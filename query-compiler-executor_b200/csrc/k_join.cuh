@@ -91,9 +91,9 @@ __device__ __forceinline__ u32 bound_from_guess(const TupleView &t, u32 lo, u32 
 }
 // [lb, ub) of `key` in the window S[w.x, w.y) whose first and last keys are ks0 <= ks1: the guess
 // interpolates the key's position between them (exact for a dense key column); scale = (wn - 1) /
-// (ks1 - ks0), computed once per tile.  Windows below QCE_JINTERP_MIN tuples are bisected: they stay in
-// L1 / L2 while a tile's 2048 lookups run over them, and a dozen cached probes beat the guess's
-// arithmetic and galloping there (config 3 lost 4 % with the guess on every window).
+// (ks1 - ks0), computed once per tile.  Windows below QCE_JINTERP_MIN tuples are bisected as before: they
+// stay in L1 / L2 while a tile's 2048 lookups run over them (a conservative threshold: on config 3, whose
+// windows are small, the two searches measured the same).
 // (not inlined: the rare path of the join kernels, and inlined its registers cost the common path spills)
 // Returns lb | ub << 32.
 #define QCE_JINTERP_MIN 65536u
