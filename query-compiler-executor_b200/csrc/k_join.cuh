@@ -305,8 +305,8 @@ k_join_fused(TupleView R, u32 nR, TupleView S, const uint2 *__restrict__ win, u3
     __shared__ u32 s_tile;
     __shared__ u64 s_gbase;
     const int tid = threadIdx.x, lane = tid & 31;
-    // tiles in launch order: a look-back only ever waits for tiles that are resident or done.  CTAs are
-    // dispatched in blockIdx order; with a ticket the order holds whatever the dispatcher does.
+    // tiles in start order (the ticket): a look-back only ever waits for tiles that are resident or done,
+    // whatever order the CTAs are dispatched in.  Without a ticket the tile is blockIdx.x.
     if (ticket) {
         if (tid == 0) s_tile = atomicAdd(ticket, 1u);
         __syncthreads();

@@ -223,13 +223,13 @@ print("ok")
 """
 
 
-@pytest.mark.parametrize("env", [{"QCE_JOIN_CAP": "1"}, {"QCE_JOIN_CAP": "70000"}, {"QCE_JOIN_TICKET": "1"},
+@pytest.mark.parametrize("env", [{"QCE_JOIN_CAP": "1"}, {"QCE_JOIN_CAP": "70000"}, {"QCE_JOIN_TICKET": "0"},
                                  {"QCE_JOIN_MINB": "4"}, {"QCE_JOIN_FUSED": "0"}],
-                         ids=["guess-1", "guess-70000", "ticket", "4-ctas", "two-phase"])
+                         ids=["guess-1", "guess-70000", "block-order", "4-ctas", "two-phase"])
 def test_merge_join_routes(env):
     """The single-pass join under its routing switches, each in a fresh process (they are read once): an output
     guess of one pair (every later tile is deferred to the chunked writer and the outputs are re-sized), a guess
-    that only some joins overflow, tiles claimed through the ticket, the 64-register build, and the two-phase
+    that only some joins overflow, tiles taken in blockIdx order instead of through the ticket, the 64-register build, and the two-phase
     join it replaces -- all against the oracle's merge."""
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
